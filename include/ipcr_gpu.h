@@ -1,0 +1,209 @@
+/*
+ * ipcr_gpu.h -- C ABI of the B200-native replacement for ipcr's core/engine scan.
+ *
+ * This is the drop-in boundary: a cgo shim binds these entry
+ * points and implements the reference's pipeline.StreamingCompiledSimulator
+ * (/root/reference/internal/pipeline/sim.go:11-39) on top of them, so that the
+ * one-line swap at internal/appcore/core.go:108 (`sim := engine.New(...)`)
+ * replaces the CPU engine with the GPU engine and nothing else changes.
+ *
+ * Conventions
+ *   - plain C types only; no exceptions cross the ABI.
+ *   - every fallible call returns 0 on success, non-zero on failure and writes a
+ *     NUL-terminated message into (err, errlen) when err != NULL.
+ *   - there is NO CPU fallback: without a usable sm_100 device every call fails.
+ *   - a panel is immutable and may be shared by any number of host threads; a
+ *     scratch (stream + device/pinned buffers) belongs to one thread at a time
+ *     (reference protocol: internal/pipeline/pipeline.go:52-69).
+ *   - coordinates are record/chunk-local, 0-based, half-open [start,end)
+ *     exactly as engine.Product (core/engine/product.go:4-35).
+ */
+#ifndef IPCR_GPU_H
+#define IPCR_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPCR_GPU_ABI_VERSION 1
+#define IPCR_GPU_MAX_PRIMER_LEN 64 /* mismatch positions travel as 64-bit masks */
+
+/* replaces engine.Config (core/engine/engine.go:10-19) */
+typedef struct ipcr_cfg {
+    int32_t max_mm;          /* --mismatches; < 0 is rejected (reference is inconsistent there) */
+    int32_t terminal_window; /* 3' protected bases; <= 0 disables */
+    int64_t min_len;         /* 0 = unbounded */
+    int64_t max_len;         /* 0 = unbounded */
+    int64_t hit_cap;         /* per orientation per record; 0 = unlimited */
+    int32_t seed_len;        /* --seed-length: only decides which orientations the reference would
+                                have seeded (hit-cap / emission-order semantics); < 0 = no seeds */
+    uint8_t circular;
+    uint8_t need_sites;      /* accepted; FwdSite/RevSite are slices of the caller's seq */
+    uint8_t reserved[2];
+} ipcr_cfg;
+
+/* replaces primer.Pair (core/primer/pair.go:4-10); strings need not be NUL-terminated */
+typedef struct ipcr_pair {
+    const char *fwd;
+    uint32_t fwd_len;
+    const char *rev;
+    uint32_t rev_len;
+    int64_t min_product; /* 0 = use cfg.min_len (core/engine/engine.go:113-120) */
+    int64_t max_product;
+} ipcr_pair;
+
+/* one FASTA record or chunk (fasta.Record.Seq, core/fasta/reader.go:9-12) */
+typedef struct ipcr_seq {
+    const uint8_t *seq;
+    uint64_t len;
+} ipcr_seq;
+
+/* A piece of a record placed on one device.  Whole records use rec_off = 0 and
+ * own_len = len.  Multi-GPU shards pass len = own_len + halo (halo >= longest
+ * primer - 1) so that a site starting in [0, own_len) is fully visible. */
+typedef struct ipcr_segment {
+    const uint8_t *seq; /* host pointer (upload) or device pointer (adopt) */
+    uint64_t len;
+    uint64_t own_len;
+    uint64_t rec_off; /* record-local coordinate of seq[0] */
+    uint32_t rec_idx;
+    uint32_t reserved;
+} ipcr_segment;
+
+/* replaces the printable part of engine.Product (core/engine/product.go:4-35).
+ * Mismatch positions are bit masks over primer 5'->3' indices: bit j of
+ * fwd_mm_mask = FwdMismatchIdx contains j; rev_mm_mask is ALREADY flipped
+ * (core/engine/engine.go:127-136).  Use ipcr_gpu_product_mismatch_idx to get
+ * the lists in the reference's order. */
+typedef struct ipcr_product {
+    int64_t start, end, length;
+    uint64_t fwd_mm_mask, rev_mm_mask;
+    uint32_t pair_idx; /* index into the panel's pairs: ExperimentID = pairs[pair_idx].ID */
+    uint32_t rec_idx;  /* index of the record within the call (0 for ipcr_gpu_scan) */
+    uint16_t fwd_mm, rev_mm;
+    uint8_t type; /* 0 = "forward", 1 = "revcomp" */
+    uint8_t reserved[11];
+} ipcr_product;
+
+/* one verified primer site (stage-1 output; what multi-GPU shards exchange) */
+typedef struct ipcr_site {
+    uint64_t pos;     /* record-local start */
+    uint64_t mm_mask; /* mismatch mask in orientation coordinates */
+    uint32_t rec_idx;
+    uint16_t orient;  /* unique-orientation id inside the panel */
+    uint8_t mm;
+    uint8_t flags;    /* IPCR_SITE_* */
+} ipcr_site;
+#define IPCR_SITE_TWVIOL 1u /* mismatch inside the protected window (kept only for hit-cap parity) */
+#define IPCR_SITE_HALO 2u   /* the reference's seed window holds a non-ACGT byte (found by its halo pass) */
+
+typedef struct ipcr_record_info {
+    uint64_t len;
+    uint8_t has_reset_byte; /* any byte outside ACGTacgt (core/engine/ac.go:141-148) */
+    uint8_t reserved[7];
+} ipcr_record_info;
+
+/* device-side timings of the last scan on a scratch, milliseconds (CUDA events
+ * on the scratch's stream) */
+typedef struct ipcr_timing {
+    float h2d_ms, pack_ms, filter_ms, verify_ms, pair_ms, d2h_ms, total_ms;
+    uint64_t candidates, sites, products;
+    uint32_t kernel_launches; /* launches issued by the last scan */
+    uint32_t used_jit;        /* 1 if the panel-specialised (NVRTC) scan kernel ran */
+} ipcr_timing;
+
+typedef struct ipcr_panel ipcr_panel;
+typedef struct ipcr_scratch ipcr_scratch;
+typedef struct ipcr_genome ipcr_genome;
+
+/* ---- process / device ---------------------------------------------------- */
+int ipcr_gpu_abi_version(void);
+/* number of visible CUDA devices, or 0 (never fails; no device => 0) */
+int ipcr_gpu_device_count(void);
+/* binds the calling thread to `device` and checks it is sm_100. */
+int ipcr_gpu_init(int device, char *err, size_t errlen);
+
+/* ---- panel: engine.CompilePanel (core/engine/compiled.go:96-136) ---------- */
+ipcr_panel *ipcr_gpu_panel_create(const ipcr_cfg *cfg, const ipcr_pair *pairs, size_t n_pairs,
+                                  char *err, size_t errlen);
+void ipcr_gpu_panel_destroy(ipcr_panel *p);
+size_t ipcr_gpu_panel_num_pairs(const ipcr_panel *p);
+size_t ipcr_gpu_panel_num_orientations(const ipcr_panel *p); /* unique strings scanned */
+/* would the reference have seeded this orientation? which in 'A','B','a','b'
+ * (compiledHas, core/engine/compiled.go:35-37) */
+int ipcr_gpu_panel_have(const ipcr_panel *p, size_t pair_idx, int which);
+/* 0 = table-driven kernel only, 1 = allow the NVRTC-specialised kernel (default),
+ * 2 = force it even for tiny inputs */
+void ipcr_gpu_panel_set_jit(ipcr_panel *p, int mode);
+
+/* ---- scratch: engine.NewSimulationScratch (core/engine/hit_collect.go:19-34) */
+ipcr_scratch *ipcr_gpu_scratch_create(ipcr_panel *p, char *err, size_t errlen);
+void ipcr_gpu_scratch_destroy(ipcr_scratch *s);
+
+/* ---- the hot path: engine.ForEachCompiledProduct (compiled.go:162-267) ---- */
+/* Products come back in the reference's emission order.  *out points into
+ * scratch-owned pinned memory, valid until the next call on that scratch. */
+int ipcr_gpu_scan(ipcr_panel *p, ipcr_scratch *s, const uint8_t *seq, uint64_t len,
+                  const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen);
+/* many records in one launch chain; products are record-major */
+int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, size_t n_recs,
+                        const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen);
+
+/* ---- resident genomes (pack once, scan with many panels) ------------------ */
+/* host segments -> pinned staging -> H2D -> pack */
+ipcr_genome *ipcr_gpu_genome_upload(ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
+                                    size_t n_recs, char *err, size_t errlen);
+/* ASCII already in device memory (segment seq pointers are device pointers that
+ * must stay valid for the genome's lifetime); only the pack kernel runs */
+ipcr_genome *ipcr_gpu_genome_adopt(ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
+                                   size_t n_recs, char *err, size_t errlen);
+void ipcr_gpu_genome_destroy(ipcr_genome *g);
+uint64_t ipcr_gpu_genome_bases(const ipcr_genome *g);
+/* per-record info for this genome's pieces (len = max rec_off+len seen) */
+int ipcr_gpu_genome_records(const ipcr_genome *g, ipcr_record_info *out, size_t n_recs);
+int ipcr_gpu_scan_genome(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g,
+                         const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen);
+
+/* ---- split phase (multi-GPU: find on every shard, gather, pair once) ------ */
+/* stage 1: *sites is a HOST pointer (scratch-owned pinned memory) */
+int ipcr_gpu_find_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g,
+                        const ipcr_site **sites, uint64_t *n_sites, char *err, size_t errlen);
+/* stage 2: host site list (any order, any shards) + whole-record info */
+int ipcr_gpu_pair_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_site *sites, uint64_t n_sites,
+                        const ipcr_record_info *recs, size_t n_recs, const ipcr_product **out,
+                        uint64_t *n_out, char *err, size_t errlen);
+
+/* ---- helpers ---------------------------------------------------------------- */
+/* which: 0 = FwdMismatchIdx (ascending), 1 = RevMismatchIdx (reference order:
+ * flipped, hence descending).  Returns the count written (<= cap). */
+int ipcr_gpu_product_mismatch_idx(const ipcr_product *pr, int which, int32_t *out, int cap);
+int ipcr_gpu_last_timing(const ipcr_scratch *s, ipcr_timing *out);
+/* fills `n` bytes of DEVICE memory with a deterministic uniform ACGT sequence
+ * (splitmix64 of seed and absolute position `first_pos + i`); bench/test input */
+int ipcr_gpu_synth_fill(ipcr_scratch *s, void *d_dst, uint64_t n, uint64_t first_pos, uint64_t seed,
+                        char *err, size_t errlen);
+
+/* ---- debug / test taps (stable, but not part of the drop-in surface) -------- */
+/* copies the packed planes of a genome to host: words[4 * units], unit order
+ * (tile, row, lane); returns W (rows per stripe) via *stripe_rows */
+int ipcr_gpu_debug_planes(const ipcr_genome *g, uint32_t *words, uint64_t max_words,
+                          uint64_t *n_words, uint32_t *stripe_rows, uint64_t *n_tiles);
+/* candidates of the last find_sites/scan on this scratch: (orient << 44 | global start) */
+int ipcr_gpu_debug_candidates(const ipcr_scratch *s, uint64_t *out, uint64_t cap, uint64_t *n);
+/* CPU evaluation of the panel's filter plan at one window (no GPU): 1 if the
+ * plan would flag `start` as a candidate for orientation `orient` */
+int ipcr_gpu_debug_plan_eval(const ipcr_panel *p, uint32_t orient, const uint8_t *seq, uint64_t len,
+                             int64_t start, int raw_mode);
+/* orientation string / type ('A' forward-type, 'a' rc-type) of a unique orientation */
+int ipcr_gpu_debug_orientation(const ipcr_panel *p, uint32_t orient, char *buf, size_t buflen,
+                               int *type);
+/* NVRTC source of the specialised kernel for this panel (for inspection) */
+int ipcr_gpu_debug_jit_source(ipcr_panel *p, int raw_mode, char *buf, size_t buflen, size_t *needed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

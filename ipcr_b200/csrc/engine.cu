@@ -1,0 +1,968 @@
+// engine.cu -- host orchestration + C ABI (include/ipcr_gpu.h) of the B200 scan.
+//
+// Mirrors the call protocol of the reference engine
+// (/root/reference/core/engine/compiled.go:96-267, internal/pipeline/pipeline.go:52-125):
+//   panel_create   == CompilePanel          (once, shared read-only)
+//   scratch_create == NewSimulationScratch  (one per worker: stream + buffers)
+//   scan           == ForEachCompiledProduct (per record / chunk)
+// Stage 1 (find sites): pack -> filter -> verify.  Stage 2 (pair): keys -> sort ->
+// hit cap / compaction -> join count -> scan -> join fill -> D2H.
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "device_types.cuh"
+#include "jit.hpp"
+#include "kernels.cuh"
+#include "plan.hpp"
+#include "sortscan.cuh"
+
+namespace ipcr {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+static std::string fmt(const char *f, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+
+#define CU(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e__ = (x);                                                                  \
+        if (e__ != cudaSuccess)                                                                 \
+            throw ipcr::Error(ipcr::fmt("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__),    \
+                                        __FILE__, __LINE__, cudaGetErrorString(e__)));          \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CU(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(bytes, (size_t)256);
+        want = (want + 255) & ~(size_t)255;
+        CU(cudaMalloc(&p, want));
+        cap = want;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CU(cudaFreeHost(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(bytes, (size_t)4096);
+        CU(cudaMallocHost(&p, want));
+        cap = want;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    ~PinBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    PinBuf() = default;
+    PinBuf(const PinBuf &) = delete;
+    PinBuf &operator=(const PinBuf &) = delete;
+};
+
+// ---- panel tables on one device ---------------------------------------------
+struct PlanTables {
+    DevBuf progs, cols, blk_len, slot_cls;
+    uint32_t n_slots = 0;
+};
+
+struct DevTables {
+    DevBuf orients, cls, pairs;
+    PlanTables plan[2];
+    JitKernel jit[2];
+    bool jit_tried[2] = {false, false};
+};
+
+}  // namespace ipcr
+
+struct ipcr_panel {
+    ipcr::Panel host;
+    std::mutex mu;
+    std::map<int, std::unique_ptr<ipcr::DevTables>> dev;
+};
+
+namespace ipcr {
+
+static void upload(DevBuf &b, const void *src, size_t bytes, cudaStream_t st) {
+    b.ensure(std::max(bytes, (size_t)16));
+    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+}
+
+static DevTables *tables_for(ipcr_panel *p, int device, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(p->mu);
+    auto it = p->dev.find(device);
+    if (it != p->dev.end()) return it->second.get();
+    auto t = std::make_unique<DevTables>();
+    const Panel &h = p->host;
+    std::vector<OrientDev> od;
+    std::vector<uint8_t> cls;
+    const int tw = h.cfg.terminal_window;
+    for (const Orient &o : h.orients) {
+        OrientDev d{};
+        d.L = (uint16_t)o.L;
+        d.seed_off = (uint16_t)o.seed_off;
+        d.seed_len = (uint16_t)o.seed_len;
+        d.rc_type = o.rc_type;
+        d.seeded = o.seeded;
+        d.cls_off = (uint32_t)cls.size();
+        uint64_t pm = 0;
+        if (tw > 0) {
+            for (int j = 0; j < o.L; j++) {
+                const bool prot = o.rc_type ? (j < tw) : (j >= o.L - tw);
+                if (prot) pm |= 1ull << j;
+            }
+        }
+        d.prot_mask = pm;
+        cls.insert(cls.end(), o.cls.begin(), o.cls.end());
+        od.push_back(d);
+    }
+    std::vector<PairDev> pd;
+    for (const PairRoles &r : h.roles) {
+        PairDev d{};
+        d.fwdA = (uint16_t)r.fwdA;
+        d.fwdB = (uint16_t)r.fwdB;
+        d.rcA = (uint16_t)r.rcA;
+        d.rcB = (uint16_t)r.rcB;
+        d.alen = (uint16_t)r.alen;
+        d.blen = (uint16_t)r.blen;
+        d.min_len = r.min_len;
+        d.max_len = r.max_len;
+        pd.push_back(d);
+    }
+    upload(t->orients, od.data(), od.size() * sizeof(OrientDev), st);
+    upload(t->cls, cls.data(), cls.size(), st);
+    upload(t->pairs, pd.data(), pd.size() * sizeof(PairDev), st);
+    for (int v = 0; v < 2; v++) {
+        const ScanPlan &sp = h.plan[v];
+        std::vector<OrientProg> progs;
+        std::vector<ColDev> cols;
+        std::vector<uint8_t> blk_len, slot_cls;
+        int slot_of[16];
+        for (int i = 0; i < 16; i++) slot_of[i] = -1;
+        auto slot = [&](uint8_t c) {
+            if (slot_of[c] < 0) {
+                slot_of[c] = (int)slot_cls.size();
+                slot_cls.push_back(c);
+            }
+            return (uint8_t)slot_of[c];
+        };
+        for (const OrientPlan &op : sp.o) {
+            OrientProg g{};
+            g.col_begin = (uint32_t)cols.size();
+            g.blk_begin = (uint32_t)blk_len.size();
+            g.n_prot = (uint16_t)op.prot.size();
+            g.n_blocks = (uint16_t)op.blocks.size();
+            g.need = (uint16_t)std::max(op.need, 0);
+            g.j0 = (uint16_t)op.j0;
+            for (const ColRef &c : op.prot) cols.push_back(ColDev{c.row, slot(c.cls)});
+            for (const auto &bl : op.blocks) {
+                blk_len.push_back((uint8_t)bl.size());
+                for (const ColRef &c : bl) cols.push_back(ColDev{c.row, slot(c.cls)});
+            }
+            progs.push_back(g);
+        }
+        if (slot_cls.empty()) slot_cls.push_back(1);
+        PlanTables &pt = t->plan[v];
+        pt.n_slots = (uint32_t)slot_cls.size();
+        upload(pt.progs, progs.data(), progs.size() * sizeof(OrientProg), st);
+        upload(pt.cols, cols.data(), cols.size() * sizeof(ColDev), st);
+        upload(pt.blk_len, blk_len.data(), blk_len.size(), st);
+        upload(pt.slot_cls, slot_cls.data(), slot_cls.size(), st);
+    }
+    CU(cudaStreamSynchronize(st));  // host vectors die here
+    DevTables *raw = t.get();
+    p->dev.emplace(device, std::move(t));
+    return raw;
+}
+
+// ---- genome --------------------------------------------------------------------
+struct GenomeData {
+    int device = 0;
+    DevBuf ascii_owned;
+    const uint8_t *ascii = nullptr;  // device pointer to the concatenated buffer
+    GenomeLayout lay{};
+    DevBuf planes, segs_dev, seg_reset;
+    std::vector<SegmentDev> segs;
+    std::vector<ipcr_record_info> recs;
+    bool any_reset = false;
+    uint64_t own_bases = 0;
+};
+
+}  // namespace ipcr
+
+struct ipcr_genome {
+    ipcr::GenomeData g;
+};
+
+struct ipcr_scratch {
+    ipcr_panel *panel = nullptr;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    ipcr::DevTables *tables = nullptr;
+    ipcr::GenomeData own;  // genome of ipcr_gpu_scan / scan_batch calls (buffers are reused)
+    ipcr::DevBuf cand, counters, sites, keys0, keys1, vals0, vals1, keep, keep_off, tmp, fkeys, fs, recs_dev,
+        entry_tasks, task_off, task_cnt, prod_off, products;
+    ipcr::PinBuf h_counts, h_products, h_sites, h_stage, h_reset;
+    uint64_t n_cand = 0;
+    ipcr_timing timing{};
+    uint32_t launches = 0;
+    ~ipcr_scratch() {
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace ipcr {
+
+static uint32_t choose_W(uint64_t total, int sm_count) {
+    // enough tiles for ~2 warps-waves of the filter grid; rows are cheap to repeat on small inputs
+    const uint64_t want_tiles = (uint64_t)sm_count * 16ull;
+    uint32_t W = 512;
+    while (W > 32 && (total + (uint64_t)kStripesPerTile * W - 1) / ((uint64_t)kStripesPerTile * W) < want_tiles) W >>= 1;
+    return W;
+}
+
+static void check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(fmt("launch of %s failed: %s", what, cudaGetErrorString(e)));
+}
+
+// K1 on the genome's concatenated ASCII buffer
+static void pack_genome(ipcr_scratch *s, GenomeData &g) {
+    cudaStream_t st = s->stream;
+    g.lay.W = choose_W(g.lay.total_len, s->sm_count);
+    g.lay.rows = g.lay.W + kExtRows;
+    const uint64_t per_tile = (uint64_t)kStripesPerTile * g.lay.W;
+    g.lay.n_tiles = std::max<uint64_t>(1, (g.lay.total_len + per_tile - 1) / per_tile);
+    g.planes.ensure((size_t)g.lay.n_tiles * g.lay.rows * kLanes * sizeof(uint4));
+    upload(g.segs_dev, g.segs.data(), g.segs.size() * sizeof(SegmentDev), st);
+    g.seg_reset.ensure(g.segs.size() * sizeof(uint32_t));
+    CU(cudaMemsetAsync(g.seg_reset.p, 0, g.segs.size() * sizeof(uint32_t), st));
+    dim3 grid((unsigned)g.lay.n_tiles, (g.lay.rows + 31) / 32), block(32, 32);
+    k_pack<<<grid, block, 0, st>>>(g.ascii, g.lay, g.planes.as<uint4>(), g.segs_dev.as<SegmentDev>(),
+                                   (uint32_t)g.segs.size(), g.seg_reset.as<uint32_t>());
+    check_launch("k_pack");
+    s->launches++;
+    s->h_reset.ensure(g.segs.size() * sizeof(uint32_t));
+    CU(cudaMemcpyAsync(s->h_reset.p, g.seg_reset.p, g.segs.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    g.any_reset = false;
+    for (auto &r : g.recs) r.has_reset_byte = 0;
+    for (size_t i = 0; i < g.segs.size(); i++) {
+        if (s->h_reset.as<uint32_t>()[i]) {
+            g.recs[g.segs[i].rec_idx].has_reset_byte = 1;
+            g.any_reset = true;
+        }
+    }
+}
+
+// builds segment / record tables; `device_src` = segment pointers are device memory (adopt)
+static void build_genome(ipcr_scratch *s, GenomeData &g, const ipcr_segment *segs, size_t n_segs, size_t n_recs,
+                         bool device_src) {
+    g.device = s->device;
+    g.segs.clear();
+    g.recs.assign(n_recs, ipcr_record_info{});
+    g.own_bases = 0;
+    uint64_t off = 0;
+    for (size_t i = 0; i < n_segs; i++) {
+        const ipcr_segment &in = segs[i];
+        if (in.rec_idx >= n_recs) throw Error(fmt("segment %zu: rec_idx %u out of range", i, in.rec_idx));
+        if (in.own_len > in.len) throw Error(fmt("segment %zu: own_len > len", i));
+        SegmentDev d{};
+        if (device_src) {
+            if (i > 0 && in.seq < segs[i - 1].seq + segs[i - 1].len)
+                throw Error("adopted segments must be ascending and non-overlapping in one device buffer");
+            d.global_off = (uint64_t)(in.seq - segs[0].seq);
+        } else {
+            d.global_off = off;
+        }
+        d.len = in.len;
+        d.own_len = in.own_len;
+        d.rec_off = in.rec_off;
+        d.rec_idx = in.rec_idx;
+        off = d.global_off + in.len;
+        g.segs.push_back(d);
+        g.recs[in.rec_idx].len = std::max<uint64_t>(g.recs[in.rec_idx].len, in.rec_off + in.len);
+        g.own_bases += in.own_len;
+    }
+    g.lay.total_len = off;
+    if (g.lay.total_len >= (1ull << kCandPosBits)) throw Error("genome too large for one device buffer");
+    if (n_segs == 0 || g.lay.total_len == 0) {
+        g.ascii = nullptr;
+        return;
+    }
+    cudaStream_t st = s->stream;
+    if (device_src) {
+        g.ascii = segs[0].seq;
+    } else {
+        g.ascii_owned.ensure((size_t)g.lay.total_len + 64);
+        g.ascii = g.ascii_owned.as<uint8_t>();
+        CU(cudaEventRecord(s->ev[0], st));
+        for (size_t i = 0; i < n_segs; i++)
+            if (segs[i].len)
+                CU(cudaMemcpyAsync(g.ascii_owned.as<uint8_t>() + g.segs[i].global_off, segs[i].seq, segs[i].len,
+                                   cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaEventRecord(s->ev[1], st));
+    pack_genome(s, g);
+    CU(cudaEventRecord(s->ev[2], st));
+}
+
+static uint64_t read_counter(ipcr_scratch *s, int idx) {
+    CU(cudaMemcpyAsync(s->h_counts.as<unsigned long long>() + idx, s->counters.as<unsigned long long>() + idx,
+                       sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return s->h_counts.as<unsigned long long>()[idx];
+}
+
+static bool jit_try_launch(ipcr_scratch *s, const GenomeData &g, int variant, uint64_t cand_cap);
+
+static void launch_filter_generic(ipcr_scratch *s, const GenomeData &g, int variant, uint64_t cand_cap) {
+    const PlanTables &pt = s->tables->plan[variant];
+    FilterArgs a{};
+    a.planes = g.planes.as<uint4>();
+    a.lay = g.lay;
+    a.progs = pt.progs.as<OrientProg>();
+    a.cols = pt.cols.as<ColDev>();
+    a.blk_len = pt.blk_len.as<uint8_t>();
+    a.slot_cls = pt.slot_cls.as<uint8_t>();
+    a.n_orient = (uint32_t)s->panel->host.orients.size();
+    a.n_slots = pt.n_slots;
+    a.cand = s->cand.as<unsigned long long>();
+    a.cand_count = s->counters.as<unsigned long long>();
+    a.cand_cap = cand_cap;
+    a.tile_begin = 0;
+    a.tile_end = g.lay.n_tiles;
+    const size_t per_warp = (size_t)32 * pt.n_slots * 32 * sizeof(uint32_t);
+    int wpb = (int)std::min<size_t>(4, (size_t)(160 * 1024) / per_warp);
+    if (wpb < 1) wpb = 1;
+    const size_t smem = per_warp * wpb;
+    static std::mutex attr_mu;
+    {
+        std::lock_guard<std::mutex> lock(attr_mu);
+        CU(cudaFuncSetAttribute(k_filter_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
+    const uint64_t want_blocks = (g.lay.n_tiles + wpb - 1) / wpb;
+    const unsigned grid = (unsigned)std::min<uint64_t>(want_blocks, (uint64_t)s->sm_count * 8);
+    k_filter_generic<<<grid, wpb * 32, smem, s->stream>>>(a);
+    check_launch("k_filter_generic");
+    s->launches++;
+}
+
+// Stage 1.  Leaves verified sites in s->sites (device) and returns their count.
+static uint64_t find_sites(ipcr_scratch *s, const GenomeData &g, bool force_raw) {
+    const Panel &h = s->panel->host;
+    cudaStream_t st = s->stream;
+    s->n_cand = 0;
+    s->timing.used_jit = 0;
+    if (g.lay.total_len == 0 || h.orients.empty()) return 0;
+    const ipcr_cfg &cfg = h.cfg;
+    bool any_rc_unseeded = false;
+    for (const Orient &o : h.orients)
+        if (o.rc_type && !o.seeded) any_rc_unseeded = true;
+    // rc orientations must keep window-violating matches only where the reference caps
+    // BEFORE filterLeftTW (compiled.go:185-190,250-257)
+    const bool raw_possible = cfg.hit_cap > 0 && cfg.max_mm > 0 && cfg.terminal_window > 0;
+    const int variant = raw_possible && (force_raw || g.any_reset || any_rc_unseeded) ? 1 : 0;
+
+    s->counters.ensure(8 * sizeof(unsigned long long));
+    s->h_counts.ensure(8 * sizeof(unsigned long long));
+    double expect = 0.0;
+    for (const OrientPlan &op : h.plan[variant].o) expect += op.cand_prob;
+    uint64_t cap = std::max<uint64_t>(1ull << 16, (uint64_t)(expect * (double)g.lay.total_len * 4.0) + 4096);
+    cap = std::min<uint64_t>(cap, 1ull << 28);
+    CU(cudaEventRecord(s->ev[3], st));
+    uint64_t n_cand = 0;
+    for (int attempt = 0;; attempt++) {
+        s->cand.ensure(cap * sizeof(unsigned long long));
+        CU(cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), st));
+        bool ran_jit = false;
+        if (h.jit_mode > 0) ran_jit = jit_try_launch(s, g, variant, cap);
+        if (!ran_jit) launch_filter_generic(s, g, variant, cap);
+        s->timing.used_jit = ran_jit ? 1 : 0;
+        n_cand = read_counter(s, 0);
+        if (n_cand <= cap) break;
+        if (attempt >= 2 || n_cand * sizeof(unsigned long long) > (32ull << 30))
+            throw Error(fmt("scan produced %llu candidate sites; the panel is too unspecific for this input",
+                            (unsigned long long)n_cand));
+        cap = n_cand + 1024;
+    }
+    CU(cudaEventRecord(s->ev[4], st));
+    s->n_cand = n_cand;
+    s->timing.candidates = n_cand;
+    uint64_t n_sites = 0;
+    if (n_cand > 0) {
+        s->sites.ensure(n_cand * sizeof(ipcr_site));
+        VerifyArgs v{};
+        v.cand = s->cand.as<unsigned long long>();
+        v.n_cand = n_cand;
+        v.ascii = g.ascii;
+        v.segs = g.segs_dev.as<SegmentDev>();
+        v.n_segs = (uint32_t)g.segs.size();
+        v.orients = s->tables->orients.as<OrientDev>();
+        v.cls = s->tables->cls.as<uint8_t>();
+        v.prm.max_mm = cfg.max_mm;
+        v.prm.terminal_window = cfg.terminal_window;
+        v.prm.hit_cap = cfg.hit_cap;
+        v.prm.circular = cfg.circular;
+        v.prm.raw_rc = (uint8_t)variant;
+        v.sites = s->sites.as<ipcr_site>();
+        v.site_count = s->counters.as<unsigned long long>() + 1;
+        v.site_cap = n_cand;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_cand + 255) / 256, (uint64_t)s->sm_count * 16);
+        k_verify<<<grid, 256, 0, st>>>(v);
+        check_launch("k_verify");
+        s->launches++;
+        n_sites = read_counter(s, 1);
+    }
+    CU(cudaEventRecord(s->ev[5], st));
+    s->timing.sites = n_sites;
+    return n_sites;
+}
+
+static uint32_t bit_length(uint64_t v) {
+    uint32_t b = 0;
+    while (v) {
+        b++;
+        v >>= 1;
+    }
+    return b;
+}
+
+// Stage 2.  d_sites: device site list (any order).  Products end up in s->h_products.
+static uint64_t pair_sites(ipcr_scratch *s, const ipcr_site *d_sites, uint64_t n_sites,
+                           const ipcr_record_info *recs, size_t n_recs) {
+    const Panel &h = s->panel->host;
+    cudaStream_t st = s->stream;
+    const size_t n_pairs = h.roles.size();
+    if (n_sites == 0 || n_pairs == 0 || n_recs == 0) return 0;
+    if (n_sites >= (1ull << 32)) throw Error("too many primer sites for one pairing pass");
+    const uint32_t U = (uint32_t)h.orients.size();
+    uint64_t max_len = 1;
+    for (size_t r = 0; r < n_recs; r++) max_len = std::max<uint64_t>(max_len, recs[r].len);
+    KeyLayout kl{};
+    kl.pos_bits = std::max(1u, bit_length(max_len));
+    kl.n_orient = U;
+    const uint32_t prefix_bits = std::max(1u, bit_length((uint64_t)n_recs * U));
+    kl.key_bits = kl.pos_bits + 1 + prefix_bits;
+    if (kl.key_bits > 62) throw Error("record count x orientations x record length exceeds the 62-bit sort key");
+    const uint64_t n_entries = (uint64_t)n_recs * n_pairs * 2ull;
+    if (n_entries >= (1ull << 31)) throw Error("records x pairs too large for one pairing pass; use smaller batches");
+
+    ScanParams prm{};
+    prm.max_mm = h.cfg.max_mm;
+    prm.terminal_window = h.cfg.terminal_window;
+    prm.hit_cap = h.cfg.hit_cap;
+    prm.circular = h.cfg.circular;
+
+    upload(s->recs_dev, recs, n_recs * sizeof(ipcr_record_info), st);
+    s->keys0.ensure(n_sites * 8);
+    s->keys1.ensure(n_sites * 8);
+    s->vals0.ensure(n_sites * 4);
+    s->vals1.ensure(n_sites * 4);
+    s->keep.ensure(n_sites * 4);
+    s->keep_off.ensure((n_sites + 1) * 4);
+    s->fkeys.ensure(n_sites * 8);
+    s->fs.ensure(n_sites * sizeof(FinalSite));
+    uint64_t tmp_words = std::max(sort_tmp_words(n_sites), scan_tmp_words(std::max<uint64_t>(n_sites, n_entries)));
+    s->tmp.ensure(tmp_words * 4);
+
+    const unsigned gs = (unsigned)((n_sites + 255) / 256);
+    k_site_keys<<<gs, 256, 0, st>>>(d_sites, n_sites, s->tables->orients.as<OrientDev>(),
+                                    s->recs_dev.as<ipcr_record_info>(), prm, kl, s->keys0.as<uint64_t>(),
+                                    s->vals0.as<uint32_t>());
+    check_launch("k_site_keys");
+    s->launches++;
+    const int where = radix_sort(st, s->keys0.as<uint64_t>(), s->vals0.as<uint32_t>(), s->keys1.as<uint64_t>(),
+                                 s->vals1.as<uint32_t>(), n_sites, kl.key_bits + 1, s->tmp.as<uint32_t>(),
+                                 &s->launches);
+    check_launch("radix_sort");
+    const uint64_t *skeys = where ? s->keys1.as<uint64_t>() : s->keys0.as<uint64_t>();
+    const uint32_t *svals = where ? s->vals1.as<uint32_t>() : s->vals0.as<uint32_t>();
+    k_site_keep<<<gs, 256, 0, st>>>(skeys, svals, n_sites, d_sites, prm, kl, s->keep.as<uint32_t>());
+    check_launch("k_site_keep");
+    exclusive_scan(st, s->keep.as<uint32_t>(), s->keep_off.as<uint32_t>(), n_sites, s->tmp.as<uint32_t>(),
+                   &s->launches);
+    k_site_compact<<<gs, 256, 0, st>>>(skeys, svals, n_sites, d_sites, s->keep.as<uint32_t>(),
+                                       s->keep_off.as<uint32_t>(), s->fkeys.as<uint64_t>(), s->fs.as<FinalSite>());
+    check_launch("k_site_compact");
+    s->launches += 2;
+    uint32_t n_final = 0;
+    CU(cudaMemcpyAsync(s->h_counts.as<unsigned long long>() + 2, s->keep_off.as<uint32_t>() + n_sites,
+                       sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    n_final = *reinterpret_cast<uint32_t *>(s->h_counts.as<unsigned long long>() + 2);
+    if (n_final == 0) return 0;
+
+    JoinArgs ja{};
+    ja.fkeys = s->fkeys.as<uint64_t>();
+    ja.fs = s->fs.as<FinalSite>();
+    ja.n_sites = n_final;
+    ja.pairs = s->tables->pairs.as<PairDev>();
+    ja.n_pairs = (uint32_t)n_pairs;
+    ja.n_recs = (uint32_t)n_recs;
+    ja.recs = s->recs_dev.as<ipcr_record_info>();
+    ja.prm = prm;
+    ja.kl = kl;
+    s->entry_tasks.ensure(n_entries * 4);
+    s->task_off.ensure((n_entries + 1) * 4);
+    ja.entry_tasks = s->entry_tasks.as<uint32_t>();
+    ja.task_off = s->task_off.as<uint32_t>();
+    k_join_entries<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(ja);
+    check_launch("k_join_entries");
+    s->launches++;
+    exclusive_scan(st, ja.entry_tasks, s->task_off.as<uint32_t>(), n_entries, s->tmp.as<uint32_t>(), &s->launches);
+    CU(cudaMemcpyAsync(s->h_counts.as<unsigned long long>() + 3, s->task_off.as<uint32_t>() + n_entries,
+                       sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint64_t n_tasks = *reinterpret_cast<uint32_t *>(s->h_counts.as<unsigned long long>() + 3);
+    if (n_tasks == 0) return 0;
+    ja.n_tasks = n_tasks;
+    s->task_cnt.ensure(n_tasks * 4);
+    s->prod_off.ensure((n_tasks + 1) * 4);
+    s->tmp.ensure(scan_tmp_words(n_tasks) * 4);
+    ja.task_cnt = s->task_cnt.as<uint32_t>();
+    ja.prod_off = s->prod_off.as<uint32_t>();
+    const unsigned gt = (unsigned)((n_tasks + 127) / 128);
+    k_join<false><<<gt, 128, 0, st>>>(ja);
+    check_launch("k_join<count>");
+    s->launches++;
+    exclusive_scan(st, ja.task_cnt, s->prod_off.as<uint32_t>(), n_tasks, s->tmp.as<uint32_t>(), &s->launches);
+    CU(cudaMemcpyAsync(s->h_counts.as<unsigned long long>() + 4, s->prod_off.as<uint32_t>() + n_tasks,
+                       sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint64_t n_prod = *reinterpret_cast<uint32_t *>(s->h_counts.as<unsigned long long>() + 4);
+    if (n_prod == 0) return 0;
+    s->products.ensure(n_prod * sizeof(ipcr_product));
+    ja.products = s->products.as<ipcr_product>();
+    ja.prod_cap = n_prod;
+    k_join<true><<<gt, 128, 0, st>>>(ja);
+    check_launch("k_join<fill>");
+    s->launches++;
+    CU(cudaEventRecord(s->ev[6], st));
+    s->h_products.ensure(n_prod * sizeof(ipcr_product));
+    CU(cudaMemcpyAsync(s->h_products.p, s->products.p, n_prod * sizeof(ipcr_product), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return n_prod;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.f;
+    }
+    return ms;
+}
+
+static void bind(ipcr_scratch *s) { CU(cudaSetDevice(s->device)); }
+
+static uint64_t scan_genome_impl(ipcr_scratch *s, const GenomeData &g, bool had_upload) {
+    cudaStream_t st = s->stream;
+    if (!had_upload) {
+        CU(cudaEventRecord(s->ev[0], st));
+        CU(cudaEventRecord(s->ev[1], st));
+        CU(cudaEventRecord(s->ev[2], st));
+    }
+    CU(cudaEventRecord(s->ev[3], st));
+    CU(cudaEventRecord(s->ev[4], st));
+    CU(cudaEventRecord(s->ev[5], st));
+    const uint64_t n_sites = find_sites(s, g, false);
+    CU(cudaEventRecord(s->ev[6], st));
+    const uint64_t n_prod = pair_sites(s, s->sites.as<ipcr_site>(), n_sites, g.recs.data(), g.recs.size());
+    if (n_prod == 0) CU(cudaEventRecord(s->ev[6], st));
+    CU(cudaEventRecord(s->ev[7], st));
+    CU(cudaStreamSynchronize(st));
+    ipcr_timing &t = s->timing;
+    t.h2d_ms = ev_ms(s->ev[0], s->ev[1]);
+    t.pack_ms = ev_ms(s->ev[1], s->ev[2]);
+    t.filter_ms = ev_ms(s->ev[3], s->ev[4]);
+    t.verify_ms = ev_ms(s->ev[4], s->ev[5]);
+    t.pair_ms = ev_ms(s->ev[5], s->ev[6]);
+    t.d2h_ms = ev_ms(s->ev[6], s->ev[7]);
+    t.total_ms = ev_ms(s->ev[0], s->ev[7]);
+    t.products = n_prod;
+    t.kernel_launches = s->launches;
+    return n_prod;
+}
+
+static void set_err(char *err, size_t errlen, const std::string &m) {
+    if (!err || errlen == 0) return;
+    snprintf(err, errlen, "%s", m.c_str());
+}
+
+}  // namespace ipcr
+
+#include "jit_launch.hpp"
+
+using namespace ipcr;
+
+#define ABI_TRY try {
+#define ABI_CATCH(ret)                                   \
+    }                                                    \
+    catch (const std::exception &e) {                    \
+        set_err(err, errlen, e.what());                  \
+        return ret;                                      \
+    }                                                    \
+    catch (...) {                                        \
+        set_err(err, errlen, "unknown error");           \
+        return ret;                                      \
+    }
+
+extern "C" {
+
+int ipcr_gpu_abi_version(void) { return IPCR_GPU_ABI_VERSION; }
+
+int ipcr_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ipcr_gpu_init(int device, char *err, size_t errlen) {
+    ABI_TRY
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        throw Error("no CUDA device visible: the ipcr GPU engine has no CPU fallback");
+    }
+    if (device < 0 || device >= n) throw Error(fmt("device %d out of range (0..%d)", device, n - 1));
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        throw Error(fmt("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                        prop.minor));
+    CU(cudaFree(0));
+    return 0;
+    ABI_CATCH(1)
+}
+
+ipcr_panel *ipcr_gpu_panel_create(const ipcr_cfg *cfg, const ipcr_pair *pairs, size_t n_pairs, char *err,
+                                  size_t errlen) {
+    ABI_TRY
+    if (!cfg) throw Error("cfg is NULL");
+    if (n_pairs && !pairs) throw Error("pairs is NULL");
+    auto p = std::make_unique<ipcr_panel>();
+    std::string m = p->host.build(*cfg, pairs, n_pairs);
+    if (!m.empty()) throw Error(m);
+    return p.release();
+    ABI_CATCH(nullptr)
+}
+
+void ipcr_gpu_panel_destroy(ipcr_panel *p) { delete p; }
+size_t ipcr_gpu_panel_num_pairs(const ipcr_panel *p) { return p ? p->host.roles.size() : 0; }
+size_t ipcr_gpu_panel_num_orientations(const ipcr_panel *p) { return p ? p->host.orients.size() : 0; }
+
+int ipcr_gpu_panel_have(const ipcr_panel *p, size_t pair_idx, int which) {
+    if (!p || pair_idx >= p->host.have.size()) return 0;
+    int bit = which == 'A' ? 0 : which == 'B' ? 1 : which == 'a' ? 2 : which == 'b' ? 3 : -1;
+    return bit < 0 ? 0 : (p->host.have[pair_idx] >> bit) & 1;
+}
+
+void ipcr_gpu_panel_set_jit(ipcr_panel *p, int mode) {
+    if (p) p->host.jit_mode = mode;
+}
+
+ipcr_scratch *ipcr_gpu_scratch_create(ipcr_panel *p, char *err, size_t errlen) {
+    ABI_TRY
+    if (!p) throw Error("panel is NULL");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        throw Error("no CUDA device visible: the ipcr GPU engine has no CPU fallback");
+    }
+    auto s = std::make_unique<ipcr_scratch>();
+    s->panel = p;
+    CU(cudaGetDevice(&s->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, s->device));
+    if (prop.major != 10)
+        throw Error(fmt("device %d is sm_%d%d; this library is built for sm_100a (B200) only", s->device,
+                        prop.major, prop.minor));
+    s->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto &e : s->ev) CU(cudaEventCreate(&e));
+    s->counters.ensure(8 * sizeof(unsigned long long));
+    s->h_counts.ensure(8 * sizeof(unsigned long long));
+    s->tables = tables_for(p, s->device, s->stream);
+    return s.release();
+    ABI_CATCH(nullptr)
+}
+
+void ipcr_gpu_scratch_destroy(ipcr_scratch *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    delete s;
+}
+
+int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, size_t n_recs,
+                        const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || s->panel != p) throw Error("scratch does not belong to this panel");
+    if (out) *out = nullptr;
+    if (n_out) *n_out = 0;
+    bind(s);
+    s->launches = 0;
+    s->timing = ipcr_timing{};
+    std::vector<ipcr_segment> segs(n_recs);
+    for (size_t i = 0; i < n_recs; i++) {
+        segs[i].seq = recs[i].seq;
+        segs[i].len = recs[i].len;
+        segs[i].own_len = recs[i].len;
+        segs[i].rec_off = 0;
+        segs[i].rec_idx = (uint32_t)i;
+        segs[i].reserved = 0;
+    }
+    build_genome(s, s->own, segs.data(), n_recs, n_recs, false);
+    const uint64_t n = scan_genome_impl(s, s->own, s->own.lay.total_len > 0);
+    if (out) *out = s->h_products.as<ipcr_product>();
+    if (n_out) *n_out = n;
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_scan(ipcr_panel *p, ipcr_scratch *s, const uint8_t *seq, uint64_t len, const ipcr_product **out,
+                  uint64_t *n_out, char *err, size_t errlen) {
+    ipcr_seq r{seq, len};
+    return ipcr_gpu_scan_batch(p, s, &r, 1, out, n_out, err, errlen);
+}
+
+static ipcr_genome *genome_make(ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs, size_t n_recs, bool dev,
+                                char *err, size_t errlen) {
+    ABI_TRY
+    if (!s) throw Error("scratch is NULL");
+    bind(s);
+    auto g = std::make_unique<ipcr_genome>();
+    build_genome(s, g->g, segs, n_segs, n_recs, dev);
+    CU(cudaStreamSynchronize(s->stream));
+    return g.release();
+    ABI_CATCH(nullptr)
+}
+
+ipcr_genome *ipcr_gpu_genome_upload(ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs, size_t n_recs,
+                                    char *err, size_t errlen) {
+    return genome_make(s, segs, n_segs, n_recs, false, err, errlen);
+}
+
+ipcr_genome *ipcr_gpu_genome_adopt(ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs, size_t n_recs,
+                                   char *err, size_t errlen) {
+    return genome_make(s, segs, n_segs, n_recs, true, err, errlen);
+}
+
+void ipcr_gpu_genome_destroy(ipcr_genome *g) {
+    if (!g) return;
+    cudaSetDevice(g->g.device);
+    delete g;
+}
+
+uint64_t ipcr_gpu_genome_bases(const ipcr_genome *g) { return g ? g->g.own_bases : 0; }
+
+int ipcr_gpu_genome_records(const ipcr_genome *g, ipcr_record_info *out, size_t n_recs) {
+    if (!g || !out) return 1;
+    for (size_t i = 0; i < n_recs && i < g->g.recs.size(); i++) out[i] = g->g.recs[i];
+    return 0;
+}
+
+int ipcr_gpu_scan_genome(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g, const ipcr_product **out,
+                         uint64_t *n_out, char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || !g || s->panel != p) throw Error("bad panel/scratch/genome");
+    if (g->g.device != s->device) throw Error("genome lives on another device than the scratch");
+    if (out) *out = nullptr;
+    if (n_out) *n_out = 0;
+    bind(s);
+    s->launches = 0;
+    s->timing = ipcr_timing{};
+    const uint64_t n = scan_genome_impl(s, g->g, false);
+    if (out) *out = s->h_products.as<ipcr_product>();
+    if (n_out) *n_out = n;
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_find_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g, const ipcr_site **sites,
+                        uint64_t *n_sites, char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || !g || s->panel != p) throw Error("bad panel/scratch/genome");
+    if (g->g.device != s->device) throw Error("genome lives on another device than the scratch");
+    bind(s);
+    s->launches = 0;
+    s->timing = ipcr_timing{};
+    for (int i = 0; i < 8; i++) CU(cudaEventRecord(s->ev[i], s->stream));
+    const uint64_t n = find_sites(s, g->g, true);
+    if (n) {
+        s->h_sites.ensure(n * sizeof(ipcr_site));
+        CU(cudaMemcpyAsync(s->h_sites.p, s->sites.p, n * sizeof(ipcr_site), cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaEventRecord(s->ev[7], s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->timing.filter_ms = ev_ms(s->ev[3], s->ev[4]);
+    s->timing.verify_ms = ev_ms(s->ev[4], s->ev[5]);
+    s->timing.total_ms = ev_ms(s->ev[3], s->ev[7]);
+    s->timing.kernel_launches = s->launches;
+    if (sites) *sites = n ? s->h_sites.as<ipcr_site>() : nullptr;
+    if (n_sites) *n_sites = n;
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_pair_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_site *sites, uint64_t n_sites,
+                        const ipcr_record_info *recs, size_t n_recs, const ipcr_product **out, uint64_t *n_out,
+                        char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || s->panel != p) throw Error("bad panel/scratch");
+    if (out) *out = nullptr;
+    if (n_out) *n_out = 0;
+    bind(s);
+    s->launches = 0;
+    const size_t n_orient = p->host.orients.size();
+    for (uint64_t i = 0; i < n_sites; i++) {
+        if (sites[i].rec_idx >= n_recs) throw Error(fmt("site %llu: rec_idx out of range", (unsigned long long)i));
+        if (sites[i].orient >= n_orient) throw Error(fmt("site %llu: orientation out of range", (unsigned long long)i));
+    }
+    CU(cudaEventRecord(s->ev[5], s->stream));
+    if (n_sites) {
+        s->sites.ensure(n_sites * sizeof(ipcr_site));
+        CU(cudaMemcpyAsync(s->sites.p, sites, n_sites * sizeof(ipcr_site), cudaMemcpyHostToDevice, s->stream));
+    }
+    const uint64_t n = pair_sites(s, s->sites.as<ipcr_site>(), n_sites, recs, n_recs);
+    CU(cudaEventRecord(s->ev[7], s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->timing.pair_ms = ev_ms(s->ev[5], s->ev[7]);
+    s->timing.products = n;
+    s->timing.kernel_launches = s->launches;
+    if (out) *out = s->h_products.as<ipcr_product>();
+    if (n_out) *n_out = n;
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_product_mismatch_idx(const ipcr_product *pr, int which, int32_t *out, int cap) {
+    if (!pr || !out) return 0;
+    int n = 0;
+    if (which == 0) {
+        for (int j = 0; j < 64 && n < cap; j++)
+            if ((pr->fwd_mm_mask >> j) & 1ull) out[n++] = j;
+    } else {
+        // flip() keeps list order, so ascending partner indices come out descending (engine.go:127-136)
+        for (int j = 63; j >= 0 && n < cap; j--)
+            if ((pr->rev_mm_mask >> j) & 1ull) out[n++] = j;
+    }
+    return n;
+}
+
+int ipcr_gpu_last_timing(const ipcr_scratch *s, ipcr_timing *out) {
+    if (!s || !out) return 1;
+    *out = s->timing;
+    return 0;
+}
+
+int ipcr_gpu_synth_fill(ipcr_scratch *s, void *d_dst, uint64_t n, uint64_t first_pos, uint64_t seed, char *err,
+                        size_t errlen) {
+    ABI_TRY
+    if (!s) throw Error("scratch is NULL");
+    bind(s);
+    if (n) {
+        const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)s->sm_count * 32);
+        k_synth_fill<<<grid, 256, 0, s->stream>>>(reinterpret_cast<uint8_t *>(d_dst), n, first_pos, seed);
+        check_launch("k_synth_fill");
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_debug_planes(const ipcr_genome *g, uint32_t *words, uint64_t max_words, uint64_t *n_words,
+                          uint32_t *stripe_rows, uint64_t *n_tiles) {
+    if (!g) return 1;
+    const GenomeData &d = g->g;
+    const uint64_t nw = d.lay.total_len ? d.lay.n_tiles * d.lay.rows * kLanes * 4ull : 0;
+    if (n_words) *n_words = nw;
+    if (stripe_rows) *stripe_rows = d.lay.W;
+    if (n_tiles) *n_tiles = d.lay.n_tiles;
+    if (words && nw && nw <= max_words) {
+        cudaSetDevice(d.device);
+        if (cudaMemcpy(words, d.planes.p, nw * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+
+int ipcr_gpu_debug_candidates(const ipcr_scratch *s, uint64_t *out, uint64_t cap, uint64_t *n) {
+    if (!s) return 1;
+    if (n) *n = s->n_cand;
+    const uint64_t k = std::min<uint64_t>(cap, s->n_cand);
+    if (out && k) {
+        cudaSetDevice(s->device);
+        if (cudaMemcpy(out, s->cand.p, k * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+
+int ipcr_gpu_debug_plan_eval(const ipcr_panel *p, uint32_t orient, const uint8_t *seq, uint64_t len, int64_t start,
+                             int raw_mode) {
+    if (!p || orient >= p->host.orients.size()) return -1;
+    const int v = raw_mode ? 1 : 0;
+    return plan_eval(p->host.orients[orient], p->host.plan[v].o[orient], seq, len, start) ? 1 : 0;
+}
+
+int ipcr_gpu_debug_orientation(const ipcr_panel *p, uint32_t orient, char *buf, size_t buflen, int *type) {
+    if (!p || orient >= p->host.orients.size()) return 1;
+    const Orient &o = p->host.orients[orient];
+    if (buf && buflen) snprintf(buf, buflen, "%s", o.seq.c_str());
+    if (type) *type = o.rc_type ? 'a' : 'A';
+    return 0;
+}
+
+int ipcr_gpu_debug_jit_source(ipcr_panel *p, int raw_mode, char *buf, size_t buflen, size_t *needed) {
+    if (!p) return 1;
+    const std::string src = jit_generate_source(p->host, raw_mode ? 1 : 0);
+    if (needed) *needed = src.size() + 1;
+    if (buf && buflen) snprintf(buf, buflen, "%s", src.c_str());
+    return 0;
+}
+
+}  // extern "C"

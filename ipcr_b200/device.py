@@ -1,0 +1,194 @@
+"""Thin wrappers over the resident-genome and split-phase entry points of the C ABI
+(include/ipcr_gpu.h): pack a genome once, scan it with many panels, or find sites
+on per-GPU shards and pair them once.  Marshalling only."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+from . import _capi
+from .engine import CompiledPanel, Engine, Product, SimulationScratch, _as_buffer
+
+
+class Genome:
+    """A packed genome resident in HBM (striped one-hot bit-planes + the raw bytes)."""
+
+    def __init__(self, handle, n_recs: int, keep=None):
+        self._h = handle
+        self.n_recs = n_recs
+        self._keep = keep
+
+    @staticmethod
+    def _segments(segments: Sequence[Tuple]):
+        """segments: (buffer, rec_idx[, rec_off[, own_len]]) ; buffer is bytes-like or a
+        tensor exposing data_ptr()/numel()."""
+        arr = (_capi.SegmentC * max(1, len(segments)))()
+        keep = []
+        n_recs = 0
+        for i, s in enumerate(segments):
+            addr, n, k = _as_buffer(s[0])
+            keep.append(k)
+            rec = int(s[1])
+            rec_off = int(s[2]) if len(s) > 2 else 0
+            own = int(s[3]) if len(s) > 3 else n
+            arr[i] = _capi.SegmentC(addr, n, own, rec_off, rec, 0)
+            n_recs = max(n_recs, rec + 1)
+        return arr, keep, n_recs
+
+    @classmethod
+    def upload(cls, scratch: SimulationScratch, segments: Sequence[Tuple], n_recs: Optional[int] = None):
+        arr, keep, nr = cls._segments(segments)
+        err = _capi.errbuf()
+        h = _capi.lib().ipcr_gpu_genome_upload(scratch._h, arr, len(segments), n_recs or nr, err, len(err))
+        if not h:
+            raise _capi.GpuError(err.value.decode("utf-8", "replace"))
+        return cls(h, n_recs or nr)
+
+    @classmethod
+    def adopt(cls, scratch: SimulationScratch, segments: Sequence[Tuple], n_recs: Optional[int] = None):
+        """Segment buffers are DEVICE memory (e.g. torch cuda uint8 tensors, views of one
+        allocation in ascending order); they must outlive the genome."""
+        arr, keep, nr = cls._segments(segments)
+        err = _capi.errbuf()
+        h = _capi.lib().ipcr_gpu_genome_adopt(scratch._h, arr, len(segments), n_recs or nr, err, len(err))
+        if not h:
+            raise _capi.GpuError(err.value.decode("utf-8", "replace"))
+        return cls(h, n_recs or nr, keep)
+
+    @property
+    def bases(self) -> int:
+        return int(_capi.lib().ipcr_gpu_genome_bases(self._h))
+
+    def records(self):
+        arr = (_capi.RecordInfoC * max(1, self.n_recs))()
+        _capi.lib().ipcr_gpu_genome_records(self._h, arr, self.n_recs)
+        return [(int(arr[i].len), bool(arr[i].has_reset_byte)) for i in range(self.n_recs)]
+
+    def planes(self):
+        """(W, n_tiles, numpy uint32 array [tile, row, lane, plane]) -- debug tap."""
+        import numpy as np
+
+        L = _capi.lib()
+        nw, W, nt = C.c_uint64(), C.c_uint32(), C.c_uint64()
+        L.ipcr_gpu_debug_planes(self._h, None, 0, C.byref(nw), C.byref(W), C.byref(nt))
+        buf = np.zeros(max(1, nw.value), dtype=np.uint32)
+        rc = L.ipcr_gpu_debug_planes(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint32)), nw.value,
+                                     C.byref(nw), C.byref(W), C.byref(nt))
+        if rc:
+            raise _capi.GpuError("debug_planes failed")
+        return W.value, nt.value, buf[: nw.value].reshape(nt.value, W.value + 31, 32, 4)
+
+    def close(self):
+        if self._h is not None:
+            _capi.lib().ipcr_gpu_genome_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _products(out, n, cp: CompiledPanel, seq_ids: Optional[Sequence[str]] = None) -> List[Product]:
+    res = []
+    for i in range(n):
+        pc = out[i]
+        sid = seq_ids[pc.rec_idx] if seq_ids else str(pc.rec_idx)
+        res.append(Engine._product(pc, sid, cp, None))
+    return res
+
+
+def scan_genome(cp: CompiledPanel, scratch: SimulationScratch, genome: Genome,
+                seq_ids: Optional[Sequence[str]] = None, raw: bool = False):
+    """ForEachCompiledProduct over every record of a resident genome (record-major)."""
+    L = _capi.lib()
+    out = C.POINTER(_capi.ProductC)()
+    n = C.c_uint64()
+    err = _capi.errbuf()
+    _capi.check(L.ipcr_gpu_scan_genome(cp._h, scratch._h, genome._h, C.byref(out), C.byref(n), err, len(err)), err)
+    if raw:
+        return out, n.value
+    return _products(out, n.value, cp, seq_ids)
+
+
+def scan_batch(cp: CompiledPanel, scratch: SimulationScratch, seqs: Sequence, seq_ids=None) -> List[Product]:
+    L = _capi.lib()
+    arr = (_capi.SeqC * max(1, len(seqs)))()
+    keep = []
+    for i, s in enumerate(seqs):
+        addr, n, k = _as_buffer(s)
+        keep.append(k)
+        arr[i] = _capi.SeqC(addr, n)
+    out = C.POINTER(_capi.ProductC)()
+    n = C.c_uint64()
+    err = _capi.errbuf()
+    _capi.check(L.ipcr_gpu_scan_batch(cp._h, scratch._h, arr, len(seqs), C.byref(out), C.byref(n), err, len(err)), err)
+    return _products(out, n.value, cp, seq_ids)
+
+
+def find_sites(cp: CompiledPanel, scratch: SimulationScratch, genome: Genome):
+    """Stage 1 on one device.  Returns a numpy structured array of ipcr_site records."""
+    import numpy as np
+
+    L = _capi.lib()
+    out = C.POINTER(_capi.SiteC)()
+    n = C.c_uint64()
+    err = _capi.errbuf()
+    _capi.check(L.ipcr_gpu_find_sites(cp._h, scratch._h, genome._h, C.byref(out), C.byref(n), err, len(err)), err)
+    if n.value == 0:
+        return np.zeros(0, dtype=SITE_DTYPE)
+    raw = C.string_at(out, n.value * C.sizeof(_capi.SiteC))
+    return np.frombuffer(raw, dtype=SITE_DTYPE).copy()
+
+
+def pair_sites(cp: CompiledPanel, scratch: SimulationScratch, sites, records: Sequence[Tuple[int, bool]],
+               seq_ids=None) -> List[Product]:
+    """Stage 2: sites gathered from any number of shards + whole-record (len, has_reset_byte)."""
+    import numpy as np
+
+    L = _capi.lib()
+    sites = np.ascontiguousarray(sites, dtype=SITE_DTYPE)
+    recs = (_capi.RecordInfoC * max(1, len(records)))()
+    for i, (ln, rs) in enumerate(records):
+        recs[i].len = ln
+        recs[i].has_reset_byte = 1 if rs else 0
+    out = C.POINTER(_capi.ProductC)()
+    n = C.c_uint64()
+    err = _capi.errbuf()
+    ptr = sites.ctypes.data_as(C.POINTER(_capi.SiteC))
+    _capi.check(L.ipcr_gpu_pair_sites(cp._h, scratch._h, ptr, len(sites), recs, len(records), C.byref(out),
+                                      C.byref(n), err, len(err)), err)
+    return _products(out, n.value, cp, seq_ids)
+
+
+def synth_fill(scratch: SimulationScratch, tensor, first_pos: int, seed: int) -> None:
+    """Fill a device uint8 tensor with the deterministic synthetic genome (bench input)."""
+    err = _capi.errbuf()
+    _capi.check(_capi.lib().ipcr_gpu_synth_fill(scratch._h, int(tensor.data_ptr()), int(tensor.numel()),
+                                                first_pos, seed, err, len(err)), err)
+
+
+def synth_bases_host(first_pos: int, n: int, seed: int) -> bytes:
+    """Host restatement of k_synth_fill (csrc/kernels.cuh) for planting / checking inputs."""
+    import numpy as np
+
+    pos = np.arange(first_pos, first_pos + n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = np.uint64(seed) ^ ((pos >> np.uint64(5)) * np.uint64(0xD6E8FEB86659FD93))
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    two = ((x >> ((pos & np.uint64(31)) * np.uint64(2))) & np.uint64(3)).astype(np.uint8)
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[two].tobytes()
+
+
+try:
+    import numpy as _np
+
+    SITE_DTYPE = _np.dtype([("pos", "<u8"), ("mm_mask", "<u8"), ("rec_idx", "<u4"), ("orient", "<u2"),
+                            ("mm", "u1"), ("flags", "u1")])
+    assert SITE_DTYPE.itemsize == 24
+except ImportError:  # pragma: no cover
+    SITE_DTYPE = None

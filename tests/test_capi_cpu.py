@@ -1,0 +1,133 @@
+"""CPU-side checks of the CUDA library: it loads, exports every symbol the
+header declares, fails loudly without a GPU, and its host-side panel compiler
+(unique orientations, `Have`, filter plans) agrees with the oracle.  No kernel
+runs here."""
+import os
+import random
+import re
+
+import pytest
+
+import ipcr_test_helpers as H
+from ipcr_b200 import Config, Engine, Pair, _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _capi.lib()
+    header = open(os.path.join(ROOT, "include", "ipcr_gpu.h")).read()
+    declared = set(re.findall(r"\b(ipcr_gpu_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_capi.SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.ipcr_gpu_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    import ctypes as C
+    assert C.sizeof(_capi.ProductC) == 64
+    assert C.sizeof(_capi.SiteC) == 24
+    assert C.sizeof(_capi.RecordInfoC) == 16
+    assert C.sizeof(_capi.SegmentC) == 40
+    assert C.sizeof(_capi.PairC) == 48
+    assert C.sizeof(_capi.Cfg) == 40
+
+
+def test_fails_loudly_without_gpu():
+    L = _capi.lib()
+    if L.ipcr_gpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_capi.GpuError, match="no CPU fallback"):
+        Engine(Config()).simulate_batch("s", b"ACGTACGTACGT", [Pair("x", "ACG", "ACG")])
+    err = _capi.errbuf()
+    assert L.ipcr_gpu_init(0, err, len(err)) != 0 and b"no CPU fallback" in err.value
+
+
+def test_panel_rejects_what_the_reference_panics_on():
+    e = Engine(Config())
+    for bad in ("ACGX", "acgt", "ACGU"):  # core/primer/rc_test.go:37-53
+        with pytest.raises(ValueError, match="reverse-complement"):
+            e.compile_panel([Pair("x", bad, "ACGT")])
+    with pytest.raises(ValueError, match="max_mm"):
+        Engine(Config(max_mm=-1)).compile_panel([Pair("x", "ACGT", "ACGT")])
+
+
+def test_unique_orientations_are_deduplicated():
+    # `--self` expands one pair into three (internal/common/primers.go:11-38) but only 4 strings
+    a, b = "AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT"
+    pairs = [Pair("m", a, b), Pair("m+A:self", a, a), Pair("m+B:self", b, b)]
+    cp = Engine(Config(max_mm=2, terminal_window=3)).compile_panel(pairs)
+    assert cp.num_orientations == 4
+    got = {cp.orientation(i) for i in range(4)}
+    assert got == {(a, "A"), (b, "A"), (H.revcomp(a), "a"), (H.revcomp(b), "a")}
+
+
+def test_have_matches_reference_seeding(oracle):
+    cases = H.load_reference_cases()
+    for c in cases["seed_structure"] + [k for k in cases["engine_known_answers"] if "have" in k["expect"]]:
+        cfgd = c["cfg"]
+        cp = Engine(Config(**{k: v for k, v in cfgd.items()})).compile_panel(
+            [Pair(f"p{i}", p[0], p[1], p[2], p[3]) for i, p in enumerate(c["pairs"])])
+        panel = oracle.Panel(oracle.make_cfg(**cfgd), [tuple(p) for p in c["pairs"]])
+        for i in range(len(c["pairs"])):
+            for w in "ABab":
+                assert cp.have(i, w) == panel.have(i, w), (c["source"], i, w)
+
+
+def test_have_matches_oracle_randomized(oracle):
+    rng = random.Random(7)
+    for _ in range(200):
+        la, lb = rng.randint(1, 40), rng.randint(1, 40)
+        a = H.random_primer(rng, la, rng.choice([0, 0.1, 0.5, 1.0]))
+        b = H.random_primer(rng, lb, rng.choice([0, 0.1, 0.5]))
+        cfgd = dict(max_mm=rng.randint(0, 4), terminal_window=rng.choice([0, 1, 3, 5]),
+                    seed_len=rng.choice([-1, 0, 4, 8, 12, 16, 33]))
+        cp = Engine(Config(**cfgd)).compile_panel([Pair("x", a, b)])
+        panel = oracle.Panel(oracle.make_cfg(**cfgd), [(a, b)])
+        for w in "ABab":
+            assert cp.have(0, w) == panel.have(0, w), (a, b, cfgd, w)
+
+
+def _true_sites(oracle, seq, orient, rc_type, mm, tw, raw):
+    if rc_type:
+        return {m[0] for m in oracle.find_matches(seq, orient, mm, 0, 0, left_tw=0 if raw else tw)}
+    return {m[0] for m in oracle.find_matches(seq, orient, mm, 0, tw)}
+
+
+def test_filter_plan_never_loses_a_true_site(oracle):
+    """The plan is only a candidate generator; it must flag every start the
+    reference accepts (same contract as the reference's seeds, approx_seed_oracle_test.go)."""
+    rng = random.Random(99)
+    checked = 0
+    for it in range(150):
+        n = rng.randint(120, 300)
+        g = H.random_genome(rng, n, n_frac=rng.choice([0, 0.03]), lower_frac=rng.choice([0, 0.03]))
+        mm, tw = rng.randint(0, 3), rng.choice([0, 1, 3, 4])
+        la, lb = rng.randint(3, 40), rng.randint(3, 40)
+        a = H.random_primer(rng, la, rng.choice([0, 0.15]))
+        b = H.random_primer(rng, lb, rng.choice([0, 0.15]))
+        for _ in range(3):
+            H.plant_amplicon(rng, g, rng.randint(0, n - la - lb - 10), a, b, la + lb + rng.randint(0, 10),
+                             rng.randint(0, mm), rng.randint(0, mm), tw, revcomp_strand=rng.random() < 0.5)
+        seq = bytes(g)
+        cp = Engine(Config(max_mm=mm, terminal_window=tw, hit_cap=rng.choice([0, 5]))).compile_panel(
+            [Pair("x", a, b)])
+        for q in range(cp.num_orientations):
+            s, t = cp.orientation(q)
+            for raw in (False, True):
+                truth = _true_sites(oracle, seq, s, t == "a", mm, tw, raw)
+                for pos in truth:
+                    assert cp.plan_eval(q, seq, pos, raw), (s, t, mm, tw, raw, pos)
+                    checked += 1
+    assert checked > 500
+
+
+def test_filter_plan_is_selective_on_random_dna(oracle):
+    rng = random.Random(5)
+    g = bytes(H.random_genome(rng, 20000))
+    cp = Engine(Config(max_mm=2, terminal_window=3)).compile_panel(
+        [Pair("16S", "AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT")])
+    for q in range(cp.num_orientations):
+        hits = sum(cp.plan_eval(q, g, p) for p in range(len(g) - 30))
+        assert hits <= 4, (q, hits)

@@ -1,0 +1,319 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bar: bit-exact -- same products, same mismatch counts and positions, and the
+same EMISSION ORDER as the reference's production path (oracle layer 2,
+compiled.go:162-267); additionally equal as a multiset to the reference's own
+brute-force oracle (bruteforce.go:11-38) whenever the hit cap does not bind.
+"""
+import random
+
+import numpy as np
+import pytest
+
+import ipcr_test_helpers as H
+from ipcr_b200 import Config, Engine, Pair, SimulationScratch, _capi
+from ipcr_b200 import device as D
+
+pytestmark = pytest.mark.gpu
+
+CASES = H.load_reference_cases()
+
+
+def _tuple(p):
+    return (p.experiment_id, p.type, p.start, p.end, p.length, p.fwd_mm, p.rev_mm,
+            tuple(p.fwd_mismatch_idx), tuple(p.rev_mismatch_idx))
+
+
+def _otuple(pairs, t):
+    return (pairs[t[0]].id,) + tuple(t[1:])
+
+
+def _mk_pairs(raw):
+    return [Pair(f"p{i}", p[0], p[1], p[2] if len(p) > 2 else 0, p[3] if len(p) > 3 else 0)
+            for i, p in enumerate(raw)]
+
+
+def _check(oracle, cfgd, raw_pairs, seq, jit=0, cap_binds=False):
+    pairs = _mk_pairs(raw_pairs)
+    eng = Engine(Config(**cfgd))
+    cp = eng.compile_panel(pairs)
+    cp.set_jit(jit)
+    got = [_tuple(p) for p in eng.simulate_compiled("seq", seq, cp)]
+    ocfg = oracle.make_cfg(**cfgd)
+    want = [_otuple(pairs, t) for t in oracle.simulate_compiled(ocfg, [tuple(p) for p in raw_pairs], seq)]
+    assert got == want, (cfgd, raw_pairs, bytes(seq)[:80])
+    if not cap_binds:
+        brute = [_otuple(pairs, t) for t in oracle.simulate_bruteforce(ocfg, [tuple(p) for p in raw_pairs], seq)]
+        assert H.multiset(got) == H.multiset(brute)
+    return got
+
+
+def test_device_is_blackwell():
+    L = _capi.lib()
+    assert L.ipcr_gpu_device_count() >= 1
+    err = _capi.errbuf()
+    assert L.ipcr_gpu_init(0, err, len(err)) == 0, err.value
+
+
+@pytest.mark.parametrize("case", CASES["engine_known_answers"], ids=lambda c: c["name"])
+def test_reference_known_answers(oracle, case):
+    got = _check(oracle, case["cfg"], case["pairs"], case["seq"].encode())
+    e = case["expect"]
+    if "count" in e:
+        assert len(got) == e["count"]
+    if "min_count" in e:
+        assert len(got) >= e["min_count"]
+    if "first" in e:
+        f = got[0]
+        d = dict(start=f[2], end=f[3], length=f[4], fwd_mm=f[5], rev_mm=f[6], fwd_idx=list(f[7]), rev_idx=list(f[8]))
+        for k, v in e["first"].items():
+            assert d[k] == v
+    if e.get("wrap"):
+        assert got[0][2] > got[0][3]
+
+
+def test_reference_equivalence_matrix(oracle):
+    eq = CASES["equivalence"]
+    n = 0
+    for c in eq["cases"]:
+        for cfgd in eq["configs"]:
+            _check(oracle, cfgd, c["pairs"], c["seq"].encode())
+            n += 1
+    assert n == 81
+    for c in CASES["equivalence_extra"]:
+        for s in c.get("seqs") or [c["seq"]]:
+            for cfgd in c["configs"]:
+                _check(oracle, cfgd, c["pairs"], s.encode())
+
+
+@pytest.mark.parametrize("case", CASES["bench_fixture"]["cases"], ids=lambda c: str(c["pair_count"]))
+def test_reference_bench_fixture(oracle, case):
+    seq, pairs = H.make_engine_bench_fixture(case["pair_count"], case["genome_len"], case["mutate_forward"],
+                                             case["reference_n"])
+    got = _check(oracle, case["cfg"], pairs, seq)
+    for i in range(len(pairs)):
+        assert any(p[0] == f"p{i}" and p[1] == "forward" and p[2] == 128 + 256 * i and p[4] == 180 for p in got)
+
+
+def test_survey_derived_rows(oracle):
+    for c in CASES["survey_derived"]["cases"]:
+        got = _check(oracle, c["cfg"], c["pairs"], c["seq"].encode())
+        want = [("p%d" % p[0], p[1], p[2], p[3], p[4], p[5], p[6], tuple(p[7]), tuple(p[8])) for p in c["products"]]
+        # SURVEY lists brute-force order; the production path emits the halo-found site
+        # last (compiled.go:211-232), which _check already pinned against oracle layer 2
+        assert sorted(got) == sorted(want)
+
+
+def test_empty_and_short_inputs(oracle):
+    cfg = dict(max_mm=1, terminal_window=3)
+    for seq in (b"", b"A", b"ACGTACGTACGT"):
+        # README.md:46 primers are longer than the record => header only
+        _check(oracle, cfg, [("AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT")], seq)
+    eng = Engine(Config())
+    assert eng.simulate_batch("s", b"ACGT", []) == []
+
+
+def test_pack_planes_match_host_packing():
+    rng = random.Random(3)
+    seq = bytes(H.random_genome(rng, 70001, n_frac=0.01, lower_frac=0.02, other_frac=0.01))
+    eng = Engine(Config())
+    cp = eng.compile_panel([Pair("x", "ACGTACGT", "TTGACC")])
+    sc = SimulationScratch(cp)
+    g = D.Genome.upload(sc, [(seq, 0)])
+    W, nt, planes = g.planes()
+    a = np.frombuffer(seq, dtype=np.uint8)
+    total = len(seq)
+    rows = W + 31
+    # position of (tile, row, lane, bit)
+    t, r, l, i = np.meshgrid(np.arange(nt), np.arange(rows), np.arange(32), np.arange(32), indexing="ij")
+    P = ((t * 1024 + l * 32 + i) * W + r).astype(np.int64)
+    valid = P < total
+    byte = np.where(valid, a[np.minimum(P, total - 1)], 0)
+    for k, base in enumerate(b"ACGT"):
+        want = ((byte == base) & valid).astype(np.uint64)
+        word = (want << np.arange(32, dtype=np.uint64)).sum(axis=3).astype(np.uint32)
+        assert np.array_equal(word, planes[..., k]), "ACGT"[k]
+    assert g.records() == [(total, True)]
+    g2 = D.Genome.upload(sc, [(b"ACGTacgtACGT", 0), (b"ACGTNACGT", 1), (b"ACGTACGT", 2)])
+    assert g2.records() == [(12, False), (9, True), (8, False)]
+
+
+def test_candidates_cover_all_true_sites(oracle):
+    rng = random.Random(11)
+    n = 200000
+    g = H.random_genome(rng, n, n_frac=0.001)
+    a, b = "AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT"
+    for k in range(20):
+        H.plant_amplicon(rng, g, 1000 + k * 9000, a, b, 1500, rng.randint(0, 2), rng.randint(0, 2), 3,
+                         revcomp_strand=k % 2 == 1)
+    seq = bytes(g)
+    eng = Engine(Config(max_mm=2, terminal_window=3, max_len=2000))
+    cp = eng.compile_panel([Pair("16S", a, b)])
+    cp.set_jit(0)
+    sc = SimulationScratch(cp)
+    prods = eng.simulate_compiled_with_scratch("s", seq, cp, sc)
+    assert len(prods) >= 20
+    cands = set(sc.candidates())
+    for q in range(cp.num_orientations):
+        s, t = cp.orientation(q)
+        truth = oracle.find_matches(seq, s, 2, 0, 0 if t == "a" else 3, left_tw=3 if t == "a" else 0)
+        assert truth
+        for pos, _mm, _idx in truth:
+            assert (q, pos) in cands
+    # and the filter is selective: far fewer candidates than positions
+    assert len(cands) < n // 100
+
+
+def _random_case(rng, big=False):
+    n = rng.randint(2000, 60000) if big else rng.randint(80, 700)
+    g = H.random_genome(rng, n, n_frac=rng.choice([0, 0, 0.01, 0.05]), lower_frac=rng.choice([0, 0.03]),
+                        other_frac=rng.choice([0, 0.005]))
+    mm, tw = rng.choice([0, 1, 2, 3]), rng.choice([0, 1, 3])
+    pairs = []
+    for _ in range(rng.randint(1, 4)):
+        la, lb = rng.randint(4, 28), rng.randint(4, 28)
+        a = H.random_primer(rng, la, rng.choice([0, 0.1]))
+        b = H.random_primer(rng, lb, rng.choice([0, 0.1]))
+        for _k in range(rng.randint(1, 3)):
+            length = rng.randint(la + lb, la + lb + 40)
+            H.plant_amplicon(rng, g, rng.randint(0, n - length), a, b, length, rng.randint(0, mm), rng.randint(0, mm),
+                             tw, revcomp_strand=rng.random() < 0.5)
+        pairs.append((a, b, rng.choice([0, 0, 12]), rng.choice([0, 0, 150])))
+        if rng.random() < 0.3:
+            pairs.append((a, a, 0, 0))  # self pair (internal/common/primers.go:11-38)
+    cfgd = dict(max_mm=mm, terminal_window=tw, min_len=rng.choice([0, 1, 30]), max_len=rng.choice([0, 120, 2000]),
+                seed_len=rng.choice([0, 4, 12]), circular=rng.random() < 0.3, hit_cap=0)
+    return cfgd, pairs, bytes(g)
+
+
+def test_randomized_parity_small(oracle):
+    rng = random.Random(2024)
+    for _ in range(120):
+        cfgd, pairs, seq = _random_case(rng)
+        _check(oracle, cfgd, pairs, seq)
+
+
+def test_randomized_parity_medium(oracle):
+    rng = random.Random(77)
+    for _ in range(12):
+        cfgd, pairs, seq = _random_case(rng, big=True)
+        _check(oracle, cfgd, pairs, seq)
+
+
+def test_hit_cap_semantics(oracle):
+    # dense short primers so that the cap binds; covers seeded, forced-fallback (reset byte)
+    # and unseeded-orientation paths (compiled.go:185-190,238-257)
+    rng = random.Random(5)
+    for it in range(60):
+        n = rng.randint(60, 400)
+        g = H.random_genome(rng, n, n_frac=rng.choice([0, 0.02]))
+        a = H.random_primer(rng, rng.randint(3, 5), rng.choice([0, 0.3]))
+        b = H.random_primer(rng, rng.randint(3, 5), rng.choice([0, 0.3]))
+        cfgd = dict(max_mm=rng.choice([0, 1, 2]), terminal_window=rng.choice([0, 1, 2]), min_len=0,
+                    max_len=rng.choice([0, 40]), seed_len=rng.choice([-1, 0, 3]), hit_cap=rng.choice([1, 2, 5, 30]),
+                    circular=rng.random() < 0.3)
+        _check(oracle, cfgd, [(a, b, 0, 0)], bytes(g), cap_binds=True)
+
+
+def test_dense_products(oracle):
+    seq = b"ACGT" * 500
+    got = _check(oracle, dict(max_mm=0, terminal_window=0, max_len=60), [("ACG", "ACG")], seq)
+    assert len(got) > 5000
+
+
+def test_need_sites_strings():
+    seq = b"TTTACGTACAAAAGGTACCTTTGGGACGTATAAAAGGTACCAAA"
+    eng = Engine(Config(max_mm=1, terminal_window=0, min_len=6, max_len=80, need_sites=True))
+    prods = eng.simulate("seq", seq, Pair("j", "ACGTAC", "GGTACC", 6, 80))
+    assert prods
+    for p in prods:
+        assert p.fwd_site == seq[p.start:p.start + len(p.fwd_primer)].decode()
+        assert len(p.rev_site) == len(p.rev_primer)
+
+
+def test_scratch_reuse_and_batch(oracle):
+    raw = [("ACGTAC", "GGTACC", 6, 60)]
+    pairs = _mk_pairs(raw)
+    cfgd = dict(max_mm=1, terminal_window=0, min_len=6, max_len=60, seed_len=4)
+    eng = Engine(Config(**cfgd))
+    cp = eng.compile_panel(pairs)
+    sc = eng.new_simulation_scratch(cp)
+    seqs = [b"TTTACGTACAAAAGGTACCTTT", b"TTTACGTATAAAAGGTACCTTT", b"TTTGGTACCAAAAGTACGTTTT",
+            b"TTTACGTACAAAACCCCCCCTTT", b"", b"ACG"]
+    ocfg = oracle.make_cfg(**cfgd)
+    per_rec = []
+    for s in seqs:
+        got = [_tuple(p) for p in eng.simulate_compiled_with_scratch("seq", s, cp, sc)]
+        want = [_otuple(pairs, t) for t in oracle.simulate_compiled(ocfg, raw, s)]
+        assert got == want
+        per_rec.append(want)
+    batch = D.scan_batch(cp, sc, seqs, seq_ids=[f"r{i}" for i in range(len(seqs))])
+    flat = [(f"r{i}",) + w for i, ws in enumerate(per_rec) for w in ws]
+    assert [(p.sequence_id,) + _tuple(p) for p in batch] == flat
+
+
+def test_split_phase_shards_equal_single_scan(oracle):
+    rng = random.Random(31)
+    n = 300000
+    g = H.random_genome(rng, n, n_frac=0.0005)
+    a, b = "AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT"
+    for k in range(12):
+        H.plant_amplicon(rng, g, 500 + k * 24000, a, b, 1400 + k, rng.randint(0, 2), rng.randint(0, 2), 3,
+                         revcomp_strand=k % 3 == 0)
+    # one amplicon straddling every shard boundary
+    shards = 4
+    cut = [n * k // shards for k in range(shards + 1)]
+    for c in cut[1:-1]:
+        H.plant_amplicon(rng, g, c - 700, a, b, 1400, 1, 1, 3)
+        g[c - 10:c + 10] = (a.replace("M", "A")).encode()  # a site straddling the cut itself
+    seq = bytes(g)
+    pairs = [Pair("16S", a, b), Pair("16S+A:self", a, a), Pair("16S+B:self", b, b)]
+    for cfgd in (dict(max_mm=2, terminal_window=3, max_len=2000, hit_cap=0),
+                 dict(max_mm=2, terminal_window=3, max_len=2000, hit_cap=10000),
+                 dict(max_mm=2, terminal_window=3, max_len=0, circular=True)):
+        eng = Engine(Config(**cfgd))
+        cp = eng.compile_panel(pairs)
+        sc = eng.new_simulation_scratch(cp)
+        whole = [_tuple(p) for p in eng.simulate_compiled_with_scratch("0", seq, cp, sc)]
+        assert whole
+        halo = 64
+        sites = []
+        for k in range(shards):
+            lo, hi = cut[k], cut[k + 1]
+            piece = seq[lo:min(n, hi + halo)]
+            gk = D.Genome.upload(sc, [(piece, 0, lo, hi - lo)])
+            sites.append(D.find_sites(cp, sc, gk))
+            gk.close()
+        allsites = np.concatenate(sites)
+        has_reset = b"N" in seq
+        got = [_tuple(p) for p in D.pair_sites(cp, sc, allsites, [(n, has_reset)])]
+        assert got == whole
+        want = [_otuple(pairs, t) for t in oracle.simulate_compiled(
+            oracle.make_cfg(**cfgd), [(p.forward, p.reverse, 0, 0) for p in pairs], seq)]
+        assert whole == want
+
+
+def test_ecoli_sized_circular_config2(oracle):
+    """BASELINE config 2: 27F/1492R --circular --mismatches 2 on a 4.6 Mbp synthetic genome
+    with planted ~1.5 kb amplicons, one spanning the origin."""
+    rng = random.Random(46)
+    n = 4_600_000
+    a, b = "AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT"
+    g = bytearray(np.frombuffer(b"ACGT", dtype=np.uint8)[np.random.default_rng(46).integers(0, 4, n)].tobytes())
+    for k in range(6):
+        H.plant_amplicon(rng, g, 100_000 + k * 700_000, a, b, 1500 + k, k % 3, (k + 1) % 3, 3, revcomp_strand=k % 2 == 1)
+    # origin-spanning: forward site near the end, reverse site near the start
+    fa = H.mutate(rng, H.concrete(rng, a), 1, 0, len(a) - 3)
+    g[n - 800:n - 800 + len(a)] = fa.encode()
+    rb = H.revcomp(H.mutate(rng, H.concrete(rng, b), 2, 0, len(b) - 3))
+    g[700 - len(b):700] = rb.encode()
+    # decoys: mismatch inside the 3' window, and 3 mismatches
+    g[2_000_000:2_000_000 + len(a)] = (H.concrete(rng, a)[:-1] + "T").encode()
+    g[2_100_000:2_100_000 + len(a)] = H.mutate(rng, H.concrete(rng, a), 3, 0, len(a) - 3).encode()
+    seq = bytes(g)
+    pairs = [("AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT", 0, 0), (a, a, 0, 0), (b, b, 0, 0)]
+    cfgd = dict(max_mm=2, terminal_window=3, max_len=2000, hit_cap=10000, circular=True, seed_len=12)
+    for jit in (0, 2):
+        got = _check(oracle, cfgd, pairs, seq, jit=jit)
+        assert sum(1 for p in got if p[0] == "p0") >= 7
+        assert any(p[2] > p[3] for p in got)  # the wrap product
