@@ -202,6 +202,9 @@ int ipcr_gpu_debug_orientation(const ipcr_panel *p, uint32_t orient, char *buf, 
                                int *type);
 /* NVRTC source of the specialised kernel for this panel (for inspection) */
 int ipcr_gpu_debug_jit_source(ipcr_panel *p, int raw_mode, char *buf, size_t buflen, size_t *needed);
+/* runs NVRTC on that source (works without a GPU) and copies the sm_100a cubin out */
+int ipcr_gpu_debug_jit_compile(ipcr_panel *p, int raw_mode, char *cubin, size_t cap, size_t *cubin_size,
+                               char *err, size_t errlen);
 
 #ifdef __cplusplus
 }

@@ -49,7 +49,8 @@ struct OrientDev {
     uint8_t rc_type;
     uint8_t seeded;
     uint32_t cls_off;    // offset into the class byte array
-    uint32_t pad;
+    uint16_t j0[2];      // filter window offset per plan variant (candidate start = window start - j0)
+
     uint64_t prot_mask;  // protected columns (bit j), empty when terminal window is off
 };
 

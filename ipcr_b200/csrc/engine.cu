@@ -115,6 +115,12 @@ struct ipcr_panel {
     ipcr::Panel host;
     std::mutex mu;
     std::map<int, std::unique_ptr<ipcr::DevTables>> dev;
+    // NVRTC output, shared by every device (compiled at most once per plan variant)
+    std::vector<char> jit_cubin[2];
+    ipcr::JitProgram jit_prog[2];
+    std::string jit_log[2];
+    bool jit_done[2] = {false, false};
+    double jit_work = 0.0;
 };
 
 namespace ipcr {
@@ -141,6 +147,8 @@ static DevTables *tables_for(ipcr_panel *p, int device, cudaStream_t st) {
         d.rc_type = o.rc_type;
         d.seeded = o.seeded;
         d.cls_off = (uint32_t)cls.size();
+        d.j0[0] = (uint16_t)h.plan[0].o[od.size()].j0;
+        d.j0[1] = (uint16_t)h.plan[1].o[od.size()].j0;
         uint64_t pm = 0;
         if (tw > 0) {
             for (int j = 0; j < o.L; j++) {
@@ -238,6 +246,7 @@ struct ipcr_scratch {
     cudaEvent_t ev[8] = {};
     ipcr::DevTables *tables = nullptr;
     ipcr::GenomeData own;  // genome of ipcr_gpu_scan / scan_batch calls (buffers are reused)
+    ipcr::DevBuf lists, list_counts, list_clamped, list_offs;  // specialised filter: candidate words
     ipcr::DevBuf cand, counters, sites, keys0, keys1, vals0, vals1, keep, keep_off, tmp, fkeys, fs, recs_dev,
         entry_tasks, task_off, task_cnt, prod_off, products;
     ipcr::PinBuf h_counts, h_products, h_sites, h_stage, h_reset;
@@ -273,7 +282,8 @@ static void pack_genome(ipcr_scratch *s, GenomeData &g) {
     g.lay.rows = g.lay.W + kExtRows;
     const uint64_t per_tile = (uint64_t)kStripesPerTile * g.lay.W;
     g.lay.n_tiles = std::max<uint64_t>(1, (g.lay.total_len + per_tile - 1) / per_tile);
-    g.planes.ensure((size_t)g.lay.n_tiles * g.lay.rows * kLanes * sizeof(uint4));
+    // + 80 rows of slack: the unrolled JIT loop reads up to 2*ring rows past a tile's end
+    g.planes.ensure(((size_t)g.lay.n_tiles * g.lay.rows + 80) * kLanes * sizeof(uint4));
     upload(g.segs_dev, g.segs.data(), g.segs.size() * sizeof(SegmentDev), st);
     g.seg_reset.ensure(g.segs.size() * sizeof(uint32_t));
     CU(cudaMemsetAsync(g.seg_reset.p, 0, g.segs.size() * sizeof(uint32_t), st));
@@ -354,7 +364,8 @@ static uint64_t read_counter(ipcr_scratch *s, int idx) {
     return s->h_counts.as<unsigned long long>()[idx];
 }
 
-static bool jit_try_launch(ipcr_scratch *s, const GenomeData &g, int variant, uint64_t cand_cap);
+struct JitRun;
+static bool jit_filter(ipcr_scratch *s, const GenomeData &g, int variant, JitRun &run);
 
 static void launch_filter_generic(ipcr_scratch *s, const GenomeData &g, int variant, uint64_t cand_cap) {
     const PlanTables &pt = s->tables->plan[variant];
@@ -389,75 +400,7 @@ static void launch_filter_generic(ipcr_scratch *s, const GenomeData &g, int vari
 }
 
 // Stage 1.  Leaves verified sites in s->sites (device) and returns their count.
-static uint64_t find_sites(ipcr_scratch *s, const GenomeData &g, bool force_raw) {
-    const Panel &h = s->panel->host;
-    cudaStream_t st = s->stream;
-    s->n_cand = 0;
-    s->timing.used_jit = 0;
-    if (g.lay.total_len == 0 || h.orients.empty()) return 0;
-    const ipcr_cfg &cfg = h.cfg;
-    bool any_rc_unseeded = false;
-    for (const Orient &o : h.orients)
-        if (o.rc_type && !o.seeded) any_rc_unseeded = true;
-    // rc orientations must keep window-violating matches only where the reference caps
-    // BEFORE filterLeftTW (compiled.go:185-190,250-257)
-    const bool raw_possible = cfg.hit_cap > 0 && cfg.max_mm > 0 && cfg.terminal_window > 0;
-    const int variant = raw_possible && (force_raw || g.any_reset || any_rc_unseeded) ? 1 : 0;
-
-    s->counters.ensure(8 * sizeof(unsigned long long));
-    s->h_counts.ensure(8 * sizeof(unsigned long long));
-    double expect = 0.0;
-    for (const OrientPlan &op : h.plan[variant].o) expect += op.cand_prob;
-    uint64_t cap = std::max<uint64_t>(1ull << 16, (uint64_t)(expect * (double)g.lay.total_len * 4.0) + 4096);
-    cap = std::min<uint64_t>(cap, 1ull << 28);
-    CU(cudaEventRecord(s->ev[3], st));
-    uint64_t n_cand = 0;
-    for (int attempt = 0;; attempt++) {
-        s->cand.ensure(cap * sizeof(unsigned long long));
-        CU(cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), st));
-        bool ran_jit = false;
-        if (h.jit_mode > 0) ran_jit = jit_try_launch(s, g, variant, cap);
-        if (!ran_jit) launch_filter_generic(s, g, variant, cap);
-        s->timing.used_jit = ran_jit ? 1 : 0;
-        n_cand = read_counter(s, 0);
-        if (n_cand <= cap) break;
-        if (attempt >= 2 || n_cand * sizeof(unsigned long long) > (32ull << 30))
-            throw Error(fmt("scan produced %llu candidate sites; the panel is too unspecific for this input",
-                            (unsigned long long)n_cand));
-        cap = n_cand + 1024;
-    }
-    CU(cudaEventRecord(s->ev[4], st));
-    s->n_cand = n_cand;
-    s->timing.candidates = n_cand;
-    uint64_t n_sites = 0;
-    if (n_cand > 0) {
-        s->sites.ensure(n_cand * sizeof(ipcr_site));
-        VerifyArgs v{};
-        v.cand = s->cand.as<unsigned long long>();
-        v.n_cand = n_cand;
-        v.ascii = g.ascii;
-        v.segs = g.segs_dev.as<SegmentDev>();
-        v.n_segs = (uint32_t)g.segs.size();
-        v.orients = s->tables->orients.as<OrientDev>();
-        v.cls = s->tables->cls.as<uint8_t>();
-        v.prm.max_mm = cfg.max_mm;
-        v.prm.terminal_window = cfg.terminal_window;
-        v.prm.hit_cap = cfg.hit_cap;
-        v.prm.circular = cfg.circular;
-        v.prm.raw_rc = (uint8_t)variant;
-        v.sites = s->sites.as<ipcr_site>();
-        v.site_count = s->counters.as<unsigned long long>() + 1;
-        v.site_cap = n_cand;
-        const unsigned grid = (unsigned)std::min<uint64_t>((n_cand + 255) / 256, (uint64_t)s->sm_count * 16);
-        k_verify<<<grid, 256, 0, st>>>(v);
-        check_launch("k_verify");
-        s->launches++;
-        n_sites = read_counter(s, 1);
-    }
-    CU(cudaEventRecord(s->ev[5], st));
-    s->timing.sites = n_sites;
-    return n_sites;
-}
+static uint64_t find_sites(ipcr_scratch *s, const GenomeData &g, bool force_raw);
 
 static uint32_t bit_length(uint64_t v) {
     uint32_t b = 0;
@@ -633,6 +576,112 @@ static void set_err(char *err, size_t errlen, const std::string &m) {
 }  // namespace ipcr
 
 #include "jit_launch.hpp"
+
+namespace ipcr {
+
+static uint64_t find_sites(ipcr_scratch *s, const GenomeData &g, bool force_raw) {
+    const Panel &h = s->panel->host;
+    cudaStream_t st = s->stream;
+    s->n_cand = 0;
+    s->timing.used_jit = 0;
+    if (g.lay.total_len == 0 || h.orients.empty()) return 0;
+    const ipcr_cfg &cfg = h.cfg;
+    bool any_rc_unseeded = false;
+    for (const Orient &o : h.orients)
+        if (o.rc_type && !o.seeded) any_rc_unseeded = true;
+    // rc orientations must keep window-violating matches only where the reference caps
+    // BEFORE filterLeftTW (compiled.go:185-190,250-257)
+    const bool raw_possible = cfg.hit_cap > 0 && cfg.max_mm > 0 && cfg.terminal_window > 0;
+    const int variant = raw_possible && (force_raw || g.any_reset || any_rc_unseeded) ? 1 : 0;
+
+    s->counters.ensure(8 * sizeof(unsigned long long));
+    s->h_counts.ensure(8 * sizeof(unsigned long long));
+
+    VerifyArgs v{};
+    v.ascii = g.ascii;
+    v.segs = g.segs_dev.as<SegmentDev>();
+    v.n_segs = (uint32_t)g.segs.size();
+    v.orients = s->tables->orients.as<OrientDev>();
+    v.cls = s->tables->cls.as<uint8_t>();
+    v.prm.max_mm = cfg.max_mm;
+    v.prm.terminal_window = cfg.terminal_window;
+    v.prm.hit_cap = cfg.hit_cap;
+    v.prm.circular = cfg.circular;
+    v.prm.raw_rc = (uint8_t)variant;
+    v.site_count = s->counters.as<unsigned long long>() + 1;
+
+    CU(cudaEventRecord(s->ev[3], st));
+    uint64_t n_sites = 0;
+    JitRun run;
+    if (jit_filter(s, g, variant, run)) {
+        // ---- specialised filter: per-thread lists of 32-position candidate words ----
+        s->timing.used_jit = 1;
+        s->n_cand = 0;
+        s->timing.candidates = run.n_bits;
+        if (run.n_entries > 0 && run.n_bits > 0) {
+            s->sites.ensure(run.n_bits * sizeof(ipcr_site));
+            v.sites = s->sites.as<ipcr_site>();
+            v.site_cap = run.n_bits;
+            WordListArgs w{};
+            w.lists = s->lists.as<uint4>();
+            w.counts = s->list_counts.as<uint32_t>();
+            w.clamped = s->list_clamped.as<uint32_t>();
+            w.offs = s->list_offs.as<uint32_t>();
+            w.n_threads = run.n_threads;
+            w.K = run.K;
+            w.stats = s->counters.as<unsigned long long>() + 4;
+            w.lay = g.lay;
+            w.variant = (uint32_t)variant;
+            const unsigned grid = (unsigned)std::min<uint64_t>((run.n_entries + 7) / 8, (uint64_t)s->sm_count * 16);
+            k_verify_words<<<grid, 256, 0, st>>>(v, w, run.n_entries);
+            check_launch("k_verify_words");
+            s->launches++;
+            n_sites = read_counter(s, 1);
+        }
+        CU(cudaEventRecord(s->ev[5], st));
+        s->timing.sites = n_sites;
+        return n_sites;
+    }
+
+    // ---- table-driven filter: candidate positions ----
+    double expect = 0.0;
+    for (const OrientPlan &op : h.plan[variant].o) expect += op.cand_prob;
+    uint64_t cap = std::max<uint64_t>(1ull << 16, (uint64_t)(expect * (double)g.lay.total_len * 4.0) + 4096);
+    cap = std::min<uint64_t>(cap, 1ull << 28);
+    CU(cudaEventRecord(s->ev[3], st));
+    uint64_t n_cand = 0;
+    for (int attempt = 0;; attempt++) {
+        s->cand.ensure(cap * sizeof(unsigned long long));
+        CU(cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), st));
+        launch_filter_generic(s, g, variant, cap);
+        n_cand = read_counter(s, 0);
+        if (n_cand <= cap) break;
+        if (attempt >= 2 || n_cand * sizeof(unsigned long long) > (32ull << 30))
+            throw Error(fmt("scan produced %llu candidate sites; the panel is too unspecific for this input",
+                            (unsigned long long)n_cand));
+        cap = n_cand + 1024;
+    }
+    CU(cudaEventRecord(s->ev[4], st));
+    s->n_cand = n_cand;
+    s->timing.candidates = n_cand;
+    if (n_cand > 0) {
+        s->sites.ensure(n_cand * sizeof(ipcr_site));
+        v.cand = s->cand.as<unsigned long long>();
+        v.n_cand = n_cand;
+        v.sites = s->sites.as<ipcr_site>();
+        v.site_cap = n_cand;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_cand + 255) / 256, (uint64_t)s->sm_count * 16);
+        k_verify<<<grid, 256, 0, st>>>(v);
+        check_launch("k_verify");
+        s->launches++;
+        n_sites = read_counter(s, 1);
+    }
+    CU(cudaEventRecord(s->ev[5], st));
+    s->timing.sites = n_sites;
+    return n_sites;
+}
+
+}  // namespace ipcr
 
 using namespace ipcr;
 
@@ -963,6 +1012,19 @@ int ipcr_gpu_debug_jit_source(ipcr_panel *p, int raw_mode, char *buf, size_t buf
     if (needed) *needed = src.size() + 1;
     if (buf && buflen) snprintf(buf, buflen, "%s", src.c_str());
     return 0;
+}
+
+int ipcr_gpu_debug_jit_compile(ipcr_panel *p, int raw_mode, char *cubin, size_t cap, size_t *cubin_size, char *err,
+                               size_t errlen) {
+    ABI_TRY
+    if (!p) throw Error("panel is NULL");
+    std::vector<char> bin;
+    const std::string log = jit_compile(jit_generate_source(p->host, raw_mode ? 1 : 0), bin);
+    if (!log.empty()) throw Error(log);
+    if (cubin_size) *cubin_size = bin.size();
+    if (cubin && cap >= bin.size()) memcpy(cubin, bin.data(), bin.size());
+    return 0;
+    ABI_CATCH(1)
 }
 
 }  // extern "C"

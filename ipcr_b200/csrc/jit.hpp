@@ -1,13 +1,331 @@
-// jit.hpp -- panel-specialised scan kernel (NVRTC).  Placeholder: filled in below.
+// jit.hpp -- the panel-specialised scan kernel.
+//
+// CompilePanel in the reference builds an Aho-Corasick automaton from the panel
+// (/root/reference/core/engine/compiled.go:119-122).  Here the panel is compiled
+// into CODE: NVRTC turns the filter plan (plan.hpp) into an sm_100a kernel in
+// which every primer column is a fixed register operand, so the hot loop is
+// nothing but LOP3 over bit-planes:
+//   * each lane keeps the last RS rows of its 32 stripes in REGISTERS (a ring of
+//     RS uint4 = {A,C,G,T} plane words); the row loop is unrolled RS times so
+//     every ring slot has a static register name -- no shifts, no shared memory,
+//     no indexing;
+//   * one fully coalesced 512-byte LDG.128 per warp per row streams the genome
+//     (0.5 B/bp), issued RS - Lmax rows ahead of first use;
+//   * per orientation: AND of the protected 3' columns, AND per pigeonhole
+//     block, "at least `need` blocks" threshold -> 32 candidate bits per word;
+//   * candidates are rare; one predicated branch per row leaves the fast path.
+// Large panels are split into orientation GROUPS; a warp walks a chunk of rows
+// once per group so the loop body stays instruction-cache resident while the
+// chunk is re-read from L2.
 #pragma once
+
+#include <nvrtc.h>
+
+#include <cstdlib>
+#include <sstream>
 #include <string>
+#include <vector>
+
 #include "plan.hpp"
+
 namespace ipcr {
+
+struct JitConfig {
+    int stage_rows = 8;       // SR: rows per TMA stage (SR * 512 bytes)
+    int stages = 4;           // NB: stages in flight per warp
+    int warps = 4;            // warps per CTA
+    int group_code_kb = 28;   // target SASS per group (RS steps x orientations)
+    int max_group = 64;
+    int min_blocks = 0;       // 0 = derive from shared memory
+    int list_cap = 64;        // K: candidate words a thread can stage per launch
+};
+
+inline JitConfig jit_config_from_env() {
+    JitConfig c;
+    if (const char *e = getenv("IPCR_JIT_STAGE_ROWS")) c.stage_rows = atoi(e);
+    if (const char *e = getenv("IPCR_JIT_STAGES")) c.stages = atoi(e);
+    if (const char *e = getenv("IPCR_JIT_WARPS")) c.warps = atoi(e);
+    if (const char *e = getenv("IPCR_JIT_GROUP_KB")) c.group_code_kb = atoi(e);
+    if (const char *e = getenv("IPCR_JIT_MAX_GROUP")) c.max_group = atoi(e);
+    if (const char *e = getenv("IPCR_JIT_MIN_BLOCKS")) c.min_blocks = atoi(e);
+    if (const char *e = getenv("IPCR_JIT_LIST_CAP")) c.list_cap = atoi(e);
+    if (c.stage_rows != 2 && c.stage_rows != 4 && c.stage_rows != 8 && c.stage_rows != 16) c.stage_rows = 8;
+    c.stages = std::max(2, std::min(c.stages, 8));
+    c.warps = std::max(1, std::min(c.warps, 8));
+    c.list_cap = std::max(4, c.list_cap);
+    return c;
+}
+
+struct JitProgram {
+    std::string source;
+    int n_groups = 0;
+    int ring_slots = 0;
+    int stage_rows = 8, stages = 4, warps = 4, list_cap = 64;
+    size_t smem_bytes = 0;
+    bool chunked = false;  // true when groups > 1: walk row chunks, not whole tiles
+};
+
+inline std::string plane_term(int slot, uint8_t cls) {
+    static const char *comp = "xyzw";
+    std::ostringstream o;
+    int n = __builtin_popcount(cls);
+    if (n > 1) o << "(";
+    bool first = true;
+    for (int b = 0; b < 4; b++) {
+        if (!((cls >> b) & 1)) continue;
+        if (!first) o << "|";
+        o << "R" << slot << "." << comp[b];
+        first = false;
+    }
+    if (n > 1) o << ")";
+    return o.str();
+}
+
+inline std::string and_expr(const std::vector<ColRef> &cols, int k, int RS) {
+    if (cols.empty()) return "0xffffffffu";
+    std::ostringstream o;
+    for (size_t i = 0; i < cols.size(); i++) {
+        if (i) o << " & ";
+        o << plane_term((k + cols[i].row) % RS, cols[i].cls);
+    }
+    return o.str();
+}
+
+// code computing `c<name>` for one orientation at unrolled step k
+inline void emit_orientation(std::ostringstream &o, const OrientPlan &pl, int k, int RS, const std::string &name) {
+    const std::string ind = "          ";
+    if (pl.need <= 0) {
+        o << ind << "const u32 " << name << " = " << and_expr(pl.prot, k, RS) << ";\n";
+        return;
+    }
+    const int B = (int)pl.blocks.size();
+    if (pl.need == 1) {
+        o << ind << "const u32 " << name << " = ";
+        if (!pl.prot.empty()) o << and_expr(pl.prot, k, RS) << " & ";
+        o << "(";
+        for (int b = 0; b < B; b++) {
+            if (b) o << " | ";
+            o << "(" << and_expr(pl.blocks[b], k, RS) << ")";
+        }
+        o << ");\n";
+        return;
+    }
+    // at least `need` of B blocks: running "at least t so far" words
+    o << ind << "u32 " << name << ";\n" << ind << "{\n";
+    for (int b = 0; b < B; b++)
+        o << ind << "  const u32 b" << b << " = " << and_expr(pl.blocks[b], k, RS) << ";\n";
+    for (int t = 1; t <= pl.need; t++) o << ind << "  u32 g" << t << " = " << (t == 1 ? "b0" : "0u") << ";\n";
+    for (int b = 1; b < B; b++) {
+        for (int t = std::min(pl.need, b + 1); t >= 2; t--) o << ind << "  g" << t << " |= g" << (t - 1) << " & b" << b << ";\n";
+        o << ind << "  g1 |= b" << b << ";\n";
+    }
+    o << ind << "  " << name << " = ";
+    if (!pl.prot.empty()) o << and_expr(pl.prot, k, RS) << " & ";
+    o << "g" << pl.need << ";\n" << ind << "}\n";
+}
+
+inline int plan_max_row(const OrientPlan &pl) {
+    int m = 0;
+    for (const ColRef &c : pl.prot) m = std::max(m, (int)c.row);
+    for (const auto &bl : pl.blocks)
+        for (const ColRef &c : bl) m = std::max(m, (int)c.row);
+    return m;
+}
+
+inline JitProgram jit_generate(const Panel &panel, int variant, const JitConfig &cfg) {
+    const ScanPlan &sp = panel.plan[variant];
+    const int U = (int)sp.o.size();
+    JitProgram prog;
+    int lmax = 1;
+    double cost_sum = 0.0;
+    for (const OrientPlan &pl : sp.o) {
+        lmax = std::max(lmax, plan_max_row(pl) + 1);
+        cost_sum += std::max(2.0, pl.cost);
+    }
+    const int SR = cfg.stage_rows, NB = cfg.stages, WARPS = cfg.warps;
+    const int RS = ((lmax + 1 + SR - 1) / SR) * SR;  // ring: window + 1 row of LDS look-ahead
+    prog.ring_slots = RS;
+    prog.stage_rows = SR;
+    prog.stages = NB;
+    prog.warps = WARPS;
+    prog.list_cap = cfg.list_cap;
+    prog.smem_bytes = (size_t)WARPS * NB * SR * 512 + (size_t)WARPS * NB * 8;
+    // group size from the code budget: RS unrolled steps x ~16 B per LOP3
+    const double per_orient_bytes = (U ? cost_sum / U : 1.0) * RS * 16.0;
+    int G = (int)std::max(1.0, std::floor(cfg.group_code_kb * 1024.0 / std::max(1.0, per_orient_bytes)));
+    G = std::min(G, cfg.max_group);
+    if (U <= 8) G = std::max(G, U);  // small panels: one pass over HBM, always
+    const int NG = U ? (U + G - 1) / G : 0;
+    prog.n_groups = NG;
+    prog.chunked = NG > 1;
+    int minb = cfg.min_blocks;
+    if (minb <= 0) minb = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(224 * 1024) / (prog.smem_bytes + 1024)));
+
+    std::ostringstream o;
+    o << "// generated by ipcr_b200 jit.hpp: " << U << " orientations, " << NG << " group(s), ring " << RS << "\n";
+    o << "typedef unsigned int u32;\ntypedef unsigned long long u64;\n";
+    o << "#define RS " << RS << "\n#define SR " << SR << "\n#define NB " << NB << "\n#define WARPS " << WARPS << "\n";
+    o << "#define STAGE_BYTES (SR * 512)\n";
+    o << R"(
+__device__ __forceinline__ u32 s2u(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+#define STAGE_BEGIN() { const u32 b_ = gs % NB; mbar_wait(bar_u + 8u * b_, (gs / NB) & 1u); \
+                        sp = sbuf + b_ * STAGE_BYTES + lane * 16u; }
+#define STAGE_END() { __syncwarp(); \
+                      if (issued < nstages) { \
+                          if (lane == 0) { const u32 b_ = gs % NB; mbar_expect_tx(bar_u + 8u * b_, STAGE_BYTES); \
+                              bulk_g2s(sbuf_u + b_ * STAGE_BYTES, gsrc + (u64)issued * STAGE_BYTES, STAGE_BYTES, bar_u + 8u * b_); } \
+                          issued++; } \
+                      gs++; }
+#define LDROW(t_) (*(const uint4*)(sp + ((t_) % SR) * 512u))
+#define STAGE_WORD(c_, q_, w_) { if (cnt < K) my_list[cnt] = make_uint4((c_), (q_), (w_), (u32)tile); cnt++; }
+)";
+    o << "\nextern \"C\" __global__ void __launch_bounds__(WARPS * 32, " << minb << ")\n";
+    o << "ipcr_scan_jit(const uint4* __restrict__ planes, u32 W, u32 rows, u64 n_tiles, u32 chunk_rows,\n"
+         "              u64* work_counter, uint4* __restrict__ lists, u32* __restrict__ counts, u32 K) {\n";
+    o << "    extern __shared__ __align__(128) unsigned char smem[];\n";
+    o << "    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;\n";
+    o << "    const unsigned char* sbuf = smem + warp * (NB * STAGE_BYTES);\n";
+    o << "    const u32 sbuf_u = s2u(sbuf);\n";
+    o << "    const u32 bar_u = s2u(smem + WARPS * NB * STAGE_BYTES) + warp * NB * 8u;\n";
+    o << "    if (lane == 0) {\n";
+    o << "        for (u32 s = 0; s < NB; s++) mbar_init(bar_u + 8u * s, 1u);\n";
+    o << "        asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n";
+    o << "    }\n    __syncwarp();\n";
+    o << "    const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n";
+    o << "    uint4* my_list = lists + gtid * K;\n";
+    o << "    u32 cnt = 0, gs = 0;\n";
+    o << "    const u32 chunks_per_tile = (W + chunk_rows - 1u) / chunk_rows;\n";
+    o << "    const u64 n_items = n_tiles * chunks_per_tile;\n";
+    o << "    for (;;) {\n";
+    o << "      u64 item = 0;\n";
+    o << "      if (lane == 0) item = atomicAdd(work_counter, 1ull);\n";
+    o << "      item = __shfl_sync(0xffffffffu, item, 0);\n";
+    o << "      if (item >= n_items) break;\n";
+    o << "      const u64 tile = item / chunks_per_tile;\n";
+    o << "      const u32 r0 = (u32)(item % chunks_per_tile) * chunk_rows;\n";
+    o << "      const u32 r1 = min(W, r0 + chunk_rows);\n";
+    o << "      const u32 nsteps = ((r1 - r0 + RS - 1u) / RS) * RS;\n";
+    o << "      const u32 nstages = (nsteps + RS - 1u + SR - 1u) / SR;\n";
+    o << "      const unsigned char* gsrc = (const unsigned char*)(planes + (tile * rows + r0) * 32ull);\n";
+    for (int g = 0; g < NG; g++) {
+        const int q0 = g * G, q1 = std::min(U, q0 + G);
+        o << "      {  // group " << g << ": orientations " << q0 << ".." << (q1 - 1) << "\n";
+        o << "        const u32 gs_end = gs + nstages;\n";
+        o << "        u32 issued = 0;\n";
+        o << "        { const u32 n0 = min((u32)NB, nstages);\n";
+        o << "          if (lane == 0) for (u32 i = 0; i < n0; i++) { const u32 b_ = (gs + i) % NB;\n";
+        o << "              mbar_expect_tx(bar_u + 8u * b_, STAGE_BYTES);\n";
+        o << "              bulk_g2s(sbuf_u + b_ * STAGE_BYTES, gsrc + (u64)i * STAGE_BYTES, STAGE_BYTES, bar_u + 8u * b_); }\n";
+        o << "          issued = n0; }\n";
+        o << "        const unsigned char* sp = sbuf;\n";
+        o << "        uint4 ";
+        for (int s = 0; s < RS; s++) o << (s ? ", " : "") << "R" << s;
+        o << ";\n";
+        for (int t = 0; t + 1 < RS; t++) {
+            if (t % SR == 0) o << "        STAGE_BEGIN();\n";
+            o << "        R" << t << " = LDROW(" << t << ");\n";
+            if (t % SR == SR - 1) o << "        STAGE_END();\n";
+        }
+        o << "        for (u32 w = r0; w < r0 + nsteps; w += RS) {\n";
+        for (int k = 0; k < RS; k++) {
+            const int slot = (k + RS - 1) % RS;
+            const int t = RS - 1 + k;
+            o << "          // step " << k << "\n";
+            if (t % SR == 0) o << "          STAGE_BEGIN();\n";
+            o << "          R" << slot << " = LDROW(" << t << ");\n";
+            if (t % SR == SR - 1) o << "          STAGE_END();\n";
+            o << "          {\n";
+            // sub-batches of 8 orientations keep the live candidate words bounded
+            for (int b0 = q0; b0 < q1; b0 += 8) {
+                const int b1 = std::min(q1, b0 + 8);
+                for (int q = b0; q < b1; q++) {
+                    std::ostringstream nm;
+                    nm << "c" << q;
+                    emit_orientation(o, sp.o[q], k, RS, nm.str());
+                }
+                o << "          if ((";
+                for (int q = b0; q < b1; q++) o << (q > b0 ? " | " : "") << "c" << q;
+                o << ") != 0u) {\n";
+                o << "            if (w + " << k << "u < r1) {\n";
+                for (int q = b0; q < b1; q++)
+                    o << "              if (c" << q << ") STAGE_WORD(c" << q << ", " << q << "u, w + " << k << "u);\n";
+                o << "            }\n          }\n";
+            }
+            o << "          }\n";
+        }
+        o << "        }\n";
+        // the last stage is only partially read (no STAGE_END): count it as consumed so that
+        // the next stream starts on a fresh buffer / barrier phase
+        o << "        gs = gs_end;\n";
+        o << "      }\n";
+    }
+    o << "    }\n";
+    o << "    counts[gtid] = cnt;\n";
+    o << "}\n";
+    prog.source = o.str();
+    return prog;
+}
+
+inline std::string jit_generate_source(const Panel &panel, int variant) {
+    return jit_generate(panel, variant, jit_config_from_env()).source;
+}
+
+// NVRTC: source -> sm_100a cubin.  Returns "" on success, else the log.
+inline std::string jit_compile(const std::string &src, std::vector<char> &cubin) {
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, src.c_str(), "ipcr_scan_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return "nvrtcCreateProgram failed";
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--extra-device-vectorization"};
+    nvrtcResult r = nvrtcCompileProgram(prog, 3, opts);
+    std::string log;
+    size_t ls = 0;
+    nvrtcGetProgramLogSize(prog, &ls);
+    if (ls > 1) {
+        log.resize(ls);
+        nvrtcGetProgramLog(prog, &log[0]);
+    }
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return "nvrtc: " + std::string(nvrtcGetErrorString(r)) + "\n" + log;
+    }
+    size_t cs = 0;
+    if (nvrtcGetCUBINSize(prog, &cs) != NVRTC_SUCCESS || cs == 0) {
+        nvrtcDestroyProgram(&prog);
+        return "nvrtc produced no cubin\n" + log;
+    }
+    cubin.resize(cs);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    return "";
+}
+
 struct JitKernel {
-    void *library = nullptr;
-    void *kernel = nullptr;
+    cudaLibrary_t library = nullptr;
+    cudaKernel_t kernel = nullptr;
     bool ok = false;
     std::string log;
 };
-inline std::string jit_generate_source(const Panel &, int) { return std::string(); }
+
 }  // namespace ipcr

@@ -1,4 +1,139 @@
+// jit_launch.hpp -- compile-once / load-per-device / launch of the NVRTC kernel, and the
+// bookkeeping that turns its per-thread candidate-word lists into verify work.
 #pragma once
+
 namespace ipcr {
-static bool jit_try_launch(ipcr_scratch *, const GenomeData &, int, uint64_t) { return false; }
+
+// cumulative position x orientation work after which compiling pays for itself
+constexpr double kJitWorkThreshold = 2.0e11;
+
+struct JitRun {
+    uint64_t n_entries = 0;  // staged candidate words
+    uint64_t n_bits = 0;     // candidate positions in them
+    uint32_t n_threads = 0;
+    uint32_t K = 0;
+};
+
+// returns the loaded kernel for this device/variant, compiling on first use; nullptr = not available
+static JitKernel *jit_get(ipcr_scratch *s, int variant, double work) {
+    ipcr_panel *p = s->panel;
+    const int mode = p->host.jit_mode;
+    if (mode <= 0) return nullptr;
+    JitKernel *k = &s->tables->jit[variant];
+    std::lock_guard<std::mutex> lock(p->mu);
+    p->jit_work += work;
+    if (mode == 1 && !p->jit_done[variant] && p->jit_work < kJitWorkThreshold) return nullptr;
+    if (!p->jit_done[variant]) {
+        p->jit_done[variant] = true;
+        p->jit_prog[variant] = jit_generate(p->host, variant, jit_config_from_env());
+        p->jit_log[variant] = jit_compile(p->jit_prog[variant].source, p->jit_cubin[variant]);
+        if (!p->jit_log[variant].empty()) p->jit_cubin[variant].clear();
+    }
+    if (p->jit_cubin[variant].empty()) {
+        if (mode >= 2) throw Error("JIT compile of the scan kernel failed: " + p->jit_log[variant]);
+        return nullptr;
+    }
+    if (!s->tables->jit_tried[variant]) {
+        s->tables->jit_tried[variant] = true;
+        cudaError_t e = cudaLibraryLoadData(&k->library, p->jit_cubin[variant].data(), nullptr, nullptr, 0, nullptr,
+                                            nullptr, 0);
+        if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kernel, k->library, "ipcr_scan_jit");
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute((const void *)k->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)p->jit_prog[variant].smem_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            k->log = std::string("loading the JIT kernel failed: ") + cudaGetErrorString(e);
+            k->ok = false;
+        } else {
+            k->ok = true;
+        }
+    }
+    if (!k->ok) {
+        if (mode >= 2) throw Error(k->log);
+        return nullptr;
+    }
+    return k;
 }
+
+// Runs the specialised filter over the whole genome.  On success the candidate words are
+// in s->lists with offsets in s->list_offs; returns false if the table-driven kernel
+// should be used instead.
+static bool jit_filter(ipcr_scratch *s, const GenomeData &g, int variant, JitRun &run) {
+    ipcr_panel *p = s->panel;
+    JitKernel *k = jit_get(s, variant, (double)g.lay.total_len * (double)p->host.orients.size());
+    if (!k) return false;
+    const JitProgram &prog = p->jit_prog[variant];
+    cudaStream_t st = s->stream;
+    const int threads = prog.warps * 32;
+    int blocks_per_sm = (int)std::max<size_t>(1, (size_t)(227 * 1024) / (prog.smem_bytes + 1024));
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, (const void *)k->kernel) == cudaSuccess && fa.numRegs > 0)
+        blocks_per_sm = std::min(blocks_per_sm, std::max(1, 65536 / (fa.numRegs * threads)));
+    else
+        cudaGetLastError();
+    blocks_per_sm = std::min(blocks_per_sm, 2048 / threads);
+    if (const char *e = getenv("IPCR_JIT_BLOCKS_PER_SM")) blocks_per_sm = std::max(1, atoi(e));
+    uint32_t chunk_rows = prog.chunked ? 128u : g.lay.W;
+    if (const char *e = getenv("IPCR_JIT_CHUNK")) chunk_rows = (uint32_t)std::max(32, atoi(e));
+    chunk_rows = std::min(chunk_rows, g.lay.W);
+    const uint64_t n_items = g.lay.n_tiles * ((g.lay.W + chunk_rows - 1) / chunk_rows);
+    const unsigned grid = (unsigned)std::max<uint64_t>(
+        1, std::min<uint64_t>((n_items + prog.warps - 1) / prog.warps, (uint64_t)s->sm_count * blocks_per_sm));
+    const uint32_t n_threads = grid * (uint32_t)threads;
+    uint32_t K = (uint32_t)prog.list_cap;
+
+    for (int attempt = 0; attempt < 2; attempt++) {
+        s->lists.ensure((size_t)n_threads * K * sizeof(uint4));
+        s->list_counts.ensure((size_t)n_threads * 4);
+        s->list_clamped.ensure((size_t)n_threads * 4);
+        s->list_offs.ensure(((size_t)n_threads + 1) * 4);
+        s->tmp.ensure(scan_tmp_words(n_threads) * 4);
+        CU(cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), st));
+        const uint4 *planes = g.planes.as<uint4>();
+        uint32_t W = g.lay.W, rows = g.lay.rows;
+        uint64_t n_tiles = g.lay.n_tiles;
+        unsigned long long *work_counter = s->counters.as<unsigned long long>() + 2;
+        uint4 *lists = s->lists.as<uint4>();
+        uint32_t *counts = s->list_counts.as<uint32_t>();
+        void *args[] = {&planes, &W, &rows, &n_tiles, &chunk_rows, &work_counter, &lists, &counts, &K};
+        cudaError_t e = cudaLaunchKernel((const void *)k->kernel, dim3(grid), dim3(threads), args, prog.smem_bytes, st);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            throw Error(std::string("launch of ipcr_scan_jit failed: ") + cudaGetErrorString(e));
+        }
+        s->launches++;
+        CU(cudaEventRecord(s->ev[4], st));  // end of the filter proper
+        WordListArgs w{};
+        w.lists = lists;
+        w.counts = counts;
+        w.clamped = s->list_clamped.as<uint32_t>();
+        w.offs = s->list_offs.as<uint32_t>();
+        w.n_threads = n_threads;
+        w.K = K;
+        w.stats = s->counters.as<unsigned long long>() + 4;
+        w.lay = g.lay;
+        w.variant = (uint32_t)variant;
+        k_list_prepare<<<(n_threads + 255) / 256, 256, 0, st>>>(w);
+        check_launch("k_list_prepare");
+        s->launches++;
+        exclusive_scan(st, w.clamped, s->list_offs.as<uint32_t>(), n_threads, s->tmp.as<uint32_t>(), &s->launches);
+        CU(cudaMemcpyAsync(s->h_counts.as<unsigned long long>() + 4, s->counters.as<unsigned long long>() + 4,
+                           2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(s->h_counts.as<unsigned long long>() + 6, s->list_offs.as<uint32_t>() + n_threads,
+                           sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint64_t max_count = s->h_counts.as<unsigned long long>()[4];
+        run.n_bits = s->h_counts.as<unsigned long long>()[5];
+        run.n_entries = *reinterpret_cast<uint32_t *>(s->h_counts.as<unsigned long long>() + 6);
+        run.n_threads = n_threads;
+        run.K = K;
+        if (max_count <= K) return true;
+        // some thread overflowed its list: retry once with room for the worst thread
+        if (attempt == 1 || max_count * (uint64_t)n_threads * sizeof(uint4) > (8ull << 30)) return false;
+        K = (uint32_t)max_count;
+    }
+    return false;
+}
+
+}  // namespace ipcr

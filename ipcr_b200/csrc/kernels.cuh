@@ -203,6 +203,55 @@ __device__ __forceinline__ uint32_t onehot_of(uint32_t b) {
     return b == 'A' ? 1u : b == 'C' ? 2u : b == 'G' ? 4u : b == 'T' ? 8u : 0u;
 }
 
+// exact check of orientation q at global start `start`; true => *s is a site
+__device__ __forceinline__ bool verify_one(const VerifyArgs &a, uint32_t q, uint64_t start, ipcr_site *s) {
+    const uint32_t si = find_segment(a.segs, a.n_segs, start);
+    const SegmentDev seg = a.segs[si];
+    const OrientDev o = a.orients[q];
+    const uint64_t local = start - seg.global_off;
+    if (!(start >= seg.global_off && local + o.L <= seg.len && local < seg.own_len)) return false;
+    const uint8_t *g = a.ascii + start;
+    const uint8_t *pc = a.cls + o.cls_off;
+    uint64_t mask = 0;
+    int mm = 0;
+    for (int j = 0; j < o.L; j++) {
+        if (!(onehot_of(g[j]) & pc[j])) {
+            mask |= 1ull << j;
+            if (++mm > a.prm.max_mm) return false;
+        }
+    }
+    const bool viol = (mask & o.prot_mask) != 0;
+    if (viol && !(a.prm.raw_rc && o.rc_type)) return false;
+    uint32_t flags = viol ? IPCR_SITE_TWVIOL : 0u;
+    if (o.seeded) {  // would the reference's AC pass have missed it? (ac.go:159-162)
+        for (int j = o.seed_off; j < o.seed_off + o.seed_len; j++) {
+            const uint32_t u = g[j] & 0xDFu;
+            if (!(u == 'A' || u == 'C' || u == 'G' || u == 'T')) { flags |= IPCR_SITE_HALO; break; }
+        }
+    }
+    s->pos = seg.rec_off + local;
+    s->mm_mask = mask;
+    s->rec_idx = seg.rec_idx;
+    s->orient = (uint16_t)q;
+    s->mm = (uint8_t)mm;
+    s->flags = (uint8_t)flags;
+    return true;
+}
+
+// warp-ballot compaction: one atomic per warp (all 32 lanes must call)
+__device__ __forceinline__ void compact_site(const VerifyArgs &a, bool ok, const ipcr_site &s) {
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, ok);
+    if (!ballot) return;
+    unsigned long long base = 0;
+    if (lane_id() == 0) base = atomicAdd(a.site_count, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (ok) {
+        const unsigned long long dst = base + __popc(ballot & ((1u << lane_id()) - 1u));
+        if (dst < a.site_cap) a.sites[dst] = s;
+    }
+}
+
+// candidates as a position list (table-driven filter)
 __global__ void __launch_bounds__(256)
 k_verify(VerifyArgs a) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -212,54 +261,61 @@ k_verify(VerifyArgs a) {
         ipcr_site s;
         if (i < a.n_cand) {
             const unsigned long long cw = a.cand[i];
-            const uint32_t q = (uint32_t)(cw >> kCandPosBits);
-            const uint64_t start = cw & kCandPosMask;
-            const uint32_t si = find_segment(a.segs, a.n_segs, start);
-            const SegmentDev seg = a.segs[si];
-            const OrientDev o = a.orients[q];
-            const uint64_t local = start - seg.global_off;
-            if (start >= seg.global_off && local + o.L <= seg.len && local < seg.own_len) {
-                const uint8_t *g = a.ascii + start;
-                const uint8_t *pc = a.cls + o.cls_off;
-                uint64_t mask = 0;
-                int mm = 0;
-                for (int j = 0; j < o.L; j++) {
-                    if (!(onehot_of(g[j]) & pc[j])) {
-                        mask |= 1ull << j;
-                        if (++mm > a.prm.max_mm) break;
-                    }
-                }
-                if (mm <= a.prm.max_mm) {
-                    const bool viol = (mask & o.prot_mask) != 0;
-                    if (!viol || (a.prm.raw_rc && o.rc_type)) {
-                        uint32_t flags = viol ? IPCR_SITE_TWVIOL : 0u;
-                        if (o.seeded) {  // would the reference's AC pass have missed it? (ac.go:159-162)
-                            for (int j = o.seed_off; j < o.seed_off + o.seed_len; j++) {
-                                const uint32_t u = g[j] & 0xDFu;
-                                if (!(u == 'A' || u == 'C' || u == 'G' || u == 'T')) { flags |= IPCR_SITE_HALO; break; }
-                            }
-                        }
-                        ok = true;
-                        s.pos = seg.rec_off + local;
-                        s.mm_mask = mask;
-                        s.rec_idx = seg.rec_idx;
-                        s.orient = (uint16_t)q;
-                        s.mm = (uint8_t)mm;
-                        s.flags = (uint8_t)flags;
-                    }
-                }
-            }
+            ok = verify_one(a, (uint32_t)(cw >> kCandPosBits), cw & kCandPosMask, &s);
         }
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, ok);
-        if (ballot) {
-            unsigned long long base = 0;
-            if (lane_id() == 0) base = atomicAdd(a.site_count, (unsigned long long)__popc(ballot));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (ok) {
-                const unsigned long long dst = base + __popc(ballot & ((1u << lane_id()) - 1u));
-                if (dst < a.site_cap) a.sites[dst] = s;
-            }
+        compact_site(a, ok, s);
+    }
+}
+
+// ---- candidates as per-thread lists of 32-position words (specialised filter) ----
+// entry = {word, orientation, row, tile}; the owning thread's lane is (thread & 31)
+struct WordListArgs {
+    const uint4 *lists;       // [n_threads][K]
+    const uint32_t *counts;   // [n_threads] entries the thread wanted to write
+    uint32_t *clamped;        // [n_threads] min(counts, K)
+    const uint32_t *offs;     // [n_threads + 1] exclusive scan of clamped
+    uint32_t n_threads;
+    uint32_t K;
+    unsigned long long *stats;  // [0] max count, [1] total candidate bits
+    GenomeLayout lay;
+    uint32_t variant;
+};
+
+__global__ void k_list_prepare(WordListArgs w) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= w.n_threads) return;
+    const uint32_t c = w.counts[t];
+    const uint32_t k = c < w.K ? c : w.K;
+    w.clamped[t] = k;
+    unsigned long long bits = 0;
+    for (uint32_t e = 0; e < k; e++) bits += __popc(w.lists[(uint64_t)t * w.K + e].x);
+    if (c) atomicMax(&w.stats[0], (unsigned long long)c);
+    if (bits) atomicAdd(&w.stats[1], bits);
+}
+
+// one warp per staged word; lane i verifies bit i
+__global__ void __launch_bounds__(256)
+k_verify_words(VerifyArgs a, WordListArgs w, uint64_t n_entries) {
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = lane_id();
+    for (uint64_t e = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < n_entries; e += warps) {
+        // owning thread: last t with offs[t] <= e
+        uint32_t lo = 0, hi = w.n_threads;
+        while (lo + 1 < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint64_t)w.offs[mid] <= e) lo = mid; else hi = mid;
         }
+        const uint4 ent = w.lists[(uint64_t)lo * w.K + (e - w.offs[lo])];
+        bool ok = false;
+        ipcr_site s;
+        if ((ent.x >> lane) & 1u) {
+            const uint32_t q = ent.y;
+            const uint64_t stripe = (uint64_t)ent.w * kStripesPerTile + (uint64_t)(lo & 31u) * 32u + lane;
+            const uint64_t P = stripe * w.lay.W + ent.z;
+            const uint32_t j0 = a.orients[q].j0[w.variant];
+            if (P < w.lay.total_len && P >= j0) ok = verify_one(a, q, P - j0, &s);
+        }
+        compact_site(a, ok, s);
     }
 }
 

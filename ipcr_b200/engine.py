@@ -152,6 +152,16 @@ class CompiledPanel:
         L.ipcr_gpu_debug_jit_source(self._h, 1 if raw_mode else 0, buf, len(buf), C.byref(need))
         return buf.value.decode()
 
+    def jit_compile(self, raw_mode: bool = False) -> bytes:
+        """NVRTC-compile the specialised kernel (no GPU needed); returns the sm_100a cubin."""
+        L = _capi.lib()
+        size = C.c_size_t()
+        err = _capi.errbuf()
+        buf = C.create_string_buffer(64 << 20)
+        _capi.check(L.ipcr_gpu_debug_jit_compile(self._h, 1 if raw_mode else 0, buf, len(buf), C.byref(size),
+                                                 err, len(err)), err)
+        return buf.raw[: size.value]
+
     def close(self):
         if self._h is not None:
             _capi.lib().ipcr_gpu_panel_destroy(self._h)

@@ -200,6 +200,27 @@ def test_randomized_parity_medium(oracle):
         _check(oracle, cfgd, pairs, seq)
 
 
+def test_jit_kernel_parity_randomized(oracle):
+    """The NVRTC-specialised scan kernel (forced, jit=2) against the oracle."""
+    rng = random.Random(4242)
+    for it in range(10):
+        cfgd, pairs, seq = _random_case(rng, big=it % 2 == 0)
+        _check(oracle, cfgd, pairs, seq, jit=2)
+    # many orientations -> several groups, chunked rows
+    rng = random.Random(9)
+    n = 400000
+    g = H.random_genome(rng, n, n_frac=0.0002)
+    pairs = []
+    for i in range(24):
+        a = H.random_primer(rng, rng.randint(18, 25), 0.05)
+        b = H.random_primer(rng, rng.randint(18, 25), 0.05)
+        H.plant_amplicon(rng, g, 2000 + i * 15000, a, b, rng.randint(80, 1500), rng.randint(0, 3), rng.randint(0, 3), 3,
+                         revcomp_strand=i % 2 == 1)
+        pairs.append((a, b, 0, 0))
+    got = _check(oracle, dict(max_mm=3, terminal_window=3, max_len=2000, hit_cap=10000), pairs, bytes(g), jit=2)
+    assert len({p[0] for p in got}) == 24
+
+
 def test_hit_cap_semantics(oracle):
     # dense short primers so that the cap binds; covers seeded, forced-fallback (reset byte)
     # and unseeded-orientation paths (compiled.go:185-190,238-257)
