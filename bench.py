@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ipcr scan hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched with torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json config 5, mm = 2 headline): a 3 Gbp synthetic genome in 24
+contigs of 50-250 Mbp, a 100-pair multiplex panel (18-25-nt primers, 10 % with IUPAC
+codes; + unique self pairs => 300 pairs / 400 unique orientations), --mismatches 2,
+--terminal-window 3, --max-length 2000, --hit-cap 10000, 1-3 planted amplicons per pair.
+
+One step = one pass of the hot path (ForEachCompiledProduct over every record):
+  value : ASCII genome already resident in HBM -> pack -> filter -> verify -> pair -> products
+          to the host; device time from CUDA events on the scratch's own stream.
+  e2e   : the same through the reference-facing call with HOST buffers (pinned), H2D and
+          D2H inside the timed region, wall clock.
+N > 1 (strong scaling): the concatenated genome is cut into N shards with a primer-length
+halo, every rank runs stage 1 on its shard, sites are gathered to rank 0 (NCCL) and paired
+once; time = max over ranks of the device time.
+--impl reference times the CPU restatement of the reference's seeded Aho-Corasick engine
+(oracle/, Go toolchain absent) on all host cores over a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Gbp scanned/sec x primer pairs (mm=2)"
+UNIT = "Gbp*pairs/s"
+SEED = 20251018
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome-mbp", type=float, default=3000.0)
+    ap.add_argument("--contigs", type=int, default=24)
+    ap.add_argument("--pairs", type=int, default=100)
+    ap.add_argument("--mm", type=int, default=2)
+    ap.add_argument("--tw", type=int, default=3)
+    ap.add_argument("--max-len", type=int, default=2000)
+    ap.add_argument("--hit-cap", type=int, default=10000)
+    ap.add_argument("--cpu-sample-mbp", type=float, default=0.0, help="0 = calibrate to ~15 s")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus, user_pairs, all_pairs, n_orient):
+    return {
+        "workload": f"C5 multiplex: {a.genome_mbp:g} Mbp synthetic genome ({a.contigs} contigs), "
+                    f"{len(user_pairs)}-pair panel (+self => {len(all_pairs)} pairs, {n_orient} unique orientations), "
+                    f"--mismatches {a.mm} --terminal-window {a.tw} --max-length {a.max_len} --hit-cap {a.hit_cap}",
+        "genome_bp": int(a.genome_mbp * 1e6),
+        "pairs": len(user_pairs),
+        "pairs_with_self": len(all_pairs),
+        "unique_orientations": n_orient,
+        "max_mm": a.mm,
+        "sharding": "none" if n_gpus == 1 else f"{n_gpus} shards of the concatenated genome, 64-base halo, sites gathered to rank 0",
+        "l2": "inputs (1 B/bp ASCII + 0.5 B/bp packed) are >> the 126 MB L2, no flush needed",
+    }
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference arm / baseline (oracle layer 2 = the reference's seeded production path)
+# --------------------------------------------------------------------------------------
+def cpu_reference_run(a, steps, warmup, sample_mbp=None):
+    from ipcr_b200 import synth
+    from ipcr_b200.device import synth_bases_host
+    from oracle import oracle as O
+
+    O.build()
+    user_pairs, all_pairs = synth.multiplex_panel(a.pairs, seed=SEED)
+    cores = os.cpu_count() or 1
+    cfg = O.make_cfg(max_mm=a.mm, terminal_window=a.tw, max_len=a.max_len, hit_cap=a.hit_cap, seed_len=12)
+    t0 = time.perf_counter()
+    panel = O.Panel(cfg, [(p.forward, p.reverse, 0, 0) for p in all_pairs])
+    compile_s = time.perf_counter() - t0
+    total = int(a.genome_mbp * 1e6)
+    lens = synth.contig_lengths(total, a.contigs)
+    planted = synth.plan_amplicons(user_pairs, lens, a.mm, a.tw, seed=SEED + 1)
+    offs = [0]
+    for ln in lens:
+        offs.append(offs[-1] + ln)
+
+    def sample(n_bp):
+        n_bp = min(n_bp, lens[0])
+        buf = bytearray(synth_bases_host(0, n_bp, SEED))
+        for pl in planted:  # amplicons that fall inside the sample (contig 0 prefix)
+            if pl.contig == 0 and pl.start + pl.length <= n_bp:
+                synth.apply_planted(buf, [0], [pl])
+        return bytes(buf)
+
+    chunk = 1_000_000  # best case for the reference: --chunk-size well above max-length, all cores busy
+    if sample_mbp is None or sample_mbp <= 0:
+        probe = sample(2_000_000)
+        t0 = time.perf_counter()
+        panel.scan_threaded([probe], chunk_size=chunk, overlap=a.max_len, threads=cores)
+        dt = max(1e-3, time.perf_counter() - t0)
+        sample_bp = int(min(lens[0], max(2_000_000, 2_000_000 * (15.0 / dt) / max(1, steps + warmup))))
+    else:
+        sample_bp = int(sample_mbp * 1e6)
+    seq = sample(sample_bp)
+    for _ in range(warmup):
+        panel.scan_threaded([seq], chunk_size=chunk, overlap=a.max_len, threads=cores)
+    t0 = time.perf_counter()
+    n_prod = 0
+    for _ in range(steps):
+        n_prod = panel.scan_threaded([seq], chunk_size=chunk, overlap=a.max_len, threads=cores)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    gbp_s = len(seq) / 1e9 / dt
+    return {
+        "value": gbp_s * len(user_pairs),
+        "gbp_per_s": gbp_s,
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{len(seq) / 1e6:.1f} Mbp prefix of contig 0 of the same genome, full {len(all_pairs)}-pair panel, "
+                  f"seeded AC engine restated in C (oracle/ipcr_seeded.c), {cores} threads over 1 Mbp chunks "
+                  f"(--chunk-size 1000000, overlap {a.max_len}); panel compile {compile_s:.1f} s not timed; "
+                  f"{n_prod} products",
+        "ms_per_step": dt * 1e3,
+        "patterns": panel.num_patterns,
+        "automaton_nodes": panel.num_nodes,
+    }, user_pairs, all_pairs
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res, user_pairs, all_pairs = cpu_reference_run(a, a.steps, a.warmup, a.cpu_sample_mbp or None)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(a, a.gpus, user_pairs, all_pairs, None),
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gbp_per_s": res["gbp_per_s"],
+        "note": "Go toolchain absent in this image: this is the C restatement of the reference's seeded engine",
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        a.gpus = world
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    from ipcr_b200 import Config, Engine, _capi, synth
+    from ipcr_b200 import device as D
+
+    L = _capi.lib()
+    err = _capi.errbuf()
+    if L.ipcr_gpu_init(torch.cuda.current_device(), err, len(err)) != 0:
+        raise RuntimeError(err.value.decode())
+
+    user_pairs, all_pairs = synth.multiplex_panel(a.pairs, seed=SEED)
+    eng = Engine(Config(max_mm=a.mm, terminal_window=a.tw, max_len=a.max_len, hit_cap=a.hit_cap, seed_len=12))
+    cp = eng.compile_panel(all_pairs)
+    cp.set_jit(2)  # compile the panel into its specialised kernel up front (CompilePanel-time work)
+    sc = eng.new_simulation_scratch(cp)
+
+    total = int(a.genome_mbp * 1e6)
+    lens = synth.contig_lengths(total, a.contigs)
+    offs = [0]
+    for ln in lens:
+        offs.append(offs[-1] + ln)
+    planted = synth.plan_amplicons(user_pairs, lens, a.mm, a.tw, seed=SEED + 1)
+    HALO = 64
+
+    # this rank's slice [lo, hi) of the concatenated genome (+ halo)
+    lo = total * rank // world
+    hi = total * (rank + 1) // world
+    piece_end = min(total, hi + HALO) if world > 1 else total
+    buf = torch.empty(piece_end - lo, dtype=torch.uint8, device=dev)
+    D.synth_fill(sc, buf, lo, SEED)
+    for pl in planted:  # write the (clipped) planted primers that fall into this slice
+        base = offs[pl.contig] + pl.start
+        for off, data in ((0, pl.left), (pl.length - len(pl.right), pl.right)):
+            s0, s1 = base + off, base + off + len(data)
+            c0, c1 = max(s0, lo), min(s1, piece_end)
+            if c0 < c1:
+                t = torch.frombuffer(bytearray(data[c0 - s0:c1 - s0]), dtype=torch.uint8)
+                buf[c0 - lo:c1 - lo].copy_(t)
+    torch.cuda.synchronize()
+
+    segments = []
+    for c, ln in enumerate(lens):
+        s0, s1 = max(offs[c], lo), min(offs[c + 1], piece_end)
+        own1 = min(offs[c + 1], hi)
+        if s0 >= s1 or own1 <= s0:
+            continue
+        segments.append((buf[s0 - lo:s1 - lo], c, s0 - offs[c], own1 - s0))
+    n_recs = len(lens)
+
+    def step_single():
+        _out, n = D.scan_device(cp, sc, segments, n_recs=n_recs, raw=True)
+        t = sc.timing()
+        return n, t["total_ms"], t
+
+    gather_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+
+    def step_multi():
+        import numpy as np
+        sites, recs = D.find_sites_device(cp, sc, segments, n_recs)
+        t = sc.timing()
+        dev_ms = t["total_ms"]
+        launches = t["kernel_launches"]
+        # gather the sparse site lists and the per-record reset flags on rank 0
+        gather_ev[0].record()
+        cnt = torch.tensor([len(sites)], dtype=torch.int64, device=dev)
+        cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        m = max(int(c.item()) for c in cnts)
+        pad = torch.zeros(max(1, m) * 24, dtype=torch.uint8, device=dev)
+        if len(sites):
+            pad[: len(sites) * 24].copy_(torch.from_numpy(sites.view(np.uint8).copy()))
+        allp = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, allp, dst=0)
+        flags = torch.tensor([[r[0], int(r[1])] for r in recs], dtype=torch.int64, device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        gather_ev[1].record()
+        gather_ev[1].synchronize()
+        dev_ms += gather_ev[0].elapsed_time(gather_ev[1])
+        n = 0
+        if rank == 0:
+            parts = [allp[r][: int(cnts[r].item()) * 24].cpu().numpy().view(D.SITE_DTYPE) for r in range(world)]
+            allsites = np.concatenate(parts) if parts else np.zeros(0, dtype=D.SITE_DTYPE)
+            records = [(lens[i], bool(flags[i, 1].item())) for i in range(n_recs)]
+            prods = D.pair_sites(cp, sc, allsites, records)
+            tp = sc.timing()
+            dev_ms += tp["pair_ms"]
+            launches += tp["kernel_launches"]
+            n = len(prods)
+        t = dict(t)
+        t["kernel_launches"] = launches
+        return n, dev_ms, t
+
+    step = step_single if world == 1 else step_multi
+
+    for _ in range(max(3, a.warmup)):
+        n_prod, _ms, tm = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms_sum, launches, filt_ms, last = 0.0, 0, 0.0, None
+    for _ in range(a.steps):
+        n_prod, ms, tm = step()
+        dev_ms_sum += ms
+        launches += tm["kernel_launches"]
+        filt_ms += tm["filter_ms"]
+        last = tm
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3 / a.steps
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = dev_ms_sum / a.steps
+    if world > 1:
+        t = torch.tensor([ms_per_step, wall_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step, wall_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    n_orient = cp.num_orientations
+    gbp = total / 1e9
+    gbp_s = gbp / (ms_per_step / 1e3)
+    value = gbp_s * len(user_pairs)
+    peak, peak_src = measured_peak()
+    n_groups = (n_orient + 3) // 4
+    my_bp = piece_end - lo
+    dur_ms = (filt_ms / a.steps) / max(1, n_groups)
+    achieved = (my_bp * 0.5 / 1e9) / (dur_ms / 1e3) if dur_ms > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": "ipcr_scan_jit (one launch per group of 4 orientations)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+        "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": my_bp * 0.5, "avg_launch_ms": dur_ms, "launches_per_step": n_groups,
+        "note": "0.5 B/bp x bases one launch streams; a 400-orientation panel needs 100 such passes, so the "
+                "whole scan is LOP3-issue bound, each pass is HBM-streaming (see DESIGN.md)",
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": workload_config(a, world, user_pairs, all_pairs, n_orient),
+        "gbp_per_s": gbp_s, "wall_ms_per_step": wall_ms, "products": n_prod, "planted_amplicons": len(planted),
+        "stage_ms": {k: last[k] for k in ("pack_ms", "filter_ms", "verify_ms", "pair_ms", "d2h_ms")} if last else None,
+        "candidates": last["candidates"] if last else None, "sites": last["sites"] if last else None,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+    }
+    if n_prod < len(planted):
+        line["warning"] = f"only {n_prod} products for {len(planted)} planted amplicons"
+
+    # ---- end to end through the reference-facing call with host buffers (N = 1 only) ----
+    if world == 1 and not a.no_e2e:
+        host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        host.copy_(buf)
+        torch.cuda.synchronize()
+        recs = [host[offs[c]:offs[c + 1]] for c in range(n_recs)]
+        D.scan_batch(cp, sc, recs)  # warm (buffer growth)
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(max(1, a.e2e_steps)):
+            prods = D.scan_batch(cp, sc, recs)
+            d2h = len(prods) * 64
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, a.e2e_steps)
+        line["e2e"] = {"value": gbp / (e2e_ms / 1e3) * len(user_pairs), "unit": UNIT, "ms_per_step": e2e_ms,
+                       "gbp_per_s": gbp / (e2e_ms / 1e3), "h2d_bytes_per_step": total, "d2h_bytes_per_step": d2h,
+                       "api": "ipcr_gpu_scan_batch(host records) -> products (C ABI; pinned host buffers)"}
+        del host
+    else:
+        line["e2e"] = None
+
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            res, _u, _p = cpu_reference_run(a, 1, 0, a.cpu_sample_mbp or None)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["gbp_per_s"] = res["gbp_per_s"]
+        except Exception as ex:  # the baseline must never sink the GPU line
+            line["cpu_baseline"] = {"value": None, "error": str(ex)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,12 @@ int ipcr_gpu_scan(ipcr_panel *p, ipcr_scratch *s, const uint8_t *seq, uint64_t l
 int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, size_t n_recs,
                         const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen);
 
+/* same, but the records already sit in DEVICE memory (segment seq pointers are device
+ * pointers, ascending, inside one allocation): pack -> filter -> verify -> pair */
+int ipcr_gpu_scan_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
+                         size_t n_recs, const ipcr_product **out, uint64_t *n_out, char *err,
+                         size_t errlen);
+
 /* ---- resident genomes (pack once, scan with many panels) ------------------ */
 /* host segments -> pinned staging -> H2D -> pack */
 ipcr_genome *ipcr_gpu_genome_upload(ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
@@ -171,6 +177,12 @@ int ipcr_gpu_scan_genome(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g,
 /* stage 1: *sites is a HOST pointer (scratch-owned pinned memory) */
 int ipcr_gpu_find_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g,
                         const ipcr_site **sites, uint64_t *n_sites, char *err, size_t errlen);
+/* stage 1 on records/shards that already sit in device memory (pack included; scratch
+ * buffers are reused, nothing is allocated per call once warm).  recs_out[n_recs]
+ * receives this shard's view of each record (len seen, reset-byte flag). */
+int ipcr_gpu_find_sites_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
+                               size_t n_recs, const ipcr_site **sites, uint64_t *n_sites,
+                               ipcr_record_info *recs_out, char *err, size_t errlen);
 /* stage 2: host site list (any order, any shards) + whole-record info */
 int ipcr_gpu_pair_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_site *sites, uint64_t n_sites,
                         const ipcr_record_info *recs, size_t n_recs, const ipcr_product **out,

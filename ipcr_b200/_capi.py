@@ -102,10 +102,10 @@ SYMBOLS = [
     "ipcr_gpu_panel_create", "ipcr_gpu_panel_destroy", "ipcr_gpu_panel_num_pairs",
     "ipcr_gpu_panel_num_orientations", "ipcr_gpu_panel_have", "ipcr_gpu_panel_set_jit",
     "ipcr_gpu_scratch_create", "ipcr_gpu_scratch_destroy",
-    "ipcr_gpu_scan", "ipcr_gpu_scan_batch",
+    "ipcr_gpu_scan", "ipcr_gpu_scan_batch", "ipcr_gpu_scan_device",
     "ipcr_gpu_genome_upload", "ipcr_gpu_genome_adopt", "ipcr_gpu_genome_destroy",
     "ipcr_gpu_genome_bases", "ipcr_gpu_genome_records", "ipcr_gpu_scan_genome",
-    "ipcr_gpu_find_sites", "ipcr_gpu_pair_sites",
+    "ipcr_gpu_find_sites", "ipcr_gpu_find_sites_device", "ipcr_gpu_pair_sites",
     "ipcr_gpu_product_mismatch_idx", "ipcr_gpu_last_timing", "ipcr_gpu_synth_fill",
     "ipcr_gpu_debug_planes", "ipcr_gpu_debug_candidates", "ipcr_gpu_debug_plan_eval",
     "ipcr_gpu_debug_orientation", "ipcr_gpu_debug_jit_source", "ipcr_gpu_debug_jit_compile",
@@ -145,6 +145,7 @@ def lib():
     sig("ipcr_gpu_scratch_destroy", None, V)
     sig("ipcr_gpu_scan", C.c_int, V, V, V, U64, P(P(ProductC)), P(U64), *ERR)
     sig("ipcr_gpu_scan_batch", C.c_int, V, V, P(SeqC), SZ, P(P(ProductC)), P(U64), *ERR)
+    sig("ipcr_gpu_scan_device", C.c_int, V, V, P(SegmentC), SZ, SZ, P(P(ProductC)), P(U64), *ERR)
     sig("ipcr_gpu_genome_upload", V, V, P(SegmentC), SZ, SZ, *ERR)
     sig("ipcr_gpu_genome_adopt", V, V, P(SegmentC), SZ, SZ, *ERR)
     sig("ipcr_gpu_genome_destroy", None, V)
@@ -152,6 +153,7 @@ def lib():
     sig("ipcr_gpu_genome_records", C.c_int, V, P(RecordInfoC), SZ)
     sig("ipcr_gpu_scan_genome", C.c_int, V, V, V, P(P(ProductC)), P(U64), *ERR)
     sig("ipcr_gpu_find_sites", C.c_int, V, V, V, P(P(SiteC)), P(U64), *ERR)
+    sig("ipcr_gpu_find_sites_device", C.c_int, V, V, P(SegmentC), SZ, SZ, P(P(SiteC)), P(U64), P(RecordInfoC), *ERR)
     sig("ipcr_gpu_pair_sites", C.c_int, V, V, P(SiteC), U64, P(RecordInfoC), SZ, P(P(ProductC)), P(U64), *ERR)
     sig("ipcr_gpu_product_mismatch_idx", C.c_int, P(ProductC), C.c_int, P(C.c_int32), C.c_int)
     sig("ipcr_gpu_last_timing", C.c_int, V, P(TimingC))

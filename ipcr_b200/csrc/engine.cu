@@ -116,7 +116,6 @@ struct ipcr_panel {
     std::mutex mu;
     std::map<int, std::unique_ptr<ipcr::DevTables>> dev;
     // NVRTC output, shared by every device (compiled at most once per plan variant)
-    std::vector<char> jit_cubin[2];
     ipcr::JitProgram jit_prog[2];
     std::string jit_log[2];
     bool jit_done[2] = {false, false};
@@ -246,7 +245,7 @@ struct ipcr_scratch {
     cudaEvent_t ev[8] = {};
     ipcr::DevTables *tables = nullptr;
     ipcr::GenomeData own;  // genome of ipcr_gpu_scan / scan_batch calls (buffers are reused)
-    ipcr::DevBuf lists, list_counts, list_clamped, list_offs;  // specialised filter: candidate words
+    ipcr::DevBuf lists, list_counts, list_clamped, list_offs, work_counters;  // specialised filter
     ipcr::DevBuf cand, counters, sites, keys0, keys1, vals0, vals1, keep, keep_off, tmp, fkeys, fs, recs_dev,
         entry_tasks, task_off, task_cnt, prod_off, products;
     ipcr::PinBuf h_counts, h_products, h_sites, h_stage, h_reset;
@@ -632,7 +631,7 @@ static uint64_t find_sites(ipcr_scratch *s, const GenomeData &g, bool force_raw)
             w.stats = s->counters.as<unsigned long long>() + 4;
             w.lay = g.lay;
             w.variant = (uint32_t)variant;
-            const unsigned grid = (unsigned)std::min<uint64_t>((run.n_entries + 7) / 8, (uint64_t)s->sm_count * 16);
+            const unsigned grid = (unsigned)std::min<uint64_t>((run.n_entries + 255) / 256, (uint64_t)s->sm_count * 16);
             k_verify_words<<<grid, 256, 0, st>>>(v, w, run.n_entries);
             check_launch("k_verify_words");
             s->launches++;
@@ -814,6 +813,24 @@ int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, si
     ABI_CATCH(1)
 }
 
+int ipcr_gpu_scan_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs, size_t n_recs,
+                         const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || s->panel != p) throw Error("scratch does not belong to this panel");
+    if (out) *out = nullptr;
+    if (n_out) *n_out = 0;
+    bind(s);
+    s->launches = 0;
+    s->timing = ipcr_timing{};
+    CU(cudaEventRecord(s->ev[0], s->stream));
+    build_genome(s, s->own, segs, n_segs, n_recs, true);
+    const uint64_t n = scan_genome_impl(s, s->own, s->own.lay.total_len > 0);
+    if (out) *out = s->h_products.as<ipcr_product>();
+    if (n_out) *n_out = n;
+    return 0;
+    ABI_CATCH(1)
+}
+
 int ipcr_gpu_scan(ipcr_panel *p, ipcr_scratch *s, const uint8_t *seq, uint64_t len, const ipcr_product **out,
                   uint64_t *n_out, char *err, size_t errlen) {
     ipcr_seq r{seq, len};
@@ -893,6 +910,36 @@ int ipcr_gpu_find_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g, co
     s->timing.verify_ms = ev_ms(s->ev[4], s->ev[5]);
     s->timing.total_ms = ev_ms(s->ev[3], s->ev[7]);
     s->timing.kernel_launches = s->launches;
+    if (sites) *sites = n ? s->h_sites.as<ipcr_site>() : nullptr;
+    if (n_sites) *n_sites = n;
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_find_sites_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
+                               size_t n_recs, const ipcr_site **sites, uint64_t *n_sites,
+                               ipcr_record_info *recs_out, char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || s->panel != p) throw Error("bad panel/scratch");
+    bind(s);
+    s->launches = 0;
+    s->timing = ipcr_timing{};
+    for (int i = 0; i < 8; i++) CU(cudaEventRecord(s->ev[i], s->stream));
+    build_genome(s, s->own, segs, n_segs, n_recs, true);
+    const uint64_t n = find_sites(s, s->own, true);
+    if (n) {
+        s->h_sites.ensure(n * sizeof(ipcr_site));
+        CU(cudaMemcpyAsync(s->h_sites.p, s->sites.p, n * sizeof(ipcr_site), cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaEventRecord(s->ev[7], s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->timing.pack_ms = ev_ms(s->ev[1], s->ev[2]);
+    s->timing.filter_ms = ev_ms(s->ev[3], s->ev[4]);
+    s->timing.verify_ms = ev_ms(s->ev[4], s->ev[5]);
+    s->timing.total_ms = ev_ms(s->ev[0], s->ev[7]);
+    s->timing.kernel_launches = s->launches;
+    if (recs_out)
+        for (size_t i = 0; i < n_recs && i < s->own.recs.size(); i++) recs_out[i] = s->own.recs[i];
     if (sites) *sites = n ? s->h_sites.as<ipcr_site>() : nullptr;
     if (n_sites) *n_sites = n;
     return 0;
@@ -1018,9 +1065,11 @@ int ipcr_gpu_debug_jit_compile(ipcr_panel *p, int raw_mode, char *cubin, size_t 
                                size_t errlen) {
     ABI_TRY
     if (!p) throw Error("panel is NULL");
-    std::vector<char> bin;
-    const std::string log = jit_compile(jit_generate_source(p->host, raw_mode ? 1 : 0), bin);
+    JitProgram prog = jit_generate(p->host, raw_mode ? 1 : 0, jit_config_from_env());
+    const std::string log = jit_compile_all(prog);
     if (!log.empty()) throw Error(log);
+    if (prog.cubins.empty()) throw Error("panel has no orientations");
+    const std::vector<char> &bin = prog.cubins[0];  // first group; all groups compiled
     if (cubin_size) *cubin_size = bin.size();
     if (cubin && cap >= bin.size()) memcpy(cubin, bin.data(), bin.size());
     return 0;

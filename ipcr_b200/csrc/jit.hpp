@@ -21,8 +21,10 @@
 
 #include <nvrtc.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <sstream>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -34,8 +36,7 @@ struct JitConfig {
     int stage_rows = 8;       // SR: rows per TMA stage (SR * 512 bytes)
     int stages = 4;           // NB: stages in flight per warp
     int warps = 4;            // warps per CTA
-    int group_code_kb = 28;   // target SASS per group (RS steps x orientations)
-    int max_group = 64;
+    int group_size = 4;       // orientations per kernel (one pass over the genome each)
     int min_blocks = 0;       // 0 = derive from shared memory
     int list_cap = 64;        // K: candidate words a thread can stage per launch
 };
@@ -45,24 +46,28 @@ inline JitConfig jit_config_from_env() {
     if (const char *e = getenv("IPCR_JIT_STAGE_ROWS")) c.stage_rows = atoi(e);
     if (const char *e = getenv("IPCR_JIT_STAGES")) c.stages = atoi(e);
     if (const char *e = getenv("IPCR_JIT_WARPS")) c.warps = atoi(e);
-    if (const char *e = getenv("IPCR_JIT_GROUP_KB")) c.group_code_kb = atoi(e);
-    if (const char *e = getenv("IPCR_JIT_MAX_GROUP")) c.max_group = atoi(e);
+    if (const char *e = getenv("IPCR_JIT_GROUP")) c.group_size = atoi(e);
     if (const char *e = getenv("IPCR_JIT_MIN_BLOCKS")) c.min_blocks = atoi(e);
     if (const char *e = getenv("IPCR_JIT_LIST_CAP")) c.list_cap = atoi(e);
     if (c.stage_rows != 2 && c.stage_rows != 4 && c.stage_rows != 8 && c.stage_rows != 16) c.stage_rows = 8;
     c.stages = std::max(2, std::min(c.stages, 8));
     c.warps = std::max(1, std::min(c.warps, 8));
     c.list_cap = std::max(4, c.list_cap);
+    c.group_size = std::max(1, std::min(c.group_size, 32));
     return c;
 }
 
+// One NVRTC program (= one kernel) per orientation group.  A large panel is scanned as a
+// sequence of small-panel kernels: every pass re-streams the packed genome, which stays
+// cheaper than the LOP3 work of the pass as long as a group holds >= ~4 orientations.
 struct JitProgram {
-    std::string source;
+    std::vector<std::string> sources;       // per group
+    std::vector<std::vector<char>> cubins;  // per group
     int n_groups = 0;
+    int group_size = 0;
     int ring_slots = 0;
     int stage_rows = 8, stages = 4, warps = 4, list_cap = 64;
     size_t smem_bytes = 0;
-    bool chunked = false;  // true when groups > 1: walk row chunks, not whole tiles
 };
 
 inline std::string plane_term(int slot, uint8_t cls) {
@@ -132,37 +137,10 @@ inline int plan_max_row(const OrientPlan &pl) {
     return m;
 }
 
-inline JitProgram jit_generate(const Panel &panel, int variant, const JitConfig &cfg) {
-    const ScanPlan &sp = panel.plan[variant];
-    const int U = (int)sp.o.size();
-    JitProgram prog;
-    int lmax = 1;
-    double cost_sum = 0.0;
-    for (const OrientPlan &pl : sp.o) {
-        lmax = std::max(lmax, plan_max_row(pl) + 1);
-        cost_sum += std::max(2.0, pl.cost);
-    }
+inline std::string jit_generate_group(const ScanPlan &sp, int q0, int q1, int RS, const JitConfig &cfg, int minb) {
     const int SR = cfg.stage_rows, NB = cfg.stages, WARPS = cfg.warps;
-    const int RS = ((lmax + 1 + SR - 1) / SR) * SR;  // ring: window + 1 row of LDS look-ahead
-    prog.ring_slots = RS;
-    prog.stage_rows = SR;
-    prog.stages = NB;
-    prog.warps = WARPS;
-    prog.list_cap = cfg.list_cap;
-    prog.smem_bytes = (size_t)WARPS * NB * SR * 512 + (size_t)WARPS * NB * 8;
-    // group size from the code budget: RS unrolled steps x ~16 B per LOP3
-    const double per_orient_bytes = (U ? cost_sum / U : 1.0) * RS * 16.0;
-    int G = (int)std::max(1.0, std::floor(cfg.group_code_kb * 1024.0 / std::max(1.0, per_orient_bytes)));
-    G = std::min(G, cfg.max_group);
-    if (U <= 8) G = std::max(G, U);  // small panels: one pass over HBM, always
-    const int NG = U ? (U + G - 1) / G : 0;
-    prog.n_groups = NG;
-    prog.chunked = NG > 1;
-    int minb = cfg.min_blocks;
-    if (minb <= 0) minb = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(224 * 1024) / (prog.smem_bytes + 1024)));
-
     std::ostringstream o;
-    o << "// generated by ipcr_b200 jit.hpp: " << U << " orientations, " << NG << " group(s), ring " << RS << "\n";
+    o << "// generated by ipcr_b200 jit.hpp: orientations " << q0 << ".." << (q1 - 1) << ", ring " << RS << "\n";
     o << "typedef unsigned int u32;\ntypedef unsigned long long u64;\n";
     o << "#define RS " << RS << "\n#define SR " << SR << "\n#define NB " << NB << "\n#define WARPS " << WARPS << "\n";
     o << "#define STAGE_BYTES (SR * 512)\n";
@@ -202,7 +180,7 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
 #define STAGE_WORD(c_, q_, w_) { if (cnt < K) my_list[cnt] = make_uint4((c_), (q_), (w_), (u32)tile); cnt++; }
 )";
     o << "\nextern \"C\" __global__ void __launch_bounds__(WARPS * 32, " << minb << ")\n";
-    o << "ipcr_scan_jit(const uint4* __restrict__ planes, u32 W, u32 rows, u64 n_tiles, u32 chunk_rows,\n"
+    o << "ipcr_scan_jit(const uint4* __restrict__ planes, u32 W, u32 rows, u64 n_tiles,\n"
          "              u64* work_counter, uint4* __restrict__ lists, u32* __restrict__ counts, u32 K) {\n";
     o << "    extern __shared__ __align__(128) unsigned char smem[];\n";
     o << "    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;\n";
@@ -215,81 +193,93 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
     o << "    }\n    __syncwarp();\n";
     o << "    const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n";
     o << "    uint4* my_list = lists + gtid * K;\n";
-    o << "    u32 cnt = 0, gs = 0;\n";
-    o << "    const u32 chunks_per_tile = (W + chunk_rows - 1u) / chunk_rows;\n";
-    o << "    const u64 n_items = n_tiles * chunks_per_tile;\n";
+    o << "    u32 cnt = counts[gtid], gs = 0;  // lists accumulate across the group kernels of one scan\n";
+    o << "    const u32 nsteps = ((W + RS - 1u) / RS) * RS;\n";
+    o << "    const u32 nstages = (nsteps + RS - 1u + SR - 1u) / SR;\n";
     o << "    for (;;) {\n";
-    o << "      u64 item = 0;\n";
-    o << "      if (lane == 0) item = atomicAdd(work_counter, 1ull);\n";
-    o << "      item = __shfl_sync(0xffffffffu, item, 0);\n";
-    o << "      if (item >= n_items) break;\n";
-    o << "      const u64 tile = item / chunks_per_tile;\n";
-    o << "      const u32 r0 = (u32)(item % chunks_per_tile) * chunk_rows;\n";
-    o << "      const u32 r1 = min(W, r0 + chunk_rows);\n";
-    o << "      const u32 nsteps = ((r1 - r0 + RS - 1u) / RS) * RS;\n";
-    o << "      const u32 nstages = (nsteps + RS - 1u + SR - 1u) / SR;\n";
-    o << "      const unsigned char* gsrc = (const unsigned char*)(planes + (tile * rows + r0) * 32ull);\n";
-    for (int g = 0; g < NG; g++) {
-        const int q0 = g * G, q1 = std::min(U, q0 + G);
-        o << "      {  // group " << g << ": orientations " << q0 << ".." << (q1 - 1) << "\n";
-        o << "        const u32 gs_end = gs + nstages;\n";
-        o << "        u32 issued = 0;\n";
-        o << "        { const u32 n0 = min((u32)NB, nstages);\n";
-        o << "          if (lane == 0) for (u32 i = 0; i < n0; i++) { const u32 b_ = (gs + i) % NB;\n";
-        o << "              mbar_expect_tx(bar_u + 8u * b_, STAGE_BYTES);\n";
-        o << "              bulk_g2s(sbuf_u + b_ * STAGE_BYTES, gsrc + (u64)i * STAGE_BYTES, STAGE_BYTES, bar_u + 8u * b_); }\n";
-        o << "          issued = n0; }\n";
-        o << "        const unsigned char* sp = sbuf;\n";
-        o << "        uint4 ";
-        for (int s = 0; s < RS; s++) o << (s ? ", " : "") << "R" << s;
-        o << ";\n";
-        for (int t = 0; t + 1 < RS; t++) {
-            if (t % SR == 0) o << "        STAGE_BEGIN();\n";
-            o << "        R" << t << " = LDROW(" << t << ");\n";
-            if (t % SR == SR - 1) o << "        STAGE_END();\n";
-        }
-        o << "        for (u32 w = r0; w < r0 + nsteps; w += RS) {\n";
-        for (int k = 0; k < RS; k++) {
-            const int slot = (k + RS - 1) % RS;
-            const int t = RS - 1 + k;
-            o << "          // step " << k << "\n";
-            if (t % SR == 0) o << "          STAGE_BEGIN();\n";
-            o << "          R" << slot << " = LDROW(" << t << ");\n";
-            if (t % SR == SR - 1) o << "          STAGE_END();\n";
-            o << "          {\n";
-            // sub-batches of 8 orientations keep the live candidate words bounded
-            for (int b0 = q0; b0 < q1; b0 += 8) {
-                const int b1 = std::min(q1, b0 + 8);
-                for (int q = b0; q < b1; q++) {
-                    std::ostringstream nm;
-                    nm << "c" << q;
-                    emit_orientation(o, sp.o[q], k, RS, nm.str());
-                }
-                o << "          if ((";
-                for (int q = b0; q < b1; q++) o << (q > b0 ? " | " : "") << "c" << q;
-                o << ") != 0u) {\n";
-                o << "            if (w + " << k << "u < r1) {\n";
-                for (int q = b0; q < b1; q++)
-                    o << "              if (c" << q << ") STAGE_WORD(c" << q << ", " << q << "u, w + " << k << "u);\n";
-                o << "            }\n          }\n";
-            }
-            o << "          }\n";
-        }
-        o << "        }\n";
-        // the last stage is only partially read (no STAGE_END): count it as consumed so that
-        // the next stream starts on a fresh buffer / barrier phase
-        o << "        gs = gs_end;\n";
-        o << "      }\n";
+    o << "      u64 tile = 0;\n";
+    o << "      if (lane == 0) tile = atomicAdd(work_counter, 1ull);\n";
+    o << "      tile = __shfl_sync(0xffffffffu, tile, 0);\n";
+    o << "      if (tile >= n_tiles) break;\n";
+    o << "      const unsigned char* gsrc = (const unsigned char*)(planes + tile * rows * 32ull);\n";
+    o << "      const u32 gs_end = gs + nstages;\n";
+    o << "      u32 issued = 0;\n";
+    o << "      { const u32 n0 = min((u32)NB, nstages);\n";
+    o << "        if (lane == 0) for (u32 i = 0; i < n0; i++) { const u32 b_ = (gs + i) % NB;\n";
+    o << "            mbar_expect_tx(bar_u + 8u * b_, STAGE_BYTES);\n";
+    o << "            bulk_g2s(sbuf_u + b_ * STAGE_BYTES, gsrc + (u64)i * STAGE_BYTES, STAGE_BYTES, bar_u + 8u * b_); }\n";
+    o << "        issued = n0; }\n";
+    o << "      const unsigned char* sp = sbuf;\n";
+    o << "      uint4 ";
+    for (int s = 0; s < RS; s++) o << (s ? ", " : "") << "R" << s;
+    o << ";\n";
+    for (int t = 0; t + 1 < RS; t++) {
+        if (t % SR == 0) o << "      STAGE_BEGIN();\n";
+        o << "      R" << t << " = LDROW(" << t << ");\n";
+        if (t % SR == SR - 1) o << "      STAGE_END();\n";
     }
+    o << "      for (u32 w = 0; w < nsteps; w += RS) {\n";
+    for (int k = 0; k < RS; k++) {
+        const int slot = (k + RS - 1) % RS;
+        const int t = RS - 1 + k;
+        o << "          // step " << k << "\n";
+        if (t % SR == 0) o << "          STAGE_BEGIN();\n";
+        o << "          R" << slot << " = LDROW(" << t << ");\n";
+        if (t % SR == SR - 1) o << "          STAGE_END();\n";
+        o << "          {\n";
+        for (int q = q0; q < q1; q++) {
+            std::ostringstream nm;
+            nm << "c" << q;
+            emit_orientation(o, sp.o[q], k, RS, nm.str());
+        }
+        o << "          if ((";
+        for (int q = q0; q < q1; q++) o << (q > q0 ? " | " : "") << "c" << q;
+        o << ") != 0u) {\n";
+        o << "            if (w + " << k << "u < W) {\n";
+        for (int q = q0; q < q1; q++)
+            o << "              if (c" << q << ") STAGE_WORD(c" << q << ", " << q << "u, w + " << k << "u);\n";
+        o << "            }\n          }\n";
+        o << "          }\n";
+    }
+    o << "      }\n";
+    // the last stage is only partially read (no STAGE_END): count it as consumed so that the
+    // next tile starts on a fresh buffer / barrier phase
+    o << "      gs = gs_end;\n";
     o << "    }\n";
     o << "    counts[gtid] = cnt;\n";
     o << "}\n";
-    prog.source = o.str();
+    return o.str();
+}
+
+inline JitProgram jit_generate(const Panel &panel, int variant, const JitConfig &cfg) {
+    const ScanPlan &sp = panel.plan[variant];
+    const int U = (int)sp.o.size();
+    JitProgram prog;
+    int lmax = 1;
+    for (const OrientPlan &pl : sp.o) lmax = std::max(lmax, plan_max_row(pl) + 1);
+    const int SR = cfg.stage_rows, NB = cfg.stages, WARPS = cfg.warps;
+    const int RS = ((lmax + 1 + SR - 1) / SR) * SR;  // ring: window + 1 row of LDS look-ahead
+    prog.ring_slots = RS;
+    prog.stage_rows = SR;
+    prog.stages = NB;
+    prog.warps = WARPS;
+    prog.list_cap = cfg.list_cap;
+    prog.smem_bytes = (size_t)WARPS * NB * SR * 512 + (size_t)WARPS * NB * 8;
+    const int G = cfg.group_size;
+    prog.group_size = G;
+    prog.n_groups = U ? (U + G - 1) / G : 0;
+    int minb = cfg.min_blocks;
+    if (minb <= 0) minb = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(224 * 1024) / (prog.smem_bytes + 1024)));
+    for (int g = 0; g < prog.n_groups; g++)
+        prog.sources.push_back(jit_generate_group(sp, g * G, std::min(U, (g + 1) * G), RS, cfg, minb));
     return prog;
 }
 
 inline std::string jit_generate_source(const Panel &panel, int variant) {
-    return jit_generate(panel, variant, jit_config_from_env()).source;
+    JitProgram p = jit_generate(panel, variant, jit_config_from_env());
+    std::string all;
+    for (const std::string &s : p.sources) all += s + "\n";
+    return all;
 }
 
 // NVRTC: source -> sm_100a cubin.  Returns "" on success, else the log.
@@ -321,9 +311,34 @@ inline std::string jit_compile(const std::string &src, std::vector<char> &cubin)
     return "";
 }
 
+// compiles every group (NVRTC is thread-safe; one program per worker at a time)
+inline std::string jit_compile_all(JitProgram &prog) {
+    const size_t n = prog.sources.size();
+    prog.cubins.assign(n, {});
+    std::vector<std::string> logs(n);
+    std::atomic<size_t> next{0};
+    unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 32u));
+    if (const char *e = getenv("IPCR_JIT_COMPILE_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+    nt = (unsigned)std::min<size_t>(nt, n);
+    auto work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            logs[i] = jit_compile(prog.sources[i], prog.cubins[i]);
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < n; i++)
+        if (!logs[i].empty()) return logs[i];
+    return "";
+}
+
 struct JitKernel {
-    cudaLibrary_t library = nullptr;
-    cudaKernel_t kernel = nullptr;
+    std::vector<cudaLibrary_t> libraries;
+    std::vector<cudaKernel_t> kernels;  // one per orientation group
     bool ok = false;
     std::string log;
 };

@@ -26,21 +26,28 @@ static JitKernel *jit_get(ipcr_scratch *s, int variant, double work) {
     if (!p->jit_done[variant]) {
         p->jit_done[variant] = true;
         p->jit_prog[variant] = jit_generate(p->host, variant, jit_config_from_env());
-        p->jit_log[variant] = jit_compile(p->jit_prog[variant].source, p->jit_cubin[variant]);
-        if (!p->jit_log[variant].empty()) p->jit_cubin[variant].clear();
+        p->jit_log[variant] = jit_compile_all(p->jit_prog[variant]);
+        if (!p->jit_log[variant].empty()) p->jit_prog[variant].cubins.clear();
     }
-    if (p->jit_cubin[variant].empty()) {
+    if (p->jit_prog[variant].cubins.empty()) {
         if (mode >= 2) throw Error("JIT compile of the scan kernel failed: " + p->jit_log[variant]);
         return nullptr;
     }
     if (!s->tables->jit_tried[variant]) {
         s->tables->jit_tried[variant] = true;
-        cudaError_t e = cudaLibraryLoadData(&k->library, p->jit_cubin[variant].data(), nullptr, nullptr, 0, nullptr,
-                                            nullptr, 0);
-        if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kernel, k->library, "ipcr_scan_jit");
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute((const void *)k->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)p->jit_prog[variant].smem_bytes);
+        cudaError_t e = cudaSuccess;
+        for (const std::vector<char> &bin : p->jit_prog[variant].cubins) {
+            cudaLibrary_t lib = nullptr;
+            cudaKernel_t kern = nullptr;
+            e = cudaLibraryLoadData(&lib, bin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+            if (e == cudaSuccess) e = cudaLibraryGetKernel(&kern, lib, "ipcr_scan_jit");
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)p->jit_prog[variant].smem_bytes);
+            if (e != cudaSuccess) break;
+            k->libraries.push_back(lib);
+            k->kernels.push_back(kern);
+        }
         if (e != cudaSuccess) {
             cudaGetLastError();
             k->log = std::string("loading the JIT kernel failed: ") + cudaGetErrorString(e);
@@ -67,21 +74,25 @@ static bool jit_filter(ipcr_scratch *s, const GenomeData &g, int variant, JitRun
     cudaStream_t st = s->stream;
     const int threads = prog.warps * 32;
     int blocks_per_sm = (int)std::max<size_t>(1, (size_t)(227 * 1024) / (prog.smem_bytes + 1024));
-    cudaFuncAttributes fa{};
-    if (cudaFuncGetAttributes(&fa, (const void *)k->kernel) == cudaSuccess && fa.numRegs > 0)
-        blocks_per_sm = std::min(blocks_per_sm, std::max(1, 65536 / (fa.numRegs * threads)));
-    else
-        cudaGetLastError();
+    int max_regs = 0;
+    for (cudaKernel_t kern : k->kernels) {
+        cudaFuncAttributes fa{};
+        if (cudaFuncGetAttributes(&fa, (const void *)kern) == cudaSuccess) max_regs = std::max(max_regs, fa.numRegs);
+        else cudaGetLastError();
+    }
+    if (max_regs > 0) blocks_per_sm = std::min(blocks_per_sm, std::max(1, 65536 / (max_regs * threads)));
     blocks_per_sm = std::min(blocks_per_sm, 2048 / threads);
     if (const char *e = getenv("IPCR_JIT_BLOCKS_PER_SM")) blocks_per_sm = std::max(1, atoi(e));
-    uint32_t chunk_rows = prog.chunked ? 128u : g.lay.W;
-    if (const char *e = getenv("IPCR_JIT_CHUNK")) chunk_rows = (uint32_t)std::max(32, atoi(e));
-    chunk_rows = std::min(chunk_rows, g.lay.W);
-    const uint64_t n_items = g.lay.n_tiles * ((g.lay.W + chunk_rows - 1) / chunk_rows);
+    const uint64_t n_items = g.lay.n_tiles;
+    const size_t n_groups = k->kernels.size();
     const unsigned grid = (unsigned)std::max<uint64_t>(
         1, std::min<uint64_t>((n_items + prog.warps - 1) / prog.warps, (uint64_t)s->sm_count * blocks_per_sm));
     const uint32_t n_threads = grid * (uint32_t)threads;
-    uint32_t K = (uint32_t)prog.list_cap;
+    // list capacity per thread: twice the modelled candidate-word count + slack
+    double expect = 0.0;
+    for (const OrientPlan &op : p->host.plan[variant].o) expect += op.cand_prob;
+    uint32_t K = (uint32_t)std::min<double>(1 << 20, std::max<double>(prog.list_cap,
+                                            2.0 * expect * (double)g.lay.total_len / n_threads + prog.list_cap));
 
     for (int attempt = 0; attempt < 2; attempt++) {
         s->lists.ensure((size_t)n_threads * K * sizeof(uint4));
@@ -89,20 +100,27 @@ static bool jit_filter(ipcr_scratch *s, const GenomeData &g, int variant, JitRun
         s->list_clamped.ensure((size_t)n_threads * 4);
         s->list_offs.ensure(((size_t)n_threads + 1) * 4);
         s->tmp.ensure(scan_tmp_words(n_threads) * 4);
+        s->work_counters.ensure(n_groups * sizeof(unsigned long long));
         CU(cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(s->work_counters.p, 0, n_groups * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(s->list_counts.p, 0, (size_t)n_threads * 4, st));
+        CU(cudaEventRecord(s->ev[3], st));
         const uint4 *planes = g.planes.as<uint4>();
         uint32_t W = g.lay.W, rows = g.lay.rows;
         uint64_t n_tiles = g.lay.n_tiles;
-        unsigned long long *work_counter = s->counters.as<unsigned long long>() + 2;
         uint4 *lists = s->lists.as<uint4>();
         uint32_t *counts = s->list_counts.as<uint32_t>();
-        void *args[] = {&planes, &W, &rows, &n_tiles, &chunk_rows, &work_counter, &lists, &counts, &K};
-        cudaError_t e = cudaLaunchKernel((const void *)k->kernel, dim3(grid), dim3(threads), args, prog.smem_bytes, st);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            throw Error(std::string("launch of ipcr_scan_jit failed: ") + cudaGetErrorString(e));
+        for (size_t gi = 0; gi < n_groups; gi++) {
+            unsigned long long *work_counter = s->work_counters.as<unsigned long long>() + gi;
+            void *args[] = {&planes, &W, &rows, &n_tiles, &work_counter, &lists, &counts, &K};
+            cudaError_t e = cudaLaunchKernel((const void *)k->kernels[gi], dim3(grid), dim3(threads), args,
+                                             prog.smem_bytes, st);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                throw Error(std::string("launch of ipcr_scan_jit failed: ") + cudaGetErrorString(e));
+            }
+            s->launches++;
         }
-        s->launches++;
         CU(cudaEventRecord(s->ev[4], st));  // end of the filter proper
         WordListArgs w{};
         w.lists = lists;
@@ -130,8 +148,9 @@ static bool jit_filter(ipcr_scratch *s, const GenomeData &g, int variant, JitRun
         run.K = K;
         if (max_count <= K) return true;
         // some thread overflowed its list: retry once with room for the worst thread
-        if (attempt == 1 || max_count * (uint64_t)n_threads * sizeof(uint4) > (8ull << 30)) return false;
-        K = (uint32_t)max_count;
+        if (attempt == 1 || 2 * max_count * (uint64_t)n_threads * sizeof(uint4) > (8ull << 30)) return false;
+        // work is handed out dynamically, so per-thread counts vary from run to run: leave headroom
+        K = (uint32_t)(max_count + max_count / 2 + 64);
     }
     return false;
 }

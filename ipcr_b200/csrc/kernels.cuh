@@ -293,29 +293,40 @@ __global__ void k_list_prepare(WordListArgs w) {
     if (bits) atomicAdd(&w.stats[1], bits);
 }
 
-// one warp per staged word; lane i verifies bit i
+// one THREAD per staged word (most words carry a single candidate bit); the warp
+// iterates while any lane still has a bit left so that the ballot compaction stays convergent
 __global__ void __launch_bounds__(256)
 k_verify_words(VerifyArgs a, WordListArgs w, uint64_t n_entries) {
-    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t lane = lane_id();
-    for (uint64_t e = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < n_entries; e += warps) {
-        // owning thread: last t with offs[t] <= e
-        uint32_t lo = 0, hi = w.n_threads;
-        while (lo + 1 < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if ((uint64_t)w.offs[mid] <= e) lo = mid; else hi = mid;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n_entries + 31ull) & ~31ull;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_round; e += stride) {
+        uint32_t word = 0, q = 0, j0 = 0;
+        uint64_t stripe0 = 0, row = 0;
+        if (e < n_entries) {
+            // owning thread: last t with offs[t] <= e
+            uint32_t lo = 0, hi = w.n_threads;
+            while (lo + 1 < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if ((uint64_t)w.offs[mid] <= e) lo = mid; else hi = mid;
+            }
+            const uint4 ent = w.lists[(uint64_t)lo * w.K + (e - w.offs[lo])];
+            word = ent.x;
+            q = ent.y;
+            row = ent.z;
+            stripe0 = (uint64_t)ent.w * kStripesPerTile + (uint64_t)(lo & 31u) * 32u;
+            j0 = a.orients[q].j0[w.variant];
         }
-        const uint4 ent = w.lists[(uint64_t)lo * w.K + (e - w.offs[lo])];
-        bool ok = false;
-        ipcr_site s;
-        if ((ent.x >> lane) & 1u) {
-            const uint32_t q = ent.y;
-            const uint64_t stripe = (uint64_t)ent.w * kStripesPerTile + (uint64_t)(lo & 31u) * 32u + lane;
-            const uint64_t P = stripe * w.lay.W + ent.z;
-            const uint32_t j0 = a.orients[q].j0[w.variant];
-            if (P < w.lay.total_len && P >= j0) ok = verify_one(a, q, P - j0, &s);
+        while (__any_sync(0xFFFFFFFFu, word != 0)) {
+            bool ok = false;
+            ipcr_site s;
+            if (word) {
+                const int i = __ffs(word) - 1;
+                word &= word - 1;
+                const uint64_t P = (stripe0 + i) * w.lay.W + row;
+                if (P < w.lay.total_len && P >= j0) ok = verify_one(a, q, P - j0, &s);
+            }
+            compact_site(a, ok, s);
         }
-        compact_site(a, ok, s);
     }
 }
 

@@ -127,6 +127,21 @@ def scan_batch(cp: CompiledPanel, scratch: SimulationScratch, seqs: Sequence, se
     return _products(out, n.value, cp, seq_ids)
 
 
+def scan_device(cp: CompiledPanel, scratch: SimulationScratch, segments: Sequence[Tuple], n_recs=None,
+                seq_ids=None, raw: bool = False):
+    """pack + scan of records that already live in device memory (one timed chain)."""
+    arr, keep, nr = Genome._segments(segments)
+    L = _capi.lib()
+    out = C.POINTER(_capi.ProductC)()
+    n = C.c_uint64()
+    err = _capi.errbuf()
+    _capi.check(L.ipcr_gpu_scan_device(cp._h, scratch._h, arr, len(segments), n_recs or nr, C.byref(out),
+                                       C.byref(n), err, len(err)), err)
+    if raw:
+        return out, n.value
+    return _products(out, n.value, cp, seq_ids)
+
+
 def find_sites(cp: CompiledPanel, scratch: SimulationScratch, genome: Genome):
     """Stage 1 on one device.  Returns a numpy structured array of ipcr_site records."""
     import numpy as np
@@ -140,6 +155,26 @@ def find_sites(cp: CompiledPanel, scratch: SimulationScratch, genome: Genome):
         return np.zeros(0, dtype=SITE_DTYPE)
     raw = C.string_at(out, n.value * C.sizeof(_capi.SiteC))
     return np.frombuffer(raw, dtype=SITE_DTYPE).copy()
+
+
+def find_sites_device(cp: CompiledPanel, scratch: SimulationScratch, segments: Sequence[Tuple], n_recs: int):
+    """Stage 1 on device-resident shards (pack + filter + verify).  Returns (sites, records)
+    where records[i] = (len seen by this shard, has_reset_byte)."""
+    import numpy as np
+
+    arr, keep, _nr = Genome._segments(segments)
+    L = _capi.lib()
+    out = C.POINTER(_capi.SiteC)()
+    n = C.c_uint64()
+    recs = (_capi.RecordInfoC * max(1, n_recs))()
+    err = _capi.errbuf()
+    _capi.check(L.ipcr_gpu_find_sites_device(cp._h, scratch._h, arr, len(segments), n_recs, C.byref(out),
+                                             C.byref(n), recs, err, len(err)), err)
+    records = [(int(recs[i].len), bool(recs[i].has_reset_byte)) for i in range(n_recs)]
+    if n.value == 0:
+        return np.zeros(0, dtype=SITE_DTYPE), records
+    raw = C.string_at(out, n.value * C.sizeof(_capi.SiteC))
+    return np.frombuffer(raw, dtype=SITE_DTYPE).copy(), records
 
 
 def pair_sites(cp: CompiledPanel, scratch: SimulationScratch, sites, records: Sequence[Tuple[int, bool]],
