@@ -238,7 +238,7 @@ def run_ours(a):
         torch.cuda.set_device(0)
     dev = torch.device("cuda", torch.cuda.current_device())
 
-    from ipcr_b200 import Config, Engine, _capi, synth
+    from ipcr_b200 import Config, Engine, _capi, sharding, synth
     from ipcr_b200 import device as D
 
     L = _capi.lib()
@@ -258,12 +258,8 @@ def run_ours(a):
     for ln in lens:
         offs.append(offs[-1] + ln)
     planted = synth.plan_amplicons(user_pairs, lens, a.mm, a.tw, seed=SEED + 1)
-    HALO = 64
-
     # this rank's slice [lo, hi) of the concatenated genome (+ halo)
-    lo = total * rank // world
-    hi = total * (rank + 1) // world
-    piece_end = min(total, hi + HALO) if world > 1 else total
+    lo, hi, piece_end = sharding.rank_slice(total, world, rank)
     buf = torch.empty(piece_end - lo, dtype=torch.uint8, device=dev)
     D.synth_fill(sc, buf, lo, SEED)
     for pl in planted:  # write the (clipped) planted primers that fall into this slice
@@ -276,13 +272,8 @@ def run_ours(a):
                 buf[c0 - lo:c1 - lo].copy_(t)
     torch.cuda.synchronize()
 
-    segments = []
-    for c, ln in enumerate(lens):
-        s0, s1 = max(offs[c], lo), min(offs[c + 1], piece_end)
-        own1 = min(offs[c + 1], hi)
-        if s0 >= s1 or own1 <= s0:
-            continue
-        segments.append((buf[s0 - lo:s1 - lo], c, s0 - offs[c], own1 - s0))
+    segments = [(buf[s0 - lo:s1 - lo], c, rec_off, own)
+                for (s0, s1, c, rec_off, own) in sharding.shard_segments(lens, world, rank)]
     n_recs = len(lens)
 
     def step_single():
@@ -293,32 +284,19 @@ def run_ours(a):
     gather_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
     def step_multi():
-        import numpy as np
         sites, recs = D.find_sites_device(cp, sc, segments, n_recs)
         t = sc.timing()
         dev_ms = t["total_ms"]
         launches = t["kernel_launches"]
         # gather the sparse site lists and the per-record reset flags on rank 0
         gather_ev[0].record()
-        cnt = torch.tensor([len(sites)], dtype=torch.int64, device=dev)
-        cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        m = max(int(c.item()) for c in cnts)
-        pad = torch.zeros(max(1, m) * 24, dtype=torch.uint8, device=dev)
-        if len(sites):
-            pad[: len(sites) * 24].copy_(torch.from_numpy(sites.view(np.uint8).copy()))
-        allp = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, allp, dst=0)
-        flags = torch.tensor([[r[0], int(r[1])] for r in recs], dtype=torch.int64, device=dev)
-        dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        allsites, records = sharding.gather_sites(dist, sites, recs, n_recs, rank, world, device=dev)
         gather_ev[1].record()
         gather_ev[1].synchronize()
         dev_ms += gather_ev[0].elapsed_time(gather_ev[1])
         n = 0
         if rank == 0:
-            parts = [allp[r][: int(cnts[r].item()) * 24].cpu().numpy().view(D.SITE_DTYPE) for r in range(world)]
-            allsites = np.concatenate(parts) if parts else np.zeros(0, dtype=D.SITE_DTYPE)
-            records = [(lens[i], bool(flags[i, 1].item())) for i in range(n_recs)]
+            records = [(lens[i], records[i][1]) for i in range(n_recs)]
             prods = D.pair_sites(cp, sc, allsites, records)
             tp = sc.timing()
             dev_ms += tp["pair_ms"]
