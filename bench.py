@@ -284,10 +284,21 @@ def run_ours(a):
     gather_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
     def step_multi():
-        sites, recs = D.find_sites_device(cp, sc, segments, n_recs)
+        # stage 1 decides from the shard's own bytes whether rc orientations must stay raw
+        sites, recs = D.find_sites_device(cp, sc, segments, n_recs, force_raw=False)
         t = sc.timing()
         dev_ms = t["total_ms"]
         launches = t["kernel_launches"]
+        if a.hit_cap > 0 and a.mm > 0 and a.tw > 0:
+            # hit-cap parity: if ANY shard saw a reset byte, shards that filtered with the protected
+            # window must redo stage 1 raw (never happens on the N-free bench genome)
+            need = torch.tensor([int(any(r[1] for r in recs))], dtype=torch.int32, device=dev)
+            dist.all_reduce(need, op=dist.ReduceOp.MAX)
+            if int(need.item()) and t["plan_variant"] == 0:
+                sites, recs = D.find_sites_device(cp, sc, segments, n_recs, force_raw=True)
+                t2 = sc.timing()
+                dev_ms += t2["total_ms"]
+                launches += t2["kernel_launches"]
         # gather the sparse site lists and the per-record reset flags on rank 0
         gather_ev[0].record()
         allsites, records = sharding.gather_sites(dist, sites, recs, n_recs, rank, world, device=dev)

@@ -113,6 +113,8 @@ typedef struct ipcr_timing {
     uint64_t candidates, sites, products;
     uint32_t kernel_launches; /* launches issued by the last scan */
     uint32_t used_jit;        /* 1 if the panel-specialised (NVRTC) scan kernel ran */
+    uint32_t plan_variant;    /* 0 = protected window enforced in the filter, 1 = rc orientations raw */
+    uint32_t reserved;
 } ipcr_timing;
 
 typedef struct ipcr_panel ipcr_panel;
@@ -181,8 +183,13 @@ int ipcr_gpu_find_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g,
  * buffers are reused, nothing is allocated per call once warm).  recs_out[n_recs]
  * receives this shard's view of each record (len seen, reset-byte flag). */
 int ipcr_gpu_find_sites_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
-                               size_t n_recs, const ipcr_site **sites, uint64_t *n_sites,
+                               size_t n_recs, int force_raw, const ipcr_site **sites, uint64_t *n_sites,
                                ipcr_record_info *recs_out, char *err, size_t errlen);
+/* force_raw: hit-cap parity needs rc orientations to keep matches that violate the 3' window
+ * whenever the WHOLE record holds a non-ACGTacgt byte (core/engine/compiled.go:185-190).  A shard
+ * only sees its own bytes: pass 0 to decide from the shard (then, if ipcr_timing.plan_variant == 0
+ * and another shard of the same record reports a reset byte while hit_cap, max_mm and
+ * terminal_window are all > 0, call again with 1), or pass 1 to be safe at ~20 % more filter work. */
 /* stage 2: host site list (any order, any shards) + whole-record info */
 int ipcr_gpu_pair_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_site *sites, uint64_t n_sites,
                         const ipcr_record_info *recs, size_t n_recs, const ipcr_product **out,

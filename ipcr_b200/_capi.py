@@ -91,6 +91,7 @@ class TimingC(C.Structure):
         ("total_ms", C.c_float),
         ("candidates", C.c_uint64), ("sites", C.c_uint64), ("products", C.c_uint64),
         ("kernel_launches", C.c_uint32), ("used_jit", C.c_uint32),
+        ("plan_variant", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -153,7 +154,8 @@ def lib():
     sig("ipcr_gpu_genome_records", C.c_int, V, P(RecordInfoC), SZ)
     sig("ipcr_gpu_scan_genome", C.c_int, V, V, V, P(P(ProductC)), P(U64), *ERR)
     sig("ipcr_gpu_find_sites", C.c_int, V, V, V, P(P(SiteC)), P(U64), *ERR)
-    sig("ipcr_gpu_find_sites_device", C.c_int, V, V, P(SegmentC), SZ, SZ, P(P(SiteC)), P(U64), P(RecordInfoC), *ERR)
+    sig("ipcr_gpu_find_sites_device", C.c_int, V, V, P(SegmentC), SZ, SZ, C.c_int, P(P(SiteC)), P(U64),
+        P(RecordInfoC), *ERR)
     sig("ipcr_gpu_pair_sites", C.c_int, V, V, P(SiteC), U64, P(RecordInfoC), SZ, P(P(ProductC)), P(U64), *ERR)
     sig("ipcr_gpu_product_mismatch_idx", C.c_int, P(ProductC), C.c_int, P(C.c_int32), C.c_int)
     sig("ipcr_gpu_last_timing", C.c_int, V, P(TimingC))

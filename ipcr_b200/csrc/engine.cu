@@ -242,6 +242,9 @@ struct ipcr_scratch {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of later slabs overlaps the scan of earlier ones
+    std::vector<cudaEvent_t> slab_ev;
+    cudaEvent_t copy_ev[2] = {};
     cudaEvent_t ev[8] = {};
     ipcr::DevTables *tables = nullptr;
     ipcr::GenomeData own;  // genome of ipcr_gpu_scan / scan_batch calls (buffers are reused)
@@ -255,7 +258,12 @@ struct ipcr_scratch {
     ~ipcr_scratch() {
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto &e : slab_ev)
+            if (e) cudaEventDestroy(e);
+        for (auto &e : copy_ev)
+            if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
 
@@ -286,9 +294,15 @@ static void pack_genome(ipcr_scratch *s, GenomeData &g) {
     upload(g.segs_dev, g.segs.data(), g.segs.size() * sizeof(SegmentDev), st);
     g.seg_reset.ensure(g.segs.size() * sizeof(uint32_t));
     CU(cudaMemsetAsync(g.seg_reset.p, 0, g.segs.size() * sizeof(uint32_t), st));
-    dim3 grid((unsigned)g.lay.n_tiles, (g.lay.rows + 31) / 32), block(32, 32);
-    k_pack<<<grid, block, 0, st>>>(g.ascii, g.lay, g.planes.as<uint4>(), g.segs_dev.as<SegmentDev>(),
-                                   (uint32_t)g.segs.size(), g.seg_reset.as<uint32_t>());
+    if ((reinterpret_cast<uintptr_t>(g.ascii) & 15u) == 0 && g.lay.W % 16 == 0) {
+        k_pack<<<(unsigned)g.lay.n_tiles, 1024, 0, st>>>(g.ascii, g.lay, g.planes.as<uint4>(),
+                                                         g.segs_dev.as<SegmentDev>(), (uint32_t)g.segs.size(),
+                                                         g.seg_reset.as<uint32_t>());
+    } else {  // unaligned adopted buffer: byte-wise variant
+        dim3 grid((unsigned)g.lay.n_tiles, (g.lay.rows + 31) / 32), block(32, 32);
+        k_pack_bytes<<<grid, block, 0, st>>>(g.ascii, g.lay, g.planes.as<uint4>(), g.segs_dev.as<SegmentDev>(),
+                                             (uint32_t)g.segs.size(), g.seg_reset.as<uint32_t>());
+    }
     check_launch("k_pack");
     s->launches++;
     s->h_reset.ensure(g.segs.size() * sizeof(uint32_t));
@@ -567,6 +581,150 @@ static uint64_t scan_genome_impl(ipcr_scratch *s, const GenomeData &g, bool had_
     return n_prod;
 }
 
+// Host records -> products with the H2D copy of slab k+1.. running under the scan of slab k
+// (the end-to-end path is PCIe-bound once the scan is fast).  The
+// concatenated records are cut into slabs exactly like multi-GPU shards (64-base halo, a site
+// belongs to the slab holding its start); stage 1 runs per slab, stage 2 once.
+static uint64_t scan_batch_streamed(ipcr_scratch *s, const ipcr_seq *recs, size_t n_recs, int n_slabs) {
+    const Panel &h = s->panel->host;
+    cudaStream_t st = s->stream, cs = s->copy_stream;
+    constexpr uint64_t kHalo = 64;
+    std::vector<uint64_t> roff(n_recs + 1, 0);
+    for (size_t r = 0; r < n_recs; r++) roff[r + 1] = roff[r] + recs[r].len;
+    const uint64_t total = roff[n_recs];
+    std::vector<ipcr_record_info> rinfo(n_recs, ipcr_record_info{});
+    for (size_t r = 0; r < n_recs; r++) rinfo[r].len = recs[r].len;
+    GenomeData &g = s->own;
+    g.device = s->device;
+    g.ascii_owned.ensure((size_t)total + 64);
+    uint8_t *base = g.ascii_owned.as<uint8_t>();
+    std::vector<uint64_t> cut((size_t)n_slabs + 1);
+    for (int k = 0; k <= n_slabs; k++) cut[k] = k == n_slabs ? total : ((total * (uint64_t)k / n_slabs) & ~15ull);
+    while ((int)s->slab_ev.size() < n_slabs) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->slab_ev.push_back(e);
+    }
+    // 1. every copy is queued now; slab k's event fires once [cut[k], cut[k+1] + halo) is resident
+    CU(cudaEventRecord(s->ev[0], st));
+    CU(cudaEventRecord(s->copy_ev[0], cs));
+    uint64_t copied_to = 0;
+    for (int k = 0; k < n_slabs; k++) {
+        const uint64_t want = std::min(total, cut[k + 1] + kHalo);
+        for (size_t r = 0; r < n_recs && copied_to < want; r++) {
+            const uint64_t a = std::max(copied_to, roff[r]), b = std::min(want, roff[r + 1]);
+            if (a < b)
+                CU(cudaMemcpyAsync(base + a, recs[r].seq + (a - roff[r]), b - a, cudaMemcpyHostToDevice, cs));
+        }
+        copied_to = std::max(copied_to, want);
+        CU(cudaEventRecord(s->slab_ev[k], cs));
+    }
+    CU(cudaEventRecord(s->copy_ev[1], cs));
+    // 2. stage 1 per slab
+    std::vector<ipcr_site> all_sites;
+    bool used_plain_variant = false;
+    uint64_t cand_total = 0;
+    float pack_ms = 0.f, filter_ms = 0.f, verify_ms = 0.f;
+    uint32_t used_jit = 0;
+    for (int k = 0; k < n_slabs; k++) {
+        const uint64_t lo = cut[k], hi = cut[k + 1], end = std::min(total, hi + kHalo);
+        if (lo >= hi) continue;
+        g.segs.clear();
+        g.recs.assign(n_recs, ipcr_record_info{});
+        for (size_t r = 0; r < n_recs; r++) {
+            g.recs[r].len = recs[r].len;
+            const uint64_t s0 = std::max(roff[r], lo), s1 = std::min(roff[r + 1], end), own1 = std::min(roff[r + 1], hi);
+            if (s0 >= s1 || own1 <= s0) continue;
+            SegmentDev d{};
+            d.global_off = s0 - lo;
+            d.len = s1 - s0;
+            d.own_len = own1 - s0;
+            d.rec_off = s0 - roff[r];
+            d.rec_idx = (uint32_t)r;
+            g.segs.push_back(d);
+        }
+        if (g.segs.empty()) continue;
+        // the first segment must start at 0 for find_segment(); pad with a dummy otherwise
+        g.lay.total_len = end - lo;
+        g.ascii = base + lo;
+        g.own_bases = hi - lo;
+        CU(cudaStreamWaitEvent(st, s->slab_ev[k], 0));
+        CU(cudaEventRecord(s->ev[1], st));
+        pack_genome(s, g);
+        CU(cudaEventRecord(s->ev[2], st));
+        for (size_t r = 0; r < n_recs; r++) rinfo[r].has_reset_byte |= g.recs[r].has_reset_byte;
+        const uint64_t n = find_sites(s, g, false);
+        if (s->timing.plan_variant == 0) used_plain_variant = true;
+        used_jit |= s->timing.used_jit;
+        cand_total += s->timing.candidates;
+        if (n) {
+            s->h_sites.ensure(n * sizeof(ipcr_site));
+            CU(cudaMemcpyAsync(s->h_sites.p, s->sites.p, n * sizeof(ipcr_site), cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaStreamSynchronize(st));
+        pack_ms += ev_ms(s->ev[1], s->ev[2]);
+        filter_ms += ev_ms(s->ev[3], s->ev[4]);
+        verify_ms += ev_ms(s->ev[4], s->ev[5]);
+        if (n) all_sites.insert(all_sites.end(), s->h_sites.as<ipcr_site>(), s->h_sites.as<ipcr_site>() + n);
+    }
+    // hit-cap parity: a record with a reset byte anywhere needs raw rc matches from EVERY slab
+    bool any_reset = false;
+    for (const auto &ri : rinfo) any_reset |= ri.has_reset_byte != 0;
+    if (any_reset && used_plain_variant && h.cfg.hit_cap > 0 && h.cfg.max_mm > 0 && h.cfg.terminal_window > 0) {
+        all_sites.clear();
+        g.segs.clear();
+        g.recs = rinfo;
+        for (size_t r = 0; r < n_recs; r++) {
+            if (!recs[r].len) continue;
+            SegmentDev d{};
+            d.global_off = roff[r];
+            d.len = d.own_len = recs[r].len;
+            d.rec_idx = (uint32_t)r;
+            g.segs.push_back(d);
+        }
+        g.lay.total_len = total;
+        g.ascii = base;
+        CU(cudaStreamWaitEvent(st, s->slab_ev[n_slabs - 1], 0));
+        pack_genome(s, g);
+        const uint64_t n = find_sites(s, g, true);
+        cand_total = s->timing.candidates;
+        if (n) {
+            s->h_sites.ensure(n * sizeof(ipcr_site));
+            CU(cudaMemcpyAsync(s->h_sites.p, s->sites.p, n * sizeof(ipcr_site), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            all_sites.assign(s->h_sites.as<ipcr_site>(), s->h_sites.as<ipcr_site>() + n);
+        }
+    }
+    // 3. stage 2 once
+    CU(cudaEventRecord(s->ev[5], st));
+    const uint64_t n_sites = all_sites.size();
+    if (n_sites) {
+        s->sites.ensure(n_sites * sizeof(ipcr_site));
+        CU(cudaMemcpyAsync(s->sites.p, all_sites.data(), n_sites * sizeof(ipcr_site), cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaEventRecord(s->ev[6], st));
+    const uint64_t n_prod = pair_sites(s, s->sites.as<ipcr_site>(), n_sites, rinfo.data(), n_recs);
+    if (n_prod == 0) CU(cudaEventRecord(s->ev[6], st));
+    CU(cudaEventRecord(s->ev[7], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(cs));
+    g.recs = rinfo;
+    ipcr_timing &t = s->timing;
+    t.h2d_ms = ev_ms(s->copy_ev[0], s->copy_ev[1]);
+    t.pack_ms = pack_ms;
+    t.filter_ms = filter_ms;
+    t.verify_ms = verify_ms;
+    t.pair_ms = ev_ms(s->ev[5], s->ev[6]);
+    t.d2h_ms = ev_ms(s->ev[6], s->ev[7]);
+    t.total_ms = ev_ms(s->ev[0], s->ev[7]);
+    t.candidates = cand_total;
+    t.sites = n_sites;
+    t.products = n_prod;
+    t.used_jit = used_jit;
+    t.kernel_launches = s->launches;
+    return n_prod;
+}
+
 static void set_err(char *err, size_t errlen, const std::string &m) {
     if (!err || errlen == 0) return;
     snprintf(err, errlen, "%s", m.c_str());
@@ -592,6 +750,7 @@ static uint64_t find_sites(ipcr_scratch *s, const GenomeData &g, bool force_raw)
     // BEFORE filterLeftTW (compiled.go:185-190,250-257)
     const bool raw_possible = cfg.hit_cap > 0 && cfg.max_mm > 0 && cfg.terminal_window > 0;
     const int variant = raw_possible && (force_raw || g.any_reset || any_rc_unseeded) ? 1 : 0;
+    s->timing.plan_variant = (uint32_t)variant;
 
     s->counters.ensure(8 * sizeof(unsigned long long));
     s->h_counts.ensure(8 * sizeof(unsigned long long));
@@ -773,7 +932,9 @@ ipcr_scratch *ipcr_gpu_scratch_create(ipcr_panel *p, char *err, size_t errlen) {
                         prop.major, prop.minor));
     s->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     for (auto &e : s->ev) CU(cudaEventCreate(&e));
+    for (auto &e : s->copy_ev) CU(cudaEventCreate(&e));
     s->counters.ensure(8 * sizeof(unsigned long long));
     s->h_counts.ensure(8 * sizeof(unsigned long long));
     s->tables = tables_for(p, s->device, s->stream);
@@ -805,8 +966,18 @@ int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, si
         segs[i].rec_idx = (uint32_t)i;
         segs[i].reserved = 0;
     }
-    build_genome(s, s->own, segs.data(), n_recs, n_recs, false);
-    const uint64_t n = scan_genome_impl(s, s->own, s->own.lay.total_len > 0);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n_recs; i++) total += recs[i].len;
+    // large inputs: overlap the PCIe copy with the scan, slab by slab
+    int n_slabs = (int)std::min<uint64_t>(8, total / (384ull << 20));
+    if (const char *e = getenv("IPCR_STREAM_SLABS")) n_slabs = atoi(e);
+    uint64_t n;
+    if (n_slabs >= 2 && total < (1ull << kCandPosBits) && n_recs <= 65535) {
+        n = scan_batch_streamed(s, recs, n_recs, n_slabs);
+    } else {
+        build_genome(s, s->own, segs.data(), n_recs, n_recs, false);
+        n = scan_genome_impl(s, s->own, s->own.lay.total_len > 0);
+    }
     if (out) *out = s->h_products.as<ipcr_product>();
     if (n_out) *n_out = n;
     return 0;
@@ -917,7 +1088,7 @@ int ipcr_gpu_find_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g, co
 }
 
 int ipcr_gpu_find_sites_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
-                               size_t n_recs, const ipcr_site **sites, uint64_t *n_sites,
+                               size_t n_recs, int force_raw, const ipcr_site **sites, uint64_t *n_sites,
                                ipcr_record_info *recs_out, char *err, size_t errlen) {
     ABI_TRY
     if (!p || !s || s->panel != p) throw Error("bad panel/scratch");
@@ -926,7 +1097,7 @@ int ipcr_gpu_find_sites_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segmen
     s->timing = ipcr_timing{};
     for (int i = 0; i < 8; i++) CU(cudaEventRecord(s->ev[i], s->stream));
     build_genome(s, s->own, segs, n_segs, n_recs, true);
-    const uint64_t n = find_sites(s, s->own, true);
+    const uint64_t n = find_sites(s, s->own, force_raw != 0);
     if (n) {
         s->h_sites.ensure(n * sizeof(ipcr_site));
         CU(cudaMemcpyAsync(s->h_sites.p, s->sites.p, n * sizeof(ipcr_site), cudaMemcpyDeviceToHost, s->stream));

@@ -32,7 +32,7 @@ __device__ __forceinline__ uint32_t find_segment(const SegmentDev *segs, uint32_
 }
 
 __global__ void __launch_bounds__(1024)
-k_pack(const uint8_t *__restrict__ ascii, GenomeLayout lay, uint4 *__restrict__ planes,
+k_pack_bytes(const uint8_t *__restrict__ ascii, GenomeLayout lay, uint4 *__restrict__ planes,
        const SegmentDev *__restrict__ segs, uint32_t n_segs, uint32_t *__restrict__ seg_reset) {
     __shared__ uint4 tile[32][33];
     const uint64_t t = blockIdx.x;
@@ -68,6 +68,62 @@ k_pack(const uint8_t *__restrict__ ascii, GenomeLayout lay, uint4 *__restrict__ 
     const uint32_t rr = blockIdx.y * 32u + threadIdx.y;
     if (rr < lay.rows)
         planes[(t * lay.rows + rr) * kLanes + threadIdx.x] = tile[threadIdx.y][threadIdx.x];
+}
+
+// K1 fast path (16-byte aligned input, W % 16 == 0).  grid = n_tiles, block = 32 warps:
+// warp y packs lane y of the tile, thread i owns stripe (tile*1024 + y*32 + i).  Each
+// thread streams ITS stripe with 16-byte loads (16 rows per load; a 128-B line is used up
+// by 8 consecutive loads of the same thread), and the byte -> bit-plane TRANSPOSE is done
+// by the warp vote unit: __ballot_sync(byte == 'A') over the 32 stripes of a lane IS the
+// A-plane word of that (row, lane).  16 rows x 32 lanes are staged in shared memory and
+// written out as 8 KB fully coalesced.
+__global__ void __launch_bounds__(1024)
+k_pack(const uint8_t *__restrict__ ascii, GenomeLayout lay, uint4 *__restrict__ planes,
+       const SegmentDev *__restrict__ segs, uint32_t n_segs, uint32_t *__restrict__ seg_reset) {
+    __shared__ uint4 stage[2][16][32];
+    const uint64_t t = blockIdx.x;
+    const uint32_t i = threadIdx.x & 31u, y = threadIdx.x >> 5;
+    const uint64_t stripe = t * kStripesPerTile + (uint64_t)y * 32u + i;
+    const uint64_t base = stripe * lay.W;  // position of row 0 of this thread's stripe
+    const uint32_t n_chunks = (lay.rows + 15u) / 16u;
+    // the whole tile (incl. repeated rows) lies inside the buffer => no per-byte bounds checks
+    const bool interior = (t + 1) * kStripesPerTile * (uint64_t)lay.W + 64u <= lay.total_len;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint64_t P0 = base + (uint64_t)c * 16u;
+        uint32_t v[4] = {0u, 0u, 0u, 0u};
+        if (interior || P0 + 16u <= lay.total_len) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(ascii + P0));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else if (P0 < lay.total_len) {  // ragged tail: byte loads, zero (= hard mismatch) padding
+            for (uint32_t k = 0; k < 16u && P0 + k < lay.total_len; k++)
+                v[k >> 2] |= (uint32_t)ascii[P0 + k] << (8u * (k & 3u));
+        }
+        uint4 *out = &stage[c & 1u][0][y];
+#pragma unroll
+        for (uint32_t k = 0; k < 16u; k++) {
+            const uint32_t b = (v[k >> 2] >> (8u * (k & 3u))) & 0xFFu;
+            const uint32_t A = __ballot_sync(0xFFFFFFFFu, b == 'A');
+            const uint32_t C = __ballot_sync(0xFFFFFFFFu, b == 'C');
+            const uint32_t G = __ballot_sync(0xFFFFFFFFu, b == 'G');
+            const uint32_t T = __ballot_sync(0xFFFFFFFFu, b == 'T');
+            if (i == 0) out[k * 32u] = make_uint4(A, C, G, T);
+            if ((A | C | G | T) != 0xFFFFFFFFu) {  // warp-uniform: some byte of this row is not ACGT
+                const uint32_t x = (b | 0x20u) - 'a';  // a,c,g,t -> 0,2,6,19
+                const bool acgt = x < 32u && ((0x00080045u >> x) & 1u);
+                const uint64_t P = P0 + k;
+                if (!acgt && P < lay.total_len && c * 16u + k < lay.W) {
+                    const uint32_t s = find_segment(segs, n_segs, P);
+                    if (P - segs[s].global_off < segs[s].len) seg_reset[s] = 1u;
+                }
+            }
+        }
+        __syncthreads();  // stage[c&1] complete; the other buffer was drained two syncs ago
+        if (threadIdx.x < 512u) {
+            const uint32_t row = c * 16u + (threadIdx.x >> 5);
+            if (row < lay.rows)
+                planes[(t * lay.rows + row) * kLanes + (threadIdx.x & 31u)] = stage[c & 1u][threadIdx.x >> 5][threadIdx.x & 31u];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

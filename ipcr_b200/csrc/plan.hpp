@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <map>
 #include <sstream>
 #include <string>
@@ -180,15 +181,37 @@ inline int and_inputs(const std::vector<ColRef> &cols) {
 
 inline double lop3_for_inputs(int inputs) { return inputs <= 1 ? 0.0 : std::ceil((inputs - 1) / 2.0); }
 
-constexpr double kVerifyCostLop3 = 600.0;  // modelled cost of one candidate, in LOP3 per lane-word
+// modelled cost of one candidate position, in lane-level LOP3 (a candidate costs ~45 warp
+// instructions between the filter's slow path and the verify kernel; measured round 1)
+inline double verify_cost_lop3() {
+    static const double v = [] {
+        const char *e = getenv("IPCR_PLAN_VERIFY_COST");
+        return e ? atof(e) : 2500.0;
+    }();
+    return v;
+}
+
+// columns of a primer the filter may look at (anchored at the 3' end).  23 keeps the
+// register ring of the specialised kernel at 24 rows (96 registers) for every primer length;
+// longer primers simply leave their 5'-most columns to the verify kernel.
+inline int filter_window() {
+    static const int v = [] {
+        const char *e = getenv("IPCR_PLAN_WINDOW");
+        const int w = e ? atoi(e) : 23;
+        return std::max(4, std::min(w, kWindow));
+    }();
+    return v;
+}
 
 inline OrientPlan plan_orientation(const Orient &o, int max_mm, int tw, bool raw) {
     OrientPlan pl;
     if (tw < 0) tw = 0;
+    const double kVerify = verify_cost_lop3();
+    const int win = filter_window();
     int L = o.L;
     int lo = 0, hi = L;  // window [lo, hi)
-    if (L > kWindow) {
-        if (o.rc_type) { lo = 0; hi = kWindow; } else { lo = L - kWindow; hi = L; }
+    if (L > win) {
+        if (o.rc_type) { lo = 0; hi = win; } else { lo = L - win; hi = L; }
     }
     pl.j0 = lo;
     int plo, phi;  // protected range
@@ -210,47 +233,58 @@ inline OrientPlan plan_orientation(const Orient &o, int max_mm, int tw, bool raw
     if (nfree < m + 1) {  // cannot force any block to be exact
         pl.need = 0;
         pl.cand_prob = prot_p;
-        pl.cost = prot_cost + pl.cand_prob * 32.0 * kVerifyCostLop3;
+        pl.cost = prot_cost + pl.cand_prob * 32.0 * kVerify;
         return pl;
     }
+    // Pigeonhole only needs DISJOINT blocks, not a partition: mismatches in unused columns can
+    // only help.  So besides the number of blocks B we also choose how many columns to use
+    // (the most informative ones), trading LOP3 per word against candidates to verify.
+    std::vector<int> order((size_t)nfree);
+    for (int i = 0; i < nfree; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return class_bits(free_cols[a].cls) > class_bits(free_cols[b].cls);
+    });
     double best_total = 1e300;
-    int bmax = std::min(nfree, m + 1 + 6);
+    const int bmax = std::min(std::min(nfree, m + 1 + 6), 15);
     for (int B = m + 1; B <= bmax; B++) {
-        // contiguous split balanced by information content
-        double total_bits = 0.0;
-        for (const ColRef &c : free_cols) total_bits += class_bits(c.cls);
-        std::vector<std::vector<ColRef>> blocks((size_t)B);
-        double acc = 0.0;
-        int b = 0;
-        for (int i = 0; i < nfree; i++) {
-            int remaining_cols = nfree - i, remaining_blocks = B - b;
-            // keep at least one column for every remaining block
-            if (!blocks[b].empty() && b + 1 < B &&
-                (acc >= total_bits * (b + 1) / B || remaining_cols <= remaining_blocks - 1)) b++;
-            blocks[b].push_back(free_cols[i]);
-            acc += class_bits(free_cols[i].cls);
-        }
-        bool ok = true;
-        for (auto &bl : blocks) if (bl.empty()) ok = false;
-        if (!ok) continue;
-        int need = B - m;
-        std::vector<double> bp;
-        double cost = prot_cost;
-        for (auto &bl : blocks) {
-            double bits = 0.0;
-            for (const ColRef &c : bl) bits += class_bits(c.cls);
-            bp.push_back(std::pow(2.0, -bits));
-            cost += lop3_for_inputs(and_inputs(bl));
-        }
-        cost += need == 1 ? std::ceil((B - 1) / 2.0) + 1.0 : (double)need * B;
-        double p = prot_p * at_least_prob(bp, need);
-        double total = cost + p * 32.0 * kVerifyCostLop3;
-        if (total < best_total) {
-            best_total = total;
-            pl.blocks = blocks;
-            pl.need = need;
-            pl.cand_prob = p;
-            pl.cost = total;
+        for (int used = B; used <= nfree; used++) {
+            std::vector<int> pick(order.begin(), order.begin() + used);
+            std::sort(pick.begin(), pick.end());
+            double total_bits = 0.0;
+            for (int i : pick) total_bits += class_bits(free_cols[i].cls);
+            // contiguous split (in primer order) balanced by information content
+            std::vector<std::vector<ColRef>> blocks((size_t)B);
+            double acc = 0.0;
+            int b = 0;
+            for (int n = 0; n < used; n++) {
+                const int remaining_cols = used - n, remaining_blocks = B - b;
+                if (!blocks[b].empty() && b + 1 < B &&
+                    (acc >= total_bits * (b + 1) / B || remaining_cols <= remaining_blocks - 1)) b++;
+                blocks[b].push_back(free_cols[pick[n]]);
+                acc += class_bits(free_cols[pick[n]].cls);
+            }
+            bool ok = true;
+            for (auto &bl : blocks) if (bl.empty()) ok = false;
+            if (!ok) continue;
+            const int need = B - m;
+            std::vector<double> bp;
+            double cost = prot_cost;
+            for (auto &bl : blocks) {
+                double bits = 0.0;
+                for (const ColRef &c : bl) bits += class_bits(c.cls);
+                bp.push_back(std::pow(2.0, -bits));
+                cost += lop3_for_inputs(and_inputs(bl));
+            }
+            cost += need == 1 ? std::ceil((B - 1) / 2.0) + 1.0 : (double)need * B;
+            const double p = prot_p * at_least_prob(bp, need);
+            const double total = cost + p * 32.0 * kVerify;
+            if (total < best_total) {
+                best_total = total;
+                pl.blocks = blocks;
+                pl.need = need;
+                pl.cand_prob = p;
+                pl.cost = total;
+            }
         }
     }
     return pl;

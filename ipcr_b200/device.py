@@ -157,7 +157,8 @@ def find_sites(cp: CompiledPanel, scratch: SimulationScratch, genome: Genome):
     return np.frombuffer(raw, dtype=SITE_DTYPE).copy()
 
 
-def find_sites_device(cp: CompiledPanel, scratch: SimulationScratch, segments: Sequence[Tuple], n_recs: int):
+def find_sites_device(cp: CompiledPanel, scratch: SimulationScratch, segments: Sequence[Tuple], n_recs: int,
+                      force_raw: bool = True):
     """Stage 1 on device-resident shards (pack + filter + verify).  Returns (sites, records)
     where records[i] = (len seen by this shard, has_reset_byte)."""
     import numpy as np
@@ -168,8 +169,9 @@ def find_sites_device(cp: CompiledPanel, scratch: SimulationScratch, segments: S
     n = C.c_uint64()
     recs = (_capi.RecordInfoC * max(1, n_recs))()
     err = _capi.errbuf()
-    _capi.check(L.ipcr_gpu_find_sites_device(cp._h, scratch._h, arr, len(segments), n_recs, C.byref(out),
-                                             C.byref(n), recs, err, len(err)), err)
+    _capi.check(L.ipcr_gpu_find_sites_device(cp._h, scratch._h, arr, len(segments), n_recs,
+                                             1 if force_raw else 0, C.byref(out), C.byref(n), recs, err,
+                                             len(err)), err)
     records = [(int(recs[i].len), bool(recs[i].has_reset_byte)) for i in range(n_recs)]
     if n.value == 0:
         return np.zeros(0, dtype=SITE_DTYPE), records

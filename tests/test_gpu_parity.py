@@ -314,6 +314,48 @@ def test_split_phase_shards_equal_single_scan(oracle):
         assert whole == want
 
 
+def test_streamed_batch_equals_plain(oracle, monkeypatch):
+    """ipcr_gpu_scan_batch overlaps H2D with the scan slab by slab on large inputs; force
+    the slab path on a small multi-record input and compare with the oracle, including the
+    raw-redo rule when only a later slab holds a reset byte."""
+    rng = random.Random(77)
+    a, b = "AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT"
+    pairs = [Pair("16S", a, b), Pair("16S+A:self", a, a), Pair("16S+B:self", b, b)]
+    raw = [(p.forward, p.reverse, 0, 0) for p in pairs]
+    lens = [90000, 500, 140000, 70000]
+    recs = []
+    for ri, n in enumerate(lens):
+        g = H.random_genome(rng, n)
+        for k in range(max(1, n // 20000)):
+            H.plant_amplicon(rng, g, 200 + k * 18000 if n > 20000 else 10, a, b, 300 + k, rng.randint(0, 2),
+                             rng.randint(0, 2), 3, revcomp_strand=k % 2 == 1)
+        recs.append(g)
+    total = sum(lens)
+    for slabs in (3, 5):
+        for c in [(total * k // slabs) & ~15 for k in range(1, slabs)]:  # a site across every slab cut
+            off = 0
+            for ri, n in enumerate(lens):
+                if off + 30 <= c < off + n - 30:
+                    recs[ri][c - off - 9:c - off + 11] = a.replace("M", "C").encode()
+                off += n
+    recs[3][60000] = ord("N")  # reset byte only in the LAST slab
+    seqs = [bytes(g) for g in recs]
+    for cfgd in (dict(max_mm=2, terminal_window=3, max_len=2000, hit_cap=0),
+                 dict(max_mm=2, terminal_window=3, max_len=2000, hit_cap=10000),
+                 dict(max_mm=1, terminal_window=0, max_len=0, hit_cap=3, circular=True)):
+        eng = Engine(Config(**cfgd))
+        cp = eng.compile_panel(pairs)
+        sc = eng.new_simulation_scratch(cp)
+        want = []
+        for ri, sq in enumerate(seqs):
+            want += [(f"r{ri}",) + _otuple(pairs, t) for t in oracle.simulate_compiled(oracle.make_cfg(**cfgd), raw, sq)]
+        for slabs in ("0", "3", "5"):
+            monkeypatch.setenv("IPCR_STREAM_SLABS", slabs)
+            got = [(p.sequence_id,) + _tuple(p) for p in D.scan_batch(cp, sc, seqs, seq_ids=[f"r{i}" for i in range(4)])]
+            assert got == want, (cfgd, slabs)
+        monkeypatch.delenv("IPCR_STREAM_SLABS")
+
+
 def test_ecoli_sized_circular_config2(oracle):
     """BASELINE config 2: 27F/1492R --circular --mismatches 2 on a 4.6 Mbp synthetic genome
     with planted ~1.5 kb amplicons, one spanning the origin."""
