@@ -396,6 +396,8 @@ def run_ours(a):
             prods = D.scan_batch(cp, sc, recs)
             d2h = len(prods) * 64
         e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, a.e2e_steps)
+        te = sc.timing()
+        line["e2e_stage_ms"] = {k: te[k] for k in ("h2d_ms", "pack_ms", "filter_ms", "verify_ms", "pair_ms", "total_ms")}
         line["e2e"] = {"value": gbp / (e2e_ms / 1e3) * len(user_pairs), "unit": UNIT, "ms_per_step": e2e_ms,
                        "gbp_per_s": gbp / (e2e_ms / 1e3), "h2d_bytes_per_step": total, "d2h_bytes_per_step": d2h,
                        "api": "ipcr_gpu_scan_batch(host records) -> products (C ABI; pinned host buffers)"}

@@ -56,13 +56,23 @@ def pair_16s(self_pairs: bool = True) -> Tuple[List[Pair], List[Pair]]:
     return base, out
 
 
-def contig_lengths(total: int, n_contigs: int, lo_frac: float = 0.2) -> List[int]:
-    """n contig lengths summing to `total`, spread between lo_frac and 1.0 of the largest
-    (24 contigs of 50-250 Mbp at 3 Gbp), deterministic."""
-    w = [lo_frac + (1.0 - lo_frac) * (((k * 37) % n_contigs) / max(1, n_contigs - 1)) for k in range(n_contigs)]
-    s = sum(w)
-    lens = [max(1000, int(total * x / s) // 1000 * 1000) for x in w]
-    lens[-1] += total - sum(lens)
+def contig_lengths(total: int, n_contigs: int) -> List[int]:
+    """n contig lengths summing to `total`, spread between total/60 and total/12 (24 contigs of
+    50-250 Mbp at 3 Gbp), deterministic: len_k = lo + (hi-lo) * u_k**g with
+    the exponent g chosen so that the sum is exact."""
+    if n_contigs == 1:
+        return [total]
+    lo, hi = total / (2.5 * n_contigs), total / (0.5 * n_contigs)
+    u = [((k * 37) % n_contigs) / (n_contigs - 1) for k in range(n_contigs)]
+    g_lo, g_hi = 0.05, 50.0
+    for _ in range(80):
+        g = (g_lo + g_hi) / 2
+        if sum(lo + (hi - lo) * x ** g for x in u) > total:
+            g_lo = g
+        else:
+            g_hi = g
+    lens = [int(lo + (hi - lo) * x ** g) // 1000 * 1000 for x in u]
+    lens[lens.index(max(lens))] += total - sum(lens)
     return lens
 
 
