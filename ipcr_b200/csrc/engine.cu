@@ -270,11 +270,14 @@ struct ipcr_scratch {
 namespace ipcr {
 
 static uint32_t choose_W(uint64_t total, int sm_count) {
-    // enough tiles for ~2 warps-waves of the filter grid; rows are cheap to repeat on small inputs
-    const uint64_t want_tiles = (uint64_t)sm_count * 16ull;
-    uint32_t W = 512;
-    while (W > 32 && (total + (uint64_t)kStripesPerTile * W - 1) / ((uint64_t)kStripesPerTile * W) < want_tiles) W >>= 1;
-    return W;
+    // rows per stripe: large W keeps the repeated rows (31/W) cheap; the scan kernels split tiles
+    // into row chunks for parallelism, so ~2 tiles per SM are enough.  480 = lcm-friendly: a
+    // multiple of 16 (pack loads), 24 and 32 (register-ring lengths of the specialised kernel).
+    const uint64_t want_tiles = (uint64_t)sm_count * 2ull;
+    static const uint32_t cand[] = {480, 240, 96, 32};
+    for (uint32_t W : cand)
+        if ((total + (uint64_t)kStripesPerTile * W - 1) / ((uint64_t)kStripesPerTile * W) >= want_tiles) return W;
+    return 32;
 }
 
 static void check_launch(const char *what) {
@@ -969,7 +972,7 @@ int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, si
     uint64_t total = 0;
     for (size_t i = 0; i < n_recs; i++) total += recs[i].len;
     // large inputs: overlap the PCIe copy with the scan, slab by slab
-    int n_slabs = (int)std::min<uint64_t>(8, total / (384ull << 20));
+    int n_slabs = (int)std::min<uint64_t>(5, total / (640ull << 20));
     if (const char *e = getenv("IPCR_STREAM_SLABS")) n_slabs = atoi(e);
     uint64_t n;
     if (n_slabs >= 2 && total < (1ull << kCandPosBits) && n_recs <= 65535) {

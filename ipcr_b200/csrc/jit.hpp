@@ -180,7 +180,7 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
 #define STAGE_WORD(c_, q_, w_) { if (cnt < K) my_list[cnt] = make_uint4((c_), (q_), (w_), (u32)tile); cnt++; }
 )";
     o << "\nextern \"C\" __global__ void __launch_bounds__(WARPS * 32, " << minb << ")\n";
-    o << "ipcr_scan_jit(const uint4* __restrict__ planes, u32 W, u32 rows, u64 n_tiles,\n"
+    o << "ipcr_scan_jit(const uint4* __restrict__ planes, u32 W, u32 rows, u64 n_tiles, u32 chunk_rows,\n"
          "              u64* work_counter, uint4* __restrict__ lists, u32* __restrict__ counts, u32 K) {\n";
     o << "    extern __shared__ __align__(128) unsigned char smem[];\n";
     o << "    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;\n";
@@ -194,14 +194,21 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
     o << "    const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n";
     o << "    uint4* my_list = lists + gtid * K;\n";
     o << "    u32 cnt = counts[gtid], gs = 0;  // lists accumulate across the group kernels of one scan\n";
-    o << "    const u32 nsteps = ((W + RS - 1u) / RS) * RS;\n";
-    o << "    const u32 nstages = (nsteps + RS - 1u + SR - 1u) / SR;\n";
+    // work item = (tile, chunk of rows): keeps W (and with it the share of repeated rows) large
+    // while still handing out several items per resident warp
+    o << "    const u32 chunks_per_tile = (W + chunk_rows - 1u) / chunk_rows;\n";
+    o << "    const u64 n_items = n_tiles * chunks_per_tile;\n";
     o << "    for (;;) {\n";
-    o << "      u64 tile = 0;\n";
-    o << "      if (lane == 0) tile = atomicAdd(work_counter, 1ull);\n";
-    o << "      tile = __shfl_sync(0xffffffffu, tile, 0);\n";
-    o << "      if (tile >= n_tiles) break;\n";
-    o << "      const unsigned char* gsrc = (const unsigned char*)(planes + tile * rows * 32ull);\n";
+    o << "      u64 item = 0;\n";
+    o << "      if (lane == 0) item = atomicAdd(work_counter, 1ull);\n";
+    o << "      item = __shfl_sync(0xffffffffu, item, 0);\n";
+    o << "      if (item >= n_items) break;\n";
+    o << "      const u64 tile = item / chunks_per_tile;\n";
+    o << "      const u32 r0 = (u32)(item % chunks_per_tile) * chunk_rows;\n";
+    o << "      const u32 r1 = min(W, r0 + chunk_rows);\n";
+    o << "      const u32 nsteps = ((r1 - r0 + RS - 1u) / RS) * RS;\n";
+    o << "      const u32 nstages = (nsteps + RS - 1u + SR - 1u) / SR;\n";
+    o << "      const unsigned char* gsrc = (const unsigned char*)(planes + (tile * rows + r0) * 32ull);\n";
     o << "      const u32 gs_end = gs + nstages;\n";
     o << "      u32 issued = 0;\n";
     o << "      { const u32 n0 = min((u32)NB, nstages);\n";
@@ -218,7 +225,7 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
         o << "      R" << t << " = LDROW(" << t << ");\n";
         if (t % SR == SR - 1) o << "      STAGE_END();\n";
     }
-    o << "      for (u32 w = 0; w < nsteps; w += RS) {\n";
+    o << "      for (u32 w = r0; w < r0 + nsteps; w += RS) {\n";
     for (int k = 0; k < RS; k++) {
         const int slot = (k + RS - 1) % RS;
         const int t = RS - 1 + k;
@@ -235,7 +242,7 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
         o << "          if ((";
         for (int q = q0; q < q1; q++) o << (q > q0 ? " | " : "") << "c" << q;
         o << ") != 0u) {\n";
-        o << "            if (w + " << k << "u < W) {\n";
+        o << "            if (w + " << k << "u < r1) {\n";
         for (int q = q0; q < q1; q++)
             o << "              if (c" << q << ") STAGE_WORD(c" << q << ", " << q << "u, w + " << k << "u);\n";
         o << "            }\n          }\n";

@@ -83,8 +83,21 @@ static bool jit_filter(ipcr_scratch *s, const GenomeData &g, int variant, JitRun
     if (max_regs > 0) blocks_per_sm = std::min(blocks_per_sm, std::max(1, 65536 / (max_regs * threads)));
     blocks_per_sm = std::min(blocks_per_sm, 2048 / threads);
     if (const char *e = getenv("IPCR_JIT_BLOCKS_PER_SM")) blocks_per_sm = std::max(1, atoi(e));
-    const uint64_t n_items = g.lay.n_tiles;
     const size_t n_groups = k->kernels.size();
+    // rows per work item: a multiple of the ring length (no wasted unrolled steps) that divides W
+    // if possible, small enough for >= 6 items per resident warp, never below 2 ring lengths
+    const uint64_t resident_warps = (uint64_t)s->sm_count * blocks_per_sm * prog.warps;
+    const uint32_t RSn = (uint32_t)prog.ring_slots;
+    uint32_t chunk_rows = g.lay.W;
+    for (uint32_t m = std::max(2u, g.lay.W / RSn); m >= 2; m--) {
+        const uint32_t c = m * RSn;
+        if (c > g.lay.W || g.lay.W % c != 0) continue;
+        chunk_rows = c;
+        if (g.lay.n_tiles * (g.lay.W / c) >= 6 * resident_warps) break;
+    }
+    if (const char *e = getenv("IPCR_JIT_CHUNK")) chunk_rows = (uint32_t)std::max(16, atoi(e));
+    chunk_rows = std::min(chunk_rows, g.lay.W);
+    const uint64_t n_items = g.lay.n_tiles * ((g.lay.W + chunk_rows - 1) / chunk_rows);
     const unsigned grid = (unsigned)std::max<uint64_t>(
         1, std::min<uint64_t>((n_items + prog.warps - 1) / prog.warps, (uint64_t)s->sm_count * blocks_per_sm));
     const uint32_t n_threads = grid * (uint32_t)threads;
@@ -112,7 +125,7 @@ static bool jit_filter(ipcr_scratch *s, const GenomeData &g, int variant, JitRun
         uint32_t *counts = s->list_counts.as<uint32_t>();
         for (size_t gi = 0; gi < n_groups; gi++) {
             unsigned long long *work_counter = s->work_counters.as<unsigned long long>() + gi;
-            void *args[] = {&planes, &W, &rows, &n_tiles, &work_counter, &lists, &counts, &K};
+            void *args[] = {&planes, &W, &rows, &n_tiles, &chunk_rows, &work_counter, &lists, &counts, &K};
             cudaError_t e = cudaLaunchKernel((const void *)k->kernels[gi], dim3(grid), dim3(threads), args,
                                              prog.smem_bytes, st);
             if (e != cudaSuccess) {
