@@ -195,6 +195,23 @@ int ipcr_gpu_pair_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_site *sites, 
                         const ipcr_record_info *recs, size_t n_recs, const ipcr_product **out,
                         uint64_t *n_out, char *err, size_t errlen);
 
+/* ---- native FASTA feeder (replaces core/fasta for the hot path) ------ */
+/* Reads and normalises a FASTA file exactly like the reference reader (header ID = first
+ * token, TrimSpace per line, a-z upper-cased, gzip by magic/suffix; core/fasta/scan.go,
+ * normalize.go, stream.go:125-131, open.go) into ONE host buffer, multi-threaded.
+ * pin != 0 asks for page-locked memory (faster H2D, slower to allocate). */
+typedef struct ipcr_fasta ipcr_fasta;
+ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *err, size_t errlen);
+void ipcr_gpu_fasta_close(ipcr_fasta *f);
+size_t ipcr_gpu_fasta_num_records(const ipcr_fasta *f);
+uint64_t ipcr_gpu_fasta_total_bases(const ipcr_fasta *f);
+int ipcr_gpu_fasta_record(const ipcr_fasta *f, size_t i, const char **id, const uint8_t **seq, uint64_t *len);
+/* ForEachCompiledProduct over every record of the file (rec_idx = record number in file
+ * order); large files stream to the device slab by slab under the scan.  *out is owned by
+ * the fasta handle and valid until the next scan on it. */
+int ipcr_gpu_scan_fasta(ipcr_panel *p, ipcr_scratch *s, ipcr_fasta *f, const ipcr_product **out,
+                        uint64_t *n_out, char *err, size_t errlen);
+
 /* ---- helpers ---------------------------------------------------------------- */
 /* which: 0 = FwdMismatchIdx (ascending), 1 = RevMismatchIdx (reference order:
  * flipped, hence descending).  Returns the count written (<= cap). */

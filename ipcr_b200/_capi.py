@@ -107,6 +107,8 @@ SYMBOLS = [
     "ipcr_gpu_genome_upload", "ipcr_gpu_genome_adopt", "ipcr_gpu_genome_destroy",
     "ipcr_gpu_genome_bases", "ipcr_gpu_genome_records", "ipcr_gpu_scan_genome",
     "ipcr_gpu_find_sites", "ipcr_gpu_find_sites_device", "ipcr_gpu_pair_sites",
+    "ipcr_gpu_fasta_open", "ipcr_gpu_fasta_close", "ipcr_gpu_fasta_num_records",
+    "ipcr_gpu_fasta_total_bases", "ipcr_gpu_fasta_record", "ipcr_gpu_scan_fasta",
     "ipcr_gpu_product_mismatch_idx", "ipcr_gpu_last_timing", "ipcr_gpu_synth_fill",
     "ipcr_gpu_debug_planes", "ipcr_gpu_debug_candidates", "ipcr_gpu_debug_plan_eval",
     "ipcr_gpu_debug_orientation", "ipcr_gpu_debug_jit_source", "ipcr_gpu_debug_jit_compile",
@@ -157,6 +159,12 @@ def lib():
     sig("ipcr_gpu_find_sites_device", C.c_int, V, V, P(SegmentC), SZ, SZ, C.c_int, P(P(SiteC)), P(U64),
         P(RecordInfoC), *ERR)
     sig("ipcr_gpu_pair_sites", C.c_int, V, V, P(SiteC), U64, P(RecordInfoC), SZ, P(P(ProductC)), P(U64), *ERR)
+    sig("ipcr_gpu_fasta_open", V, C.c_char_p, C.c_int, C.c_int, *ERR)
+    sig("ipcr_gpu_fasta_close", None, V)
+    sig("ipcr_gpu_fasta_num_records", SZ, V)
+    sig("ipcr_gpu_fasta_total_bases", U64, V)
+    sig("ipcr_gpu_fasta_record", C.c_int, V, SZ, P(C.c_char_p), P(V), P(U64))
+    sig("ipcr_gpu_scan_fasta", C.c_int, V, V, V, P(P(ProductC)), P(U64), *ERR)
     sig("ipcr_gpu_product_mismatch_idx", C.c_int, P(ProductC), C.c_int, P(C.c_int32), C.c_int)
     sig("ipcr_gpu_last_timing", C.c_int, V, P(TimingC))
     sig("ipcr_gpu_synth_fill", C.c_int, V, V, U64, U64, U64, *ERR)

@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     lib64 = os.path.join(CUDA_HOME, "lib64")
     cmd = [nvcc] + NVCC_FLAGS + [
         "-o", LIB, os.path.join(CSRC, "engine.cu"),
-        "-L" + lib64, "-lnvrtc", "-Xlinker", "-rpath," + lib64,
+        "-L" + lib64, "-lnvrtc", "-lz", "-Xlinker", "-rpath," + lib64,
     ]
     if verbose:
         cmd += ["-Xptxas", "-v"]

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "device_types.cuh"
+#include "fasta_host.hpp"
 #include "jit.hpp"
 #include "kernels.cuh"
 #include "plan.hpp"
@@ -951,15 +952,22 @@ void ipcr_gpu_scratch_destroy(ipcr_scratch *s) {
     delete s;
 }
 
-int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, size_t n_recs,
-                        const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen) {
-    ABI_TRY
-    if (!p || !s || s->panel != p) throw Error("scratch does not belong to this panel");
-    if (out) *out = nullptr;
-    if (n_out) *n_out = 0;
-    bind(s);
-    s->launches = 0;
-    s->timing = ipcr_timing{};
+struct ipcr_fasta {
+    std::vector<ipcr::FastaRecord> recs;
+    uint8_t *seq = nullptr;
+    uint64_t total = 0;
+    bool pinned = false;
+    std::vector<ipcr_product> products;
+    ~ipcr_fasta() {
+        if (seq) {
+            if (pinned) cudaFreeHost(seq);
+            else free(seq);
+        }
+    }
+};
+
+// host records -> products in s->h_products (shared by scan_batch and scan_fasta)
+static uint64_t scan_records(ipcr_scratch *s, const ipcr_seq *recs, size_t n_recs) {
     std::vector<ipcr_segment> segs(n_recs);
     for (size_t i = 0; i < n_recs; i++) {
         segs[i].seq = recs[i].seq;
@@ -981,8 +989,105 @@ int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, si
         build_genome(s, s->own, segs.data(), n_recs, n_recs, false);
         n = scan_genome_impl(s, s->own, s->own.lay.total_len > 0);
     }
+    return n;
+}
+
+int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, size_t n_recs,
+                        const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || s->panel != p) throw Error("scratch does not belong to this panel");
+    if (out) *out = nullptr;
+    if (n_out) *n_out = 0;
+    bind(s);
+    s->launches = 0;
+    s->timing = ipcr_timing{};
+    const uint64_t n = scan_records(s, recs, n_recs);
     if (out) *out = s->h_products.as<ipcr_product>();
     if (n_out) *n_out = n;
+    return 0;
+    ABI_CATCH(1)
+}
+
+ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *err, size_t errlen) {
+    ABI_TRY
+    if (!path) throw Error("path is NULL");
+    auto f = std::make_unique<ipcr_fasta>();
+    FastaBytes fb;
+    fasta_read_file(path, fb);
+    if (threads <= 0) threads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    ipcr_fasta *fp = f.get();
+    fasta_parse(fb.data, fb.size, threads, f->recs, f->total, [&](uint64_t total) -> uint8_t * {
+        const size_t bytes = (size_t)std::max<uint64_t>(total, 1) + 64;
+        if (pin) {
+            void *q = nullptr;
+            if (cudaMallocHost(&q, bytes) == cudaSuccess) {
+                fp->pinned = true;
+                fp->seq = static_cast<uint8_t *>(q);
+                return fp->seq;
+            }
+            cudaGetLastError();
+        }
+        fp->seq = static_cast<uint8_t *>(malloc(bytes));
+        if (!fp->seq) throw Error("out of host memory for the FASTA records");
+        return fp->seq;
+    });
+    return f.release();
+    ABI_CATCH(nullptr)
+}
+
+void ipcr_gpu_fasta_close(ipcr_fasta *f) { delete f; }
+size_t ipcr_gpu_fasta_num_records(const ipcr_fasta *f) { return f ? f->recs.size() : 0; }
+uint64_t ipcr_gpu_fasta_total_bases(const ipcr_fasta *f) { return f ? f->total : 0; }
+
+int ipcr_gpu_fasta_record(const ipcr_fasta *f, size_t i, const char **id, const uint8_t **seq, uint64_t *len) {
+    if (!f || i >= f->recs.size()) return 1;
+    if (id) *id = f->recs[i].id.c_str();
+    if (seq) *seq = f->seq + f->recs[i].off;
+    if (len) *len = f->recs[i].len;
+    return 0;
+}
+
+int ipcr_gpu_scan_fasta(ipcr_panel *p, ipcr_scratch *s, ipcr_fasta *f, const ipcr_product **out, uint64_t *n_out,
+                        char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || !f || s->panel != p) throw Error("bad panel/scratch/fasta");
+    if (out) *out = nullptr;
+    if (n_out) *n_out = 0;
+    bind(s);
+    s->launches = 0;
+    s->timing = ipcr_timing{};
+    f->products.clear();
+    ipcr_timing acc{};
+    // batches: <= 60000 records and < 2^43 bases per launch chain (sort-key / candidate-word budgets)
+    size_t i = 0;
+    while (i < f->recs.size()) {
+        std::vector<ipcr_seq> batch;
+        uint64_t bases = 0;
+        const size_t base = i;
+        while (i < f->recs.size() && batch.size() < 60000 && bases + f->recs[i].len < (1ull << 43)) {
+            batch.push_back(ipcr_seq{f->seq + f->recs[i].off, f->recs[i].len});
+            bases += f->recs[i].len;
+            i++;
+        }
+        if (batch.empty()) throw Error("a single FASTA record is too large for one device pass");
+        const uint64_t n = scan_records(s, batch.data(), batch.size());
+        const ipcr_product *pr = s->h_products.as<ipcr_product>();
+        for (uint64_t k = 0; k < n; k++) {
+            ipcr_product q = pr[k];
+            q.rec_idx += (uint32_t)base;
+            f->products.push_back(q);
+        }
+        const ipcr_timing &t = s->timing;
+        acc.h2d_ms += t.h2d_ms; acc.pack_ms += t.pack_ms; acc.filter_ms += t.filter_ms; acc.verify_ms += t.verify_ms;
+        acc.pair_ms += t.pair_ms; acc.d2h_ms += t.d2h_ms; acc.total_ms += t.total_ms;
+        acc.candidates += t.candidates; acc.sites += t.sites; acc.used_jit |= t.used_jit;
+        acc.plan_variant |= t.plan_variant;
+    }
+    acc.products = f->products.size();
+    acc.kernel_launches = s->launches;
+    s->timing = acc;
+    if (out) *out = f->products.data();
+    if (n_out) *n_out = f->products.size();
     return 0;
     ABI_CATCH(1)
 }

@@ -1,0 +1,228 @@
+// fasta_host.hpp -- native feeder for the scan: FASTA file -> normalised records in one host
+// buffer, ready for slab-wise H2D.
+//
+// Record semantics follow the reference reader exactly
+// (/root/reference/core/fasta/scan.go:10-69, normalize.go:5-14, stream.go:125-131,
+//  path_ctx.go:40-81, open.go:29-50):
+//   * a line whose FIRST byte is '>' is a header; ID = TrimSpace(header) up to the first
+//     space or tab; a record with an empty ID is dropped together with its sequence lines;
+//     sequence lines before the first header are ignored;
+//   * every other line is TrimSpace'd (ASCII \t \n \v \f \r and space at both ends only),
+//     a-z are upper-cased, every other byte is kept as is;
+//   * gzip input is detected by magic number or a .gz suffix.
+// (One deliberate difference: the reference hands lines longer than 1 MiB to TrimSpace in
+//  1 MiB fragments; here a line is always trimmed as a whole.)
+// The work is split over threads at line boundaries: pass 1 counts, pass 2 copies.
+#pragma once
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace ipcr {
+
+struct FastaRecord {
+    std::string id;
+    uint64_t off = 0;  // into the sequence buffer
+    uint64_t len = 0;
+};
+
+inline bool fasta_is_space(uint8_t c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+inline std::string fasta_header_id(const uint8_t *h, size_t n) {  // stream.go:125-131
+    size_t a = 0, b = n;
+    while (a < b && fasta_is_space(h[a])) a++;
+    while (b > a && fasta_is_space(h[b - 1])) b--;
+    size_t e = a;
+    while (e < b && h[e] != ' ' && h[e] != '\t') e++;
+    return std::string(reinterpret_cast<const char *>(h + a), e - a);
+}
+
+struct FastaPiece {      // what one thread found in its byte range
+    uint64_t head_kept = 0;  // kept bytes before the first header of the range (belong to the open record)
+    struct Hdr { std::string id; uint64_t kept; };
+    std::vector<Hdr> hdrs;
+};
+
+// calls f(line_begin, line_end_exclusive_of_newline) for every line starting in [lo, hi)
+template <class F>
+inline void fasta_for_lines(const uint8_t *d, size_t n, size_t lo, size_t hi, F &&f) {
+    size_t p = lo;
+    while (p < hi) {
+        const uint8_t *nl = static_cast<const uint8_t *>(memchr(d + p, '\n', n - p));
+        const size_t q = nl ? (size_t)(nl - d) : n;
+        f(p, q);
+        p = q + 1;
+    }
+}
+
+inline void fasta_trim(const uint8_t *d, size_t &a, size_t &b) {
+    while (a < b && fasta_is_space(d[a])) a++;
+    while (b > a && fasta_is_space(d[b - 1])) b--;
+}
+
+// Parses `n` bytes of FASTA text.  `alloc(total)` must return a buffer for the sequence bytes.
+template <class Alloc>
+inline void fasta_parse(const uint8_t *d, size_t n, int threads, std::vector<FastaRecord> &recs, uint64_t &total,
+                        Alloc &&alloc) {
+    recs.clear();
+    total = 0;
+    if (threads < 1) threads = 1;
+    if (n < (size_t)(8u << 20)) threads = 1;
+    // range starts snapped to line starts
+    std::vector<size_t> cut((size_t)threads + 1, n);
+    cut[0] = 0;
+    for (int t = 1; t < threads; t++) {
+        size_t p = n / threads * t;
+        if (p < cut[t - 1]) p = cut[t - 1];
+        if (p > 0 && p < n && d[p - 1] != '\n') {
+            const uint8_t *nl = static_cast<const uint8_t *>(memchr(d + p, '\n', n - p));
+            p = nl ? (size_t)(nl - d) + 1 : n;
+        }
+        cut[t] = std::min(p, n);
+    }
+    std::vector<FastaPiece> pieces((size_t)threads);
+    auto pass1 = [&](int t) {
+        FastaPiece &pc = pieces[t];
+        uint64_t *cur = &pc.head_kept;
+        fasta_for_lines(d, n, cut[t], cut[t + 1], [&](size_t a, size_t b) {
+            if (b > a && d[a] == '>') {
+                pc.hdrs.push_back({fasta_header_id(d + a + 1, b - a - 1), 0});
+                cur = &pc.hdrs.back().kept;
+                return;
+            }
+            fasta_trim(d, a, b);
+            *cur += b - a;
+        });
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < threads; t++) th.emplace_back(pass1, t);
+        pass1(0);
+        for (auto &x : th) x.join();
+    }
+    // merge: record table, and for every thread its output cursor and whether the record that
+    // is open at its range start is kept (non-empty ID)
+    std::vector<uint64_t> start_off((size_t)threads, 0);
+    std::vector<char> start_open((size_t)threads, 0);
+    bool open = false;  // a record with a non-empty ID is being filled
+    for (int t = 0; t < threads; t++) {
+        start_off[t] = total;
+        start_open[t] = open;
+        if (open) {
+            recs.back().len += pieces[t].head_kept;
+            total += pieces[t].head_kept;
+        }
+        for (auto &h : pieces[t].hdrs) {
+            open = !h.id.empty();
+            if (open) {
+                FastaRecord r;
+                r.id = h.id;
+                r.off = total;
+                r.len = h.kept;
+                recs.push_back(std::move(r));
+                total += h.kept;
+            }
+        }
+    }
+    uint8_t *out = alloc(total);
+    auto pass2 = [&](int t) {
+        uint64_t w = start_off[t];
+        bool keep = start_open[t] != 0;
+        size_t hi = 0;
+        fasta_for_lines(d, n, cut[t], cut[t + 1], [&](size_t a, size_t b) {
+            if (b > a && d[a] == '>') {
+                keep = !pieces[t].hdrs[hi++].id.empty();
+                return;
+            }
+            if (!keep) return;
+            fasta_trim(d, a, b);
+            const uint8_t *src = d + a;
+            uint8_t *dst = out + w;
+            const size_t k = b - a;
+            for (size_t i = 0; i < k; i++) {  // normalize.go:8-10 (auto-vectorised)
+                const uint8_t c = src[i];
+                dst[i] = (uint8_t)(c - (((uint8_t)(c - 'a') < 26u) ? 32u : 0u));
+            }
+            w += k;
+        });
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < threads; t++) th.emplace_back(pass2, t);
+        pass2(0);
+        for (auto &x : th) x.join();
+    }
+}
+
+// whole-file read: mmap for plain files, zlib for gzip (open.go:39-49)
+struct FastaBytes {
+    const uint8_t *data = nullptr;
+    size_t size = 0;
+    void *map = nullptr;
+    size_t map_len = 0;
+    std::vector<uint8_t> owned;
+    ~FastaBytes() {
+        if (map) munmap(map, map_len);
+    }
+};
+
+inline void fasta_read_file(const std::string &path, FastaBytes &fb) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::runtime_error("open " + path + ": " + strerror(errno));
+    uint8_t sig[2] = {0, 0};
+    const ssize_t got = ::pread(fd, sig, 2, 0);
+    const bool gz = (got == 2 && sig[0] == 0x1f && sig[1] == 0x8b) ||
+                    (path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0);
+    if (gz) {
+        gzFile g = gzdopen(fd, "rb");
+        if (!g) {
+            ::close(fd);
+            throw std::runtime_error("gzip open failed: " + path);
+        }
+        gzbuffer(g, 1 << 20);
+        std::vector<uint8_t> buf(8u << 20);
+        for (;;) {
+            const int r = gzread(g, buf.data(), (unsigned)buf.size());
+            if (r < 0) {
+                gzclose(g);
+                throw std::runtime_error("gzip read failed: " + path);
+            }
+            if (r == 0) break;
+            fb.owned.insert(fb.owned.end(), buf.begin(), buf.begin() + r);
+        }
+        gzclose(g);
+        fb.data = fb.owned.data();
+        fb.size = fb.owned.size();
+        return;
+    }
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        ::close(fd);
+        throw std::runtime_error("stat failed: " + path);
+    }
+    if (st.st_size == 0) {
+        ::close(fd);
+        return;
+    }
+    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (m == MAP_FAILED) throw std::runtime_error("mmap failed: " + path);
+    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+    fb.map = m;
+    fb.map_len = (size_t)st.st_size;
+    fb.data = static_cast<const uint8_t *>(m);
+    fb.size = (size_t)st.st_size;
+}
+
+}  // namespace ipcr

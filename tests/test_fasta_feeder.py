@@ -1,0 +1,146 @@
+"""The native FASTA feeder against a line-by-line restatement of the reference reader
+(core/fasta/scan.go:10-69, normalize.go:5-14, stream.go:125-131, path_ctx.go:40-81).
+Parsing needs no GPU."""
+import gzip
+import os
+import random
+
+import pytest
+
+from ipcr_b200.fasta import FastaFile
+
+SPACE = b" \t\n\v\f\r"
+
+
+def ref_reader(data: bytes):
+    """streamWholeRecords over scanFASTALines (lines <= 1 MiB)."""
+    recs, rid, seq = [], "", bytearray()
+
+    def flush():
+        if rid != "":
+            recs.append((rid, bytes(seq)))
+
+    pos, n = 0, len(data)
+    while pos < n:
+        nl = data.find(b"\n", pos)
+        frag = data[pos:] if nl < 0 else data[pos:nl + 1]
+        pos = n if nl < 0 else nl + 1
+        if frag[:1] == b">":
+            flush()
+            hdr = frag[1:].strip(SPACE)
+            for i, c in enumerate(hdr):
+                if c in b" \t":
+                    hdr = hdr[:i]
+                    break
+            rid = hdr.decode("latin-1")
+            seq = bytearray()
+        elif rid != "":
+            line = frag.strip(SPACE)
+            seq += bytes(c - 32 if 97 <= c <= 122 else c for c in line)
+    flush()
+    return recs
+
+
+CASES = {
+    "demo": b">s\nACGTACGTACGT\n",
+    "no trailing newline": b">s desc here\nACGT\nacgt",
+    "crlf + lowercase + blank lines": b">chr1 x\r\nacgtn\r\n\r\nNNNN\r\n>chr2\tz\r\nAC GT\r\n",
+    "leading junk before first header": b"ACGT\nGGGG\n>a\nAC\n",
+    "empty id drops the record": b">\nACGT\n> \nGG\n>ok\nTT\n",
+    "gt not at line start": b">a\nAC>GT\n >b\nTT\n",
+    "header only + empty record": b">a\n>b\n\n>c",
+    "whitespace inside and around": b">a\n  AC GT\t\n\x0bAC\x0c\n",
+    "iupac digits stars kept": b">a\nRYKM*-12\nxyz\n",
+    "empty file": b"",
+    "only newline": b"\n\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_feeder_matches_reference_reader(tmp_path, name):
+    data = CASES[name]
+    p = tmp_path / "x.fa"
+    p.write_bytes(data)
+    f = FastaFile(str(p), threads=3)
+    assert f.records() == ref_reader(data)
+    assert f.total_bases == sum(len(s) for _i, s in ref_reader(data))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/demo.fa"), reason="reference tree not mounted")
+def test_bundled_demo_files_of_the_reference():
+    # BASELINE config 1 inputs: demo.fa = 12-bp record `s`, demo.fa.gz = a different 8-bp `s`
+    assert FastaFile("/root/reference/demo.fa").records() == [("s", b"ACGTACGTACGT")]
+    assert FastaFile("/root/reference/demo.fa.gz").records() == [("s", b"ACGTACGT")]
+
+
+def test_gzip_by_magic_and_suffix(tmp_path):
+    data = b">s\nACGTACGT\n>t\nacgtnn\n"
+    p1 = tmp_path / "demo.fa.gz"
+    p1.write_bytes(gzip.compress(data))
+    p2 = tmp_path / "renamed.fasta"  # gzip magic without the suffix (open.go:39-49)
+    p2.write_bytes(gzip.compress(data))
+    for p in (p1, p2):
+        assert FastaFile(str(p)).records() == [("s", b"ACGTACGT"), ("t", b"ACGTNN")]
+
+
+def test_missing_file_raises():
+    with pytest.raises(OSError):
+        FastaFile("/nonexistent/file.fa")
+
+
+def test_multithreaded_large_file(tmp_path):
+    rng = random.Random(4)
+    parts = []
+    for r in range(40):
+        parts.append(f">rec{r} len\n".encode() if r % 7 else b">\n")
+        n = rng.randint(1000, 600_000)
+        body = bytes(rng.choice(b"ACGTacgtNn") for _ in range(2000)) * (n // 2000 + 1)
+        body = body[:n]
+        w = rng.choice([60, 80, 61, 4096])
+        eol = rng.choice([b"\n", b"\r\n"])
+        parts.append(eol.join(body[i:i + w] for i in range(0, n, w)) + eol)
+    data = b"".join(parts)
+    assert len(data) > (8 << 20)
+    p = tmp_path / "big.fa"
+    p.write_bytes(data)
+    want = ref_reader(data)
+    for threads in (1, 2, 5, 16):
+        assert FastaFile(str(p), threads=threads).records() == want
+
+
+@pytest.mark.gpu
+def test_scan_fasta_matches_per_record_oracle(tmp_path, oracle, monkeypatch):
+    import ipcr_test_helpers as H
+    from ipcr_b200 import Config, Engine, Pair
+
+    rng = random.Random(21)
+    a, b = "AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT"
+    pairs = [Pair("16S", a, b), Pair("16S+A:self", a, a), Pair("16S+B:self", b, b)]
+    recs = []
+    text = bytearray()
+    for r in range(6):
+        n = rng.randint(3000, 90000)
+        g = H.random_genome(rng, n, n_frac=0.001 if r % 2 else 0, lower_frac=0.3)
+        H.plant_amplicon(rng, g, 100, a, b, 1500, 1, 2, 3, revcomp_strand=r % 2 == 1)
+        text += f">contig{r} some description\n".encode()
+        for i in range(0, n, 70):
+            text += bytes(g[i:i + 70]) + b"\n"
+        recs.append((f"contig{r}", bytes(g).upper()))
+    p = tmp_path / "g.fa"
+    p.write_bytes(bytes(text))
+    cfgd = dict(max_mm=2, terminal_window=3, max_len=2000, hit_cap=10000)
+    eng = Engine(Config(**cfgd))
+    cp = eng.compile_panel(pairs)
+    sc = eng.new_simulation_scratch(cp)
+    f = FastaFile(str(p), pin=True)
+    assert f.records() == recs
+    raw = [(q.forward, q.reverse, 0, 0) for q in pairs]
+    want = []
+    for rid, sq in recs:
+        for t in oracle.simulate_compiled(oracle.make_cfg(**cfgd), raw, sq):
+            want.append((rid, pairs[t[0]].id) + tuple(t[1:]))
+    for slabs in ("0", "3"):
+        monkeypatch.setenv("IPCR_STREAM_SLABS", slabs)
+        got = [(q.sequence_id, q.experiment_id, q.type, q.start, q.end, q.length, q.fwd_mm, q.rev_mm,
+                q.fwd_mismatch_idx, q.rev_mismatch_idx) for q in f.scan(cp, sc)]
+        assert got == want and len(got) >= 6
