@@ -212,6 +212,34 @@ int ipcr_gpu_fasta_record(const ipcr_fasta *f, size_t i, const char **id, const 
 int ipcr_gpu_scan_fasta(ipcr_panel *p, ipcr_scratch *s, ipcr_fasta *f, const ipcr_product **out,
                         uint64_t *n_out, char *err, size_t errlen);
 
+/* ---- visitors on the device ---------------------------------------- */
+/* These work on the records of the LAST ipcr_gpu_scan / _scan_batch / _scan_device call on the
+ * scratch (their bytes are still resident in HBM); `products` are products of that call. */
+typedef struct ipcr_probe_hit {
+    int64_t pos;    /* 0-based in the amplicon */
+    uint16_t mm;
+    uint8_t found;
+    uint8_t strand; /* '+' or '-' */
+    uint8_t reserved[4];
+} ipcr_probe_hit;
+/* probe.AnnotateAmplicon / oligo.BestHit (core/oligo/oligo.go:19-77) for every product.
+ * `probe` must already be normalised uppercase IUPAC (oligo.Validate). */
+int ipcr_gpu_probe_annotate(ipcr_scratch *s, const ipcr_product *products, uint64_t n, const char *probe,
+                            uint32_t probe_len, int32_t max_mm, ipcr_probe_hit *out, char *err, size_t errlen);
+/* Product.Seq of every product (internal/pipeline/pipeline.go:81-88): amplicon i occupies
+ * out[offsets[i], offsets[i+1]); offsets has n + 1 entries.  Returns the bytes needed in *need
+ * (call with out == NULL first). */
+int ipcr_gpu_amplicons(ipcr_scratch *s, const ipcr_product *products, uint64_t n, uint8_t *out, uint64_t cap,
+                       uint64_t *offsets, uint64_t *need, char *err, size_t errlen);
+/* visitors.Nested (internal/visitors/nested.go:17-66): scan every amplicon with the INNER
+ * panel (all amplicons in one batched launch chain on inner_scratch) and pick the best inner
+ * product per amplicon: fewest total mismatches, then longest, leftmost start, end, pair ID
+ * (inner_ids[pair] supplies the IDs for the last tie-break; may be NULL).  best[i].length == -1
+ * when amplicon i has no inner product. */
+int ipcr_gpu_nested(ipcr_scratch *outer_scratch, const ipcr_product *products, uint64_t n,
+                    ipcr_panel *inner_panel, ipcr_scratch *inner_scratch, const char *const *inner_ids,
+                    ipcr_product *best, char *err, size_t errlen);
+
 /* ---- helpers ---------------------------------------------------------------- */
 /* which: 0 = FwdMismatchIdx (ascending), 1 = RevMismatchIdx (reference order:
  * flipped, hence descending).  Returns the count written (<= cap). */

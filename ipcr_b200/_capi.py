@@ -84,6 +84,11 @@ class RecordInfoC(C.Structure):
     _fields_ = [("len", C.c_uint64), ("has_reset_byte", C.c_uint8), ("reserved", C.c_uint8 * 7)]
 
 
+class ProbeHitC(C.Structure):
+    _fields_ = [("pos", C.c_int64), ("mm", C.c_uint16), ("found", C.c_uint8), ("strand", C.c_uint8),
+                ("reserved", C.c_uint8 * 4)]
+
+
 class TimingC(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_float), ("pack_ms", C.c_float), ("filter_ms", C.c_float),
@@ -109,6 +114,7 @@ SYMBOLS = [
     "ipcr_gpu_find_sites", "ipcr_gpu_find_sites_device", "ipcr_gpu_pair_sites",
     "ipcr_gpu_fasta_open", "ipcr_gpu_fasta_close", "ipcr_gpu_fasta_num_records",
     "ipcr_gpu_fasta_total_bases", "ipcr_gpu_fasta_record", "ipcr_gpu_scan_fasta",
+    "ipcr_gpu_probe_annotate", "ipcr_gpu_amplicons", "ipcr_gpu_nested",
     "ipcr_gpu_product_mismatch_idx", "ipcr_gpu_last_timing", "ipcr_gpu_synth_fill",
     "ipcr_gpu_debug_planes", "ipcr_gpu_debug_candidates", "ipcr_gpu_debug_plan_eval",
     "ipcr_gpu_debug_orientation", "ipcr_gpu_debug_jit_source", "ipcr_gpu_debug_jit_compile",
@@ -165,6 +171,9 @@ def lib():
     sig("ipcr_gpu_fasta_total_bases", U64, V)
     sig("ipcr_gpu_fasta_record", C.c_int, V, SZ, P(C.c_char_p), P(V), P(U64))
     sig("ipcr_gpu_scan_fasta", C.c_int, V, V, V, P(P(ProductC)), P(U64), *ERR)
+    sig("ipcr_gpu_probe_annotate", C.c_int, V, P(ProductC), U64, C.c_char_p, C.c_uint32, C.c_int32, P(ProbeHitC), *ERR)
+    sig("ipcr_gpu_amplicons", C.c_int, V, P(ProductC), U64, V, U64, P(U64), P(U64), *ERR)
+    sig("ipcr_gpu_nested", C.c_int, V, P(ProductC), U64, V, V, P(C.c_char_p), P(ProductC), *ERR)
     sig("ipcr_gpu_product_mismatch_idx", C.c_int, P(ProductC), C.c_int, P(C.c_int32), C.c_int)
     sig("ipcr_gpu_last_timing", C.c_int, V, P(TimingC))
     sig("ipcr_gpu_synth_fill", C.c_int, V, V, U64, U64, U64, *ERR)

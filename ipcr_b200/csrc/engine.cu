@@ -254,6 +254,12 @@ struct ipcr_scratch {
         entry_tasks, task_off, task_cnt, prod_off, products;
     ipcr::PinBuf h_counts, h_products, h_sites, h_stage, h_reset;
     uint64_t n_cand = 0;
+    // records of the last scan that are still resident (for the device-side visitors)
+    std::vector<uint64_t> last_rec_base, last_rec_len;
+    const uint8_t *last_ascii = nullptr;
+    bool last_valid = false;
+    ipcr::DevBuf v_rec_base, v_rec_len, v_products, v_cls, v_hits, v_amp, v_offs;
+    ipcr::PinBuf h_hits, h_amp;
     ipcr_timing timing{};
     uint32_t launches = 0;
     ~ipcr_scratch() {
@@ -355,6 +361,7 @@ static void build_genome(ipcr_scratch *s, GenomeData &g, const ipcr_segment *seg
     if (g.lay.total_len >= (1ull << kCandPosBits)) throw Error("genome too large for one device buffer");
     if (n_segs == 0 || g.lay.total_len == 0) {
         g.ascii = nullptr;
+        s->last_valid = false;
         return;
     }
     cudaStream_t st = s->stream;
@@ -372,6 +379,18 @@ static void build_genome(ipcr_scratch *s, GenomeData &g, const ipcr_segment *seg
     CU(cudaEventRecord(s->ev[1], st));
     pack_genome(s, g);
     CU(cudaEventRecord(s->ev[2], st));
+    // whole records stay addressable for the device-side visitors
+    s->last_valid = true;
+    s->last_ascii = g.ascii;
+    s->last_rec_base.assign(n_recs, 0);
+    s->last_rec_len.assign(n_recs, 0);
+    std::vector<char> seen(n_recs, 0);
+    for (const SegmentDev &d : g.segs) {
+        if (d.rec_off != 0 || d.own_len != d.len || seen[d.rec_idx]) s->last_valid = false;
+        seen[d.rec_idx] = 1;
+        s->last_rec_base[d.rec_idx] = d.global_off;
+        s->last_rec_len[d.rec_idx] = d.len;
+    }
 }
 
 static uint64_t read_counter(ipcr_scratch *s, int idx) {
@@ -713,6 +732,11 @@ static uint64_t scan_batch_streamed(ipcr_scratch *s, const ipcr_seq *recs, size_
     CU(cudaStreamSynchronize(st));
     CU(cudaStreamSynchronize(cs));
     g.recs = rinfo;
+    s->last_valid = true;
+    s->last_ascii = base;
+    s->last_rec_base.assign(roff.begin(), roff.begin() + n_recs);
+    s->last_rec_len.resize(n_recs);
+    for (size_t r = 0; r < n_recs; r++) s->last_rec_len[r] = recs[r].len;
     ipcr_timing &t = s->timing;
     t.h2d_ms = ev_ms(s->copy_ev[0], s->copy_ev[1]);
     t.pack_ms = pack_ms;
@@ -1252,6 +1276,149 @@ int ipcr_gpu_pair_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_site *sites, 
     s->timing.kernel_launches = s->launches;
     if (out) *out = s->h_products.as<ipcr_product>();
     if (n_out) *n_out = n;
+    return 0;
+    ABI_CATCH(1)
+}
+
+// uploads the product list and the record table of the last scan; validates the products
+static void visitor_setup(ipcr_scratch *s, const ipcr_product *products, uint64_t n, AmpliconArgs &a) {
+    if (!s->last_valid || !s->last_ascii)
+        throw Error("no resident records: run ipcr_gpu_scan / _scan_batch / _scan_device on this scratch first");
+    const size_t nr = s->last_rec_len.size();
+    for (uint64_t i = 0; i < n; i++) {
+        const ipcr_product &p = products[i];
+        if (p.rec_idx >= nr) throw Error(fmt("product %llu: rec_idx out of range", (unsigned long long)i));
+        const int64_t rl = (int64_t)s->last_rec_len[p.rec_idx];
+        if (p.start < 0 || p.start >= rl || p.length < 0 || p.length > rl || p.end < 0 || p.end > rl)
+            throw Error(fmt("product %llu does not lie inside its record", (unsigned long long)i));
+    }
+    cudaStream_t st = s->stream;
+    upload(s->v_rec_base, s->last_rec_base.data(), nr * 8, st);
+    upload(s->v_rec_len, s->last_rec_len.data(), nr * 8, st);
+    upload(s->v_products, products, n * sizeof(ipcr_product), st);
+    a.ascii = s->last_ascii;
+    a.rec_base = s->v_rec_base.as<uint64_t>();
+    a.rec_len = s->v_rec_len.as<uint64_t>();
+    a.products = s->v_products.as<ipcr_product>();
+    a.n_products = n;
+}
+
+int ipcr_gpu_probe_annotate(ipcr_scratch *s, const ipcr_product *products, uint64_t n, const char *probe,
+                            uint32_t probe_len, int32_t max_mm, ipcr_probe_hit *out, char *err, size_t errlen) {
+    ABI_TRY
+    if (!s) throw Error("scratch is NULL");
+    if (n == 0) return 0;
+    if (!products || !out) throw Error("products/out is NULL");
+    bind(s);
+    std::string pr(probe ? probe : "", probe_len), rc;
+    if (pr.empty()) {  // oligo.go:21-23: empty probe => no hit
+        for (uint64_t i = 0; i < n; i++) out[i] = ipcr_probe_hit{};
+        return 0;
+    }
+    size_t bad = 0;
+    if (!revcomp(pr, rc, bad))
+        throw Error(fmt("invalid probe base at position %zu; allowed: A C G T R Y S W K M B D H V N", bad));
+    if (max_mm < 0) max_mm = 0;
+    std::vector<uint8_t> cls(2 * pr.size());
+    bool strict = true;
+    for (size_t i = 0; i < pr.size(); i++) {
+        cls[i] = iupac_class((uint8_t)pr[i]);
+        cls[pr.size() + i] = iupac_class((uint8_t)rc[i]);
+        if (__builtin_popcount(cls[i]) != 1) strict = false;
+    }
+    ProbeArgs a{};
+    visitor_setup(s, products, n, a.amp);
+    cudaStream_t st = s->stream;
+    upload(s->v_cls, cls.data(), cls.size(), st);
+    s->v_hits.ensure(n * sizeof(ipcr_probe_hit));
+    a.cls_plus = s->v_cls.as<uint8_t>();
+    a.cls_minus = s->v_cls.as<uint8_t>() + pr.size();
+    a.L = (uint32_t)pr.size();
+    a.max_mm = max_mm;
+    a.exact_strict = (max_mm == 0 && strict) ? 1u : 0u;
+    a.out = s->v_hits.as<ipcr_probe_hit>();
+    k_probe_annotate<<<(unsigned)n, 128, 0, st>>>(a);
+    check_launch("k_probe_annotate");
+    s->launches++;
+    CU(cudaMemcpyAsync(out, s->v_hits.p, n * sizeof(ipcr_probe_hit), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_amplicons(ipcr_scratch *s, const ipcr_product *products, uint64_t n, uint8_t *out, uint64_t cap,
+                       uint64_t *offsets, uint64_t *need, char *err, size_t errlen) {
+    ABI_TRY
+    if (!s) throw Error("scratch is NULL");
+    std::vector<uint64_t> offs(n + 1, 0);
+    for (uint64_t i = 0; i < n; i++) offs[i + 1] = offs[i] + (uint64_t)std::max<int64_t>(0, products[i].length);
+    if (need) *need = offs[n];
+    if (offsets) memcpy(offsets, offs.data(), (n + 1) * 8);
+    if (!out || n == 0 || offs[n] == 0) return 0;
+    if (cap < offs[n]) throw Error("amplicon buffer too small");
+    bind(s);
+    AmpliconArgs a{};
+    visitor_setup(s, products, n, a);
+    cudaStream_t st = s->stream;
+    upload(s->v_offs, offs.data(), (n + 1) * 8, st);
+    s->v_amp.ensure(offs[n]);
+    k_gather_amplicons<<<(unsigned)n, 128, 0, st>>>(a, s->v_offs.as<uint64_t>(), s->v_amp.as<uint8_t>());
+    check_launch("k_gather_amplicons");
+    s->launches++;
+    CU(cudaMemcpyAsync(out, s->v_amp.p, offs[n], cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_nested(ipcr_scratch *outer, const ipcr_product *products, uint64_t n, ipcr_panel *inner_panel,
+                    ipcr_scratch *inner, const char *const *inner_ids, ipcr_product *best, char *err, size_t errlen) {
+    ABI_TRY
+    if (!outer || !inner || !inner_panel || inner->panel != inner_panel) throw Error("bad scratch/panel");
+    if (n == 0) return 0;
+    if (!products || !best) throw Error("products/best is NULL");
+    // 1. all amplicons, gathered on the device that still holds the outer records
+    std::vector<uint64_t> offs(n + 1);
+    uint64_t need = 0;
+    char e2[512];
+    if (ipcr_gpu_amplicons(outer, products, n, nullptr, 0, offs.data(), &need, e2, sizeof e2)) throw Error(e2);
+    outer->h_amp.ensure(std::max<uint64_t>(need, 1));
+    if (ipcr_gpu_amplicons(outer, products, n, outer->h_amp.as<uint8_t>(), need, offs.data(), &need, e2, sizeof e2))
+        throw Error(e2);
+    // 2. one batched inner scan (the reference builds an engine per amplicon, nested.go:19-20)
+    for (uint64_t i = 0; i < n; i++) {
+        best[i] = ipcr_product{};
+        best[i].length = -1;
+    }
+    bind(inner);
+    inner->launches = 0;
+    auto better = [&](const ipcr_product &x, const ipcr_product &y) {  // nested.go:35-51
+        const int mx = x.fwd_mm + x.rev_mm, my = y.fwd_mm + y.rev_mm;
+        if (mx != my) return mx < my;
+        if (x.length != y.length) return x.length > y.length;
+        if (x.start != y.start) return x.start < y.start;
+        if (x.end != y.end) return x.end < y.end;
+        if (inner_ids && x.pair_idx != y.pair_idx) {
+            const int c = strcmp(inner_ids[x.pair_idx], inner_ids[y.pair_idx]);
+            if (c != 0) return c < 0;
+        }
+        return false;  // stable: the earlier emission stays
+    };
+    const uint8_t *amp = outer->h_amp.as<uint8_t>();
+    for (uint64_t b0 = 0; b0 < n; b0 += 60000) {
+        const uint64_t b1 = std::min<uint64_t>(n, b0 + 60000);
+        std::vector<ipcr_seq> recs;
+        for (uint64_t i = b0; i < b1; i++) recs.push_back(ipcr_seq{amp + offs[i], offs[i + 1] - offs[i]});
+        const uint64_t np = scan_records(inner, recs.data(), recs.size());
+        const ipcr_product *pr = inner->h_products.as<ipcr_product>();
+        for (uint64_t k = 0; k < np; k++) {
+            ipcr_product &cur = best[b0 + pr[k].rec_idx];
+            if (cur.length < 0 || better(pr[k], cur)) {
+                cur = pr[k];
+                cur.rec_idx = (uint32_t)(b0 + pr[k].rec_idx);
+            }
+        }
+    }
     return 0;
     ABI_CATCH(1)
 }

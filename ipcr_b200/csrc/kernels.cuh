@@ -639,6 +639,96 @@ k_join(JoinArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// K6: visitors on the device.
+// ---------------------------------------------------------------------------
+// amplicon byte i of a product: record bytes [start, end) or, for a circular wrap
+// (start > end), seq[start:] + seq[:end] (internal/pipeline/pipeline.go:81-88)
+struct AmpliconArgs {
+    const uint8_t *ascii;
+    const uint64_t *rec_base;  // concatenated coordinate of position 0 of each record
+    const uint64_t *rec_len;
+    const ipcr_product *products;
+    uint64_t n_products;
+};
+
+__device__ __forceinline__ uint8_t amplicon_byte(const AmpliconArgs &a, const ipcr_product &p, uint64_t i) {
+    const uint64_t rl = a.rec_len[p.rec_idx];
+    uint64_t pos = (uint64_t)p.start + i;
+    if (pos >= rl) pos -= rl;
+    return a.ascii[a.rec_base[p.rec_idx] + pos];
+}
+
+__device__ __forceinline__ uint32_t to_upper(uint32_t c) { return (c - 'a') < 26u ? c - 32u : c; }
+
+// oligo.BestHit (/root/reference/core/oligo/oligo.go:19-77): best probe hit on either strand
+// of every amplicon.  One CTA per product; threads stride over start positions and count
+// IUPAC mismatches with early exit; a block-wide min over (mm, pos) picks the best per strand.
+struct ProbeArgs {
+    AmpliconArgs amp;
+    const uint8_t *cls_plus;   // IUPAC class per probe column
+    const uint8_t *cls_minus;  // of the reverse complement
+    uint32_t L;
+    int32_t max_mm;
+    uint32_t exact_strict;     // maxMM == 0 and strict-ACGT probe: '+' anywhere beats '-' (oligo.go:33-42)
+    ipcr_probe_hit *out;
+};
+
+__global__ void __launch_bounds__(128)
+k_probe_annotate(ProbeArgs a) {
+    __shared__ unsigned long long best[2];
+    const uint64_t pi = blockIdx.x;
+    if (pi >= a.amp.n_products) return;
+    const ipcr_product p = a.amp.products[pi];
+    if (threadIdx.x < 2) best[threadIdx.x] = ~0ull;
+    __syncthreads();
+    const uint64_t alen = (uint64_t)p.length;
+    if (alen >= a.L && a.L > 0) {
+        unsigned long long mine[2] = {~0ull, ~0ull};
+        for (uint64_t s0 = threadIdx.x; s0 + a.L <= alen; s0 += blockDim.x) {
+            int mp = 0, mn = 0;
+            for (uint32_t j = 0; j < a.L; j++) {
+                const uint32_t one = onehot_of(to_upper(amplicon_byte(a.amp, p, s0 + j)));
+                mp += !(one & a.cls_plus[j]);
+                mn += !(one & a.cls_minus[j]);
+                if (mp > a.max_mm && mn > a.max_mm) break;
+            }
+            if (mp <= a.max_mm) mine[0] = min(mine[0], ((unsigned long long)mp << 48) | s0);
+            if (mn <= a.max_mm) mine[1] = min(mine[1], ((unsigned long long)mn << 48) | s0);
+        }
+        if (mine[0] != ~0ull) atomicMin(&best[0], mine[0]);
+        if (mine[1] != ~0ull) atomicMin(&best[1], mine[1]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ipcr_probe_hit h;
+        h.pos = 0; h.mm = 0; h.found = 0; h.strand = 0;
+        for (int z = 0; z < 4; z++) h.reserved[z] = 0;
+        const unsigned long long bp = best[0], bm = best[1];
+        int pick = -1;
+        if (a.exact_strict) pick = bp != ~0ull ? 0 : (bm != ~0ull ? 1 : -1);
+        else if (bp != ~0ull && (bm == ~0ull || bp <= bm)) pick = 0;  // equal (mm, pos): '+' wins (oligo.go:54)
+        else if (bm != ~0ull) pick = 1;
+        if (pick >= 0) {
+            const unsigned long long v = pick == 0 ? bp : bm;
+            h.found = 1;
+            h.strand = pick == 0 ? '+' : '-';
+            h.mm = (uint16_t)(v >> 48);
+            h.pos = (int64_t)(v & ((1ull << 48) - 1));
+        }
+        a.out[pi] = h;
+    }
+}
+
+// amplicon sequences of a product list, back to back (offs[i] = start of amplicon i)
+__global__ void k_gather_amplicons(AmpliconArgs a, const uint64_t *__restrict__ offs, uint8_t *__restrict__ out) {
+    const uint64_t pi = blockIdx.x;
+    if (pi >= a.n_products) return;
+    const ipcr_product p = a.products[pi];
+    uint8_t *dst = out + offs[pi];
+    for (uint64_t i = threadIdx.x; i < (uint64_t)p.length; i += blockDim.x) dst[i] = amplicon_byte(a, p, i);
+}
+
+// ---------------------------------------------------------------------------
 // synthetic input: uniform ACGT from splitmix64(seed, absolute position / 32)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
