@@ -289,22 +289,23 @@ def run_ours(a):
         t = sc.timing()
         dev_ms = t["total_ms"]
         launches = t["kernel_launches"]
-        if a.hit_cap > 0 and a.mm > 0 and a.tw > 0:
-            # hit-cap parity: if ANY shard saw a reset byte, shards that filtered with the protected
-            # window must redo stage 1 raw (never happens on the N-free bench genome)
-            need = torch.tensor([int(any(r[1] for r in recs))], dtype=torch.int32, device=dev)
-            dist.all_reduce(need, op=dist.ReduceOp.MAX)
-            if int(need.item()) and t["plan_variant"] == 0:
-                sites, recs = D.find_sites_device(cp, sc, segments, n_recs, force_raw=True)
-                t2 = sc.timing()
-                dev_ms += t2["total_ms"]
-                launches += t2["kernel_launches"]
-        # gather the sparse site lists and the per-record reset flags on rank 0
+        # ONE collective: every rank learns all sites and the merged per-record reset flags
         gather_ev[0].record()
         allsites, records = sharding.gather_sites(dist, sites, recs, n_recs, rank, world, device=dev)
         gather_ev[1].record()
         gather_ev[1].synchronize()
         dev_ms += gather_ev[0].elapsed_time(gather_ev[1])
+        # hit-cap parity: if ANY shard saw a reset byte, shards that filtered with the protected
+        # window redo stage 1 raw (never happens on the N-free bench genome); every rank takes
+        # the same decision from the same merged flags
+        redo = a.hit_cap > 0 and a.mm > 0 and a.tw > 0 and any(r[1] for r in records)
+        if redo:
+            if t["plan_variant"] == 0:
+                sites, recs = D.find_sites_device(cp, sc, segments, n_recs, force_raw=True)
+                t2 = sc.timing()
+                dev_ms += t2["total_ms"]
+                launches += t2["kernel_launches"]
+            allsites, records = sharding.gather_sites(dist, sites, recs, n_recs, rank, world, device=dev)
         n = 0
         if rank == 0:
             records = [(lens[i], records[i][1]) for i in range(n_recs)]
@@ -412,12 +413,17 @@ def run_ours(a):
             line["cpu_baseline"]["gbp_per_s"] = res["gbp_per_s"]
         except Exception as ex:  # the baseline must never sink the GPU line
             line["cpu_baseline"] = {"value": None, "error": str(ex)}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is set; keep stdout for the JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ.pop("NCCL_DEBUG")
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

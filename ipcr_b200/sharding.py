@@ -41,32 +41,63 @@ def shard_segments(lens: Sequence[int], world: int, rank: int, halo: int = HALO)
     return out
 
 
+SITE_CAP = 4096  # sites per rank that travel in the single fixed-size collective (96 KB)
+
+
 def gather_sites(dist, sites, records, n_recs: int, rank: int, world: int, device=None):
     """All ranks call this with their numpy site array (ipcr_site records) and their view of
-    the records [(len, has_reset_byte)].  Rank 0 gets (all sites, merged records); others
-    (None, merged records)."""
+    the records [(len, has_reset_byte)].  EVERY rank gets (all sites, merged records) from ONE
+    all_gather of a fixed-size block [count | per-record len, flag | up to SITE_CAP sites];
+    ranks with more sites than SITE_CAP send the rest in a second, padded round (rare)."""
     import numpy as np
     import torch
 
     from .device import SITE_DTYPE
 
     kw = {"device": device} if device is not None else {}
-    cnt = torch.tensor([len(sites)], dtype=torch.int64, **kw)
-    cnts = [torch.zeros(1, dtype=torch.int64, **kw) for _ in range(world)]
-    dist.all_gather(cnts, cnt)
-    m = max(int(c.item()) for c in cnts)
-    pad = torch.zeros(max(1, m) * SITE_DTYPE.itemsize, dtype=torch.uint8, **kw)
-    if len(sites):
-        raw = torch.from_numpy(np.ascontiguousarray(sites).view(np.uint8).copy())
-        pad[: raw.numel()].copy_(raw)
-    allp = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-    dist.gather(pad, allp, dst=0)
-    flags = torch.tensor([[int(r[0]), int(r[1])] for r in records], dtype=torch.int64, **kw).reshape(n_recs, 2)
-    dist.all_reduce(flags, op=dist.ReduceOp.MAX)
-    merged = [(int(flags[i, 0].item()), bool(flags[i, 1].item())) for i in range(n_recs)]
-    if rank != 0:
-        return None, merged
-    parts = [allp[r][: int(cnts[r].item()) * SITE_DTYPE.itemsize].cpu().numpy().view(SITE_DTYPE)
-             for r in range(world)]
+    isz = SITE_DTYPE.itemsize
+    hdr_words = 1 + 2 * n_recs
+    hdr_bytes = 8 * hdr_words
+    block = hdr_bytes + SITE_CAP * isz
+    hdr = np.zeros(hdr_words, dtype=np.int64)
+    hdr[0] = len(sites)
+    for i, r in enumerate(records):
+        hdr[1 + 2 * i], hdr[2 + 2 * i] = int(r[0]), int(r[1])
+    mine = np.zeros(block, dtype=np.uint8)
+    mine[:hdr_bytes] = hdr.view(np.uint8)
+    raw = np.ascontiguousarray(sites).view(np.uint8).reshape(-1)
+    n_first = min(len(sites), SITE_CAP)
+    mine[hdr_bytes:hdr_bytes + n_first * isz] = raw[: n_first * isz]
+    send = torch.from_numpy(mine)
+    if device is not None:
+        send = send.to(device)
+    recv = torch.empty(world * block, dtype=torch.uint8, **kw)
+    dist.all_gather_into_tensor(recv, send)
+    allb = recv.cpu().numpy().reshape(world, block)
+    counts, merged_len, merged_flag, parts = [], [0] * n_recs, [False] * n_recs, []
+    for r in range(world):
+        h = allb[r, :hdr_bytes].view(np.int64)
+        counts.append(int(h[0]))
+        for i in range(n_recs):
+            merged_len[i] = max(merged_len[i], int(h[1 + 2 * i]))
+            merged_flag[i] = merged_flag[i] or bool(h[2 + 2 * i])
+        k = min(counts[r], SITE_CAP)
+        parts.append(allb[r, hdr_bytes:hdr_bytes + k * isz].copy().view(SITE_DTYPE))
+    extra = max(0, max(counts) - SITE_CAP)
+    if extra:  # overflow round, padded to the largest remainder
+        rest = np.zeros(extra * isz, dtype=np.uint8)
+        if len(sites) > SITE_CAP:
+            rest[: (len(sites) - SITE_CAP) * isz] = raw[SITE_CAP * isz:]
+        send2 = torch.from_numpy(rest)
+        if device is not None:
+            send2 = send2.to(device)
+        recv2 = torch.empty(world * extra * isz, dtype=torch.uint8, **kw)
+        dist.all_gather_into_tensor(recv2, send2)
+        all2 = recv2.cpu().numpy().reshape(world, extra * isz)
+        for r in range(world):
+            k = max(0, counts[r] - SITE_CAP)
+            if k:
+                parts.append(all2[r, : k * isz].copy().view(SITE_DTYPE))
+    merged = list(zip(merged_len, merged_flag))
     allsites = np.concatenate(parts) if parts else np.zeros(0, dtype=SITE_DTYPE)
     return allsites, merged

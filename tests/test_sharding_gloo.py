@@ -40,8 +40,7 @@ def _worker(rank, world, port, seq, orients, lens, q):
         has_n = b"N" in seq[s0:s1]
         recs[c] = (max(recs[c][0], rec_off + (s1 - s0)), recs[c][1] or has_n)
     allsites, merged = sharding.gather_sites(dist, arr, recs, len(lens), rank, world)
-    if rank == 0:
-        q.put((sorted(map(tuple, allsites.tolist())), merged))
+    q.put((rank, sorted(map(tuple, allsites.tolist())), merged))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -76,13 +75,54 @@ def test_two_rank_sharding_matches_whole_scan(oracle):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, seq, orients, lens, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got, merged = q.get(timeout=120)
+    results = [q.get(timeout=120) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert got == sorted(want)
-    assert [m[0] for m in merged] == lens
-    assert [m[1] for m in merged] == [b"N" in seq[offs[c]:offs[c] + lens[c]] for c in range(4)]
+    assert sorted(r[0] for r in results) == [0, 1]
+    for _rank, got, merged in results:  # every rank ends up with the same global view
+        assert got == sorted(want)
+        assert [m[0] for m in merged] == lens
+        assert [m[1] for m in merged] == [b"N" in seq[offs[c]:offs[c] + lens[c]] for c in range(4)]
+
+
+def test_gather_overflow_round(monkeypatch):
+    """more sites than SITE_CAP on one rank: the second padded round carries the rest"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_overflow_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for n, ok in res:
+        assert n == 50 + 7 and ok
+
+
+def _overflow_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from ipcr_b200 import sharding
+    from ipcr_b200.device import SITE_DTYPE
+
+    sharding.SITE_CAP = 16
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 50 if rank == 0 else 7
+    arr = np.zeros(n, dtype=SITE_DTYPE)
+    arr["pos"] = np.arange(n) + 1000 * rank
+    arr["orient"] = rank
+    allsites, merged = sharding.gather_sites(dist, arr, [(10 + rank, rank == 1)], 1, rank, world)
+    want = sorted([(i, 0) for i in range(50)] + [(1000 + i, 1) for i in range(7)])
+    got = sorted((int(s["pos"]), int(s["orient"])) for s in allsites)
+    q.put((len(allsites), got == want and merged == [(11, True)]))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def test_shard_segments_cover_every_start_once():
