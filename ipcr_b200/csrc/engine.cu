@@ -244,6 +244,8 @@ struct ipcr_scratch {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of later slabs overlaps the scan of earlier ones
+    std::vector<cudaStream_t> aux_streams;  // group kernels of the specialised filter run round-robin
+    std::vector<cudaEvent_t> aux_events;
     std::vector<cudaEvent_t> slab_ev;
     cudaEvent_t copy_ev[2] = {};
     cudaEvent_t ev[8] = {};
@@ -271,6 +273,8 @@ struct ipcr_scratch {
             if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (auto &x : aux_streams) cudaStreamDestroy(x);
+        for (auto &e : aux_events) cudaEventDestroy(e);
     }
 };
 

@@ -194,18 +194,23 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
     o << "    const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n";
     o << "    uint4* my_list = lists + gtid * K;\n";
     o << "    u32 cnt = counts[gtid], gs = 0;  // lists accumulate across the group kernels of one scan\n";
-    // work item = (tile, chunk of rows): keeps W (and with it the share of repeated rows) large
-    // while still handing out several items per resident warp
-    o << "    const u32 chunks_per_tile = (W + chunk_rows - 1u) / chunk_rows;\n";
-    o << "    const u64 n_items = n_tiles * chunks_per_tile;\n";
+    // work item = `chunk_rows` consecutive rows of the VIRTUAL row space [0, n_tiles * W): a warp
+    // walks its rows tile segment by tile segment, so it pays the ring prologue only when it
+    // enters a new tile, whatever the item size (items need not divide W)
+    o << "    const u64 total_rows = n_tiles * (u64)W;\n";
+    o << "    const u64 n_items = (total_rows + chunk_rows - 1ull) / chunk_rows;\n";
     o << "    for (;;) {\n";
     o << "      u64 item = 0;\n";
     o << "      if (lane == 0) item = atomicAdd(work_counter, 1ull);\n";
     o << "      item = __shfl_sync(0xffffffffu, item, 0);\n";
     o << "      if (item >= n_items) break;\n";
-    o << "      const u64 tile = item / chunks_per_tile;\n";
-    o << "      const u32 r0 = (u32)(item % chunks_per_tile) * chunk_rows;\n";
-    o << "      const u32 r1 = min(W, r0 + chunk_rows);\n";
+    o << "      u64 v0 = item * chunk_rows;\n";
+    o << "      const u64 v1 = min(total_rows, v0 + chunk_rows);\n";
+    o << "     while (v0 < v1) {\n";
+    o << "      const u64 tile = v0 / W;\n";
+    o << "      const u32 r0 = (u32)(v0 - tile * W);\n";
+    o << "      const u32 r1 = (u32)min((u64)W, (u64)r0 + (v1 - v0));\n";
+    o << "      v0 += r1 - r0;\n";
     o << "      const u32 nsteps = ((r1 - r0 + RS - 1u) / RS) * RS;\n";
     o << "      const u32 nstages = (nsteps + RS - 1u + SR - 1u) / SR;\n";
     o << "      const unsigned char* gsrc = (const unsigned char*)(planes + (tile * rows + r0) * 32ull);\n";
@@ -252,6 +257,7 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
     // the last stage is only partially read (no STAGE_END): count it as consumed so that the
     // next tile starts on a fresh buffer / barrier phase
     o << "      gs = gs_end;\n";
+    o << "     }\n";
     o << "    }\n";
     o << "    counts[gtid] = cnt;\n";
     o << "}\n";

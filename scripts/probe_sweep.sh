@@ -1,4 +1,7 @@
-for cfg in "IPCR_X=1" "IPCR_JIT_STAGES=3 IPCR_JIT_MIN_BLOCKS=4" "IPCR_JIT_STAGE_ROWS=4 IPCR_JIT_STAGES=6 IPCR_JIT_MIN_BLOCKS=4" "IPCR_JIT_STAGE_ROWS=4 IPCR_JIT_STAGES=8" "IPCR_JIT_STAGE_ROWS=16 IPCR_JIT_STAGES=3 IPCR_JIT_WARPS=2" "IPCR_JIT_STAGES=6 IPCR_JIT_WARPS=2 IPCR_JIT_MIN_BLOCKS=6" "IPCR_JIT_STAGES=5 IPCR_JIT_WARPS=3 IPCR_JIT_MIN_BLOCKS=4"; do
-echo "== $cfg"
-env $cfg python scripts/perf_probe.py --mbp 3000 --pairs 1 --jit 2 --iters 3 2>&1 | grep -E "filter:" | tail -1
+for st in 1 2 3; do
+echo "== streams $st"
+IPCR_JIT_STREAMS=$st python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['stage_ms'], d['products']); print(d['e2e']['ms_per_step'], d['e2e_stage_ms'])"
+IPCR_JIT_STREAMS=$st python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --genome-mbp 375 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('375Mbp', d['ms_per_step'], d['stage_ms'], d['products'])"
 done
