@@ -15,6 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libipcr_b200.so")
+CLI = os.path.join(HERE, "ipcr_gpu_cli")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 
 NVCC_FLAGS = [
@@ -36,9 +37,9 @@ def sources():
 
 
 def is_stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(CLI):
         return True
-    t = os.path.getmtime(LIB)
+    t = min(os.path.getmtime(LIB), os.path.getmtime(CLI))
     return any(os.path.getmtime(s) > t for s in sources() if os.path.exists(s))
 
 
@@ -57,6 +58,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    # the C++ host (flags, FASTA, visitors, --sort, TSV) above the C ABI
+    gxx = shutil.which("g++") or "g++"
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-Wall", "-o", CLI,
+                           os.path.join(CSRC, "host", "ipcr_gpu_cli.cpp"),
+                           "-L" + HERE, "-lipcr_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath," + lib64])
     return LIB
 
 
