@@ -316,6 +316,8 @@ def run_ours(a):
             n = len(prods)
         t = dict(t)
         t["kernel_launches"] = launches
+        t["gather_ms"] = gather_ev[0].elapsed_time(gather_ev[1])
+        t["find_total_ms"] = t["total_ms"]
         return n, dev_ms, t
 
     step = step_single if world == 1 else step_multi
@@ -379,6 +381,7 @@ def run_ours(a):
         "gbp_per_s": gbp_s, "wall_ms_per_step": wall_ms, "products": n_prod, "planted_amplicons": len(planted),
         "stage_ms": {k: last[k] for k in ("pack_ms", "filter_ms", "verify_ms", "pair_ms", "d2h_ms")} if last else None,
         "candidates": last["candidates"] if last else None, "sites": last["sites"] if last else None,
+        "rank0_ms": ({k: last.get(k) for k in ("find_total_ms", "gather_ms")} if last and world > 1 else None),
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
     if n_prod < len(planted):
