@@ -112,7 +112,7 @@ typedef struct ipcr_timing {
     float h2d_ms, pack_ms, filter_ms, verify_ms, pair_ms, d2h_ms, total_ms;
     uint64_t candidates, sites, products;
     uint32_t kernel_launches; /* launches issued by the last scan */
-    uint32_t used_jit;        /* 1 if the panel-specialised (NVRTC) scan kernel ran */
+    uint32_t used_jit;        /* filter that ran: 0 table-driven, 1 NVRTC-specialised, 2 seed index */
     uint32_t plan_variant;    /* 0 = protected window enforced in the filter, 1 = rc orientations raw */
     uint32_t reserved;
 } ipcr_timing;
@@ -137,8 +137,10 @@ size_t ipcr_gpu_panel_num_orientations(const ipcr_panel *p); /* unique strings s
 /* would the reference have seeded this orientation? which in 'A','B','a','b'
  * (compiledHas, core/engine/compiled.go:35-37) */
 int ipcr_gpu_panel_have(const ipcr_panel *p, size_t pair_idx, int which);
-/* 0 = table-driven kernel only, 1 = allow the NVRTC-specialised kernel (default),
- * 2 = force it even for tiny inputs */
+/* which candidate filter serves the panel: 0 = table-driven bit-parallel kernel only,
+ * 1 = automatic (default: the seed index when it is selective, else bit-parallel, specialised
+ * by NVRTC once the work pays for the compile), 2 = force the NVRTC-specialised bit-parallel
+ * kernel, 3 = force the seed index */
 void ipcr_gpu_panel_set_jit(ipcr_panel *p, int mode);
 
 /* ---- scratch: engine.NewSimulationScratch (core/engine/hit_collect.go:19-34) */
@@ -262,6 +264,11 @@ int ipcr_gpu_debug_candidates(const ipcr_scratch *s, uint64_t *out, uint64_t cap
 int ipcr_gpu_debug_plan_eval(const ipcr_panel *p, uint32_t orient, const uint8_t *seq, uint64_t len,
                              int64_t start, int raw_mode);
 /* orientation string / type ('A' forward-type, 'a' rc-type) of a unique orientation */
+/* host evaluation of the panel's seed index on one sequence: the (orientation << 44 | start)
+ * candidates the seed filter hands to verify; info[5] = {S, entries, table_bits, bloom used,
+ * bloom fill ppm} */
+int ipcr_gpu_debug_seed_eval(ipcr_panel *p, int raw_mode, const uint8_t *seq, uint64_t len, uint64_t *out,
+                             uint64_t cap, uint64_t *n, int32_t *info);
 int ipcr_gpu_debug_orientation(const ipcr_panel *p, uint32_t orient, char *buf, size_t buflen,
                                int *type);
 /* NVRTC source of the specialised kernel for this panel (for inspection) */

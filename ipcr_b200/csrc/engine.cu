@@ -26,6 +26,8 @@
 #include "jit.hpp"
 #include "kernels.cuh"
 #include "plan.hpp"
+#include "seed.hpp"
+#include "seed_kernels.cuh"
 #include "sortscan.cuh"
 
 namespace ipcr {
@@ -108,6 +110,8 @@ struct DevTables {
     PlanTables plan[2];
     JitKernel jit[2];
     bool jit_tried[2] = {false, false};
+    DevBuf seed_table[2], seed_bloom[2], seed_coloff[2];  // seed-index filter, per plan variant
+    bool seed_ready[2] = {false, false};
 };
 
 }  // namespace ipcr
@@ -121,6 +125,9 @@ struct ipcr_panel {
     std::string jit_log[2];
     bool jit_done[2] = {false, false};
     double jit_work = 0.0;
+    // k-mer index of the whole panel (seed.hpp), built on first use per plan variant
+    ipcr::SeedIndex seed[2];
+    bool seed_done[2] = {false, false};
 };
 
 namespace ipcr {
@@ -226,6 +233,10 @@ struct GenomeData {
     const uint8_t *ascii = nullptr;  // device pointer to the concatenated buffer
     GenomeLayout lay{};
     DevBuf planes, segs_dev, seg_reset;
+    DevBuf codes, inval;  // seed-index filter: 2-bit codes + hard-mismatch bitmap
+    uint64_t n_groups = 0;  // 32-base groups in codes/inval (incl. padding)
+    bool planes_ready = false, codes_ready = false;  // packed on demand, whichever filter runs
+    std::mutex pack_mu;
     std::vector<SegmentDev> segs;
     std::vector<ipcr_record_info> recs;
     bool any_reset = false;
@@ -252,6 +263,7 @@ struct ipcr_scratch {
     ipcr::DevTables *tables = nullptr;
     ipcr::GenomeData own;  // genome of ipcr_gpu_scan / scan_batch calls (buffers are reused)
     ipcr::DevBuf lists, list_counts, list_clamped, list_offs, work_counters;  // specialised filter
+    ipcr::DevBuf dirty, dcand;  // seed-index filter: dirty windows and their candidates
     ipcr::DevBuf cand, counters, sites, keys0, keys1, vals0, vals1, keep, keep_off, tmp, fkeys, fs, recs_dev,
         entry_tasks, task_off, task_cnt, prod_off, products;
     ipcr::PinBuf h_counts, h_products, h_sites, h_stage, h_reset;
@@ -296,8 +308,27 @@ static void check_launch(const char *what) {
     if (e != cudaSuccess) throw Error(fmt("launch of %s failed: %s", what, cudaGetErrorString(e)));
 }
 
-// K1 on the genome's concatenated ASCII buffer
-static void pack_genome(ipcr_scratch *s, GenomeData &g) {
+// which filter serves this panel: 0 table-driven, 1 NVRTC-specialised, 2 seed index
+enum { kPathGeneric = 0, kPathJit = 1, kPathSeed = 2 };
+
+static const SeedIndex &seed_host(ipcr_panel *p, int variant) {
+    std::lock_guard<std::mutex> lock(p->mu);
+    if (!p->seed_done[variant]) {
+        p->seed[variant] = seed_build(p->host, variant);
+        p->seed_done[variant] = true;
+    }
+    return p->seed[variant];
+}
+
+// jit_mode: 0 table-driven only, 1 automatic, 2 force the specialised kernel, 3 force the seed index
+static bool prefer_seed(ipcr_panel *p) {
+    const int mode = p->host.jit_mode;
+    if (mode == 3) return true;
+    if (mode != 1 || p->host.orients.empty()) return false;
+    return seed_host(p, 0).use_bloom;  // a saturated bitmap means the index has lost its selectivity
+}
+
+static void launch_pack_planes(ipcr_scratch *s, GenomeData &g) {
     cudaStream_t st = s->stream;
     g.lay.W = choose_W(g.lay.total_len, s->sm_count);
     g.lay.rows = g.lay.W + kExtRows;
@@ -305,9 +336,6 @@ static void pack_genome(ipcr_scratch *s, GenomeData &g) {
     g.lay.n_tiles = std::max<uint64_t>(1, (g.lay.total_len + per_tile - 1) / per_tile);
     // + 80 rows of slack: the unrolled JIT loop reads up to 2*ring rows past a tile's end
     g.planes.ensure(((size_t)g.lay.n_tiles * g.lay.rows + 80) * kLanes * sizeof(uint4));
-    upload(g.segs_dev, g.segs.data(), g.segs.size() * sizeof(SegmentDev), st);
-    g.seg_reset.ensure(g.segs.size() * sizeof(uint32_t));
-    CU(cudaMemsetAsync(g.seg_reset.p, 0, g.segs.size() * sizeof(uint32_t), st));
     if ((reinterpret_cast<uintptr_t>(g.ascii) & 15u) == 0 && g.lay.W % 16 == 0) {
         k_pack<<<(unsigned)g.lay.n_tiles, 1024, 0, st>>>(g.ascii, g.lay, g.planes.as<uint4>(),
                                                          g.segs_dev.as<SegmentDev>(), (uint32_t)g.segs.size(),
@@ -319,6 +347,41 @@ static void pack_genome(ipcr_scratch *s, GenomeData &g) {
     }
     check_launch("k_pack");
     s->launches++;
+    g.planes_ready = true;
+}
+
+static void launch_pack_codes(ipcr_scratch *s, GenomeData &g) {
+    cudaStream_t st = s->stream;
+    const uint64_t n_chunks = (g.lay.total_len + kSeedChunk - 1) / kSeedChunk;
+    g.n_groups = n_chunks * (kSeedChunk / 32u) + 1;  // + one padding group (look-ahead of the last lane)
+    g.codes.ensure((size_t)g.n_groups * 8 + 64);
+    g.inval.ensure((size_t)g.n_groups * 4 + 64);
+    Pack2Args a{};
+    a.ascii = g.ascii;
+    a.total_len = g.lay.total_len;
+    a.n_groups = g.n_groups;
+    a.codes = g.codes.as<uint32_t>();
+    a.inval = g.inval.as<uint32_t>();
+    a.segs = g.segs_dev.as<SegmentDev>();
+    a.n_segs = (uint32_t)g.segs.size();
+    a.seg_reset = g.seg_reset.as<uint32_t>();
+    a.aligned = (reinterpret_cast<uintptr_t>(g.ascii) & 15u) == 0;
+    const unsigned grid = (unsigned)std::min<uint64_t>((g.n_groups + 255) / 256, (uint64_t)s->sm_count * 32);
+    k_pack2<<<grid, 256, 0, st>>>(a);
+    check_launch("k_pack2");
+    s->launches++;
+    g.codes_ready = true;
+}
+
+// K1 on the genome's concatenated ASCII buffer, in the format the panel's filter reads
+static void pack_genome(ipcr_scratch *s, GenomeData &g) {
+    cudaStream_t st = s->stream;
+    g.planes_ready = g.codes_ready = false;
+    upload(g.segs_dev, g.segs.data(), g.segs.size() * sizeof(SegmentDev), st);
+    g.seg_reset.ensure(g.segs.size() * sizeof(uint32_t));
+    CU(cudaMemsetAsync(g.seg_reset.p, 0, g.segs.size() * sizeof(uint32_t), st));
+    if (prefer_seed(s->panel)) launch_pack_codes(s, g);
+    else launch_pack_planes(s, g);
     s->h_reset.ensure(g.segs.size() * sizeof(uint32_t));
     CU(cudaMemcpyAsync(s->h_reset.p, g.seg_reset.p, g.segs.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -329,6 +392,23 @@ static void pack_genome(ipcr_scratch *s, GenomeData &g) {
             g.recs[g.segs[i].rec_idx].has_reset_byte = 1;
             g.any_reset = true;
         }
+    }
+}
+
+// a genome handle may meet panels that want the other format: pack it then (once)
+static void ensure_planes(ipcr_scratch *s, GenomeData &g) {
+    std::lock_guard<std::mutex> lock(g.pack_mu);
+    if (!g.planes_ready) {
+        launch_pack_planes(s, g);
+        CU(cudaStreamSynchronize(s->stream));
+    }
+}
+
+static void ensure_codes(ipcr_scratch *s, GenomeData &g) {
+    std::lock_guard<std::mutex> lock(g.pack_mu);
+    if (!g.codes_ready) {
+        launch_pack_codes(s, g);
+        CU(cudaStreamSynchronize(s->stream));
     }
 }
 
@@ -406,6 +486,8 @@ static uint64_t read_counter(ipcr_scratch *s, int idx) {
 
 struct JitRun;
 static bool jit_filter(ipcr_scratch *s, const GenomeData &g, int variant, JitRun &run);
+struct VerifyArgs;
+static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs &v, uint64_t &n_sites);
 
 static void launch_filter_generic(ipcr_scratch *s, const GenomeData &g, int variant, uint64_t cand_cap) {
     const PlanTables &pt = s->tables->plan[variant];
@@ -440,7 +522,7 @@ static void launch_filter_generic(ipcr_scratch *s, const GenomeData &g, int vari
 }
 
 // Stage 1.  Leaves verified sites in s->sites (device) and returns their count.
-static uint64_t find_sites(ipcr_scratch *s, const GenomeData &g, bool force_raw);
+static uint64_t find_sites(ipcr_scratch *s, GenomeData &g, bool force_raw);
 
 static uint32_t bit_length(uint64_t v) {
     uint32_t b = 0;
@@ -579,7 +661,7 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 
 static void bind(ipcr_scratch *s) { CU(cudaSetDevice(s->device)); }
 
-static uint64_t scan_genome_impl(ipcr_scratch *s, const GenomeData &g, bool had_upload) {
+static uint64_t scan_genome_impl(ipcr_scratch *s, GenomeData &g, bool had_upload) {
     cudaStream_t st = s->stream;
     if (!had_upload) {
         CU(cudaEventRecord(s->ev[0], st));
@@ -768,7 +850,136 @@ static void set_err(char *err, size_t errlen, const std::string &m) {
 
 namespace ipcr {
 
-static uint64_t find_sites(ipcr_scratch *s, const GenomeData &g, bool force_raw) {
+// more dirty-window candidates than this and the bit-parallel filter (which handles non-ACGT
+// bytes natively) is the better tool
+constexpr uint64_t kSeedDirtyMax = 1ull << 26;
+
+static const SeedIndex &seed_get(ipcr_scratch *s, int variant) {
+    ipcr_panel *p = s->panel;
+    const SeedIndex &ix = seed_host(p, variant);
+    DevTables *t = s->tables;
+    std::lock_guard<std::mutex> lock(p->mu);
+    if (!t->seed_ready[variant]) {
+        upload(t->seed_table[variant], ix.slots.data(), ix.slots.size() * sizeof(uint64_t), s->stream);
+        upload(t->seed_bloom[variant], ix.bloom.data(), ix.bloom.size() * sizeof(uint32_t), s->stream);
+        upload(t->seed_coloff[variant], ix.col_off.data(), ix.col_off.size() * sizeof(uint16_t), s->stream);
+        CU(cudaStreamSynchronize(s->stream));
+        static std::mutex attr_mu;
+        std::lock_guard<std::mutex> l2(attr_mu);
+        CU(cudaFuncSetAttribute(k_seed_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kSeedBloomWords * 4)));
+        t->seed_ready[variant] = true;
+    }
+    return ix;
+}
+
+// Seed-index filter + verify.  Returns false (nothing changed) when the input is too dirty for
+// it; on success the verified sites are in s->sites.
+static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs &v, uint64_t &n_sites) {
+    const Panel &h = s->panel->host;
+    const SeedIndex &ix = seed_get(s, variant);
+    if (ix.S <= 0) return false;
+    ensure_codes(s, g);
+    cudaStream_t st = s->stream;
+    DevTables *t = s->tables;
+    const uint64_t U = h.orients.size();
+    const uint64_t n_chunks = (g.lay.total_len + kSeedChunk - 1) / kSeedChunk;
+    uint64_t cap = std::max<uint64_t>(1ull << 16, (uint64_t)(ix.cand_prob * (double)g.lay.total_len * 1.5) + 4096);
+    cap = std::min<uint64_t>(cap, 1ull << 28);
+    uint64_t dirty_cap = 1ull << 16;
+    uint64_t n_cand = 0, n_dirty = 0;
+    unsigned long long *ctr = s->counters.as<unsigned long long>();
+    for (int attempt = 0;; attempt++) {
+        s->cand.ensure(cap * sizeof(unsigned long long));
+        s->dirty.ensure(dirty_cap * sizeof(unsigned long long));
+        CU(cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), st));
+        CU(cudaEventRecord(s->ev[3], st));
+        if (h.cfg.max_mm > 0) {
+            SeedDirtyArgs d{};
+            d.inval = g.inval.as<uint32_t>();
+            d.n_groups = g.n_groups;
+            d.total_len = g.lay.total_len;
+            d.S = (uint32_t)ix.S;
+            d.max_mm = (uint32_t)h.cfg.max_mm;
+            d.dirty = s->dirty.as<unsigned long long>();
+            d.dirty_count = ctr + 2;
+            d.dirty_cap = dirty_cap;
+            const unsigned grid = (unsigned)std::min<uint64_t>((g.n_groups + 255) / 256, (uint64_t)s->sm_count * 16);
+            k_seed_dirty<<<grid, 256, 0, st>>>(d);
+            check_launch("k_seed_dirty");
+            s->launches++;
+        }
+        SeedScanArgs a{};
+        a.codes = g.codes.as<uint32_t>();
+        a.inval = g.inval.as<uint32_t>();
+        a.n_chunks = n_chunks;
+        a.S = (uint32_t)ix.S;
+        a.kmer_mask = ix.kmer_mask;
+        a.bloom = t->seed_bloom[variant].as<uint32_t>();
+        a.table = t->seed_table[variant].as<unsigned long long>();
+        a.table_shift = 32u - ix.table_bits;
+        a.table_mask = (uint32_t)((1ull << ix.table_bits) - 1);
+        a.cand = s->cand.as<unsigned long long>();
+        a.cand_count = ctr;
+        a.cand_cap = cap;
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + 31) / 32, (uint64_t)s->sm_count));
+        if (ix.use_bloom) k_seed_scan<true><<<grid, 1024, kSeedBloomWords * 4, st>>>(a);
+        else k_seed_scan<false><<<grid, 1024, 0, st>>>(a);
+        check_launch("k_seed_scan");
+        s->launches++;
+        CU(cudaMemcpyAsync(s->h_counts.p, s->counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        n_cand = s->h_counts.as<unsigned long long>()[0];
+        n_dirty = s->h_counts.as<unsigned long long>()[2];
+        if (n_dirty * U > kSeedDirtyMax) return false;
+        if (n_cand <= cap && n_dirty <= dirty_cap) break;
+        if (attempt >= 2 || n_cand * sizeof(unsigned long long) > (32ull << 30))
+            throw Error(fmt("scan produced %llu candidate sites; the panel is too unspecific for this input",
+                            (unsigned long long)n_cand));
+        cap = std::max(cap, n_cand + 1024);
+        dirty_cap = std::max(dirty_cap, n_dirty + 1024);
+    }
+    CU(cudaEventRecord(s->ev[4], st));
+    const uint64_t n_dcand = n_dirty * U;
+    s->n_cand = n_cand;  // the k-mer hits; dirty-window candidates live in s->dcand
+    s->timing.candidates = n_cand + n_dcand;
+    n_sites = 0;
+    if (n_cand + n_dcand == 0) return true;
+    s->sites.ensure((n_cand + n_dcand) * sizeof(ipcr_site));
+    v.sites = s->sites.as<ipcr_site>();
+    v.site_cap = n_cand + n_dcand;
+    if (n_cand) {
+        v.cand = s->cand.as<unsigned long long>();
+        v.n_cand = n_cand;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_cand + 255) / 256, (uint64_t)s->sm_count * 16);
+        k_verify<<<grid, 256, 0, st>>>(v);
+        check_launch("k_verify");
+        s->launches++;
+    }
+    if (n_dcand) {
+        s->dcand.ensure(n_dcand * sizeof(unsigned long long));
+        SeedExpandArgs e{};
+        e.dirty = s->dirty.as<unsigned long long>();
+        e.n_dirty = n_dirty;
+        e.col_off = t->seed_coloff[variant].as<uint16_t>();
+        e.orients = t->orients.as<OrientDev>();
+        e.n_orient = (uint32_t)U;
+        e.S = (uint32_t)ix.S;
+        e.cand = s->dcand.as<unsigned long long>();
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_dcand + 255) / 256, (uint64_t)s->sm_count * 16);
+        k_seed_dirty_expand<<<grid, 256, 0, st>>>(e);
+        check_launch("k_seed_dirty_expand");
+        v.cand = s->dcand.as<unsigned long long>();
+        v.n_cand = n_dcand;
+        k_verify<<<grid, 256, 0, st>>>(v);
+        check_launch("k_verify");
+        s->launches += 2;
+    }
+    n_sites = read_counter(s, 1);
+    return true;
+}
+
+static uint64_t find_sites(ipcr_scratch *s, GenomeData &g, bool force_raw) {
     const Panel &h = s->panel->host;
     cudaStream_t st = s->stream;
     s->n_cand = 0;
@@ -802,10 +1013,17 @@ static uint64_t find_sites(ipcr_scratch *s, const GenomeData &g, bool force_raw)
 
     CU(cudaEventRecord(s->ev[3], st));
     uint64_t n_sites = 0;
+    if (prefer_seed(s->panel) && seed_filter(s, g, variant, v, n_sites)) {
+        s->timing.used_jit = kPathSeed;
+        CU(cudaEventRecord(s->ev[5], st));
+        s->timing.sites = n_sites;
+        return n_sites;
+    }
+    ensure_planes(s, g);
     JitRun run;
     if (jit_filter(s, g, variant, run)) {
         // ---- specialised filter: per-thread lists of 32-position candidate words ----
-        s->timing.used_jit = 1;
+        s->timing.used_jit = kPathJit;
         s->n_cand = 0;
         s->timing.candidates = run.n_bits;
         if (run.n_entries > 0 && run.n_bits > 0) {
@@ -1190,7 +1408,8 @@ int ipcr_gpu_scan_genome(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g, c
     bind(s);
     s->launches = 0;
     s->timing = ipcr_timing{};
-    const uint64_t n = scan_genome_impl(s, g->g, false);
+    // the handle is logically const: packing the other format on demand is cached state (pack_mu)
+    const uint64_t n = scan_genome_impl(s, const_cast<GenomeData &>(g->g), false);
     if (out) *out = s->h_products.as<ipcr_product>();
     if (n_out) *n_out = n;
     return 0;
@@ -1206,7 +1425,7 @@ int ipcr_gpu_find_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g, co
     s->launches = 0;
     s->timing = ipcr_timing{};
     for (int i = 0; i < 8; i++) CU(cudaEventRecord(s->ev[i], s->stream));
-    const uint64_t n = find_sites(s, g->g, true);
+    const uint64_t n = find_sites(s, const_cast<GenomeData &>(g->g), true);
     if (n) {
         s->h_sites.ensure(n * sizeof(ipcr_site));
         CU(cudaMemcpyAsync(s->h_sites.p, s->sites.p, n * sizeof(ipcr_site), cudaMemcpyDeviceToHost, s->stream));
@@ -1493,6 +1712,28 @@ int ipcr_gpu_debug_plan_eval(const ipcr_panel *p, uint32_t orient, const uint8_t
     if (!p || orient >= p->host.orients.size()) return -1;
     const int v = raw_mode ? 1 : 0;
     return plan_eval(p->host.orients[orient], p->host.plan[v].o[orient], seq, len, start) ? 1 : 0;
+}
+
+int ipcr_gpu_debug_seed_eval(ipcr_panel *p, int raw_mode, const uint8_t *seq, uint64_t len, uint64_t *out,
+                             uint64_t cap, uint64_t *n, int32_t *info) {
+    if (!p) return 1;
+    try {
+        const SeedIndex &ix = seed_host(p, raw_mode ? 1 : 0);
+        std::vector<uint64_t> c;
+        seed_eval(p->host, ix, seq, len, c);
+        if (n) *n = c.size();
+        for (uint64_t i = 0; out && i < c.size() && i < cap; i++) out[i] = c[i];
+        if (info) {
+            info[0] = ix.S;
+            info[1] = (int32_t)std::min<uint64_t>(ix.n_entries, 0x7FFFFFFF);
+            info[2] = (int32_t)ix.table_bits;
+            info[3] = ix.use_bloom ? 1 : 0;
+            info[4] = (int32_t)(ix.bloom_fill * 1e6);
+        }
+    } catch (const std::exception &) {
+        return 1;
+    }
+    return 0;
 }
 
 int ipcr_gpu_debug_orientation(const ipcr_panel *p, uint32_t orient, char *buf, size_t buflen, int *type) {

@@ -17,7 +17,7 @@ struct JitRun {
 // returns the loaded kernel for this device/variant, compiling on first use; nullptr = not available
 static JitKernel *jit_get(ipcr_scratch *s, int variant, double work) {
     ipcr_panel *p = s->panel;
-    const int mode = p->host.jit_mode;
+    const int mode = p->host.jit_mode == 3 ? 1 : p->host.jit_mode;  // 3: seed index first, then automatic
     if (mode <= 0) return nullptr;
     JitKernel *k = &s->tables->jit[variant];
     std::lock_guard<std::mutex> lock(p->mu);

@@ -265,6 +265,7 @@ __device__ __forceinline__ bool verify_one(const VerifyArgs &a, uint32_t q, uint
     const SegmentDev seg = a.segs[si];
     const OrientDev o = a.orients[q];
     const uint64_t local = start - seg.global_off;
+    if (o.L == 0) return false;  // match.go:32-34
     if (!(start >= seg.global_off && local + o.L <= seg.len && local < seg.own_len)) return false;
     const uint8_t *g = a.ascii + start;
     const uint8_t *pc = a.cls + o.cls_off;

@@ -1,0 +1,215 @@
+// seed.hpp -- host side of the SEED-INDEX filter: the whole panel becomes one k-mer index, so
+// one pass over the genome serves every orientation (the bit-parallel filter of plan.hpp /
+// jit.hpp needs one pass per group of four).
+//
+// Same idea as the reference's candidate generator (buildSeedPatterns + enumerateSeedVariants,
+// /root/reference/core/engine/seed.go:152-367, fed to an Aho-Corasick automaton, ac.go:64-139),
+// re-designed for the GPU: no automaton (a dependent load per base), but
+//   * ONE seed window per unique orientation, S <= 16 columns anchored at the protected (3')
+//     end, S uniform over the panel so that a genome position has exactly one k-mer;
+//   * every concrete k-mer a true site can show in that window (<= max_mm mismatches in the
+//     free columns, none in the protected ones, IUPAC columns expanded) is enumerated;
+//   * the k-mers go into an open-addressing hash table (8-byte slots: k-mer, orientation,
+//     seed offset) that stays L2-resident, fronted by a 200 KB one-hash Bloom bitmap that the
+//     scan kernel keeps in SHARED memory: one LDS per genome position decides whether the
+//     table is consulted at all.
+// Completeness: a site with <= max_mm mismatches and a clean protected window shows one of the
+// enumerated k-mers in its seed window unless that window holds a non-ACGT byte; those "dirty"
+// windows are verified directly (kernels: k_seed_dirty), like the reference's halo pass
+// (halo.go:47-108).  Exactness still lives in the verify kernel.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <utility>
+#include <vector>
+
+#include "plan.hpp"
+
+namespace ipcr {
+
+constexpr uint32_t kSeedBloomWords = 51200;  // 200 KB of shared memory
+constexpr uint32_t kSeedBloomBits = kSeedBloomWords * 32u;
+constexpr uint32_t kSeedBloomMul = 0x85EBCA6Bu;
+constexpr uint32_t kSeedHashMul = 0x9E3779B1u;
+constexpr int kSeedMaxLen = 16;                    // 2 bits per base in a 32-bit k-mer
+constexpr uint64_t kSeedMaxEntries = 16ull << 20;  // table <= 512 MB
+
+// 2-bit code of a base = (ascii >> 1) & 3: A 0, C 1, T 2, G 3; index = one-hot bit (A,C,G,T)
+constexpr uint32_t kSeedCodeOfBit[4] = {0u, 1u, 3u, 2u};
+
+// slot = occupied(63) | seed offset(55:48) | orientation(47:32) | k-mer(31:0)
+inline uint64_t seed_slot(uint32_t kmer, uint32_t orient, uint32_t col_off) {
+    return (1ull << 63) | ((uint64_t)col_off << 48) | ((uint64_t)orient << 32) | kmer;
+}
+
+// bitmap bit of a k-mer: word from the high half of the multiplicative hash, bit from its low bits
+inline uint32_t seed_bloom_index(uint32_t kmer) {
+    const uint32_t h = kmer * kSeedBloomMul;
+    return (uint32_t)(((uint64_t)h * kSeedBloomWords) >> 32) * 32u + (h & 31u);
+}
+
+struct SeedIndex {
+    int S = 0;
+    uint32_t kmer_mask = 0;
+    uint32_t table_bits = 0;
+    std::vector<uint64_t> slots;
+    std::vector<uint32_t> bloom;
+    bool use_bloom = false;
+    uint64_t n_entries = 0;
+    double bloom_fill = 0.0;  // fraction of bitmap bits set
+    double cand_prob = 0.0;   // expected candidates per genome position
+    std::vector<uint16_t> col_off;  // per orientation: site start = k-mer start - col_off
+};
+
+inline int seed_col_off(const Orient &o, int S) { return o.rc_type ? 0 : o.L - S; }
+
+inline bool seed_col_protected(const Orient &o, int col, int tw, bool raw) {
+    if (tw <= 0 || (raw && o.rc_type)) return false;
+    return o.rc_type ? col < tw : col >= o.L - tw;
+}
+
+// number of k-mers seed_enumerate() emits for one orientation (saturating)
+inline uint64_t seed_variant_count(const Orient &o, int S, int max_mm, int tw, bool raw) {
+    const uint64_t kSat = 1ull << 40;
+    const int off = seed_col_off(o, S);
+    std::vector<uint64_t> ways((size_t)max_mm + 1, 0);
+    ways[0] = 1;
+    for (int j = 0; j < S; j++) {
+        const uint64_t km = (uint64_t)class_popcount(o.cls[off + j]);
+        const uint64_t kx = seed_col_protected(o, off + j, tw, raw) ? 0 : 4 - km;
+        std::vector<uint64_t> nw((size_t)max_mm + 1, 0);
+        for (int m = 0; m <= max_mm; m++) {
+            if (!ways[m]) continue;
+            nw[m] = std::min(kSat, nw[m] + ways[m] * km);
+            if (m + 1 <= max_mm) nw[m + 1] = std::min(kSat, nw[m + 1] + ways[m] * kx);
+        }
+        ways.swap(nw);
+    }
+    uint64_t total = 0;
+    for (uint64_t w : ways) total = std::min(kSat, total + w);
+    return total;
+}
+
+inline void seed_enumerate(const Orient &o, int S, int max_mm, int tw, bool raw, std::vector<uint32_t> &out) {
+    const int off = seed_col_off(o, S);
+    struct Frame { int j; uint32_t kmer; int mm; };
+    std::vector<Frame> stack;
+    stack.push_back({0, 0u, 0});
+    while (!stack.empty()) {
+        const Frame f = stack.back();
+        stack.pop_back();
+        if (f.j == S) {
+            out.push_back(f.kmer);
+            continue;
+        }
+        const uint8_t cls = o.cls[off + f.j];
+        const bool prot = seed_col_protected(o, off + f.j, tw, raw);
+        for (int b = 0; b < 4; b++) {
+            const bool match = (cls >> b) & 1;
+            if (!match && (prot || f.mm >= max_mm)) continue;
+            stack.push_back({f.j + 1, f.kmer | (kSeedCodeOfBit[b] << (2 * f.j)), f.mm + (match ? 0 : 1)});
+        }
+    }
+}
+
+// modelled cost of the seed filter per genome position (same unit for every S: ~ issue
+// slots of the scan kernel's fast path), used to pick S
+inline double seed_cost(double entries, int S) {
+    const double fill = 1.0 - std::exp(-entries / (double)kSeedBloomBits);
+    const double prob = entries / std::pow(4.0, S);
+    const double probe = fill <= 0.6 ? 4.0 * fill : 6.0;  // table probes per position
+    return 1.0 + probe + prob * 600.0;
+}
+
+inline SeedIndex seed_build(const Panel &h, int variant) {
+    SeedIndex ix;
+    const bool raw = variant != 0;
+    const int mm = std::max(0, h.cfg.max_mm), tw = std::max(0, h.cfg.terminal_window);
+    if (h.orients.empty()) return ix;
+    int min_len = 1 << 30;
+    for (const Orient &o : h.orients)
+        if (o.L > 0) min_len = std::min(min_len, o.L);
+    if (min_len == 1 << 30) min_len = 1;
+    const int s_max = std::max(1, std::min(kSeedMaxLen, min_len));
+    int best_s = 0;
+    double best_cost = 1e300;
+    for (int S = s_max; S >= 1; S--) {
+        uint64_t e = 0;
+        for (const Orient &o : h.orients)
+            if (o.L >= S) e = std::min<uint64_t>(1ull << 40, e + seed_variant_count(o, S, mm, tw, raw));
+        if (e > kSeedMaxEntries) continue;
+        const double c = seed_cost((double)e, S);
+        if (c < best_cost) { best_cost = c; best_s = S; }
+    }
+    if (best_s == 0) best_s = std::min(s_max, 6);  // 4^6 x 2048 orientations always fits
+    if (const char *e = getenv("IPCR_SEED_LEN")) best_s = std::max(1, std::min(atoi(e), s_max));
+    ix.S = best_s;
+    ix.kmer_mask = best_s == 16 ? 0xFFFFFFFFu : ((1u << (2 * best_s)) - 1u);
+    std::vector<std::pair<uint32_t, uint32_t>> entries;  // (k-mer, orientation)
+    std::vector<uint32_t> tmp;
+    for (size_t q = 0; q < h.orients.size(); q++) {
+        const Orient &o = h.orients[q];
+        ix.col_off.push_back((uint16_t)seed_col_off(o, ix.S));
+        tmp.clear();
+        if (o.L >= ix.S) seed_enumerate(o, ix.S, mm, tw, raw, tmp);
+        for (uint32_t k : tmp) entries.emplace_back(k, (uint32_t)q);
+    }
+    ix.n_entries = entries.size();
+    ix.table_bits = 10;
+    while ((1ull << ix.table_bits) < ix.n_entries * 5 / 2) ix.table_bits++;
+    ix.slots.assign((size_t)1 << ix.table_bits, 0ull);
+    ix.bloom.assign(kSeedBloomWords, 0u);
+    const uint32_t tmask = (uint32_t)((1ull << ix.table_bits) - 1);
+    uint64_t bits_set = 0;
+    for (const auto &e : entries) {
+        uint32_t hh = (uint32_t)(e.first * kSeedHashMul) >> (32 - ix.table_bits);
+        while (ix.slots[hh]) hh = (hh + 1) & tmask;
+        ix.slots[hh] = seed_slot(e.first, e.second, ix.col_off[e.second]);
+        const uint32_t b = seed_bloom_index(e.first);
+        if (!((ix.bloom[b >> 5] >> (b & 31)) & 1u)) bits_set++;
+        ix.bloom[b >> 5] |= 1u << (b & 31);
+    }
+    ix.bloom_fill = (double)bits_set / (double)kSeedBloomBits;
+    ix.use_bloom = ix.bloom_fill <= 0.6;
+    if (const char *e = getenv("IPCR_SEED_BLOOM")) ix.use_bloom = atoi(e) != 0;
+    ix.cand_prob = (double)ix.n_entries / std::pow(4.0, ix.S);
+    return ix;
+}
+
+// CPU evaluation of the index on one sequence (test tap; mirrors k_pack2 + k_seed_dirty +
+// k_seed_scan): every (orientation << 44 | start) the device filter would hand to verify
+inline void seed_eval(const Panel &h, const SeedIndex &ix, const uint8_t *seq, uint64_t len,
+                      std::vector<uint64_t> &out) {
+    out.clear();
+    const uint64_t S = (uint64_t)ix.S;
+    if (S == 0 || len < S) return;
+    const uint32_t tmask = (uint32_t)((1ull << ix.table_bits) - 1);
+    for (uint64_t p = 0; p + S <= len; p++) {
+        uint32_t kmer = 0, n_inv = 0;
+        for (uint64_t j = 0; j < S; j++) {
+            const uint8_t b = seq[p + j];
+            if (!(b == 'A' || b == 'C' || b == 'G' || b == 'T')) n_inv++;
+            kmer |= (uint32_t)((b >> 1) & 3u) << (2 * j);
+        }
+        if (n_inv == 0) {
+            if (ix.use_bloom) {
+                const uint32_t b = seed_bloom_index(kmer);
+                if (!((ix.bloom[b >> 5] >> (b & 31)) & 1u)) continue;
+            }
+            for (uint32_t hh = (uint32_t)(kmer * kSeedHashMul) >> (32 - ix.table_bits); ix.slots[hh]; hh = (hh + 1) & tmask) {
+                const uint64_t slot = ix.slots[hh];
+                const uint64_t c = (slot >> 48) & 0xFF;
+                if ((uint32_t)slot == kmer && p >= c) out.push_back((((slot >> 32) & 0xFFFF) << 44) | (p - c));
+            }
+        } else if ((int)n_inv <= h.cfg.max_mm) {
+            for (size_t q = 0; q < h.orients.size(); q++) {
+                const uint64_t c = ix.col_off[q];
+                if (h.orients[q].L >= ix.S && p >= c) out.push_back(((uint64_t)q << 44) | (p - c));
+            }
+        }
+    }
+}
+
+}  // namespace ipcr

@@ -1,0 +1,245 @@
+// seed_kernels.cuh -- kernels of the seed-index filter (host side: seed.hpp).
+//   K1s k_pack2        ASCII -> 2-bit codes (16 bases / word) + hard-mismatch bitmap (32 / word)
+//   K2d k_seed_dirty   seed windows holding 1..max_mm non-ACGT bytes (the halo of halo.go:47-108)
+//   K2s k_seed_scan    one k-mer per genome position: Bloom bitmap in shared memory, then the
+//                      L2-resident hash table; hits become (orientation, start) candidates
+//   K2e k_seed_dirty_expand  dirty windows x orientations -> candidates
+// All of it is integer/byte work; exactness is in k_verify (kernels.cuh).
+#pragma once
+
+#include "device_types.cuh"
+#include "kernels.cuh"
+
+namespace ipcr {
+
+constexpr uint32_t kSeedChunk = 4096;  // positions one warp takes at a time (128 per lane)
+constexpr uint32_t kSeedBloomWordsDev = 51200;
+constexpr uint32_t kSeedBloomMulDev = 0x85EBCA6Bu;
+constexpr uint32_t kSeedHashMulDev = 0x9E3779B1u;
+
+// ---------------------------------------------------------------------------
+// K1s.  Four bytes at a time, no table and no per-byte branch:
+//   code  = (byte >> 1) & 3                       A 0, C 1, T 2, G 3
+//   valid = byte == 0x41 + 2*code + 15*[code==2]  (re-encode and compare: only uppercase
+//           A/C/G/T survive, core/primer/iupac.go:62-67)
+// and two multiplies gather the 4x2 code bits / 4x1 invalid bits.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pack4(uint32_t w, uint32_t &code8, uint32_t &inv4) {
+    const uint32_t t = (w >> 1) & 0x03030303u;
+    code8 = (t * 0x01041040u) >> 24;
+    const uint32_t e2 = (t >> 1) & ~t & 0x01010101u;
+    const uint32_t expect = 0x41414141u + 2u * t + 15u * e2;
+    const uint32_t d = expect ^ w;
+    const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+    inv4 = ((nz >> 7) * 0x10204080u) >> 28;
+}
+
+struct Pack2Args {
+    const uint8_t *ascii;
+    uint64_t total_len;
+    uint64_t n_groups;  // 32-base groups to write (covers total_len plus padding)
+    uint32_t *codes;    // [2 * n_groups]
+    uint32_t *inval;    // [n_groups]
+    const SegmentDev *segs;
+    uint32_t n_segs;
+    uint32_t *seg_reset;
+    uint32_t aligned;   // ascii is 16-byte aligned
+};
+
+__global__ void __launch_bounds__(256)
+k_pack2(Pack2Args a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t gidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < a.n_groups; gidx += stride) {
+        const uint64_t P0 = gidx * 32ull;
+        uint32_t w[8];
+        if (a.aligned && P0 + 32ull <= a.total_len) {
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(a.ascii + P0));
+            const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(a.ascii + P0) + 1);
+            w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
+            w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+        } else {  // ragged tail / unaligned buffer: byte loads, zero (= invalid) padding
+#pragma unroll
+            for (int k = 0; k < 8; k++) w[k] = 0u;
+            for (uint32_t k = 0; k < 32u && P0 + k < a.total_len; k++)
+                w[k >> 2] |= (uint32_t)a.ascii[P0 + k] << (8u * (k & 3u));
+        }
+        uint32_t c0 = 0, c1 = 0, inv = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t c8, i4;
+            pack4(w[k], c8, i4);
+            if (k < 4) c0 |= c8 << (8 * k); else c1 |= c8 << (8 * (k - 4));
+            inv |= i4 << (4 * k);
+        }
+        reinterpret_cast<uint2 *>(a.codes)[gidx] = make_uint2(c0, c1);
+        a.inval[gidx] = inv;
+        if (inv != 0u) {  // rare: which of them are reset bytes (not even lowercase acgt)?
+            for (uint32_t k = 0; k < 32u; k++) {
+                if (!((inv >> k) & 1u) || P0 + k >= a.total_len) continue;
+                const uint32_t b = (w[k >> 2] >> (8u * (k & 3u))) & 0xFFu;
+                const uint32_t x = (b | 0x20u) - 'a';  // a,c,g,t -> 0,2,6,19
+                const bool acgt = x < 32u && ((0x00080045u >> x) & 1u);
+                if (!acgt) {
+                    const uint32_t s = find_segment(a.segs, a.n_segs, P0 + k);
+                    if (P0 + k - a.segs[s].global_off < a.segs[s].len) a.seg_reset[s] = 1u;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2d.  One thread per 32 positions of the hard-mismatch bitmap.
+// ---------------------------------------------------------------------------
+struct SeedDirtyArgs {
+    const uint32_t *inval;
+    uint64_t n_groups;
+    uint64_t total_len;
+    uint32_t S;
+    uint32_t max_mm;
+    unsigned long long *dirty;        // positions (k-mer starts)
+    unsigned long long *dirty_count;  // wanted
+    uint64_t dirty_cap;
+};
+
+__global__ void __launch_bounds__(256)
+k_seed_dirty(SeedDirtyArgs a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t smask = a.S >= 64u ? ~0ull : ((1ull << a.S) - 1ull);
+    for (uint64_t gidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx + 1 < a.n_groups; gidx += stride) {
+        const uint64_t v = (uint64_t)a.inval[gidx] | ((uint64_t)a.inval[gidx + 1] << 32);
+        if (v == 0ull) continue;
+        for (uint32_t j = 0; j < 32u; j++) {
+            const uint32_t n = (uint32_t)__popcll((v >> j) & smask);
+            const uint64_t p = gidx * 32ull + j;
+            if (n >= 1u && n <= a.max_mm && p + a.S <= a.total_len) {
+                const unsigned long long i = atomicAdd(a.dirty_count, 1ull);
+                if (i < a.dirty_cap) a.dirty[i] = p;
+            }
+        }
+    }
+}
+
+struct SeedExpandArgs {
+    const unsigned long long *dirty;
+    uint64_t n_dirty;
+    const uint16_t *col_off;
+    const OrientDev *orients;
+    uint32_t n_orient;
+    uint32_t S;
+    unsigned long long *cand;  // already offset to the first free entry
+};
+
+__global__ void __launch_bounds__(256)
+k_seed_dirty_expand(SeedExpandArgs a) {
+    const uint64_t n = a.n_dirty * a.n_orient;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t q = (uint32_t)(i % a.n_orient);
+        const uint64_t p = a.dirty[i / a.n_orient];
+        const uint32_t c = a.col_off[q];
+        const bool ok = a.orients[q].L >= a.S && p >= c;
+        a.cand[i] = ((unsigned long long)q << kCandPosBits) | (ok ? p - c : kCandPosMask);  // else: never a site
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2s.  block = 32 warps, one CTA per SM (200 KB Bloom bitmap in shared memory).  A warp takes
+// 4096 consecutive positions; lane l owns the 128 k-mer starts at +128*l: its 8 code words
+// (+1 look-ahead) and 4 bitmap words (+1) sit in registers, every shift is an immediate.
+// Per position: funnel-shift + mask -> k-mer; two IMADs -> bitmap index; ONE LDS; the answer
+// bit is funnel-shifted into a 32-position hit word.  Set bits (and nothing else) walk the
+// hash table.  Windows holding an invalid byte are masked out here and served by k_seed_dirty.
+// ---------------------------------------------------------------------------
+struct SeedScanArgs {
+    const uint32_t *codes;
+    const uint32_t *inval;
+    uint64_t n_chunks;
+    uint32_t S;
+    uint32_t kmer_mask;
+    const uint32_t *bloom;
+    const unsigned long long *table;
+    uint32_t table_shift;  // 32 - table_bits
+    uint32_t table_mask;
+    unsigned long long *cand;
+    unsigned long long *cand_count;
+    uint64_t cand_cap;
+};
+
+__device__ __forceinline__ void seed_probe(const SeedScanArgs &a, uint32_t kmer, uint64_t p) {
+    uint32_t h = (kmer * kSeedHashMulDev) >> a.table_shift;
+    for (;;) {
+        const unsigned long long slot = __ldg(a.table + h);
+        if (slot == 0ull) break;
+        if ((uint32_t)slot == kmer) {
+            const uint64_t c = (slot >> 48) & 0xFFull;
+            if (p >= c) {
+                const unsigned long long i = atomicAdd(a.cand_count, 1ull);
+                if (i < a.cand_cap) a.cand[i] = (((slot >> 32) & 0xFFFFull) << kCandPosBits) | (p - c);
+            }
+        }
+        h = (h + 1u) & a.table_mask;
+    }
+}
+
+template <bool USE_BLOOM>
+__global__ void __launch_bounds__(1024, 1)
+k_seed_scan(SeedScanArgs a) {
+    extern __shared__ uint32_t sbloom[];
+    if (USE_BLOOM) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.bloom);
+        uint4 *dst = reinterpret_cast<uint4 *>(sbloom);
+        for (uint32_t i = threadIdx.x; i < kSeedBloomWordsDev / 4u; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t ch = warp; ch < a.n_chunks; ch += n_warps) {
+        const uint64_t P0 = ch * kSeedChunk + (uint64_t)lane * 128u;
+        uint32_t c[9], iv[5];
+        {
+            const uint4 *cp = reinterpret_cast<const uint4 *>(a.codes + (P0 >> 4));
+            const uint4 q0 = __ldg(cp), q1 = __ldg(cp + 1);
+            c[0] = q0.x; c[1] = q0.y; c[2] = q0.z; c[3] = q0.w;
+            c[4] = q1.x; c[5] = q1.y; c[6] = q1.z; c[7] = q1.w;
+            c[8] = __ldg(a.codes + (P0 >> 4) + 8);
+            const uint4 qi = __ldg(reinterpret_cast<const uint4 *>(a.inval + (P0 >> 5)));
+            iv[0] = qi.x; iv[1] = qi.y; iv[2] = qi.z; iv[3] = qi.w;
+            iv[4] = __ldg(a.inval + (P0 >> 5) + 4);
+        }
+#pragma unroll
+        for (int blk = 0; blk < 4; blk++) {
+            const uint32_t w0 = c[2 * blk], w1 = c[2 * blk + 1], w2 = c[2 * blk + 2];
+            uint32_t hits = 0u;
+            if (USE_BLOOM) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t kmer = (j < 16 ? __funnelshift_r(w0, w1, 2 * j) : __funnelshift_r(w1, w2, 2 * (j - 16))) &
+                                          a.kmer_mask;
+                    const uint32_t h = kmer * kSeedBloomMulDev;
+                    const uint32_t bit = __funnelshift_r(sbloom[__umulhi(h, kSeedBloomWordsDev)], 0u, h);
+                    hits = __funnelshift_r(hits, bit, 1);
+                }
+            } else {
+                hits = 0xFFFFFFFFu;
+            }
+            const uint32_t ilo = iv[blk], ihi = iv[blk + 1];
+            if ((ilo | ihi) != 0u) {  // rare: drop every window that holds an invalid byte
+                const uint64_t v = (uint64_t)ilo | ((uint64_t)ihi << 32);
+                uint64_t d = 0ull;
+                for (uint32_t k = 0; k < a.S; k++) d |= v >> k;
+                hits &= ~(uint32_t)d;
+            }
+            while (hits) {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1u;
+                const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
+                const uint32_t kmer = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
+                seed_probe(a, kmer, P0 + (uint64_t)(blk * 32 + j));
+            }
+        }
+    }
+}
+
+}  // namespace ipcr

@@ -131,3 +131,51 @@ def test_filter_plan_is_selective_on_random_dna(oracle):
     for q in range(cp.num_orientations):
         hits = sum(cp.plan_eval(q, g, p) for p in range(len(g) - 30))
         assert hits <= 4, (q, hits)
+
+
+def test_seed_index_never_loses_a_true_site_and_never_repeats_one(oracle):
+    """The seed index (csrc/seed.hpp) is the other candidate generator: one k-mer per genome
+    position against every enumerated seed variant of the panel.  Same contract as the
+    reference's seeds (core/engine/approx_seed_oracle_test.go): every start the brute force
+    accepts is a candidate -- and no (orientation, start) comes twice, because a duplicate
+    candidate would become a duplicate site."""
+    rng = random.Random(4242)
+    checked = 0
+    for it in range(120):
+        n = rng.randint(120, 320)
+        g = H.random_genome(rng, n, n_frac=rng.choice([0, 0.02, 0.1]), lower_frac=rng.choice([0, 0.03]))
+        mm, tw = rng.randint(0, 3), rng.choice([0, 1, 3, 4])
+        pairs = []
+        for k in range(rng.randint(1, 3)):
+            la, lb = rng.randint(3, 40), rng.randint(3, 40)
+            a = H.random_primer(rng, la, rng.choice([0, 0.15]))
+            b = H.random_primer(rng, lb, rng.choice([0, 0.15]))
+            pairs.append(Pair(f"p{k}", a, b))
+            for _ in range(2):
+                H.plant_amplicon(rng, g, rng.randint(0, max(0, n - la - lb - 10)), a, b, la + lb + rng.randint(0, 10),
+                                 rng.randint(0, mm), rng.randint(0, mm), tw, revcomp_strand=rng.random() < 0.5)
+        seq = bytes(g)
+        cp = Engine(Config(max_mm=mm, terminal_window=tw, hit_cap=rng.choice([0, 5]))).compile_panel(pairs)
+        for raw in (False, True):
+            cands, info = cp.seed_eval(seq, raw)
+            assert len(cands) == len(set(cands)), "duplicate candidate"
+            cset = set(cands)
+            assert 1 <= info["S"] <= 16
+            for q in range(cp.num_orientations):
+                s, t = cp.orientation(q)
+                for pos in _true_sites(oracle, seq, s, t == "a", mm, tw, raw):
+                    assert (q, pos) in cset, (s, t, mm, tw, raw, pos, info)
+                    checked += 1
+    assert checked > 800
+
+
+def test_seed_index_shape_on_the_benchmark_panel():
+    from ipcr_b200 import synth
+    _, allp = synth.multiplex_panel(100, seed=7)
+    cp = Engine(Config(max_mm=2, terminal_window=3, max_len=2000, hit_cap=10000)).compile_panel(allp)
+    rng = random.Random(3)
+    g = bytes(H.random_genome(rng, 50000))
+    cands, info = cp.seed_eval(g)
+    assert info["S"] >= 12 and info["bloom"] and info["bloom_fill"] < 0.35
+    assert info["entries"] < 1 << 20
+    assert len(cands) < 400  # ~ entries / 4^S per position

@@ -88,11 +88,12 @@ def test_config3_100mbp_multicontig(oracle):
     torch.cuda.synchronize()
     exp = _expected(oracle, user, lens, planted)
     results = {}
-    for jit in (0, 2):
+    for jit in (0, 2, 3):
         prods = _scan(cp, sc, buf, lens, jit)
+        assert sc.timing()["used_jit"] == {0: 0, 2: 1, 3: 2}[jit]
         results[jit] = [(_key(p), p.fwd_mismatch_idx, p.rev_mismatch_idx) for p in prods]
         assert exp <= {_key(p) for p in prods}
-    assert results[0] == results[2]  # same products, same order, both kernels
+    assert results[0] == results[2] == results[3]  # same products, same order, all three filters
     again = _scan(cp, sc, buf, lens, 2)
     assert [(_key(p), p.fwd_mismatch_idx, p.rev_mismatch_idx) for p in again] == results[2]  # idempotent
     _check_window(oracle, cfgd, allp, buf, lens, again, rng)
@@ -118,6 +119,11 @@ def test_config4_500mbp_outer_pairs(oracle):
     assert sc.timing()["used_jit"] == 1
     assert exp <= {_key(p) for p in prods}
     _check_window(oracle, cfgd, allp, buf, lens, prods, rng, n_windows=2)
+    seeded = _scan(cp, sc, buf, lens, 3)  # the seed index reproduces the bit-parallel scan exactly
+    assert sc.timing()["used_jit"] == 2
+    assert [(_key(p), p.fwd_mismatch_idx, p.rev_mismatch_idx) for p in seeded] == \
+           [(_key(p), p.fwd_mismatch_idx, p.rev_mismatch_idx) for p in prods]
+    cp.set_jit(2)
     # shard-and-gather (4 shards) reproduces the single scan exactly
     offs = sharding.contig_offsets(lens)
     sites, recs = [], [(0, False)] * len(lens)
@@ -156,3 +162,9 @@ def test_config5_3gbp_multiplex_mm3(oracle):
     assert all(0 <= p.start < p.end <= lens[int(p.sequence_id)] and p.length == p.end - p.start <= 2000 for p in prods)
     assert all(p.fwd_mm <= 3 and p.rev_mm <= 3 and len(p.fwd_mismatch_idx) == p.fwd_mm for p in prods)
     _check_window(oracle, cfgd, allp, buf, lens, prods, rng, n_windows=2, width=150_000)
+    # mm 3 x 400 orientations saturates the shared-memory bitmap: the seed index then probes its
+    # hash table for every position -- slower, still exact
+    seeded = _scan(cp, sc, buf, lens, 3)
+    assert sc.timing()["used_jit"] == 2
+    assert [(_key(p), p.fwd_mismatch_idx, p.rev_mismatch_idx) for p in seeded] == \
+           [(_key(p), p.fwd_mismatch_idx, p.rev_mismatch_idx) for p in prods]

@@ -37,11 +37,13 @@ def _check(oracle, cfgd, raw_pairs, seq, jit=0, cap_binds=False):
     pairs = _mk_pairs(raw_pairs)
     eng = Engine(Config(**cfgd))
     cp = eng.compile_panel(pairs)
-    cp.set_jit(jit)
-    got = [_tuple(p) for p in eng.simulate_compiled("seq", seq, cp)]
     ocfg = oracle.make_cfg(**cfgd)
     want = [_otuple(pairs, t) for t in oracle.simulate_compiled(ocfg, [tuple(p) for p in raw_pairs], seq)]
-    assert got == want, (cfgd, raw_pairs, bytes(seq)[:80])
+    # every case runs through the requested bit-parallel filter AND through the seed index (3)
+    for mode in dict.fromkeys((jit, 3)):
+        cp.set_jit(mode)
+        got = [_tuple(p) for p in eng.simulate_compiled("seq", seq, cp)]
+        assert got == want, (mode, cfgd, raw_pairs, bytes(seq)[:80])
     if not cap_binds:
         brute = [_otuple(pairs, t) for t in oracle.simulate_bruteforce(ocfg, [tuple(p) for p in raw_pairs], seq)]
         assert H.multiset(got) == H.multiset(brute)
