@@ -44,10 +44,22 @@ inline uint64_t seed_slot(uint32_t kmer, uint32_t orient, uint32_t col_off) {
     return (1ull << 63) | ((uint64_t)col_off << 48) | ((uint64_t)orient << 32) | kmer;
 }
 
-// bitmap bit of a k-mer: word from the high half of the multiplicative hash, bit from its low bits
-inline uint32_t seed_bloom_index(uint32_t kmer) {
+// bitmap bits of a k-mer (k = 1: word from the high half of the multiplicative hash, bit from
+// its low bits; k = 2: word and both bits from the top 26 bits).  Returns word index, sets mask.
+inline uint32_t seed_bloom_word(uint32_t kmer, int k, uint32_t &mask) {
     const uint32_t h = kmer * kSeedBloomMul;
-    return (uint32_t)(((uint64_t)h * kSeedBloomWords) >> 32) * 32u + (h & 31u);
+    if (k == 1) {
+        mask = 1u << (h & 31u);
+        return (uint32_t)(((uint64_t)h * kSeedBloomWords) >> 32);
+    }
+    if (k == 2) {
+        const uint32_t g = (uint32_t)(((uint64_t)h * ((uint64_t)kSeedBloomWords << 10)) >> 32);
+        mask = (1u << ((g >> 5) & 31u)) | (1u << (g & 31u));
+        return g >> 10;
+    }
+    const uint32_t g = (uint32_t)(((uint64_t)h * ((uint64_t)kSeedBloomWords << 15)) >> 32);
+    mask = (1u << ((g >> 10) & 31u)) | (1u << ((g >> 5) & 31u)) | (1u << (g & 31u));
+    return g >> 15;
 }
 
 struct SeedIndex {
@@ -57,6 +69,7 @@ struct SeedIndex {
     std::vector<uint64_t> slots;
     std::vector<uint32_t> bloom;
     bool use_bloom = false;
+    int bloom_k = 1;  // bits per k-mer
     uint64_t n_entries = 0;
     double bloom_fill = 0.0;  // fraction of bitmap bits set
     double cand_prob = 0.0;   // expected candidates per genome position
@@ -114,13 +127,23 @@ inline void seed_enumerate(const Orient &o, int S, int max_mm, int tw, bool raw,
     }
 }
 
-// modelled cost of the seed filter per genome position (same unit for every S: ~ issue
-// slots of the scan kernel's fast path), used to pick S
+// modelled cost of the seed filter per genome position, in units of the scan kernel's fast
+// path (one bitmap lookup).  Fitted to B200 measurements on 3 Gbp x 400 orientations
+// (profiles/r01_seed_sweep.txt): a position that passes the bitmap costs ~10 fast paths in the
+// divergent table walk, growing with the pass rate (the warp waits for its busiest lane); a
+// candidate costs ~600 (atomic append + verify).
+constexpr int kSeedBloomK = 2;  // bitmap bits per k-mer (same word)
+
+inline double seed_pass_rate(double entries, int S, int k) {
+    const double fill = 1.0 - std::exp(-(double)k * entries / (double)kSeedBloomBits);
+    return std::min(1.0, std::pow(fill, k) + entries / std::pow(4.0, S));
+}
+
 inline double seed_cost(double entries, int S) {
-    const double fill = 1.0 - std::exp(-entries / (double)kSeedBloomBits);
     const double prob = entries / std::pow(4.0, S);
-    const double probe = fill <= 0.6 ? 4.0 * fill : 6.0;  // table probes per position
-    return 1.0 + probe + prob * 600.0;
+    const double pass = seed_pass_rate(entries, S, kSeedBloomK);
+    const double walk = pass <= 0.5 ? 10.0 * pass * (1.0 + 8.0 * pass) : 12.0;  // > 0.5: no bitmap, every position walks
+    return 1.0 + walk + prob * 600.0;
 }
 
 inline SeedIndex seed_build(const Panel &h, int variant) {
@@ -162,17 +185,20 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
     ix.slots.assign((size_t)1 << ix.table_bits, 0ull);
     ix.bloom.assign(kSeedBloomWords, 0u);
     const uint32_t tmask = (uint32_t)((1ull << ix.table_bits) - 1);
-    uint64_t bits_set = 0;
+    ix.bloom_k = kSeedBloomK;
+    if (const char *e = getenv("IPCR_SEED_BLOOM_K")) ix.bloom_k = std::max(1, std::min(atoi(e), 3));
     for (const auto &e : entries) {
         uint32_t hh = (uint32_t)(e.first * kSeedHashMul) >> (32 - ix.table_bits);
         while (ix.slots[hh]) hh = (hh + 1) & tmask;
         ix.slots[hh] = seed_slot(e.first, e.second, ix.col_off[e.second]);
-        const uint32_t b = seed_bloom_index(e.first);
-        if (!((ix.bloom[b >> 5] >> (b & 31)) & 1u)) bits_set++;
-        ix.bloom[b >> 5] |= 1u << (b & 31);
+        uint32_t m;
+        const uint32_t w = seed_bloom_word(e.first, ix.bloom_k, m);
+        ix.bloom[w] |= m;
     }
+    uint64_t bits_set = 0;
+    for (uint32_t w : ix.bloom) bits_set += (uint64_t)__builtin_popcount(w);
     ix.bloom_fill = (double)bits_set / (double)kSeedBloomBits;
-    ix.use_bloom = ix.bloom_fill <= 0.6;
+    ix.use_bloom = seed_pass_rate((double)ix.n_entries, ix.S, ix.bloom_k) <= 0.5;
     if (const char *e = getenv("IPCR_SEED_BLOOM")) ix.use_bloom = atoi(e) != 0;
     ix.cand_prob = (double)ix.n_entries / std::pow(4.0, ix.S);
     return ix;
@@ -195,8 +221,9 @@ inline void seed_eval(const Panel &h, const SeedIndex &ix, const uint8_t *seq, u
         }
         if (n_inv == 0) {
             if (ix.use_bloom) {
-                const uint32_t b = seed_bloom_index(kmer);
-                if (!((ix.bloom[b >> 5] >> (b & 31)) & 1u)) continue;
+                uint32_t m;
+                const uint32_t w = seed_bloom_word(kmer, ix.bloom_k, m);
+                if ((ix.bloom[w] & m) != m) continue;
             }
             for (uint32_t hh = (uint32_t)(kmer * kSeedHashMul) >> (32 - ix.table_bits); ix.slots[hh]; hh = (hh + 1) & tmask) {
                 const uint64_t slot = ix.slots[hh];

@@ -166,27 +166,21 @@ struct SeedScanArgs {
     uint64_t cand_cap;
 };
 
-__device__ __forceinline__ void seed_probe(const SeedScanArgs &a, uint32_t kmer, uint64_t p) {
-    uint32_t h = (kmer * kSeedHashMulDev) >> a.table_shift;
-    for (;;) {
-        const unsigned long long slot = __ldg(a.table + h);
-        if (slot == 0ull) break;
-        if ((uint32_t)slot == kmer) {
-            const uint64_t c = (slot >> 48) & 0xFFull;
-            if (p >= c) {
-                const unsigned long long i = atomicAdd(a.cand_count, 1ull);
-                if (i < a.cand_cap) a.cand[i] = (((slot >> 32) & 0xFFFFull) << kCandPosBits) | (p - c);
-            }
-        }
-        h = (h + 1u) & a.table_mask;
+__device__ __forceinline__ void seed_emit(const SeedScanArgs &a, unsigned long long slot, uint64_t p) {
+    const uint64_t c = (slot >> 48) & 0xFFull;
+    if (p >= c) {
+        const unsigned long long i = atomicAdd(a.cand_count, 1ull);
+        if (i < a.cand_cap) a.cand[i] = (((slot >> 32) & 0xFFFFull) << kCandPosBits) | (p - c);
     }
 }
 
-template <bool USE_BLOOM>
+// BLOOM: 0 = no bitmap (every position walks the table), k = 1..3 bits per k-mer, all in
+// the same word.  BATCH: hash-table probes a lane keeps in flight.
+template <int BLOOM, int BATCH>
 __global__ void __launch_bounds__(1024, 1)
 k_seed_scan(SeedScanArgs a) {
     extern __shared__ uint32_t sbloom[];
-    if (USE_BLOOM) {
+    if (BLOOM) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.bloom);
         uint4 *dst = reinterpret_cast<uint4 *>(sbloom);
         for (uint32_t i = threadIdx.x; i < kSeedBloomWordsDev / 4u; i += blockDim.x) dst[i] = __ldg(src + i);
@@ -212,13 +206,24 @@ k_seed_scan(SeedScanArgs a) {
         for (int blk = 0; blk < 4; blk++) {
             const uint32_t w0 = c[2 * blk], w1 = c[2 * blk + 1], w2 = c[2 * blk + 2];
             uint32_t hits = 0u;
-            if (USE_BLOOM) {
+            if (BLOOM) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const uint32_t kmer = (j < 16 ? __funnelshift_r(w0, w1, 2 * j) : __funnelshift_r(w1, w2, 2 * (j - 16))) &
                                           a.kmer_mask;
                     const uint32_t h = kmer * kSeedBloomMulDev;
-                    const uint32_t bit = __funnelshift_r(sbloom[__umulhi(h, kSeedBloomWordsDev)], 0u, h);
+                    uint32_t bit;
+                    if (BLOOM == 1) {
+                        bit = __funnelshift_r(sbloom[__umulhi(h, kSeedBloomWordsDev)], 0u, h);
+                    } else if (BLOOM == 2) {  // word | bit 1 | bit 2 from the top 26 bits of the hash
+                        const uint32_t g = __umulhi(h, kSeedBloomWordsDev << 10);
+                        const uint32_t w = sbloom[g >> 10];
+                        bit = __funnelshift_r(w, 0u, g >> 5) & __funnelshift_r(w, 0u, g);
+                    } else {  // word | bit 1 | bit 2 | bit 3 from the top 31 bits
+                        const uint32_t g = __umulhi(h, kSeedBloomWordsDev << 15);
+                        const uint32_t w = sbloom[g >> 15];
+                        bit = __funnelshift_r(w, 0u, g >> 10) & __funnelshift_r(w, 0u, g >> 5) & __funnelshift_r(w, 0u, g);
+                    }
                     hits = __funnelshift_r(hits, bit, 1);
                 }
             } else {
@@ -231,12 +236,48 @@ k_seed_scan(SeedScanArgs a) {
                 for (uint32_t k = 0; k < a.S; k++) d |= v >> k;
                 hits &= ~(uint32_t)d;
             }
-            while (hits) {
-                const int j = __ffs(hits) - 1;
-                hits &= hits - 1u;
-                const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
-                const uint32_t kmer = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
-                seed_probe(a, kmer, P0 + (uint64_t)(blk * 32 + j));
+            // table walk for the set bits
+            if (BATCH == 1) {
+                while (hits) {
+                    const int j = __ffs(hits) - 1;
+                    hits &= hits - 1u;
+                    const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
+                    const uint32_t kmer = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
+                    uint32_t h = (kmer * kSeedHashMulDev) >> a.table_shift;
+                    for (;;) {
+                        const unsigned long long slot = __ldg(a.table + h);
+                        if (slot == 0ull) break;
+                        if ((uint32_t)slot == kmer) seed_emit(a, slot, P0 + (uint64_t)(blk * 32 + j));
+                        h = (h + 1u) & a.table_mask;
+                    }
+                }
+            }
+            // BATCH independent probes in flight per lane: the first slot of each is fetched before
+            // any of them is looked at
+            while (BATCH > 1 && hits) {
+                uint32_t km[BATCH], hh[BATCH];
+                int jj[BATCH];
+                unsigned long long sl[BATCH];
+#pragma unroll
+                for (int u = 0; u < BATCH; u++) {
+                    jj[u] = hits ? __ffs(hits) - 1 : -1;
+                    hits &= hits - 1u;
+                    const int j = jj[u] & 31;
+                    const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
+                    km[u] = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
+                    hh[u] = (km[u] * kSeedHashMulDev) >> a.table_shift;
+                    sl[u] = jj[u] >= 0 ? __ldg(a.table + hh[u]) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < BATCH; u++) {
+                    unsigned long long slot = sl[u];
+                    uint32_t h = hh[u];
+                    while (slot != 0ull) {
+                        if ((uint32_t)slot == km[u]) seed_emit(a, slot, P0 + (uint64_t)(blk * 32 + jj[u]));
+                        h = (h + 1u) & a.table_mask;
+                        slot = __ldg(a.table + h);
+                    }
+                }
             }
         }
     }
