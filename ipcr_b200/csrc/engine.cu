@@ -110,7 +110,7 @@ struct DevTables {
     PlanTables plan[2];
     JitKernel jit[2];
     bool jit_tried[2] = {false, false};
-    DevBuf seed_table[2], seed_bloom[2], seed_coloff[2];  // seed-index filter, per plan variant
+    DevBuf seed_table[2], seed_bloom[2], seed_bitmap2[2], seed_coloff[2];  // seed-index filter, per plan variant
     bool seed_ready[2] = {false, false};
 };
 
@@ -862,11 +862,12 @@ static const SeedIndex &seed_get(ipcr_scratch *s, int variant) {
     if (!t->seed_ready[variant]) {
         upload(t->seed_table[variant], ix.slots.data(), ix.slots.size() * sizeof(uint64_t), s->stream);
         upload(t->seed_bloom[variant], ix.bloom.data(), ix.bloom.size() * sizeof(uint32_t), s->stream);
+        upload(t->seed_bitmap2[variant], ix.bitmap2.data(), ix.bitmap2.size() * sizeof(uint32_t), s->stream);
         upload(t->seed_coloff[variant], ix.col_off.data(), ix.col_off.size() * sizeof(uint16_t), s->stream);
         CU(cudaStreamSynchronize(s->stream));
         static std::mutex attr_mu;
         std::lock_guard<std::mutex> l2(attr_mu);
-        for (auto fn : {k_seed_scan<1, 1>, k_seed_scan<2, 1>, k_seed_scan<3, 1>, k_seed_scan<2, 2>})
+        for (auto fn : {k_seed_scan<1, 1>, k_seed_scan<2, 1>, k_seed_scan<2, 2>})
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSeedBloomWords * 4)));
         t->seed_ready[variant] = true;
     }
@@ -915,7 +916,11 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         a.n_chunks = n_chunks;
         a.S = (uint32_t)ix.S;
         a.kmer_mask = ix.kmer_mask;
+        a.bloom_mul = seed_bloom_mul(ix.S);
         a.bloom = t->seed_bloom[variant].as<uint32_t>();
+        a.bitmap2 = t->seed_bitmap2[variant].as<uint32_t>();
+        a.bitmap2_mul = ix.bitmap2_mul;
+        a.bitmap2_shift = ix.bitmap2_shift;
         a.table = t->seed_table[variant].as<unsigned long long>();
         a.table_shift = 32u - ix.table_bits;
         a.table_mask = (uint32_t)((1ull << ix.table_bits) - 1);
@@ -930,7 +935,6 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         const size_t smem = kSeedBloomWords * 4;
         if (!ix.use_bloom) k_seed_scan<0, 1><<<grid, 1024, 0, st>>>(a);
         else if (ix.bloom_k == 1) k_seed_scan<1, 1><<<grid, 1024, smem, st>>>(a);
-        else if (ix.bloom_k == 3) k_seed_scan<3, 1><<<grid, 1024, smem, st>>>(a);
         else if (batch >= 2) k_seed_scan<2, 2><<<grid, 1024, smem, st>>>(a);
         else k_seed_scan<2, 1><<<grid, 1024, smem, st>>>(a);
         check_launch("k_seed_scan");

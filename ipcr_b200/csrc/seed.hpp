@@ -10,7 +10,7 @@
 //   * every concrete k-mer a true site can show in that window (<= max_mm mismatches in the
 //     free columns, none in the protected ones, IUPAC columns expanded) is enumerated;
 //   * the k-mers go into an open-addressing hash table (8-byte slots: k-mer, orientation,
-//     seed offset) that stays L2-resident, fronted by a 200 KB one-hash Bloom bitmap that the
+//     seed offset) that stays L2-resident, fronted by a 224 KB blocked Bloom bitmap that the
 //     scan kernel keeps in SHARED memory: one LDS per genome position decides whether the
 //     table is consulted at all.
 // Completeness: a site with <= max_mm mismatches and a clean protected window shows one of the
@@ -29,7 +29,7 @@
 
 namespace ipcr {
 
-constexpr uint32_t kSeedBloomWords = 51200;  // 200 KB of shared memory
+constexpr uint32_t kSeedBloomWords = 57344;  // 224 KB of shared memory
 constexpr uint32_t kSeedBloomBits = kSeedBloomWords * 32u;
 constexpr uint32_t kSeedBloomMul = 0x85EBCA6Bu;
 constexpr uint32_t kSeedHashMul = 0x9E3779B1u;
@@ -44,22 +44,17 @@ inline uint64_t seed_slot(uint32_t kmer, uint32_t orient, uint32_t col_off) {
     return (1ull << 63) | ((uint64_t)col_off << 48) | ((uint64_t)orient << 32) | kmer;
 }
 
-// bitmap bits of a k-mer (k = 1: word from the high half of the multiplicative hash, bit from
-// its low bits; k = 2: word and both bits from the top 26 bits).  Returns word index, sets mask.
-inline uint32_t seed_bloom_word(uint32_t kmer, int k, uint32_t &mask) {
-    const uint32_t h = kmer * kSeedBloomMul;
-    if (k == 1) {
-        mask = 1u << (h & 31u);
-        return (uint32_t)(((uint64_t)h * kSeedBloomWords) >> 32);
-    }
-    if (k == 2) {
-        const uint32_t g = (uint32_t)(((uint64_t)h * ((uint64_t)kSeedBloomWords << 10)) >> 32);
-        mask = (1u << ((g >> 5) & 31u)) | (1u << (g & 31u));
-        return g >> 10;
-    }
-    const uint32_t g = (uint32_t)(((uint64_t)h * ((uint64_t)kSeedBloomWords << 15)) >> 32);
-    mask = (1u << ((g >> 10) & 31u)) | (1u << ((g >> 5) & 31u)) | (1u << (g & 31u));
-    return g >> 15;
+// bitmap bits of a k-mer: the word comes from the top of a multiplicative hash of the k-mer,
+// the first bit position from the k-mer's low five bits, the second (k = 2) from hash bits
+// 11..15 (a function of the k-mer's low 16 bits, so not determined by the first).
+// Returns the word index, sets mask.  Needs S >= 3.
+inline uint32_t seed_bloom_mul(int S) { return kSeedBloomMul << (32 - 2 * S); }
+
+inline uint32_t seed_bloom_word(uint32_t kmer, int S, int k, uint32_t &mask) {
+    const uint32_t hw = kmer * seed_bloom_mul(S);
+    mask = 1u << (kmer & 31u);
+    if (k >= 2) mask |= 1u << ((hw >> 11) & 31u);
+    return (uint32_t)(((uint64_t)hw * kSeedBloomWords) >> 32);
 }
 
 struct SeedIndex {
@@ -68,6 +63,9 @@ struct SeedIndex {
     uint32_t table_bits = 0;
     std::vector<uint64_t> slots;
     std::vector<uint32_t> bloom;
+    // second level, L2-resident: one bit per k-mer value (2S <= 28: exact) or per hashed k-mer
+    std::vector<uint32_t> bitmap2;
+    uint32_t bitmap2_mul = 1, bitmap2_shift = 0;  // bit index = (k-mer * mul) >> shift
     bool use_bloom = false;
     int bloom_k = 1;  // bits per k-mer
     uint64_t n_entries = 0;
@@ -128,10 +126,11 @@ inline void seed_enumerate(const Orient &o, int S, int max_mm, int tw, bool raw,
 }
 
 // modelled cost of the seed filter per genome position, in units of the scan kernel's fast
-// path (one bitmap lookup).  Fitted to B200 measurements on 3 Gbp x 400 orientations
-// (profiles/r01_seed_sweep.txt): a position that passes the bitmap costs ~10 fast paths in the
-// divergent table walk, growing with the pass rate (the warp waits for its busiest lane); a
-// candidate costs ~600 (atomic append + verify).
+// path (one shared-memory bitmap lookup).  Fitted to B200 measurements on 3 Gbp x 400
+// orientations (profiles/r01_seed_sweep.txt): positions passing the bitmap go through a
+// divergent second-level lookup whose cost grows faster than the pass rate (the warp waits
+// for its busiest lane): ~50 * pass^1.8; a candidate costs ~675 (table walk, atomic append,
+// verify).
 constexpr int kSeedBloomK = 2;  // bitmap bits per k-mer (same word)
 
 inline double seed_pass_rate(double entries, int S, int k) {
@@ -142,8 +141,8 @@ inline double seed_pass_rate(double entries, int S, int k) {
 inline double seed_cost(double entries, int S) {
     const double prob = entries / std::pow(4.0, S);
     const double pass = seed_pass_rate(entries, S, kSeedBloomK);
-    const double walk = pass <= 0.5 ? 10.0 * pass * (1.0 + 8.0 * pass) : 12.0;  // > 0.5: no bitmap, every position walks
-    return 1.0 + walk + prob * 600.0;
+    const double walk = pass <= 0.5 ? 50.0 * std::pow(pass, 1.8) : 15.0;  // > 0.5: no bitmap, every position walks
+    return 1.0 + walk + prob * 675.0;
 }
 
 inline SeedIndex seed_build(const Panel &h, int variant) {
@@ -186,19 +185,27 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
     ix.bloom.assign(kSeedBloomWords, 0u);
     const uint32_t tmask = (uint32_t)((1ull << ix.table_bits) - 1);
     ix.bloom_k = kSeedBloomK;
-    if (const char *e = getenv("IPCR_SEED_BLOOM_K")) ix.bloom_k = std::max(1, std::min(atoi(e), 3));
+    {
+        const int bits2 = std::max(10, std::min(2 * ix.S, 28));
+        if (2 * ix.S <= 28) { ix.bitmap2_mul = 1u; ix.bitmap2_shift = 0u; }
+        else { ix.bitmap2_mul = kSeedHashMul; ix.bitmap2_shift = 32u - (uint32_t)bits2; }
+        ix.bitmap2.assign((size_t)1 << (bits2 - 5), 0u);
+    }
+    if (const char *e = getenv("IPCR_SEED_BLOOM_K")) ix.bloom_k = std::max(1, std::min(atoi(e), 2));
     for (const auto &e : entries) {
         uint32_t hh = (uint32_t)(e.first * kSeedHashMul) >> (32 - ix.table_bits);
         while (ix.slots[hh]) hh = (hh + 1) & tmask;
         ix.slots[hh] = seed_slot(e.first, e.second, ix.col_off[e.second]);
         uint32_t m;
-        const uint32_t w = seed_bloom_word(e.first, ix.bloom_k, m);
+        const uint32_t w = seed_bloom_word(e.first, ix.S, ix.bloom_k, m);
         ix.bloom[w] |= m;
+        const uint32_t i2 = (uint32_t)(e.first * ix.bitmap2_mul) >> ix.bitmap2_shift;
+        ix.bitmap2[i2 >> 5] |= 1u << (i2 & 31u);
     }
     uint64_t bits_set = 0;
     for (uint32_t w : ix.bloom) bits_set += (uint64_t)__builtin_popcount(w);
     ix.bloom_fill = (double)bits_set / (double)kSeedBloomBits;
-    ix.use_bloom = seed_pass_rate((double)ix.n_entries, ix.S, ix.bloom_k) <= 0.5;
+    ix.use_bloom = ix.S >= 3 && seed_pass_rate((double)ix.n_entries, ix.S, ix.bloom_k) <= 0.5;
     if (const char *e = getenv("IPCR_SEED_BLOOM")) ix.use_bloom = atoi(e) != 0;
     ix.cand_prob = (double)ix.n_entries / std::pow(4.0, ix.S);
     return ix;
@@ -222,9 +229,11 @@ inline void seed_eval(const Panel &h, const SeedIndex &ix, const uint8_t *seq, u
         if (n_inv == 0) {
             if (ix.use_bloom) {
                 uint32_t m;
-                const uint32_t w = seed_bloom_word(kmer, ix.bloom_k, m);
+                const uint32_t w = seed_bloom_word(kmer, ix.S, ix.bloom_k, m);
                 if ((ix.bloom[w] & m) != m) continue;
             }
+            const uint32_t i2 = (uint32_t)(kmer * ix.bitmap2_mul) >> ix.bitmap2_shift;
+            if (!((ix.bitmap2[i2 >> 5] >> (i2 & 31u)) & 1u)) continue;
             for (uint32_t hh = (uint32_t)(kmer * kSeedHashMul) >> (32 - ix.table_bits); ix.slots[hh]; hh = (hh + 1) & tmask) {
                 const uint64_t slot = ix.slots[hh];
                 const uint64_t c = (slot >> 48) & 0xFF;

@@ -13,7 +13,7 @@
 namespace ipcr {
 
 constexpr uint32_t kSeedChunk = 4096;  // positions one warp takes at a time (128 per lane)
-constexpr uint32_t kSeedBloomWordsDev = 51200;
+constexpr uint32_t kSeedBloomWordsDev = 57344;  // 224 KB
 constexpr uint32_t kSeedBloomMulDev = 0x85EBCA6Bu;
 constexpr uint32_t kSeedHashMulDev = 0x9E3779B1u;
 
@@ -144,7 +144,7 @@ k_seed_dirty_expand(SeedExpandArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// K2s.  block = 32 warps, one CTA per SM (200 KB Bloom bitmap in shared memory).  A warp takes
+// K2s.  block = 32 warps, one CTA per SM (224 KB Bloom bitmap in shared memory).  A warp takes
 // 4096 consecutive positions; lane l owns the 128 k-mer starts at +128*l: its 8 code words
 // (+1 look-ahead) and 4 bitmap words (+1) sit in registers, every shift is an immediate.
 // Per position: funnel-shift + mask -> k-mer; two IMADs -> bitmap index; ONE LDS; the answer
@@ -157,7 +157,10 @@ struct SeedScanArgs {
     uint64_t n_chunks;
     uint32_t S;
     uint32_t kmer_mask;
+    uint32_t bloom_mul;  // kSeedBloomMul << (32 - 2S)
     const uint32_t *bloom;
+    const uint32_t *bitmap2;  // second level (global, L2-resident)
+    uint32_t bitmap2_mul, bitmap2_shift;
     const unsigned long long *table;
     uint32_t table_shift;  // 32 - table_bits
     uint32_t table_mask;
@@ -174,7 +177,7 @@ __device__ __forceinline__ void seed_emit(const SeedScanArgs &a, unsigned long l
     }
 }
 
-// BLOOM: 0 = no bitmap (every position walks the table), k = 1..3 bits per k-mer, all in
+// BLOOM: 0 = no bitmap (every position walks the table), k = 1..2 bits per k-mer, both in
 // the same word.  BATCH: hash-table probes a lane keeps in flight.
 template <int BLOOM, int BATCH>
 __global__ void __launch_bounds__(1024, 1)
@@ -207,23 +210,17 @@ k_seed_scan(SeedScanArgs a) {
             const uint32_t w0 = c[2 * blk], w1 = c[2 * blk + 1], w2 = c[2 * blk + 2];
             uint32_t hits = 0u;
             if (BLOOM) {
+                const char *sb = reinterpret_cast<const char *>(sbloom);
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    const uint32_t kmer = (j < 16 ? __funnelshift_r(w0, w1, 2 * j) : __funnelshift_r(w1, w2, 2 * (j - 16))) &
-                                          a.kmer_mask;
-                    const uint32_t h = kmer * kSeedBloomMulDev;
-                    uint32_t bit;
-                    if (BLOOM == 1) {
-                        bit = __funnelshift_r(sbloom[__umulhi(h, kSeedBloomWordsDev)], 0u, h);
-                    } else if (BLOOM == 2) {  // word | bit 1 | bit 2 from the top 26 bits of the hash
-                        const uint32_t g = __umulhi(h, kSeedBloomWordsDev << 10);
-                        const uint32_t w = sbloom[g >> 10];
-                        bit = __funnelshift_r(w, 0u, g >> 5) & __funnelshift_r(w, 0u, g);
-                    } else {  // word | bit 1 | bit 2 | bit 3 from the top 31 bits
-                        const uint32_t g = __umulhi(h, kSeedBloomWordsDev << 15);
-                        const uint32_t w = sbloom[g >> 15];
-                        bit = __funnelshift_r(w, 0u, g >> 10) & __funnelshift_r(w, 0u, g >> 5) & __funnelshift_r(w, 0u, g);
-                    }
+                    // x: 32-bit window whose low 2S bits are the k-mer.  The multiplier is pre-shifted
+                    // by 32-2S, so the product ignores the bits above the k-mer: no mask needed.
+                    const uint32_t x = j < 16 ? __funnelshift_r(w0, w1, 2 * j) : __funnelshift_r(w1, w2, 2 * (j - 16));
+                    const uint32_t hw = x * a.bloom_mul;
+                    const uint32_t off = __umulhi(hw, kSeedBloomWordsDev) * 4u;
+                    const uint32_t w = *reinterpret_cast<const uint32_t *>(sb + off);
+                    uint32_t bit = __funnelshift_r(w, 0u, x);  // bit (k-mer & 31)
+                    if (BLOOM == 2) bit &= __funnelshift_r(w, 0u, hw >> 11);  // second bit: hash bits 11..15
                     hits = __funnelshift_r(hits, bit, 1);
                 }
             } else {
@@ -243,6 +240,8 @@ k_seed_scan(SeedScanArgs a) {
                     hits &= hits - 1u;
                     const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
                     const uint32_t kmer = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
+                    const uint32_t i2 = (kmer * a.bitmap2_mul) >> a.bitmap2_shift;
+                    if (!(__funnelshift_r(__ldg(a.bitmap2 + (i2 >> 5)), 0u, i2) & 1u)) continue;
                     uint32_t h = (kmer * kSeedHashMulDev) >> a.table_shift;
                     for (;;) {
                         const unsigned long long slot = __ldg(a.table + h);

@@ -14,6 +14,5 @@ for l in sys.stdin:
 EXTRA="--pairs 1" run IPCR_SEED_BLOOM_K=1
 EXTRA="--pairs 1" run IPCR_SEED_BLOOM_K=2
 EXTRA=""
-for S in 13 14 15 16; do for K in 1 2 3; do run IPCR_SEED_LEN=$S IPCR_SEED_BLOOM_K=$K; done; done
-run IPCR_SEED_LEN=14 IPCR_SEED_BLOOM_K=2 IPCR_SEED_BATCH=2
+for S in 14 15 16; do for K in 1 2; do run IPCR_SEED_LEN=$S IPCR_SEED_BLOOM_K=$K; done; done
 cat $out
