@@ -58,6 +58,7 @@ def parse_args():
                     help="candidate filter: auto = the library's own choice (seed index when selective)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bitparallel", action="store_true", help="skip the bit-parallel comparison pass")
     return ap.parse_args()
 
 
@@ -72,7 +73,7 @@ def workload_config(a, n_gpus, user_pairs, all_pairs, n_orient):
         "unique_orientations": n_orient,
         "max_mm": a.mm,
         "sharding": "none" if n_gpus == 1 else f"{n_gpus} shards of the concatenated genome, 64-base halo, sites gathered to rank 0",
-        "l2": "inputs (1 B/bp ASCII + 0.5 B/bp packed) are >> the 126 MB L2, no flush needed",
+        "l2": "inputs (1 B/bp ASCII + 0.375-0.5 B/bp packed, per GPU) are >> the 126 MB L2, no flush needed",
     }
 
 
@@ -207,6 +208,11 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# dram bytes (read + write) of one launch from the committed `ncu --set full` capture of the
+# bench command (profiles/README.md says which file); None until captured
+NCU_TRAFFIC = {"k_seed_scan": None, "ipcr_scan_jit": None}
 
 
 def measured_peak():
@@ -371,7 +377,7 @@ def run_ours(a):
     roofline = {
         "bound": "hbm", "kernel": "ipcr_scan_jit (one launch per group of 4 orientations)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": NCU_TRAFFIC.get("ipcr_scan_jit"), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": my_bp * 0.5, "avg_launch_ms": dur_ms, "launches_per_step": n_groups,
         "note": "0.5 B/bp x bases one launch streams; a 400-orientation panel needs 100 such passes, so the "
                 "whole scan is LOP3-issue bound, each pass is HBM-streaming (see DESIGN.md)",
@@ -379,13 +385,23 @@ def run_ours(a):
     if path == 2:  # seed index: ONE pass over 2-bit codes + hard-mismatch bitmap serves the whole panel
         dur_ms = filt_ms / a.steps
         achieved = (my_bp * 0.375 / 1e9) / (dur_ms / 1e3) if dur_ms > 0 else 0.0
+        sm_hz = 1.965e9
+        lds_peak = 148 * 32 * sm_hz / 3.53  # random 32-lane access: E[max bank load] = 3.53 cycles per warp lookup
+        pack_ms = last["pack_ms"]
         roofline = {
             "bound": "hbm", "kernel": "k_seed_scan (+ k_seed_dirty): one launch for all orientations",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": NCU_TRAFFIC.get("k_seed_scan"), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": my_bp * 0.375, "avg_launch_ms": dur_ms, "launches_per_step": 1,
-            "note": "0.25 B/bp codes + 0.125 B/bp bitmap; the kernel is bound by one random shared-memory "
-                    "lookup per position, not by HBM (see DESIGN.md)",
+            "note": "0.25 B/bp codes + 0.125 B/bp bitmap, read once for the WHOLE panel (the bit-parallel filter "
+                    "re-reads 0.5 B/bp per group of 4 orientations).  Not HBM-bound by design: the binding "
+                    "resource is one random shared-memory lookup per genome position (see DESIGN.md)",
+            "shared_memory_lookups": {"achieved_per_s": my_bp / (dur_ms / 1e3) if dur_ms > 0 else None,
+                                      "peak_per_s_random_banks": lds_peak,
+                                      "frac": (my_bp / (dur_ms / 1e3)) / lds_peak if dur_ms > 0 else None},
+            "pack_kernel": {"kernel": "k_pack2", "bound": "hbm", "bytes": my_bp * 1.375, "ms": pack_ms,
+                            "achieved": my_bp * 1.375 / 1e9 / (pack_ms / 1e3) if pack_ms > 0 else None,
+                            "frac": (my_bp * 1.375 / 1e9 / (pack_ms / 1e3)) / peak if pack_ms > 0 and peak else None},
         }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
@@ -423,6 +439,27 @@ def run_ours(a):
         del host
     else:
         line["e2e"] = None
+
+    # ---- the bit-parallel filter on the same input, for the per-pass HBM roofline (N = 1) ----
+    if world == 1 and path == 2 and not a.no_bitparallel:
+        cp.set_jit(2)
+        for _ in range(2):
+            step_single()
+        f_ms, tot_ms, k = 0.0, 0.0, 2
+        for _ in range(k):
+            _n, ms, tmb = step_single()
+            f_ms += tmb["filter_ms"]
+            tot_ms += ms
+        per_launch = f_ms / k / max(1, n_groups)
+        ach = (my_bp * 0.5 / 1e9) / (per_launch / 1e3) if per_launch > 0 else 0.0
+        line["bitparallel"] = {
+            "kernel": "ipcr_scan_jit (NVRTC, one launch per group of 4 orientations)", "ms_per_step": tot_ms / k,
+            "filter_ms": f_ms / k, "launches_per_step": n_groups, "avg_launch_ms": per_launch,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak if peak else None, "algorithmic_bytes_per_launch": my_bp * 0.5},
+            "note": "same products; kept for panels whose seed index is not selective (e.g. mm 3 x 400 orientations)",
+        }
+        cp.set_jit({"auto": 1, "seed": 3, "bitparallel": 2, "generic": 0}[a.filter])
 
     if world == 1 and not a.no_cpu_baseline:
         try:

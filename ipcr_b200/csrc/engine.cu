@@ -320,12 +320,13 @@ static const SeedIndex &seed_host(ipcr_panel *p, int variant) {
     return p->seed[variant];
 }
 
-// jit_mode: 0 table-driven only, 1 automatic, 2 force the specialised kernel, 3 force the seed index
+// jit_mode: 0 table-driven only, 1 automatic, 2 force the specialised kernel, 3 force the seed index.
+// Automatic = the seed index: measured on B200 it beats the bit-parallel filter from 4 to 400
+// orientations and at mm 0..3 (profiles/), because its cost does not grow with the panel.  The
+// bit-parallel filter takes over per call when the input is too dirty (kSeedDirtyMax).
 static bool prefer_seed(ipcr_panel *p) {
     const int mode = p->host.jit_mode;
-    if (mode == 3) return true;
-    if (mode != 1 || p->host.orients.empty()) return false;
-    return seed_host(p, 0).use_bloom;  // a saturated bitmap means the index has lost its selectivity
+    return (mode == 3 || mode == 1) && !p->host.orients.empty();
 }
 
 static void launch_pack_planes(ipcr_scratch *s, GenomeData &g) {
@@ -935,7 +936,7 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         const size_t smem = kSeedBloomWords * 4;
         if (!ix.use_bloom) k_seed_scan<0, 1><<<grid, 1024, 0, st>>>(a);
         else if (ix.bloom_k == 1) k_seed_scan<1, 1><<<grid, 1024, smem, st>>>(a);
-        else if (batch >= 2) k_seed_scan<2, 2><<<grid, 1024, smem, st>>>(a);
+        else if (batch >= 2) k_seed_scan<2, 2><<<grid, 1024, smem, st>>>(a);  // measured: no gain over 1
         else k_seed_scan<2, 1><<<grid, 1024, smem, st>>>(a);
         check_launch("k_seed_scan");
         s->launches++;

@@ -177,8 +177,18 @@ __device__ __forceinline__ void seed_emit(const SeedScanArgs &a, unsigned long l
     }
 }
 
+__device__ __forceinline__ void seed_walk(const SeedScanArgs &a, uint32_t kmer, uint64_t p) {
+    uint32_t h = (kmer * kSeedHashMulDev) >> a.table_shift;
+    for (;;) {
+        const unsigned long long slot = __ldg(a.table + h);
+        if (slot == 0ull) break;
+        if ((uint32_t)slot == kmer) seed_emit(a, slot, p);
+        h = (h + 1u) & a.table_mask;
+    }
+}
+
 // BLOOM: 0 = no bitmap (every position walks the table), k = 1..2 bits per k-mer, both in
-// the same word.  BATCH: hash-table probes a lane keeps in flight.
+// the same word.  BATCH: second-level lookups a lane keeps in flight.
 template <int BLOOM, int BATCH>
 __global__ void __launch_bounds__(1024, 1)
 k_seed_scan(SeedScanArgs a) {
@@ -233,30 +243,12 @@ k_seed_scan(SeedScanArgs a) {
                 for (uint32_t k = 0; k < a.S; k++) d |= v >> k;
                 hits &= ~(uint32_t)d;
             }
-            // table walk for the set bits
-            if (BATCH == 1) {
-                while (hits) {
-                    const int j = __ffs(hits) - 1;
-                    hits &= hits - 1u;
-                    const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
-                    const uint32_t kmer = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
-                    const uint32_t i2 = (kmer * a.bitmap2_mul) >> a.bitmap2_shift;
-                    if (!(__funnelshift_r(__ldg(a.bitmap2 + (i2 >> 5)), 0u, i2) & 1u)) continue;
-                    uint32_t h = (kmer * kSeedHashMulDev) >> a.table_shift;
-                    for (;;) {
-                        const unsigned long long slot = __ldg(a.table + h);
-                        if (slot == 0ull) break;
-                        if ((uint32_t)slot == kmer) seed_emit(a, slot, P0 + (uint64_t)(blk * 32 + j));
-                        h = (h + 1u) & a.table_mask;
-                    }
-                }
-            }
-            // BATCH independent probes in flight per lane: the first slot of each is fetched before
-            // any of them is looked at
-            while (BATCH > 1 && hits) {
-                uint32_t km[BATCH], hh[BATCH];
+            // second level for the set bits: one bit per (hashed) k-mer in an L2-resident bitmap;
+            // only its hits walk the hash table.  BATCH lookups are in flight per lane before the
+            // first answer is looked at, so the L2 latency is paid once per batch.
+            while (hits) {
+                uint32_t km[BATCH], i2[BATCH], wv[BATCH];
                 int jj[BATCH];
-                unsigned long long sl[BATCH];
 #pragma unroll
                 for (int u = 0; u < BATCH; u++) {
                     jj[u] = hits ? __ffs(hits) - 1 : -1;
@@ -264,19 +256,12 @@ k_seed_scan(SeedScanArgs a) {
                     const int j = jj[u] & 31;
                     const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
                     km[u] = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
-                    hh[u] = (km[u] * kSeedHashMulDev) >> a.table_shift;
-                    sl[u] = jj[u] >= 0 ? __ldg(a.table + hh[u]) : 0ull;
+                    i2[u] = (km[u] * a.bitmap2_mul) >> a.bitmap2_shift;
+                    wv[u] = jj[u] >= 0 ? __ldg(a.bitmap2 + (i2[u] >> 5)) : 0u;
                 }
 #pragma unroll
-                for (int u = 0; u < BATCH; u++) {
-                    unsigned long long slot = sl[u];
-                    uint32_t h = hh[u];
-                    while (slot != 0ull) {
-                        if ((uint32_t)slot == km[u]) seed_emit(a, slot, P0 + (uint64_t)(blk * 32 + jj[u]));
-                        h = (h + 1u) & a.table_mask;
-                        slot = __ldg(a.table + h);
-                    }
-                }
+                for (int u = 0; u < BATCH; u++)
+                    if (__funnelshift_r(wv[u], 0u, i2[u]) & 1u) seed_walk(a, km[u], P0 + (uint64_t)(blk * 32 + jj[u]));
             }
         }
     }
