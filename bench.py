@@ -14,9 +14,12 @@ One step = one pass of the hot path (ForEachCompiledProduct over every record):
           to the host; device time from CUDA events on the scratch's own stream.
   e2e   : the same through the reference-facing call with HOST buffers (pinned), H2D and
           D2H inside the timed region, wall clock.
-N > 1 (strong scaling): the concatenated genome is cut into N shards with a primer-length
-halo, every rank runs stage 1 on its shard, sites are gathered to rank 0 (NCCL) and paired
-once; time = max over ranks of the device time.
+N > 1, --scaling weak (default): the path partitions into independent records, so every rank
+scans its OWN 3 Gbp genome (same layout, different bases) with no data-path collective;
+value = bases of all ranks / max-over-ranks device time.
+N > 1, --scaling strong: ONE 3 Gbp genome is cut into N shards with a primer-length halo,
+every rank runs stage 1 on its shard, sites are gathered (one NCCL all-gather) and paired once
+on rank 0; time = max over ranks of the device time.
 --impl reference times the CPU restatement of the reference's seeded Aho-Corasick engine
 (oracle/, Go toolchain absent) on all host cores over a bounded sample of the same workload.
 """
@@ -56,6 +59,9 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--filter", default="auto", choices=["auto", "seed", "bitparallel", "generic"],
                     help="candidate filter: auto = the library's own choice (seed index when selective)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one whole genome per GPU (independent records, no collective); "
+                         "strong = one genome sharded over the GPUs, sites gathered, paired once")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bitparallel", action="store_true", help="skip the bit-parallel comparison pass")
@@ -63,16 +69,24 @@ def parse_args():
 
 
 def workload_config(a, n_gpus, user_pairs, all_pairs, n_orient):
+    if n_gpus == 1:
+        sharding = "none"
+    elif a.scaling == "weak":
+        sharding = (f"{n_gpus} genomes of {a.genome_mbp:g} Mbp, one per GPU (independent records, "
+                    "no data-path collective)")
+    else:
+        sharding = f"{n_gpus} shards of ONE genome, 64-base halo, sites gathered (one all-gather), paired on rank 0"
     return {
         "workload": f"C5 multiplex: {a.genome_mbp:g} Mbp synthetic genome ({a.contigs} contigs), "
                     f"{len(user_pairs)}-pair panel (+self => {len(all_pairs)} pairs, {n_orient} unique orientations), "
                     f"--mismatches {a.mm} --terminal-window {a.tw} --max-length {a.max_len} --hit-cap {a.hit_cap}",
         "genome_bp": int(a.genome_mbp * 1e6),
+        "genome_bp_all_gpus": int(a.genome_mbp * 1e6) * (n_gpus if a.scaling == "weak" else 1),
         "pairs": len(user_pairs),
         "pairs_with_self": len(all_pairs),
         "unique_orientations": n_orient,
         "max_mm": a.mm,
-        "sharding": "none" if n_gpus == 1 else f"{n_gpus} shards of the concatenated genome, 64-base halo, sites gathered to rank 0",
+        "sharding": sharding,
         "l2": "inputs (1 B/bp ASCII + 0.375-0.5 B/bp packed, per GPU) are >> the 126 MB L2, no flush needed",
     }
 
@@ -150,7 +164,7 @@ def run_reference(a):
         "impl": "reference",
         "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "scaling": a.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(a, a.gpus, user_pairs, all_pairs, None),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,7 +226,8 @@ class ClockSampler:
 
 # dram bytes (read + write) of one launch from the committed `ncu --set full` capture of the
 # bench command (profiles/README.md says which file); None until captured
-NCU_TRAFFIC = {"k_seed_scan": None, "ipcr_scan_jit": None}
+NCU_TRAFFIC = {"k_seed_scan": 1.2497e9,    # profiles/r01_ncu_full_k_seed_scan.csv (3 Gbp, 400 orientations)
+               "ipcr_scan_jit": 1.635e9}   # profiles/r01_ncu_full_scan_jit_and_pack_raw.csv (3 Gbp, one group)
 
 
 def measured_peak():
@@ -266,10 +281,12 @@ def run_ours(a):
     for ln in lens:
         offs.append(offs[-1] + ln)
     planted = synth.plan_amplicons(user_pairs, lens, a.mm, a.tw, seed=SEED + 1)
-    # this rank's slice [lo, hi) of the concatenated genome (+ halo)
-    lo, hi, piece_end = sharding.rank_slice(total, world, rank)
+    weak = world > 1 and a.scaling == "weak"
+    shards, shard_rank = (1, 0) if weak else (world, rank)
+    # this rank's slice [lo, hi) of the concatenated genome (+ halo); weak: its own whole genome
+    lo, hi, piece_end = sharding.rank_slice(total, shards, shard_rank)
     buf = torch.empty(piece_end - lo, dtype=torch.uint8, device=dev)
-    D.synth_fill(sc, buf, lo, SEED)
+    D.synth_fill(sc, buf, lo, SEED + (7919 * rank if weak else 0))
     for pl in planted:  # write the (clipped) planted primers that fall into this slice
         base = offs[pl.contig] + pl.start
         for off, data in ((0, pl.left), (pl.length - len(pl.right), pl.right)):
@@ -281,7 +298,7 @@ def run_ours(a):
     torch.cuda.synchronize()
 
     segments = [(buf[s0 - lo:s1 - lo], c, rec_off, own)
-                for (s0, s1, c, rec_off, own) in sharding.shard_segments(lens, world, rank)]
+                for (s0, s1, c, rec_off, own) in sharding.shard_segments(lens, shards, shard_rank)]
     n_recs = len(lens)
 
     def step_single():
@@ -317,18 +334,17 @@ def run_ours(a):
         n = 0
         if rank == 0:
             records = [(lens[i], records[i][1]) for i in range(n_recs)]
-            prods = D.pair_sites(cp, sc, allsites, records)
+            _out, n = D.pair_sites(cp, sc, allsites, records, raw=True)
             tp = sc.timing()
             dev_ms += tp["pair_ms"]
             launches += tp["kernel_launches"]
-            n = len(prods)
         t = dict(t)
         t["kernel_launches"] = launches
         t["gather_ms"] = gather_ev[0].elapsed_time(gather_ev[1])
         t["find_total_ms"] = t["total_ms"]
         return n, dev_ms, t
 
-    step = step_single if world == 1 else step_multi
+    step = step_single if world == 1 or weak else step_multi
 
     for _ in range(max(3, a.warmup)):
         n_prod, _ms, tm = step()
@@ -356,16 +372,51 @@ def run_ours(a):
         t = torch.tensor([ms_per_step, wall_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_per_step, wall_ms = float(t[0]), float(t[1])
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        lt = torch.tensor([launches, n_prod if weak else 0], dtype=torch.int64, device=dev)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
+        launches = int(lt[0].item())
+        if weak:
+            n_prod = int(lt[1].item())
+    # ---- end to end through the reference-facing call with host buffers: every rank feeds its own
+    # genome from pinned host memory (N = 1, or weak scaling); wall clock, max over ranks ----
+    e2e, e2e_stage = None, None
+    n_units = world if weak else 1
+    if (world == 1 or weak) and not a.no_e2e:
+        host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        host.copy_(buf)
+        torch.cuda.synchronize()
+        recs = [host[offs[c]:offs[c + 1]] for c in range(n_recs)]
+        D.scan_batch(cp, sc, recs)  # warm (buffer growth)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(max(1, a.e2e_steps)):
+            prods = D.scan_batch(cp, sc, recs)
+            d2h = len(prods) * 64
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, a.e2e_steps)
+        te = sc.timing()
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t[0])
+            t = torch.tensor([d2h], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            d2h = int(t[0])
+        e2e_stage = {k: te[k] for k in ("h2d_ms", "pack_ms", "filter_ms", "verify_ms", "pair_ms", "total_ms")}
+        g = n_units * total / 1e9
+        e2e = {"value": g / (e2e_ms / 1e3) * len(user_pairs), "unit": UNIT, "ms_per_step": e2e_ms,
+               "gbp_per_s": g / (e2e_ms / 1e3), "h2d_bytes_per_step": n_units * total, "d2h_bytes_per_step": d2h,
+               "api": "ipcr_gpu_scan_batch(host records) -> products (C ABI; pinned host buffers)"}
+        del host, recs
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     n_orient = cp.num_orientations
-    gbp = total / 1e9
+    gbp = n_units * total / 1e9
     gbp_s = gbp / (ms_per_step / 1e3)
     value = gbp_s * len(user_pairs)
     peak, peak_src = measured_peak()
@@ -377,7 +428,7 @@ def run_ours(a):
     roofline = {
         "bound": "hbm", "kernel": "ipcr_scan_jit (one launch per group of 4 orientations)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-        "traffic": NCU_TRAFFIC.get("ipcr_scan_jit"), "peak_source": peak_src,
+        "traffic": NCU_TRAFFIC.get("ipcr_scan_jit") if my_bp == 3_000_000_000 else None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": my_bp * 0.5, "avg_launch_ms": dur_ms, "launches_per_step": n_groups,
         "note": "0.5 B/bp x bases one launch streams; a 400-orientation panel needs 100 such passes, so the "
                 "whole scan is LOP3-issue bound, each pass is HBM-streaming (see DESIGN.md)",
@@ -389,9 +440,9 @@ def run_ours(a):
         lds_peak = 148 * 32 * sm_hz / 3.53  # random 32-lane access: E[max bank load] = 3.53 cycles per warp lookup
         pack_ms = last["pack_ms"]
         roofline = {
-            "bound": "hbm", "kernel": "k_seed_scan (+ k_seed_dirty): one launch for all orientations",
+            "bound": "hbm", "kernel": "k_seed_scan: one launch for all orientations",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-            "traffic": NCU_TRAFFIC.get("k_seed_scan"), "peak_source": peak_src,
+            "traffic": NCU_TRAFFIC.get("k_seed_scan") if my_bp == 3_000_000_000 and a.mm == 2 and a.pairs == 100 else None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": my_bp * 0.375, "avg_launch_ms": dur_ms, "launches_per_step": 1,
             "note": "0.25 B/bp codes + 0.125 B/bp bitmap, read once for the WHOLE panel (the bit-parallel filter "
                     "re-reads 0.5 B/bp per group of 4 orientations).  Not HBM-bound by design: the binding "
@@ -405,40 +456,22 @@ def run_ours(a):
         }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": workload_config(a, world, user_pairs, all_pairs, n_orient),
-        "gbp_per_s": gbp_s, "wall_ms_per_step": wall_ms, "products": n_prod, "planted_amplicons": len(planted),
+        "gbp_per_s": gbp_s, "wall_ms_per_step": wall_ms, "products": n_prod, "planted_amplicons": len(planted) * n_units,
         "stage_ms": {k: last[k] for k in ("pack_ms", "filter_ms", "verify_ms", "pair_ms", "d2h_ms")} if last else None,
         "candidates": last["candidates"] if last else None, "sites": last["sites"] if last else None,
         "rank0_ms": ({k: last.get(k) for k in ("find_total_ms", "gather_ms")} if last and world > 1 else None),
         "filter_path": {0: "table-driven bit-parallel", 1: "NVRTC bit-parallel", 2: "seed index"}.get(path),
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
-    if n_prod < len(planted):
-        line["warning"] = f"only {n_prod} products for {len(planted)} planted amplicons"
+    if n_prod < len(planted) * n_units:
+        line["warning"] = f"only {n_prod} products for {len(planted) * n_units} planted amplicons"
 
-    # ---- end to end through the reference-facing call with host buffers (N = 1 only) ----
-    if world == 1 and not a.no_e2e:
-        host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
-        host.copy_(buf)
-        torch.cuda.synchronize()
-        recs = [host[offs[c]:offs[c + 1]] for c in range(n_recs)]
-        D.scan_batch(cp, sc, recs)  # warm (buffer growth)
-        t0 = time.perf_counter()
-        d2h = 0
-        for _ in range(max(1, a.e2e_steps)):
-            prods = D.scan_batch(cp, sc, recs)
-            d2h = len(prods) * 64
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, a.e2e_steps)
-        te = sc.timing()
-        line["e2e_stage_ms"] = {k: te[k] for k in ("h2d_ms", "pack_ms", "filter_ms", "verify_ms", "pair_ms", "total_ms")}
-        line["e2e"] = {"value": gbp / (e2e_ms / 1e3) * len(user_pairs), "unit": UNIT, "ms_per_step": e2e_ms,
-                       "gbp_per_s": gbp / (e2e_ms / 1e3), "h2d_bytes_per_step": total, "d2h_bytes_per_step": d2h,
-                       "api": "ipcr_gpu_scan_batch(host records) -> products (C ABI; pinned host buffers)"}
-        del host
-    else:
-        line["e2e"] = None
+    line["e2e"] = e2e
+    if e2e_stage is not None:
+        line["e2e_stage_ms"] = e2e_stage
 
     # ---- the bit-parallel filter on the same input, for the per-pass HBM roofline (N = 1) ----
     if world == 1 and path == 2 and not a.no_bitparallel:

@@ -896,21 +896,6 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         s->dirty.ensure(dirty_cap * sizeof(unsigned long long));
         CU(cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), st));
         CU(cudaEventRecord(s->ev[3], st));
-        if (h.cfg.max_mm > 0) {
-            SeedDirtyArgs d{};
-            d.inval = g.inval.as<uint32_t>();
-            d.n_groups = g.n_groups;
-            d.total_len = g.lay.total_len;
-            d.S = (uint32_t)ix.S;
-            d.max_mm = (uint32_t)h.cfg.max_mm;
-            d.dirty = s->dirty.as<unsigned long long>();
-            d.dirty_count = ctr + 2;
-            d.dirty_cap = dirty_cap;
-            const unsigned grid = (unsigned)std::min<uint64_t>((g.n_groups + 255) / 256, (uint64_t)s->sm_count * 16);
-            k_seed_dirty<<<grid, 256, 0, st>>>(d);
-            check_launch("k_seed_dirty");
-            s->launches++;
-        }
         SeedScanArgs a{};
         a.codes = g.codes.as<uint32_t>();
         a.inval = g.inval.as<uint32_t>();
@@ -928,6 +913,11 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         a.cand = s->cand.as<unsigned long long>();
         a.cand_count = ctr;
         a.cand_cap = cap;
+        a.total_len = g.lay.total_len;
+        a.max_mm = (uint32_t)std::max(0, h.cfg.max_mm);
+        a.dirty = s->dirty.as<unsigned long long>();
+        a.dirty_count = ctr + 2;
+        a.dirty_cap = dirty_cap;
         const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + 31) / 32, (uint64_t)s->sm_count));
         static const int batch = [] {
             const char *e = getenv("IPCR_SEED_BATCH");

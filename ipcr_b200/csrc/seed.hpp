@@ -15,7 +15,7 @@
 //     table is consulted at all.
 // Completeness: a site with <= max_mm mismatches and a clean protected window shows one of the
 // enumerated k-mers in its seed window unless that window holds a non-ACGT byte; those "dirty"
-// windows are verified directly (kernels: k_seed_dirty), like the reference's halo pass
+// windows are verified directly (listed by k_seed_scan, expanded by k_seed_dirty_expand), like the reference's halo pass
 // (halo.go:47-108).  Exactness still lives in the verify kernel.
 #pragma once
 
@@ -211,8 +211,7 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
     return ix;
 }
 
-// CPU evaluation of the index on one sequence (test tap; mirrors k_pack2 + k_seed_dirty +
-// k_seed_scan): every (orientation << 44 | start) the device filter would hand to verify
+// CPU evaluation of the index on one sequence (test tap; mirrors k_pack2 + k_seed_scan): every (orientation << 44 | start) the device filter would hand to verify
 inline void seed_eval(const Panel &h, const SeedIndex &ix, const uint8_t *seq, uint64_t len,
                       std::vector<uint64_t> &out) {
     out.clear();

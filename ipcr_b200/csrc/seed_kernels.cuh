@@ -1,8 +1,8 @@
 // seed_kernels.cuh -- kernels of the seed-index filter (host side: seed.hpp).
 //   K1s k_pack2        ASCII -> 2-bit codes (16 bases / word) + hard-mismatch bitmap (32 / word)
-//   K2d k_seed_dirty   seed windows holding 1..max_mm non-ACGT bytes (the halo of halo.go:47-108)
-//   K2s k_seed_scan    one k-mer per genome position: Bloom bitmap in shared memory, then the
-//                      L2-resident hash table; hits become (orientation, start) candidates
+//   K2s k_seed_scan    one k-mer per genome position: Bloom bitmap in shared memory, then an
+//                      L2-resident bitmap and hash table; hits become (orientation, start)
+//                      candidates; seed windows holding 1..max_mm non-ACGT bytes are listed
 //   K2e k_seed_dirty_expand  dirty windows x orientations -> candidates
 // All of it is integer/byte work; exactness is in k_verify (kernels.cuh).
 #pragma once
@@ -88,38 +88,6 @@ k_pack2(Pack2Args a) {
     }
 }
 
-// ---------------------------------------------------------------------------
-// K2d.  One thread per 32 positions of the hard-mismatch bitmap.
-// ---------------------------------------------------------------------------
-struct SeedDirtyArgs {
-    const uint32_t *inval;
-    uint64_t n_groups;
-    uint64_t total_len;
-    uint32_t S;
-    uint32_t max_mm;
-    unsigned long long *dirty;        // positions (k-mer starts)
-    unsigned long long *dirty_count;  // wanted
-    uint64_t dirty_cap;
-};
-
-__global__ void __launch_bounds__(256)
-k_seed_dirty(SeedDirtyArgs a) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t smask = a.S >= 64u ? ~0ull : ((1ull << a.S) - 1ull);
-    for (uint64_t gidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx + 1 < a.n_groups; gidx += stride) {
-        const uint64_t v = (uint64_t)a.inval[gidx] | ((uint64_t)a.inval[gidx + 1] << 32);
-        if (v == 0ull) continue;
-        for (uint32_t j = 0; j < 32u; j++) {
-            const uint32_t n = (uint32_t)__popcll((v >> j) & smask);
-            const uint64_t p = gidx * 32ull + j;
-            if (n >= 1u && n <= a.max_mm && p + a.S <= a.total_len) {
-                const unsigned long long i = atomicAdd(a.dirty_count, 1ull);
-                if (i < a.dirty_cap) a.dirty[i] = p;
-            }
-        }
-    }
-}
-
 struct SeedExpandArgs {
     const unsigned long long *dirty;
     uint64_t n_dirty;
@@ -149,7 +117,7 @@ k_seed_dirty_expand(SeedExpandArgs a) {
 // (+1 look-ahead) and 4 bitmap words (+1) sit in registers, every shift is an immediate.
 // Per position: funnel-shift + mask -> k-mer; two IMADs -> bitmap index; ONE LDS; the answer
 // bit is funnel-shifted into a 32-position hit word.  Set bits (and nothing else) walk the
-// hash table.  Windows holding an invalid byte are masked out here and served by k_seed_dirty.
+// hash table.  Windows holding an invalid byte are masked out and, if still viable, listed as dirty.
 // ---------------------------------------------------------------------------
 struct SeedScanArgs {
     const uint32_t *codes;
@@ -167,6 +135,12 @@ struct SeedScanArgs {
     unsigned long long *cand;
     unsigned long long *cand_count;
     uint64_t cand_cap;
+    // dirty windows (k-mer starts whose window holds 1..max_mm invalid bytes)
+    uint64_t total_len;
+    uint32_t max_mm;
+    unsigned long long *dirty;
+    unsigned long long *dirty_count;
+    uint64_t dirty_cap;
 };
 
 __device__ __forceinline__ void seed_emit(const SeedScanArgs &a, unsigned long long slot, uint64_t p) {
@@ -237,11 +211,24 @@ k_seed_scan(SeedScanArgs a) {
                 hits = 0xFFFFFFFFu;
             }
             const uint32_t ilo = iv[blk], ihi = iv[blk + 1];
-            if ((ilo | ihi) != 0u) {  // rare: drop every window that holds an invalid byte
+            if ((ilo | ihi) != 0u) {
+                // rare: a window holding an invalid byte has no k-mer.  Drop it here; if it holds
+                // 1..max_mm of them it may still be a site (genome N = one mismatch): those "dirty"
+                // windows are listed and verified against every orientation (halo.go:47-108).
                 const uint64_t v = (uint64_t)ilo | ((uint64_t)ihi << 32);
-                uint64_t d = 0ull;
-                for (uint32_t k = 0; k < a.S; k++) d |= v >> k;
-                hits &= ~(uint32_t)d;
+                const uint64_t smask = (1ull << a.S) - 1ull;
+                uint32_t d = 0u;
+                for (uint32_t j = 0; j < 32u; j++) {
+                    const uint32_t n = (uint32_t)__popcll((v >> j) & smask);
+                    if (n == 0u) continue;
+                    d |= 1u << j;
+                    const uint64_t p = P0 + (uint64_t)(blk * 32) + j;
+                    if (n <= a.max_mm && p + a.S <= a.total_len) {
+                        const unsigned long long i = atomicAdd(a.dirty_count, 1ull);
+                        if (i < a.dirty_cap) a.dirty[i] = p;
+                    }
+                }
+                hits &= ~d;
             }
             // second level for the set bits: one bit per (hashed) k-mer in an L2-resident bitmap;
             // only its hits walk the hash table.  BATCH lookups are in flight per lane before the

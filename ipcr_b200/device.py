@@ -180,8 +180,9 @@ def find_sites_device(cp: CompiledPanel, scratch: SimulationScratch, segments: S
 
 
 def pair_sites(cp: CompiledPanel, scratch: SimulationScratch, sites, records: Sequence[Tuple[int, bool]],
-               seq_ids=None) -> List[Product]:
-    """Stage 2: sites gathered from any number of shards + whole-record (len, has_reset_byte)."""
+               seq_ids=None, raw: bool = False):
+    """Stage 2: sites gathered from any number of shards + whole-record (len, has_reset_byte).
+    raw=True returns (ctypes product pointer, count) without building Product objects."""
     import numpy as np
 
     L = _capi.lib()
@@ -196,6 +197,8 @@ def pair_sites(cp: CompiledPanel, scratch: SimulationScratch, sites, records: Se
     ptr = sites.ctypes.data_as(C.POINTER(_capi.SiteC))
     _capi.check(L.ipcr_gpu_pair_sites(cp._h, scratch._h, ptr, len(sites), recs, len(records), C.byref(out),
                                       C.byref(n), err, len(err)), err)
+    if raw:
+        return out, n.value
     return _products(out, n.value, cp, seq_ids)
 
 

@@ -61,8 +61,8 @@ def gather_sites(dist, sites, records, n_recs: int, rank: int, world: int, devic
     block = hdr_bytes + SITE_CAP * isz
     hdr = np.zeros(hdr_words, dtype=np.int64)
     hdr[0] = len(sites)
-    for i, r in enumerate(records):
-        hdr[1 + 2 * i], hdr[2 + 2 * i] = int(r[0]), int(r[1])
+    if n_recs:
+        hdr[1:] = np.asarray(records, dtype=np.int64).reshape(-1)[: 2 * n_recs]
     mine = np.zeros(block, dtype=np.uint8)
     mine[:hdr_bytes] = hdr.view(np.uint8)
     raw = np.ascontiguousarray(sites).view(np.uint8).reshape(-1)
@@ -74,15 +74,15 @@ def gather_sites(dist, sites, records, n_recs: int, rank: int, world: int, devic
     recv = torch.empty(world * block, dtype=torch.uint8, **kw)
     dist.all_gather_into_tensor(recv, send)
     allb = recv.cpu().numpy().reshape(world, block)
-    counts, merged_len, merged_flag, parts = [], [0] * n_recs, [False] * n_recs, []
+    heads = np.ascontiguousarray(allb[:, :hdr_bytes]).view(np.int64).reshape(world, hdr_words)
+    counts = [int(c) for c in heads[:, 0]]
+    merged_len = heads[:, 1::2].max(axis=0).tolist()
+    merged_flag = (heads[:, 2::2] != 0).any(axis=0).tolist()
+    parts = []
     for r in range(world):
-        h = allb[r, :hdr_bytes].view(np.int64)
-        counts.append(int(h[0]))
-        for i in range(n_recs):
-            merged_len[i] = max(merged_len[i], int(h[1 + 2 * i]))
-            merged_flag[i] = merged_flag[i] or bool(h[2 + 2 * i])
         k = min(counts[r], SITE_CAP)
-        parts.append(allb[r, hdr_bytes:hdr_bytes + k * isz].copy().view(SITE_DTYPE))
+        if k:
+            parts.append(np.ascontiguousarray(allb[r, hdr_bytes:hdr_bytes + k * isz]).view(SITE_DTYPE))
     extra = max(0, max(counts) - SITE_CAP)
     if extra:  # overflow round, padded to the largest remainder
         rest = np.zeros(extra * isz, dtype=np.uint8)
