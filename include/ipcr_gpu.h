@@ -258,6 +258,10 @@ int ipcr_gpu_synth_fill(ipcr_scratch *s, void *d_dst, uint64_t n, uint64_t first
 int ipcr_gpu_debug_planes(const ipcr_genome *g, uint32_t *words, uint64_t max_words,
                           uint64_t *n_words, uint32_t *stripe_rows, uint64_t *n_tiles);
 /* candidates of the last find_sites/scan on this scratch: (orient << 44 | global start) */
+/* the 2-bit codes (2 words per 32 bases) and hard-mismatch bitmap (1 word per 32 bases) of a genome
+ * packed for the seed-index filter; *n_groups = 0 if it holds bit-planes instead */
+int ipcr_gpu_debug_codes(const ipcr_genome *g, uint32_t *codes, uint32_t *inval, uint64_t max_groups,
+                         uint64_t *n_groups);
 int ipcr_gpu_debug_candidates(const ipcr_scratch *s, uint64_t *out, uint64_t cap, uint64_t *n);
 /* CPU evaluation of the panel's filter plan at one window (no GPU): 1 if the
  * plan would flag `start` as a candidate for orientation `orient` */

@@ -118,7 +118,7 @@ SYMBOLS = [
     "ipcr_gpu_product_mismatch_idx", "ipcr_gpu_last_timing", "ipcr_gpu_synth_fill",
     "ipcr_gpu_debug_planes", "ipcr_gpu_debug_candidates", "ipcr_gpu_debug_plan_eval",
     "ipcr_gpu_debug_orientation", "ipcr_gpu_debug_jit_source", "ipcr_gpu_debug_jit_compile",
-    "ipcr_gpu_debug_seed_eval",
+    "ipcr_gpu_debug_seed_eval", "ipcr_gpu_debug_codes",
 ]
 
 _lib = None
@@ -179,6 +179,7 @@ def lib():
     sig("ipcr_gpu_last_timing", C.c_int, V, P(TimingC))
     sig("ipcr_gpu_synth_fill", C.c_int, V, V, U64, U64, U64, *ERR)
     sig("ipcr_gpu_debug_planes", C.c_int, V, P(C.c_uint32), U64, P(U64), P(C.c_uint32), P(U64))
+    sig("ipcr_gpu_debug_codes", C.c_int, V, P(C.c_uint32), P(C.c_uint32), U64, P(U64))
     sig("ipcr_gpu_debug_candidates", C.c_int, V, P(U64), U64, P(U64))
     sig("ipcr_gpu_debug_plan_eval", C.c_int, V, C.c_uint32, C.c_char_p, U64, C.c_int64, C.c_int)
     sig("ipcr_gpu_debug_seed_eval", C.c_int, V, C.c_int, C.c_char_p, U64, P(U64), U64, P(U64), P(C.c_int32))

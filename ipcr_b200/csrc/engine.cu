@@ -323,7 +323,7 @@ static const SeedIndex &seed_host(ipcr_panel *p, int variant) {
 // jit_mode: 0 table-driven only, 1 automatic, 2 force the specialised kernel, 3 force the seed index.
 // Automatic = the seed index: measured on B200 it beats the bit-parallel filter from 4 to 400
 // orientations and at mm 0..3 (profiles/), because its cost does not grow with the panel.  The
-// bit-parallel filter takes over per call when the input is too dirty (kSeedDirtyMax).
+// bit-parallel filter takes over per call when the input is too dirty (seed_dirty_max()).
 static bool prefer_seed(ipcr_panel *p) {
     const int mode = p->host.jit_mode;
     return (mode == 3 || mode == 1) && !p->host.orients.empty();
@@ -853,7 +853,10 @@ namespace ipcr {
 
 // more dirty-window candidates than this and the bit-parallel filter (which handles non-ACGT
 // bytes natively) is the better tool
-constexpr uint64_t kSeedDirtyMax = 1ull << 26;
+static uint64_t seed_dirty_max() {
+    const char *e = getenv("IPCR_SEED_DIRTY_MAX");  // read per call: tests lower it
+    return e ? (uint64_t)atoll(e) : (1ull << 26);
+}
 
 static const SeedIndex &seed_get(ipcr_scratch *s, int variant) {
     ipcr_panel *p = s->panel;
@@ -934,7 +937,7 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         CU(cudaStreamSynchronize(st));
         n_cand = s->h_counts.as<unsigned long long>()[0];
         n_dirty = s->h_counts.as<unsigned long long>()[2];
-        if (n_dirty * U > kSeedDirtyMax) return false;
+        if (n_dirty * U > seed_dirty_max()) return false;
         if (n_cand <= cap && n_dirty <= dirty_cap) break;
         if (attempt >= 2 || n_cand * sizeof(unsigned long long) > (32ull << 30))
             throw Error(fmt("scan produced %llu candidate sites; the panel is too unspecific for this input",
@@ -1688,13 +1691,27 @@ int ipcr_gpu_debug_planes(const ipcr_genome *g, uint32_t *words, uint64_t max_wo
                           uint32_t *stripe_rows, uint64_t *n_tiles) {
     if (!g) return 1;
     const GenomeData &d = g->g;
-    const uint64_t nw = d.lay.total_len ? d.lay.n_tiles * d.lay.rows * kLanes * 4ull : 0;
+    const uint64_t nw = d.lay.total_len && d.planes_ready ? d.lay.n_tiles * d.lay.rows * kLanes * 4ull : 0;
     if (n_words) *n_words = nw;
     if (stripe_rows) *stripe_rows = d.lay.W;
     if (n_tiles) *n_tiles = d.lay.n_tiles;
     if (words && nw && nw <= max_words) {
         cudaSetDevice(d.device);
         if (cudaMemcpy(words, d.planes.p, nw * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+
+int ipcr_gpu_debug_codes(const ipcr_genome *g, uint32_t *codes, uint32_t *inval, uint64_t max_groups,
+                         uint64_t *n_groups) {
+    if (!g) return 1;
+    const GenomeData &d = g->g;
+    const uint64_t ng = d.codes_ready ? d.n_groups : 0;
+    if (n_groups) *n_groups = ng;
+    if (codes && inval && ng && ng <= max_groups) {
+        cudaSetDevice(d.device);
+        if (cudaMemcpy(codes, d.codes.p, ng * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+        if (cudaMemcpy(inval, d.inval.p, ng * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
     }
     return 0;
 }

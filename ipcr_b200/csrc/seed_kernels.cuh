@@ -200,11 +200,17 @@ k_seed_scan(SeedScanArgs a) {
                     // x: 32-bit window whose low 2S bits are the k-mer.  The multiplier is pre-shifted
                     // by 32-2S, so the product ignores the bits above the k-mer: no mask needed.
                     const uint32_t x = j < 16 ? __funnelshift_r(w0, w1, 2 * j) : __funnelshift_r(w1, w2, 2 * (j - 16));
+                    // The ALU pipe (SHF/LOP3/LEA, half rate) is the busy one: the byte offset and the
+                    // second bit position are formed with multiplies on the FMA pipe instead.
                     const uint32_t hw = x * a.bloom_mul;
-                    const uint32_t off = __umulhi(hw, kSeedBloomWordsDev) * 4u;
+                    uint32_t off, b2;
+                    off = __umulhi(hw, kSeedBloomWordsDev) * 4u;
                     const uint32_t w = *reinterpret_cast<const uint32_t *>(sb + off);
                     uint32_t bit = __funnelshift_r(w, 0u, x);  // bit (k-mer & 31)
-                    if (BLOOM == 2) bit &= __funnelshift_r(w, 0u, hw >> 11);  // second bit: hash bits 11..15
+                    if (BLOOM == 2) {
+                        asm("mul.hi.u32 %0, %1, 2097152;" : "=r"(b2) : "r"(hw));  // hw >> 11: hash bits 11..15
+                        bit &= __funnelshift_r(w, 0u, b2);
+                    }
                     hits = __funnelshift_r(hits, bit, 1);
                 }
             } else {
@@ -218,6 +224,7 @@ k_seed_scan(SeedScanArgs a) {
                 const uint64_t v = (uint64_t)ilo | ((uint64_t)ihi << 32);
                 const uint64_t smask = (1ull << a.S) - 1ull;
                 uint32_t d = 0u;
+#pragma unroll 1
                 for (uint32_t j = 0; j < 32u; j++) {
                     const uint32_t n = (uint32_t)__popcll((v >> j) & smask);
                     if (n == 0u) continue;

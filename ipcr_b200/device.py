@@ -78,6 +78,20 @@ class Genome:
             raise _capi.GpuError("debug_planes failed")
         return W.value, nt.value, buf[: nw.value].reshape(nt.value, W.value + 31, 32, 4)
 
+    def codes(self):
+        """(codes uint32[2 * n_groups], inval uint32[n_groups]) of the seed-index format -- debug tap."""
+        import numpy as np
+
+        L = _capi.lib()
+        ng = C.c_uint64()
+        L.ipcr_gpu_debug_codes(self._h, None, None, 0, C.byref(ng))
+        codes = np.zeros(max(1, 2 * ng.value), dtype=np.uint32)
+        inval = np.zeros(max(1, ng.value), dtype=np.uint32)
+        if L.ipcr_gpu_debug_codes(self._h, codes.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                  inval.ctypes.data_as(C.POINTER(C.c_uint32)), ng.value, C.byref(ng)):
+            raise _capi.GpuError("debug_codes failed")
+        return codes[: 2 * ng.value], inval[: ng.value]
+
     def close(self):
         if self._h is not None:
             _capi.lib().ipcr_gpu_genome_destroy(self._h)

@@ -120,9 +120,11 @@ def test_pack_planes_match_host_packing():
     seq = bytes(H.random_genome(rng, 70001, n_frac=0.01, lower_frac=0.02, other_frac=0.01))
     eng = Engine(Config())
     cp = eng.compile_panel([Pair("x", "ACGTACGT", "TTGACC")])
+    cp.set_jit(0)  # the bit-parallel filter reads bit-planes
     sc = SimulationScratch(cp)
     g = D.Genome.upload(sc, [(seq, 0)])
     W, nt, planes = g.planes()
+    assert nt >= 1 and W >= 32
     a = np.frombuffer(seq, dtype=np.uint8)
     total = len(seq)
     rows = W + 31
@@ -138,6 +140,64 @@ def test_pack_planes_match_host_packing():
     assert g.records() == [(total, True)]
     g2 = D.Genome.upload(sc, [(b"ACGTacgtACGT", 0), (b"ACGTNACGT", 1), (b"ACGTACGT", 2)])
     assert g2.records() == [(12, False), (9, True), (8, False)]
+
+
+def test_pack_codes_match_host_packing():
+    """k_pack2 (seed-index format): 2-bit codes, hard-mismatch bitmap and reset flags against a
+    numpy restatement, incl. lowercase, N, other bytes and the ragged tail / padding."""
+    rng = random.Random(5)
+    for n in (70001, 4096, 33, 1):
+        seq = bytes(H.random_genome(rng, n, n_frac=0.01, lower_frac=0.02, other_frac=0.01))
+        eng = Engine(Config())
+        cp = eng.compile_panel([Pair("x", "ACGTACGT", "TTGACC")])
+        cp.set_jit(3)
+        sc = SimulationScratch(cp)
+        g = D.Genome.upload(sc, [(seq, 0)])
+        codes, inval = g.codes()
+        ng = len(inval)
+        assert ng == (n + 4095) // 4096 * 128 + 1 and len(codes) == 2 * ng
+        a = np.zeros(ng * 32, dtype=np.uint8)
+        a[:n] = np.frombuffer(seq, dtype=np.uint8)
+        valid = np.isin(a, np.frombuffer(b"ACGT", dtype=np.uint8))
+        want_inv = (~valid).reshape(ng, 32).astype(np.uint64)
+        want_inv = (want_inv << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+        assert np.array_equal(inval, want_inv)
+        c2 = ((a >> 1) & 3).reshape(2 * ng, 16).astype(np.uint64)
+        want_codes = (c2 << (2 * np.arange(16, dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+        # codes of invalid bytes are don't-care for the scan but deterministic: (byte >> 1) & 3
+        assert np.array_equal(codes, want_codes)
+        has_reset = any(chr(c) not in "ACGTacgt" for c in seq)
+        assert g.records() == [(n, has_reset)]
+        W, nt, planes = g.planes()
+        assert nt == 0  # this handle holds codes, not planes
+
+
+def test_dirty_input_falls_back_to_bit_parallel(oracle, monkeypatch):
+    """An input with too many non-ACGT seed windows leaves the seed index for the bit-parallel
+    filter inside the same call (threshold lowered here); the result is the same."""
+    rng = random.Random(31)
+    a, b = "AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT"
+    g = H.random_genome(rng, 60000, n_frac=0.02)
+    for k in range(6):
+        H.plant_amplicon(rng, g, 500 + k * 9000, a, b, 700, rng.randint(0, 2), rng.randint(0, 2), 3,
+                         revcomp_strand=k % 2 == 1)
+    seq = bytes(g)
+    cfgd = dict(max_mm=2, terminal_window=3, max_len=2000, hit_cap=0)
+    pairs = [Pair("16S", a, b), Pair("16S+A:self", a, a)]
+    raw = [(p.forward, p.reverse, 0, 0) for p in pairs]
+    want = [_otuple(pairs, t) for t in oracle.simulate_compiled(oracle.make_cfg(**cfgd), raw, seq)]
+    assert want
+    eng = Engine(Config(**cfgd))
+    cp = eng.compile_panel(pairs)
+    sc = eng.new_simulation_scratch(cp)
+    got = [_tuple(p) for p in eng.simulate_compiled_with_scratch("s", seq, cp, sc)]
+    assert got == want and sc.timing()["used_jit"] == 2  # seed index handles a few thousand dirty windows
+    monkeypatch.setenv("IPCR_SEED_DIRTY_MAX", "100")
+    got = [_tuple(p) for p in eng.simulate_compiled_with_scratch("s", seq, cp, sc)]
+    assert got == want and sc.timing()["used_jit"] in (0, 1)
+    monkeypatch.delenv("IPCR_SEED_DIRTY_MAX")
+    got = [_tuple(p) for p in eng.simulate_compiled_with_scratch("s", seq, cp, sc)]
+    assert got == want and sc.timing()["used_jit"] == 2
 
 
 def test_candidates_cover_all_true_sites(oracle):
