@@ -67,6 +67,47 @@ k_scan_add(uint32_t *__restrict__ out, uint64_t n, const uint32_t *__restrict__ 
 
 __global__ void k_scan_total1(uint32_t *out, uint64_t n, const uint32_t *bsum) { out[n] = bsum[0]; }
 
+// Small inputs (the usual case: a scan leaves a few thousand sites): ONE block scans the whole
+// array -- each thread sums a contiguous chunk, the 1024 partials are scanned with shuffles.
+constexpr int kScanSmallThreads = 1024;
+constexpr uint64_t kScanSmallMax = 1ull << 16;
+
+__global__ void __launch_bounds__(kScanSmallThreads)
+k_scan_small(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n) {
+    __shared__ uint32_t wsum[kScanSmallThreads / 32];
+    const uint32_t per = (n + kScanSmallThreads - 1) / kScanSmallThreads;
+    const uint32_t b = threadIdx.x * per, e = min(n, b + per);
+    uint32_t tsum = 0;
+    for (uint32_t i = b; i < e; i++) tsum += in[i];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t x = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = wsum[lane];
+        uint32_t xi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xi, d);
+            if (lane >= (uint32_t)d) xi += y;
+        }
+        wsum[lane] = xi - w;
+        if (lane == 31) out[n] = xi;
+    }
+    __syncthreads();
+    uint32_t run = x - tsum + wsum[warp];
+    for (uint32_t i = b; i < e; i++) {
+        const uint32_t v = in[i];  // read before the write: in and out never alias in this file
+        out[i] = run;
+        run += v;
+    }
+}
+
 // words of temporary storage exclusive_scan needs for n items
 inline uint64_t scan_tmp_words(uint64_t n) {
     uint64_t words = 0;
@@ -84,6 +125,11 @@ inline void exclusive_scan(cudaStream_t st, const uint32_t *in, uint32_t *out, u
                            uint32_t *launches) {
     if (n == 0) {
         cudaMemsetAsync(out, 0, sizeof(uint32_t), st);
+        return;
+    }
+    if (n <= kScanSmallMax) {
+        k_scan_small<<<1, kScanSmallThreads, 0, st>>>(in, out, (uint32_t)n);
+        if (launches) (*launches)++;
         return;
     }
     const uint64_t nb = (n + kScanTile - 1) / kScanTile;
@@ -161,6 +207,38 @@ k_sort_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ v
     }
 }
 
+// Small inputs: ONE block sorts in shared memory (bitonic network on key << 13 | index, so the
+// order of equal keys is the input order, like the stable radix sort).
+constexpr uint32_t kSortSmallMax = 8192;
+constexpr uint32_t kSortSmallIdxBits = 13;
+
+__global__ void __launch_bounds__(1024)
+k_sort_small(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t *__restrict__ keys_out,
+             uint32_t *__restrict__ vals_out, uint32_t n, uint32_t m, uint64_t key_mask) {
+    extern __shared__ unsigned long long sk[];
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+        sk[i] = i < n ? (((keys[i] & key_mask) << kSortSmallIdxBits) | i) : ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= m; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+                const uint32_t lo = ((t & ~(j - 1u)) << 1) | (t & (j - 1u)), hi = lo + j;
+                const unsigned long long a = sk[lo], b = sk[hi];
+                if ((a > b) == ((lo & k) == 0u)) {
+                    sk[lo] = b;
+                    sk[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t src = (uint32_t)sk[i] & ((1u << kSortSmallIdxBits) - 1u);
+        keys_out[i] = keys[src];
+        vals_out[i] = vals[src];
+    }
+}
+
 inline uint64_t sort_tmp_words(uint64_t n) {
     const uint64_t nb = (n + kSortTile - 1) / kSortTile;
     const uint64_t hn = 256 * nb;
@@ -172,6 +250,17 @@ inline uint64_t sort_tmp_words(uint64_t n) {
 inline int radix_sort(cudaStream_t st, uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint64_t n,
                       uint32_t key_bits, uint32_t *tmp, uint32_t *launches) {
     if (n <= 1) return 0;
+    if (n <= kSortSmallMax && key_bits + kSortSmallIdxBits <= 64) {
+        uint32_t m = 2;
+        while (m < n) m <<= 1;
+        if (m * sizeof(unsigned long long) > 48 * 1024)  // per device: cheap enough to repeat
+            cudaFuncSetAttribute(k_sort_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kSortSmallMax * sizeof(unsigned long long)));
+        const uint64_t key_mask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1ull);
+        k_sort_small<<<1, 1024, m * sizeof(unsigned long long), st>>>(k0, v0, k1, v1, (uint32_t)n, m, key_mask);
+        if (launches) (*launches)++;
+        return 1;
+    }
     const uint64_t nb = (n + kSortTile - 1) / kSortTile;
     const uint64_t hn = 256 * nb;
     uint32_t *hist = tmp, *hoff = tmp + hn, *stmp = tmp + hn + (hn + 1);

@@ -304,6 +304,14 @@ def test_dense_products(oracle):
     assert len(got) > 5000
 
 
+def test_many_sites_take_the_multi_block_sort(oracle):
+    """> 8192 sites: the device-wide radix sort / multi-level scan instead of the single-block
+    kernels used for small site lists."""
+    seq = (b"ACGT" * 9000) + b"TTTTT" + (b"GGCA" * 3000)
+    got = _check(oracle, dict(max_mm=0, terminal_window=0, max_len=16), [("ACG", "ACG"), ("GCA", "GGC")], seq)
+    assert len(got) > 20000
+
+
 def test_need_sites_strings():
     seq = b"TTTACGTACAAAAGGTACCTTTGGGACGTATAAAAGGTACCAAA"
     eng = Engine(Config(max_mm=1, terminal_window=0, min_len=6, max_len=80, need_sites=True))
