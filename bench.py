@@ -155,6 +155,17 @@ def cpu_reference_run(a, steps, warmup, sample_mbp=None):
     }, user_pairs, all_pairs
 
 
+def unique_orientations(pairs):
+    """A, B, rc(A), rc(B) de-duplicated over the panel, like CompilePanel on the GPU side."""
+    from ipcr_b200 import synth
+    seen = set()
+    for p in pairs:
+        for s_ in (p.forward, p.reverse):
+            seen.add((s_, False))
+            seen.add((synth.revcomp(s_), True))
+    return len(seen)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -165,7 +176,7 @@ def run_reference(a):
         "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": a.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(a, a.gpus, user_pairs, all_pairs, None),
+        "config": workload_config(a, a.gpus, user_pairs, all_pairs, unique_orientations(all_pairs)),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gbp_per_s": res["gbp_per_s"],

@@ -871,7 +871,7 @@ static const SeedIndex &seed_get(ipcr_scratch *s, int variant) {
         CU(cudaStreamSynchronize(s->stream));
         static std::mutex attr_mu;
         std::lock_guard<std::mutex> l2(attr_mu);
-        for (auto fn : {k_seed_scan<1, 1>, k_seed_scan<2, 1>, k_seed_scan<2, 2>})
+        for (auto fn : {k_seed_scan<1>, k_seed_scan<2>})
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSeedBloomWords * 4)));
         t->seed_ready[variant] = true;
     }
@@ -922,15 +922,10 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         a.dirty_count = ctr + 2;
         a.dirty_cap = dirty_cap;
         const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + 31) / 32, (uint64_t)s->sm_count));
-        static const int batch = [] {
-            const char *e = getenv("IPCR_SEED_BATCH");
-            return e ? atoi(e) : 1;
-        }();
         const size_t smem = kSeedBloomWords * 4;
-        if (!ix.use_bloom) k_seed_scan<0, 1><<<grid, 1024, 0, st>>>(a);
-        else if (ix.bloom_k == 1) k_seed_scan<1, 1><<<grid, 1024, smem, st>>>(a);
-        else if (batch >= 2) k_seed_scan<2, 2><<<grid, 1024, smem, st>>>(a);  // measured: no gain over 1
-        else k_seed_scan<2, 1><<<grid, 1024, smem, st>>>(a);
+        if (!ix.use_bloom) k_seed_scan<0><<<grid, 1024, 0, st>>>(a);
+        else if (ix.bloom_k == 1) k_seed_scan<1><<<grid, 1024, smem, st>>>(a);
+        else k_seed_scan<2><<<grid, 1024, smem, st>>>(a);
         check_launch("k_seed_scan");
         s->launches++;
         CU(cudaMemcpyAsync(s->h_counts.p, s->counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

@@ -161,9 +161,9 @@ __device__ __forceinline__ void seed_walk(const SeedScanArgs &a, uint32_t kmer, 
     }
 }
 
-// BLOOM: 0 = no bitmap (every position walks the table), k = 1..2 bits per k-mer, both in
-// the same word.  BATCH: second-level lookups a lane keeps in flight.
-template <int BLOOM, int BATCH>
+// BLOOM: 0 = no shared-memory bitmap (every position goes to the second level), k = 1..2 bits
+// per k-mer, both in the same word.
+template <int BLOOM>
 __global__ void __launch_bounds__(1024, 1)
 k_seed_scan(SeedScanArgs a) {
     extern __shared__ uint32_t sbloom[];
@@ -238,24 +238,16 @@ k_seed_scan(SeedScanArgs a) {
                 hits &= ~d;
             }
             // second level for the set bits: one bit per (hashed) k-mer in an L2-resident bitmap;
-            // only its hits walk the hash table.  BATCH lookups are in flight per lane before the
-            // first answer is looked at, so the L2 latency is paid once per batch.
+            // only its hits walk the hash table.  (Keeping 2-4 of these lookups in flight per lane,
+            // or moving them to a second, warp-balanced kernel, measured slower: profiles/README.md.)
             while (hits) {
-                uint32_t km[BATCH], i2[BATCH], wv[BATCH];
-                int jj[BATCH];
-#pragma unroll
-                for (int u = 0; u < BATCH; u++) {
-                    jj[u] = hits ? __ffs(hits) - 1 : -1;
-                    hits &= hits - 1u;
-                    const int j = jj[u] & 31;
-                    const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
-                    km[u] = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
-                    i2[u] = (km[u] * a.bitmap2_mul) >> a.bitmap2_shift;
-                    wv[u] = jj[u] >= 0 ? __ldg(a.bitmap2 + (i2[u] >> 5)) : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < BATCH; u++)
-                    if (__funnelshift_r(wv[u], 0u, i2[u]) & 1u) seed_walk(a, km[u], P0 + (uint64_t)(blk * 32 + jj[u]));
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1u;
+                const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
+                const uint32_t kmer = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
+                const uint32_t i2 = (kmer * a.bitmap2_mul) >> a.bitmap2_shift;
+                if (__funnelshift_r(__ldg(a.bitmap2 + (i2 >> 5)), 0u, i2) & 1u)
+                    seed_walk(a, kmer, P0 + (uint64_t)(blk * 32 + j));
             }
         }
     }

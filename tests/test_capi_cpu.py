@@ -169,6 +169,35 @@ def test_seed_index_never_loses_a_true_site_and_never_repeats_one(oracle):
     assert checked > 800
 
 
+def test_seed_index_complete_on_a_multiplex_panel(oracle):
+    """Panel scale: 40 pairs + self pairs, planted amplicons with mismatches, N and lowercase in
+    the genome; every site the brute force accepts for any of the ~160 orientations is a
+    candidate of the index, for both plan variants."""
+    from ipcr_b200 import synth
+    rng = random.Random(99)
+    user, allp = synth.multiplex_panel(40, seed=3)
+    for mm in (1, 2):
+        lens = [600000]
+        g = H.random_genome(rng, lens[0], n_frac=0.001, lower_frac=0.001)
+        for pl in synth.plan_amplicons(user, lens, mm, 3, seed=5 + mm, per_pair=(1, 1), len_range=(60, 400)):
+            g[pl.start:pl.start + len(pl.left)] = pl.left
+            e = pl.start + pl.length
+            g[e - len(pl.right):e] = pl.right
+        seq = bytes(g)
+        cp = Engine(Config(max_mm=mm, terminal_window=3, max_len=2000, hit_cap=10000)).compile_panel(allp)
+        n_true = 0
+        for raw in (False, True):
+            cands, info = cp.seed_eval(seq, raw)
+            assert len(cands) == len(set(cands))
+            cset = set(cands)
+            for q in range(cp.num_orientations):
+                s, t = cp.orientation(q)
+                for pos in _true_sites(oracle, seq, s, t == "a", mm, 3, raw):
+                    assert (q, pos) in cset, (s, t, mm, raw, pos, info)
+                    n_true += 1
+        assert n_true >= 2 * 2 * 36  # both primer sites of (nearly) every planted amplicon, both variants
+
+
 def test_seed_index_shape_on_the_benchmark_panel():
     from ipcr_b200 import synth
     _, allp = synth.multiplex_panel(100, seed=7)
