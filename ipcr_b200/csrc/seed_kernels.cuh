@@ -143,6 +143,36 @@ struct SeedScanArgs {
     uint64_t dirty_cap;
 };
 
+// L2 residency: the second-level bitmap (<= 32 MB) and the hash table are hit at random by
+// every SM and must stay in the 126 MB L2 while 1+ GB of packed genome streams through it.
+// Lookups carry an evict_last policy, the streaming loads an evict_first one.
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t ld_u32_policy(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_u64_policy(const unsigned long long *p, uint64_t pol) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_u128_policy(const uint4 *p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+
 __device__ __forceinline__ void seed_emit(const SeedScanArgs &a, unsigned long long slot, uint64_t p) {
     const uint64_t c = (slot >> 48) & 0xFFull;
     if (p >= c) {
@@ -151,10 +181,10 @@ __device__ __forceinline__ void seed_emit(const SeedScanArgs &a, unsigned long l
     }
 }
 
-__device__ __forceinline__ void seed_walk(const SeedScanArgs &a, uint32_t kmer, uint64_t p) {
+__device__ __forceinline__ void seed_walk(const SeedScanArgs &a, uint32_t kmer, uint64_t p, uint64_t keep) {
     uint32_t h = (kmer * kSeedHashMulDev) >> a.table_shift;
     for (;;) {
-        const unsigned long long slot = __ldg(a.table + h);
+        const unsigned long long slot = ld_u64_policy(a.table + h, keep);
         if (slot == 0ull) break;
         if ((uint32_t)slot == kmer) seed_emit(a, slot, p);
         h = (h + 1u) & a.table_mask;
@@ -176,18 +206,19 @@ k_seed_scan(SeedScanArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const uint64_t keep = l2_policy_keep(), stream = l2_policy_stream();
     for (uint64_t ch = warp; ch < a.n_chunks; ch += n_warps) {
         const uint64_t P0 = ch * kSeedChunk + (uint64_t)lane * 128u;
         uint32_t c[9], iv[5];
         {
             const uint4 *cp = reinterpret_cast<const uint4 *>(a.codes + (P0 >> 4));
-            const uint4 q0 = __ldg(cp), q1 = __ldg(cp + 1);
+            const uint4 q0 = ld_u128_policy(cp, stream), q1 = ld_u128_policy(cp + 1, stream);
             c[0] = q0.x; c[1] = q0.y; c[2] = q0.z; c[3] = q0.w;
             c[4] = q1.x; c[5] = q1.y; c[6] = q1.z; c[7] = q1.w;
-            c[8] = __ldg(a.codes + (P0 >> 4) + 8);
-            const uint4 qi = __ldg(reinterpret_cast<const uint4 *>(a.inval + (P0 >> 5)));
+            c[8] = ld_u32_policy(a.codes + (P0 >> 4) + 8, stream);
+            const uint4 qi = ld_u128_policy(reinterpret_cast<const uint4 *>(a.inval + (P0 >> 5)), stream);
             iv[0] = qi.x; iv[1] = qi.y; iv[2] = qi.z; iv[3] = qi.w;
-            iv[4] = __ldg(a.inval + (P0 >> 5) + 4);
+            iv[4] = ld_u32_policy(a.inval + (P0 >> 5) + 4, stream);
         }
 #pragma unroll
         for (int blk = 0; blk < 4; blk++) {
@@ -246,8 +277,8 @@ k_seed_scan(SeedScanArgs a) {
                 const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
                 const uint32_t kmer = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
                 const uint32_t i2 = (kmer * a.bitmap2_mul) >> a.bitmap2_shift;
-                if (__funnelshift_r(__ldg(a.bitmap2 + (i2 >> 5)), 0u, i2) & 1u)
-                    seed_walk(a, kmer, P0 + (uint64_t)(blk * 32 + j));
+                if (__funnelshift_r(ld_u32_policy(a.bitmap2 + (i2 >> 5), keep), 0u, i2) & 1u)
+                    seed_walk(a, kmer, P0 + (uint64_t)(blk * 32 + j), keep);
             }
         }
     }
