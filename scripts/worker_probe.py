@@ -27,13 +27,19 @@ segs = [(buf[offs[c]:offs[c + 1]], c, 0, lens[c]) for c in range(24)]
 
 
 def split(w):
-    order = sorted(range(24), key=lambda c: -lens[c])
-    groups, load = [[] for _ in range(w)], [0] * w
-    for c in order:
-        k = load.index(min(load))
-        groups[k].append(c)
-        load[k] += lens[c]
-    return [[segs[c] for c in sorted(g)] for g in groups]
+    # contiguous runs of contigs (adopted segments of one call are scanned as ONE span of the buffer,
+    # so the groups must not interleave), balanced by length
+    groups, c = [], 0
+    for k in range(w):
+        target = total * (k + 1) // w
+        g = []
+        while c < 24 and (offs[c + 1] <= target or not g or k == w - 1):
+            g.append(segs[c])
+            c += 1
+            if k < w - 1 and offs[c] >= target:
+                break
+        groups.append(g)
+    return groups
 
 
 def one_pass(groups):
@@ -64,4 +70,4 @@ for w in (1, 2, 3, 4):
         n = one_pass(groups)
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) * 100
-    print(f"workers={w} wall_ms_per_pass={ms:.3f} products={n} device_ms_each={[round(s.timing()['total_ms'], 3) for s in scs[:w]]}", flush=True)
+    print(f"turns={os.environ.get('IPCR_DEVICE_TURNS', '1')} bases={[sum(int(x[3]) for x in g) for g in groups]} workers={w} wall_ms_per_pass={ms:.3f} products={n} device_ms_each={[round(s.timing()['total_ms'], 3) for s in scs[:w]]}", flush=True)
