@@ -70,4 +70,4 @@ for w in (1, 2, 3, 4):
         n = one_pass(groups)
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) * 100
-    print(f"turns={os.environ.get('IPCR_DEVICE_TURNS', '1')} bases={[sum(int(x[3]) for x in g) for g in groups]} workers={w} wall_ms_per_pass={ms:.3f} products={n} device_ms_each={[round(s.timing()['total_ms'], 3) for s in scs[:w]]}", flush=True)
+    print(f"bases={[sum(int(x[3]) for x in g) for g in groups]} workers={w} wall_ms_per_pass={ms:.3f} products={n} device_ms_each={[round(s.timing()['total_ms'], 3) for s in scs[:w]]}", flush=True)
