@@ -254,9 +254,11 @@ k_seed_scan(SeedScanArgs a) {
                 // windows are listed and verified against every orientation (halo.go:47-108).
                 const uint64_t v = (uint64_t)ilo | ((uint64_t)ihi << 32);
                 const uint64_t smask = (1ull << a.S) - 1ull;
-                uint32_t d = 0u;
+                // inside an N run every window holds S > max_mm invalid bytes: nothing to list
+                const bool all_invalid = (ilo & ihi) == 0xFFFFFFFFu && a.S > a.max_mm;
+                uint32_t d = all_invalid ? 0xFFFFFFFFu : 0u;
 #pragma unroll 1
-                for (uint32_t j = 0; j < 32u; j++) {
+                for (uint32_t j = 0; j < 32u && !all_invalid; j++) {
                     const uint32_t n = (uint32_t)__popcll((v >> j) & smask);
                     if (n == 0u) continue;
                     d |= 1u << j;
