@@ -157,7 +157,10 @@ int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, si
                         const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen);
 
 /* same, but the records already sit in DEVICE memory (segment seq pointers are device
- * pointers, ascending, inside one allocation): pack -> filter -> verify -> pair */
+ * pointers, ascending, inside one allocation): pack -> filter -> verify -> pair.
+ * The call scans the span from the first to the last segment as one buffer; bytes between
+ * segments belong to no record (their sites are discarded) but are still scanned, so pass
+ * segments that lie (nearly) back to back. */
 int ipcr_gpu_scan_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
                          size_t n_recs, const ipcr_product **out, uint64_t *n_out, char *err,
                          size_t errlen);

@@ -304,6 +304,36 @@ def test_dense_products(oracle):
     assert len(got) > 5000
 
 
+def _n_run_genome(rng, a, b):
+    """9 kbp with four N runs; between consecutive runs an amplicon whose forward site starts k
+    bases INSIDE the run before it (its 5' end is N) and whose reverse site ends k bases inside
+    the next run, k = 1, 2, 3."""
+    runs = ((700, 64), (2000, 200), (4000, 1000), (7000, 33))
+    g = H.random_genome(rng, 9000)
+    for start, ln in runs:
+        g[start:start + ln] = b"N" * ln
+    ca, cb = a.replace("M", "C"), H.revcomp(b.replace("Y", "T"))
+    for k in (1, 2, 3):
+        (s0, l0), (s1, _l1) = runs[k - 1], runs[k]
+        e0 = s0 + l0
+        g[e0:e0 + len(ca) - k] = ca[k:].encode()        # forward primer, first k bases fall into the run
+        g[s1 - (len(cb) - k):s1] = cb[:len(cb) - k].encode()  # rc(reverse) site, last k bases fall into the run
+    return bytes(g)
+
+
+def test_long_n_runs(oracle):
+    """Assembly gaps: primer sites overlapping a run boundary by 1..3 bases (genome N = one
+    mismatch each, outside the 3' window), runs longer than the scan kernel's 64-position view."""
+    rng = random.Random(8)
+    a, b = "AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT"
+    seq = _n_run_genome(rng, a, b)
+    for mm in (1, 2, 3):
+        cfgd = dict(max_mm=mm, terminal_window=3, max_len=3000, hit_cap=0)
+        got = _check(oracle, cfgd, [(a, b, 0, 0), (a, a, 0, 0), (b, b, 0, 0)], seq)
+        assert len(got) == mm  # the amplicon with k N's per site needs max_mm >= k
+        _check(oracle, dict(cfgd, terminal_window=0, hit_cap=100), [(a, b, 0, 0)], seq, cap_binds=True)
+
+
 def test_many_sites_take_the_multi_block_sort(oracle):
     """> 8192 sites: the device-wide radix sort / multi-level scan instead of the single-block
     kernels used for small site lists."""
