@@ -263,7 +263,7 @@ struct ipcr_scratch {
     ipcr::DevTables *tables = nullptr;
     ipcr::GenomeData own;  // genome of ipcr_gpu_scan / scan_batch calls (buffers are reused)
     ipcr::DevBuf lists, list_counts, list_clamped, list_offs, work_counters;  // specialised filter
-    ipcr::DevBuf dirty, dcand;  // seed-index filter: dirty windows and their candidates
+    ipcr::DevBuf dirty, dcand, dirty_over, ocand;  // seed-index filter: dirty windows, their candidates, overflow
     ipcr::DevBuf cand, counters, sites, keys0, keys1, vals0, vals1, keep, keep_off, tmp, fkeys, fs, recs_dev,
         entry_tasks, task_off, task_cnt, prod_off, products;
     ipcr::PinBuf h_counts, h_products, h_sites, h_stage, h_reset;
@@ -851,8 +851,8 @@ static void set_err(char *err, size_t errlen, const std::string &m) {
 
 namespace ipcr {
 
-// more dirty-window candidates than this and the bit-parallel filter (which handles non-ACGT
-// bytes natively) is the better tool
+// more dirty windows (or unresolved dirty-window candidates) than this and the bit-parallel filter,
+// which handles non-ACGT bytes natively, is the better tool
 static uint64_t seed_dirty_max() {
     const char *e = getenv("IPCR_SEED_DIRTY_MAX");  // read per call: tests lower it
     return e ? (uint64_t)atoll(e) : (1ull << 26);
@@ -932,7 +932,7 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         CU(cudaStreamSynchronize(st));
         n_cand = s->h_counts.as<unsigned long long>()[0];
         n_dirty = s->h_counts.as<unsigned long long>()[2];
-        if (n_dirty * U > seed_dirty_max()) return false;
+        if (n_dirty > seed_dirty_max()) return false;
         if (n_cand <= cap && n_dirty <= dirty_cap) break;
         if (attempt >= 2 || n_cand * sizeof(unsigned long long) > (32ull << 30))
             throw Error(fmt("scan produced %llu candidate sites; the panel is too unspecific for this input",
@@ -941,40 +941,82 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         dirty_cap = std::max(dirty_cap, n_dirty + 1024);
     }
     CU(cudaEventRecord(s->ev[4], st));
-    const uint64_t n_dcand = n_dirty * U;
-    s->n_cand = n_cand;  // the k-mer hits; dirty-window candidates live in s->dcand
-    s->timing.candidates = n_cand + n_dcand;
+    // dirty windows: replacement lookups (k_seed_dirty_probe); the few windows it cannot resolve
+    // are expanded against every orientation
+    uint64_t n_dcand = 0, n_over = 0;
+    if (n_dirty) {
+        uint64_t dcap = n_dirty * 4 + 1024;
+        s->dirty_over.ensure(n_dirty * sizeof(unsigned long long));
+        for (int attempt = 0;; attempt++) {
+            s->dcand.ensure(dcap * sizeof(unsigned long long));
+            CU(cudaMemsetAsync(ctr + 3, 0, sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(ctr + 5, 0, sizeof(unsigned long long), st));
+            SeedDirtyProbeArgs d{};
+            d.dirty = s->dirty.as<unsigned long long>();
+            d.n_dirty = n_dirty;
+            d.codes = g.codes.as<uint32_t>();
+            d.inval = g.inval.as<uint32_t>();
+            d.S = (uint32_t)ix.S;
+            d.kmer_mask = ix.kmer_mask;
+            d.bitmap2 = t->seed_bitmap2[variant].as<uint32_t>();
+            d.bitmap2_mul = ix.bitmap2_mul;
+            d.bitmap2_shift = ix.bitmap2_shift;
+            d.table = t->seed_table[variant].as<unsigned long long>();
+            d.table_shift = 32u - ix.table_bits;
+            d.table_mask = (uint32_t)((1ull << ix.table_bits) - 1);
+            d.cand = s->dcand.as<unsigned long long>();
+            d.cand_count = ctr + 3;
+            d.cand_cap = dcap;
+            d.over = s->dirty_over.as<unsigned long long>();
+            d.over_count = ctr + 5;
+            const unsigned grid = (unsigned)std::min<uint64_t>((n_dirty + 127) / 128, (uint64_t)s->sm_count * 16);
+            k_seed_dirty_probe<<<grid, 128, 0, st>>>(d);
+            check_launch("k_seed_dirty_probe");
+            s->launches++;
+            CU(cudaMemcpyAsync(s->h_counts.p, s->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            n_dcand = s->h_counts.as<unsigned long long>()[3];
+            n_over = s->h_counts.as<unsigned long long>()[5];
+            if (n_dcand <= dcap) break;
+            if (attempt >= 1) throw Error("dirty-window candidates overflowed twice");
+            dcap = n_dcand + 1024;
+        }
+        if (n_over * U > seed_dirty_max()) return false;
+    }
+    const uint64_t n_ocand = n_over * U;
+    s->n_cand = n_cand;  // the k-mer hits; dirty-window candidates live in s->dcand / s->ocand
+    s->timing.candidates = n_cand + n_dcand + n_ocand;
     n_sites = 0;
-    if (n_cand + n_dcand == 0) return true;
-    s->sites.ensure((n_cand + n_dcand) * sizeof(ipcr_site));
+    if (n_cand + n_dcand + n_ocand == 0) return true;
+    s->sites.ensure((n_cand + n_dcand + n_ocand) * sizeof(ipcr_site));
     v.sites = s->sites.as<ipcr_site>();
-    v.site_cap = n_cand + n_dcand;
-    if (n_cand) {
-        v.cand = s->cand.as<unsigned long long>();
-        v.n_cand = n_cand;
-        const unsigned grid = (unsigned)std::min<uint64_t>((n_cand + 255) / 256, (uint64_t)s->sm_count * 16);
+    v.site_cap = n_cand + n_dcand + n_ocand;
+    auto verify = [&](const DevBuf &buf, uint64_t n) {
+        if (!n) return;
+        v.cand = buf.as<unsigned long long>();
+        v.n_cand = n;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)s->sm_count * 16);
         k_verify<<<grid, 256, 0, st>>>(v);
         check_launch("k_verify");
         s->launches++;
-    }
-    if (n_dcand) {
-        s->dcand.ensure(n_dcand * sizeof(unsigned long long));
+    };
+    verify(s->cand, n_cand);
+    verify(s->dcand, n_dcand);
+    if (n_ocand) {
+        s->ocand.ensure(n_ocand * sizeof(unsigned long long));
         SeedExpandArgs e{};
-        e.dirty = s->dirty.as<unsigned long long>();
-        e.n_dirty = n_dirty;
+        e.dirty = s->dirty_over.as<unsigned long long>();
+        e.n_dirty = n_over;
         e.col_off = t->seed_coloff[variant].as<uint16_t>();
         e.orients = t->orients.as<OrientDev>();
         e.n_orient = (uint32_t)U;
         e.S = (uint32_t)ix.S;
-        e.cand = s->dcand.as<unsigned long long>();
-        const unsigned grid = (unsigned)std::min<uint64_t>((n_dcand + 255) / 256, (uint64_t)s->sm_count * 16);
+        e.cand = s->ocand.as<unsigned long long>();
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_ocand + 255) / 256, (uint64_t)s->sm_count * 16);
         k_seed_dirty_expand<<<grid, 256, 0, st>>>(e);
         check_launch("k_seed_dirty_expand");
-        v.cand = s->dcand.as<unsigned long long>();
-        v.n_cand = n_dcand;
-        k_verify<<<grid, 256, 0, st>>>(v);
-        check_launch("k_verify");
-        s->launches += 2;
+        s->launches++;
+        verify(s->ocand, n_ocand);
     }
     n_sites = read_counter(s, 1);
     return true;

@@ -19,6 +19,7 @@
 // (halo.go:47-108).  Exactness still lives in the verify kernel.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -239,9 +240,44 @@ inline void seed_eval(const Panel &h, const SeedIndex &ix, const uint8_t *seq, u
                 if ((uint32_t)slot == kmer && p >= c) out.push_back((((slot >> 32) & 0xFFFF) << 44) | (p - c));
             }
         } else if ((int)n_inv <= h.cfg.max_mm) {
-            for (size_t q = 0; q < h.orients.size(); q++) {
-                const uint64_t c = ix.col_off[q];
-                if (h.orients[q].L >= ix.S && p >= c) out.push_back(((uint64_t)q << 44) | (p - c));
+            // dirty window: every replacement of the invalid bytes is looked up (k_seed_dirty_probe);
+            // more than 16 distinct hits or more than 4 invalid bytes => all orientations
+            std::vector<uint32_t> pos;
+            uint32_t base = kmer;
+            for (uint64_t j = 0; j < S; j++) {
+                const uint8_t b = seq[p + j];
+                if (!(b == 'A' || b == 'C' || b == 'G' || b == 'T')) {
+                    pos.push_back((uint32_t)j);
+                    base &= ~(3u << (2 * j));
+                }
+            }
+            bool overflow = pos.size() > 4;
+            std::vector<uint32_t> seen;
+            for (uint32_t combo = 0; !overflow && combo < (1u << (2 * pos.size())); combo++) {
+                uint32_t km = base;
+                for (size_t u = 0; u < pos.size(); u++) km |= ((combo >> (2 * u)) & 3u) << (2 * pos[u]);
+                const uint32_t i2 = (uint32_t)(km * ix.bitmap2_mul) >> ix.bitmap2_shift;
+                if (!((ix.bitmap2[i2 >> 5] >> (i2 & 31u)) & 1u)) continue;
+                for (uint32_t hh = (uint32_t)(km * kSeedHashMul) >> (32 - ix.table_bits); ix.slots[hh] && !overflow;
+                     hh = (hh + 1) & tmask) {
+                    const uint64_t slot = ix.slots[hh];
+                    if ((uint32_t)slot != km) continue;
+                    const uint32_t key = (uint32_t)(slot >> 32) & 0x00FFFFFFu;
+                    if (std::find(seen.begin(), seen.end(), key) != seen.end()) continue;
+                    if (seen.size() == 16) overflow = true;
+                    else seen.push_back(key);
+                }
+            }
+            if (overflow) {
+                for (size_t q = 0; q < h.orients.size(); q++) {
+                    const uint64_t c = ix.col_off[q];
+                    if (h.orients[q].L >= ix.S && p >= c) out.push_back(((uint64_t)q << 44) | (p - c));
+                }
+            } else {
+                for (uint32_t key : seen) {
+                    const uint64_t c = key >> 16;
+                    if (p >= c) out.push_back(((uint64_t)(key & 0xFFFFu) << 44) | (p - c));
+                }
             }
         }
     }

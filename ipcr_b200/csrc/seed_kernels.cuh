@@ -3,7 +3,8 @@
 //   K2s k_seed_scan    one k-mer per genome position: Bloom bitmap in shared memory, then an
 //                      L2-resident bitmap and hash table; hits become (orientation, start)
 //                      candidates; seed windows holding 1..max_mm non-ACGT bytes are listed
-//   K2e k_seed_dirty_expand  dirty windows x orientations -> candidates
+//   K2d k_seed_dirty_probe   dirty windows: 4^t base replacements looked up in the index
+//   K2e k_seed_dirty_expand  (overflow only) dirty windows x orientations -> candidates
 // All of it is integer/byte work; exactness is in k_verify (kernels.cuh).
 #pragma once
 
@@ -282,6 +283,88 @@ k_seed_scan(SeedScanArgs a) {
                 if (__funnelshift_r(ld_u32_policy(a.bitmap2 + (i2 >> 5), keep), 0u, i2) & 1u)
                     seed_walk(a, kmer, P0 + (uint64_t)(blk * 32 + j), keep);
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2d.  Dirty windows (1..max_mm invalid bytes): an invalid genome byte is a mismatch at its
+// column whatever the primer says, so a site through this window shows, after replacing each
+// invalid byte by SOME base, a k-mer of the index.  One thread per window tries all 4^t
+// replacements (t <= 4), collects the distinct (orientation, seed offset) hits and appends
+// them as candidates.  Windows with more than kDirtySeen hits or t > 4 go to the overflow
+// list and are expanded against every orientation (k_seed_dirty_expand).
+// Replaces the direct verification of scanNonACGTHalos (core/engine/halo.go:47-108).
+// ---------------------------------------------------------------------------
+constexpr int kDirtySeen = 16;
+constexpr uint32_t kDirtyMaxInvalid = 4;
+
+struct SeedDirtyProbeArgs {
+    const unsigned long long *dirty;
+    uint64_t n_dirty;
+    const uint32_t *codes;
+    const uint32_t *inval;
+    uint32_t S;
+    uint32_t kmer_mask;
+    const uint32_t *bitmap2;
+    uint32_t bitmap2_mul, bitmap2_shift;
+    const unsigned long long *table;
+    uint32_t table_shift, table_mask;
+    unsigned long long *cand;
+    unsigned long long *cand_count;
+    uint64_t cand_cap;
+    unsigned long long *over;  // capacity n_dirty
+    unsigned long long *over_count;
+};
+
+__global__ void __launch_bounds__(128)
+k_seed_dirty_probe(SeedDirtyProbeArgs a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_dirty; i += stride) {
+        const uint64_t p = a.dirty[i];
+        const uint32_t sh = (uint32_t)p & 15u;
+        const uint32_t kmer0 = __funnelshift_r(a.codes[p >> 4], a.codes[(p >> 4) + 1], 2u * sh) & a.kmer_mask;
+        const uint64_t ivw = (uint64_t)a.inval[p >> 5] | ((uint64_t)a.inval[(p >> 5) + 1] << 32);
+        uint32_t iv = (uint32_t)(ivw >> (p & 31u)) & ((1u << a.S) - 1u);  // S <= 16
+        const uint32_t t = __popc(iv);
+        bool overflow = t > kDirtyMaxInvalid;
+        uint32_t seen[kDirtySeen];
+        int n_seen = 0;
+        if (!overflow) {
+            uint32_t pos[kDirtyMaxInvalid] = {0u, 0u, 0u, 0u};
+            uint32_t base = kmer0;
+            for (uint32_t u = 0; u < t; u++) {
+                pos[u] = (uint32_t)(__ffs(iv) - 1);
+                iv &= iv - 1u;
+                base &= ~(3u << (2u * pos[u]));
+            }
+            for (uint32_t combo = 0; combo < (1u << (2u * t)) && !overflow; combo++) {
+                uint32_t km = base;
+                for (uint32_t u = 0; u < t; u++) km |= ((combo >> (2u * u)) & 3u) << (2u * pos[u]);
+                const uint32_t i2 = (km * a.bitmap2_mul) >> a.bitmap2_shift;
+                if (!((a.bitmap2[i2 >> 5] >> (i2 & 31u)) & 1u)) continue;
+                for (uint32_t h = (km * kSeedHashMulDev) >> a.table_shift;; h = (h + 1u) & a.table_mask) {
+                    const unsigned long long slot = a.table[h];
+                    if (slot == 0ull) break;
+                    if ((uint32_t)slot != km) continue;
+                    const uint32_t key = (uint32_t)(slot >> 32) & 0x00FFFFFFu;  // orientation | seed offset << 16
+                    bool dup = false;
+                    for (int k = 0; k < n_seen; k++) dup |= seen[k] == key;
+                    if (dup) continue;
+                    if (n_seen == kDirtySeen) { overflow = true; break; }
+                    seen[n_seen++] = key;
+                }
+            }
+        }
+        if (overflow) {
+            a.over[atomicAdd(a.over_count, 1ull)] = p;
+            continue;
+        }
+        for (int k = 0; k < n_seen; k++) {
+            const uint64_t c = seen[k] >> 16;
+            if (p < c) continue;
+            const unsigned long long idx = atomicAdd(a.cand_count, 1ull);
+            if (idx < a.cand_cap) a.cand[idx] = ((unsigned long long)(seen[k] & 0xFFFFu) << kCandPosBits) | (p - c);
         }
     }
 }
