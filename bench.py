@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = one whole genome per GPU (independent records, no collective); "
                          "strong = one genome sharded over the GPUs, sites gathered, paired once")
+    ap.add_argument("--n-per-mbp", type=float, default=0.0,
+                    help="scatter this many N bytes per Mbp over the genome (robustness runs; default off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bitparallel", action="store_true", help="skip the bit-parallel comparison pass")
@@ -86,6 +88,7 @@ def workload_config(a, n_gpus, user_pairs, all_pairs, n_orient):
         "pairs_with_self": len(all_pairs),
         "unique_orientations": n_orient,
         "max_mm": a.mm,
+        "scattered_n_per_mbp": a.n_per_mbp,
         "sharding": sharding,
         "l2": "inputs (1 B/bp ASCII + 0.375-0.5 B/bp packed, per GPU) are >> the 126 MB L2, no flush needed",
     }
@@ -306,6 +309,12 @@ def run_ours(a):
             if c0 < c1:
                 t = torch.frombuffer(bytearray(data[c0 - s0:c1 - s0]), dtype=torch.uint8)
                 buf[c0 - lo:c1 - lo].copy_(t)
+    if a.n_per_mbp > 0:  # scattered ambiguity codes (input generation, untimed)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(SEED + 17 + rank)
+        k = int(a.n_per_mbp * (piece_end - lo) / 1e6)
+        idx = torch.randint(0, piece_end - lo, (k,), generator=gen, device=dev)
+        buf[idx] = ord("N")
     torch.cuda.synchronize()
 
     segments = [(buf[s0 - lo:s1 - lo], c, rec_off, own)

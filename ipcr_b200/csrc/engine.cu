@@ -268,6 +268,7 @@ struct ipcr_scratch {
         entry_tasks, task_off, task_cnt, prod_off, products;
     ipcr::PinBuf h_counts, h_products, h_sites, h_stage, h_reset;
     uint64_t n_cand = 0;
+    uint64_t seed_cap_hint = 0, seed_dirty_hint = 0;  // capacities that sufficed last time (no re-scan)
     // records of the last scan that are still resident (for the device-side visitors)
     std::vector<uint64_t> last_rec_base, last_rec_len;
     const uint8_t *last_ascii = nullptr;
@@ -890,8 +891,8 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
     const uint64_t U = h.orients.size();
     const uint64_t n_chunks = (g.lay.total_len + kSeedChunk - 1) / kSeedChunk;
     uint64_t cap = std::max<uint64_t>(1ull << 16, (uint64_t)(ix.cand_prob * (double)g.lay.total_len * 1.5) + 4096);
-    cap = std::min<uint64_t>(cap, 1ull << 28);
-    uint64_t dirty_cap = 1ull << 16;
+    cap = std::max(std::min<uint64_t>(cap, 1ull << 28), s->seed_cap_hint);
+    uint64_t dirty_cap = std::max<uint64_t>(1ull << 16, s->seed_dirty_hint);
     uint64_t n_cand = 0, n_dirty = 0;
     unsigned long long *ctr = s->counters.as<unsigned long long>();
     for (int attempt = 0;; attempt++) {
@@ -940,6 +941,8 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         cap = std::max(cap, n_cand + 1024);
         dirty_cap = std::max(dirty_cap, n_dirty + 1024);
     }
+    s->seed_cap_hint = std::max(s->seed_cap_hint, n_cand + n_cand / 4);
+    s->seed_dirty_hint = std::max(s->seed_dirty_hint, n_dirty + n_dirty / 4);
     CU(cudaEventRecord(s->ev[4], st));
     // dirty windows: replacement lookups (k_seed_dirty_probe); the few windows it cannot resolve
     // are expanded against every orientation

@@ -74,15 +74,27 @@ k_pack2(Pack2Args a) {
         }
         reinterpret_cast<uint2 *>(a.codes)[gidx] = make_uint2(c0, c1);
         a.inval[gidx] = inv;
-        if (inv != 0u) {  // rare: which of them are reset bytes (not even lowercase acgt)?
-            for (uint32_t k = 0; k < 32u; k++) {
+        if (inv != 0u) {  // rare: is one of them a reset byte (not even lowercase acgt)?
+            uint32_t first = 32u;
+            for (uint32_t k = 0; k < 32u && first == 32u; k++) {
                 if (!((inv >> k) & 1u) || P0 + k >= a.total_len) continue;
                 const uint32_t b = (w[k >> 2] >> (8u * (k & 3u))) & 0xFFu;
                 const uint32_t x = (b | 0x20u) - 'a';  // a,c,g,t -> 0,2,6,19
-                const bool acgt = x < 32u && ((0x00080045u >> x) & 1u);
-                if (!acgt) {
-                    const uint32_t s = find_segment(a.segs, a.n_segs, P0 + k);
-                    if (P0 + k - a.segs[s].global_off < a.segs[s].len) a.seg_reset[s] = 1u;
+                if (!(x < 32u && ((0x00080045u >> x) & 1u))) first = k;
+            }
+            if (first < 32u) {
+                const uint32_t s0 = find_segment(a.segs, a.n_segs, P0 + first);
+                const uint64_t seg_end = a.segs[s0].global_off + a.segs[s0].len;
+                if (P0 + first < seg_end && a.seg_reset[s0] == 0u) a.seg_reset[s0] = 1u;
+                if (seg_end < P0 + 32u) {  // the group straddles a segment boundary: look at every byte
+                    for (uint32_t k = first + 1; k < 32u; k++) {
+                        if (!((inv >> k) & 1u) || P0 + k >= a.total_len) continue;
+                        const uint32_t b = (w[k >> 2] >> (8u * (k & 3u))) & 0xFFu;
+                        const uint32_t x = (b | 0x20u) - 'a';
+                        if (x < 32u && ((0x00080045u >> x) & 1u)) continue;
+                        const uint32_t s1 = find_segment(a.segs, a.n_segs, P0 + k);
+                        if (P0 + k - a.segs[s1].global_off < a.segs[s1].len) a.seg_reset[s1] = 1u;
+                    }
                 }
             }
         }
@@ -255,18 +267,22 @@ k_seed_scan(SeedScanArgs a) {
                 // windows are listed and verified against every orientation (halo.go:47-108).
                 const uint64_t v = (uint64_t)ilo | ((uint64_t)ihi << 32);
                 const uint64_t smask = (1ull << a.S) - 1ull;
-                // inside an N run every window holds S > max_mm invalid bytes: nothing to list
-                const bool all_invalid = (ilo & ihi) == 0xFFFFFFFFu && a.S > a.max_mm;
-                uint32_t d = all_invalid ? 0xFFFFFFFFu : 0u;
-#pragma unroll 1
-                for (uint32_t j = 0; j < 32u && !all_invalid; j++) {
-                    const uint32_t n = (uint32_t)__popcll((v >> j) & smask);
-                    if (n == 0u) continue;
-                    d |= 1u << j;
-                    const uint64_t p = P0 + (uint64_t)(blk * 32) + j;
-                    if (n <= a.max_mm && p + a.S <= a.total_len) {
-                        const unsigned long long i = atomicAdd(a.dirty_count, 1ull);
-                        if (i < a.dirty_cap) a.dirty[i] = p;
+                // d: windows [j, j+S) that hold an invalid byte; only those with <= max_mm of them
+                // can still be sites (inside an N run none can)
+                uint64_t spread = 0ull;
+                for (uint32_t k = 0; k < a.S; k++) spread |= v >> k;
+                const uint32_t d = (uint32_t)spread;
+                if (a.max_mm > 0u && ((ilo & ihi) != 0xFFFFFFFFu || a.S <= a.max_mm)) {
+                    uint32_t elig = 0u;  // dirty windows that can still be sites
+                    for (uint32_t todo = d; todo; todo &= todo - 1u) {
+                        const uint32_t j = (uint32_t)(__ffs(todo) - 1);
+                        const uint32_t n = (uint32_t)__popcll((v >> j) & smask);
+                        if (n <= a.max_mm && P0 + (uint64_t)(blk * 32) + j + a.S <= a.total_len) elig |= 1u << j;
+                    }
+                    if (elig) {  // one atomic per lane and block, not per window
+                        unsigned long long i = atomicAdd(a.dirty_count, (unsigned long long)__popc(elig));
+                        for (; elig; elig &= elig - 1u, i++)
+                            if (i < a.dirty_cap) a.dirty[i] = P0 + (uint64_t)(blk * 32) + (uint32_t)(__ffs(elig) - 1);
                     }
                 }
                 hits &= ~d;
