@@ -126,3 +126,27 @@ def multiset(products):
     from collections import Counter
 
     return Counter(products)
+
+
+def shared_seed_case(rng, n_pairs=12, genome_len=6000):
+    """Pairs whose primers share their 3' 12-mer (only the 5' parts differ): with a seed of <= 12
+    columns every forward orientation has the same seed k-mers, so one dirty seed window yields
+    more than 16 index hits (the overflow path of the dirty-window probe).  Returns (pairs, seq)
+    with sites planted so that an N falls into the seed window of each."""
+    core_a, core_b = "GATCCTGGCTCA", "CCTTGTTACGAC"
+    pairs = []
+    for _ in range(n_pairs):
+        pa = "".join(rng.choice("ACGT") for _ in range(8)) + core_a
+        pb = "".join(rng.choice("ACGT") for _ in range(9)) + core_b
+        pairs.append((pa, pb, 0, 0))
+    g = random_genome(rng, genome_len)
+    for i, (pa, pb, _x, _y) in enumerate(pairs):
+        start = 100 + i * 450
+        site_a = bytearray(pa.encode())
+        site_a[len(pa) - 8] = ord("N")            # inside the 3' 12-mer, outside the 3-base window
+        rb = bytearray(revcomp(pb).encode())
+        rb[7] = ord("N")                          # rc(B): protected window is its LEFT end
+        g[start:start + len(site_a)] = site_a
+        e = start + 200
+        g[e - len(rb):e] = rb
+    return pairs, bytes(g)

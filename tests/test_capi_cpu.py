@@ -198,6 +198,33 @@ def test_seed_index_complete_on_a_multiplex_panel(oracle):
         assert n_true >= 2 * 2 * 36  # both primer sites of (nearly) every planted amplicon, both variants
 
 
+def test_seed_index_dirty_window_overflow(oracle, monkeypatch):
+    """More than 16 orientations behind one dirty seed window: the probe gives up on the window
+    and every orientation is verified there -- still complete, still duplicate-free."""
+    monkeypatch.setenv("IPCR_SEED_LEN", "10")
+    rng = random.Random(12)
+    raw_pairs, seq = H.shared_seed_case(rng)
+    pairs = [Pair(f"p{i}", p[0], p[1]) for i, p in enumerate(raw_pairs)]
+    cp = Engine(Config(max_mm=2, terminal_window=3, max_len=400)).compile_panel(pairs)
+    n_true = 0
+    for raw in (False, True):
+        cands, info = cp.seed_eval(seq, raw)
+        assert info["S"] == 10
+        assert len(cands) == len(set(cands))
+        cset = set(cands)
+        for q in range(cp.num_orientations):
+            s, t = cp.orientation(q)
+            for pos in _true_sites(oracle, seq, s, t == "a", 2, 3, raw):
+                assert (q, pos) in cset
+                n_true += 1
+    assert n_true >= 2 * 2 * 12
+    # the shared window really overflows: all 48 orientations are candidates at one k-mer start
+    per_start = {}
+    for q, pos in cp.seed_eval(seq)[0]:
+        per_start.setdefault(pos, set()).add(q)
+    assert max(len(v) for v in per_start.values()) >= 12
+
+
 def test_seed_index_shape_on_the_benchmark_panel():
     from ipcr_b200 import synth
     _, allp = synth.multiplex_panel(100, seed=7)

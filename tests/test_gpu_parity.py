@@ -334,6 +334,17 @@ def test_long_n_runs(oracle):
         _check(oracle, dict(cfgd, terminal_window=0, hit_cap=100), [(a, b, 0, 0)], seq, cap_binds=True)
 
 
+def test_dirty_window_overflow_path(oracle, monkeypatch):
+    """> 16 orientations share the k-mers of one dirty seed window (k_seed_dirty_probe gives up
+    on it and k_seed_dirty_expand verifies every orientation there)."""
+    monkeypatch.setenv("IPCR_SEED_LEN", "10")
+    rng = random.Random(12)
+    raw_pairs, seq = H.shared_seed_case(rng)
+    got = _check(oracle, dict(max_mm=2, terminal_window=3, max_len=400, hit_cap=0), raw_pairs, seq)
+    assert len(got) >= 12
+    _check(oracle, dict(max_mm=2, terminal_window=3, max_len=400, hit_cap=5), raw_pairs, seq, cap_binds=True)
+
+
 def test_many_sites_take_the_multi_block_sort(oracle):
     """> 8192 sites: the device-wide radix sort / multi-level scan instead of the single-block
     kernels used for small site lists."""
