@@ -142,6 +142,12 @@ int ipcr_gpu_panel_have(const ipcr_panel *p, size_t pair_idx, int which);
  * by NVRTC once the work pays for the compile), 2 = force the NVRTC-specialised bit-parallel
  * kernel, 3 = force the seed index */
 void ipcr_gpu_panel_set_jit(ipcr_panel *p, int mode);
+/* the same switch under its proper name */
+#define IPCR_FILTER_BITPARALLEL_TABLE 0
+#define IPCR_FILTER_AUTO 1
+#define IPCR_FILTER_BITPARALLEL_JIT 2
+#define IPCR_FILTER_SEED_INDEX 3
+void ipcr_gpu_panel_set_filter(ipcr_panel *p, int filter);
 
 /* ---- scratch: engine.NewSimulationScratch (core/engine/hit_collect.go:19-34) */
 ipcr_scratch *ipcr_gpu_scratch_create(ipcr_panel *p, char *err, size_t errlen);

@@ -106,7 +106,7 @@ assert C.sizeof(ProductC) == 64 and C.sizeof(SiteC) == 24
 SYMBOLS = [
     "ipcr_gpu_abi_version", "ipcr_gpu_device_count", "ipcr_gpu_init",
     "ipcr_gpu_panel_create", "ipcr_gpu_panel_destroy", "ipcr_gpu_panel_num_pairs",
-    "ipcr_gpu_panel_num_orientations", "ipcr_gpu_panel_have", "ipcr_gpu_panel_set_jit",
+    "ipcr_gpu_panel_num_orientations", "ipcr_gpu_panel_have", "ipcr_gpu_panel_set_jit", "ipcr_gpu_panel_set_filter",
     "ipcr_gpu_scratch_create", "ipcr_gpu_scratch_destroy",
     "ipcr_gpu_scan", "ipcr_gpu_scan_batch", "ipcr_gpu_scan_device",
     "ipcr_gpu_genome_upload", "ipcr_gpu_genome_adopt", "ipcr_gpu_genome_destroy",
@@ -151,6 +151,7 @@ def lib():
     sig("ipcr_gpu_panel_num_orientations", SZ, V)
     sig("ipcr_gpu_panel_have", C.c_int, V, SZ, C.c_int)
     sig("ipcr_gpu_panel_set_jit", None, V, C.c_int)
+    sig("ipcr_gpu_panel_set_filter", None, V, C.c_int)
     sig("ipcr_gpu_scratch_create", V, V, *ERR)
     sig("ipcr_gpu_scratch_destroy", None, V)
     sig("ipcr_gpu_scan", C.c_int, V, V, V, U64, P(P(ProductC)), P(U64), *ERR)

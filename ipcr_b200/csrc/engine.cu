@@ -1210,6 +1210,8 @@ void ipcr_gpu_panel_set_jit(ipcr_panel *p, int mode) {
     if (p) p->host.jit_mode = mode;
 }
 
+void ipcr_gpu_panel_set_filter(ipcr_panel *p, int filter) { ipcr_gpu_panel_set_jit(p, filter); }
+
 ipcr_scratch *ipcr_gpu_scratch_create(ipcr_panel *p, char *err, size_t errlen) {
     ABI_TRY
     if (!p) throw Error("panel is NULL");

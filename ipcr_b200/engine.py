@@ -129,6 +129,13 @@ class CompiledPanel:
     def num_orientations(self) -> int:
         return int(_capi.lib().ipcr_gpu_panel_num_orientations(self._h)) if self._h else 0
 
+    FILTER_BITPARALLEL_TABLE, FILTER_AUTO, FILTER_BITPARALLEL_JIT, FILTER_SEED_INDEX = 0, 1, 2, 3
+
+    def set_filter(self, which: int) -> None:
+        """Candidate filter: FILTER_AUTO (default: seed index with automatic fallback), FILTER_SEED_INDEX,
+        FILTER_BITPARALLEL_JIT, FILTER_BITPARALLEL_TABLE.  All produce the same products."""
+        self.set_jit(which)
+
     def set_jit(self, mode: int) -> None:
         if self._h:
             _capi.lib().ipcr_gpu_panel_set_jit(self._h, mode)
