@@ -1791,6 +1791,7 @@ int ipcr_gpu_debug_seed_eval(ipcr_panel *p, int raw_mode, const uint8_t *seq, ui
             info[2] = (int32_t)ix.table_bits;
             info[3] = ix.use_bloom ? 1 : 0;
             info[4] = (int32_t)(ix.bloom_fill * 1e6);
+            info[5] = ix.bloom_k;
         }
     } catch (const std::exception &) {
         return 1;

@@ -132,18 +132,19 @@ inline void seed_enumerate(const Orient &o, int S, int max_mm, int tw, bool raw,
 // divergent second-level lookup whose cost grows faster than the pass rate (the warp waits
 // for its busiest lane): ~50 * pass^1.8; a candidate costs ~675 (table walk, atomic append,
 // verify).
-constexpr int kSeedBloomK = 2;  // bitmap bits per k-mer (same word)
+// The second bitmap bit costs ~12 % of the fast path (measured 1.69 vs 1.50 ms per 3 Gbp) and
+// pays for itself only once the bitmap is reasonably full.
 
 inline double seed_pass_rate(double entries, int S, int k) {
     const double fill = 1.0 - std::exp(-(double)k * entries / (double)kSeedBloomBits);
     return std::min(1.0, std::pow(fill, k) + entries / std::pow(4.0, S));
 }
 
-inline double seed_cost(double entries, int S) {
+inline double seed_cost(double entries, int S, int k) {
     const double prob = entries / std::pow(4.0, S);
-    const double pass = seed_pass_rate(entries, S, kSeedBloomK);
+    const double pass = seed_pass_rate(entries, S, k);
     const double walk = pass <= 0.5 ? 50.0 * std::pow(pass, 1.8) : 15.0;  // > 0.5: no bitmap, every position walks
-    return 1.0 + walk + prob * 675.0;
+    return (k == 2 ? 1.12 : 1.0) + walk + prob * 675.0;
 }
 
 inline SeedIndex seed_build(const Panel &h, int variant) {
@@ -156,15 +157,17 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
         if (o.L > 0) min_len = std::min(min_len, o.L);
     if (min_len == 1 << 30) min_len = 1;
     const int s_max = std::max(1, std::min(kSeedMaxLen, min_len));
-    int best_s = 0;
+    int best_s = 0, best_k = 2;
     double best_cost = 1e300;
     for (int S = s_max; S >= 1; S--) {
         uint64_t e = 0;
         for (const Orient &o : h.orients)
             if (o.L >= S) e = std::min<uint64_t>(1ull << 40, e + seed_variant_count(o, S, mm, tw, raw));
         if (e > kSeedMaxEntries) continue;
-        const double c = seed_cost((double)e, S);
-        if (c < best_cost) { best_cost = c; best_s = S; }
+        for (int k = 1; k <= 2; k++) {
+            const double c = seed_cost((double)e, S, k);
+            if (c < best_cost) { best_cost = c; best_s = S; best_k = k; }
+        }
     }
     if (best_s == 0) best_s = std::min(s_max, 6);  // 4^6 x 2048 orientations always fits
     if (const char *e = getenv("IPCR_SEED_LEN")) best_s = std::max(1, std::min(atoi(e), s_max));
@@ -185,7 +188,7 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
     ix.slots.assign((size_t)1 << ix.table_bits, 0ull);
     ix.bloom.assign(kSeedBloomWords, 0u);
     const uint32_t tmask = (uint32_t)((1ull << ix.table_bits) - 1);
-    ix.bloom_k = kSeedBloomK;
+    ix.bloom_k = best_k;
     {
         const int bits2 = std::max(10, std::min(2 * ix.S, 28));
         if (2 * ix.S <= 28) { ix.bitmap2_mul = 1u; ix.bitmap2_shift = 0u; }

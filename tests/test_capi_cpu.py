@@ -232,6 +232,8 @@ def test_seed_index_shape_on_the_benchmark_panel():
     rng = random.Random(3)
     g = bytes(H.random_genome(rng, 50000))
     cands, info = cp.seed_eval(g)
-    assert info["S"] >= 12 and info["bloom"] and info["bloom_fill"] < 0.35
+    assert info["S"] >= 12 and info["bloom"] and info["bloom_fill"] < 0.35 and info["bloom_k"] == 2
+    cp1 = Engine(Config(max_mm=1, terminal_window=3)).compile_panel(allp)
+    assert cp1.seed_eval(g)[1]["bloom_k"] == 1  # a sparse bitmap does not need the second bit
     assert info["entries"] < 1 << 20
     assert len(cands) < 400  # ~ entries / 4^S per position

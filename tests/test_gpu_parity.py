@@ -334,6 +334,18 @@ def test_long_n_runs(oracle):
         _check(oracle, dict(cfgd, terminal_window=0, hit_cap=100), [(a, b, 0, 0)], seq, cap_binds=True)
 
 
+def test_both_bitmap_widths(oracle, monkeypatch):
+    """The shared-memory bitmap sets one or two bits per k-mer (chosen by the cost model from its
+    fill); force each on the same inputs."""
+    rng = random.Random(606)
+    cases = [_random_case(rng, big=True) for _ in range(3)]
+    for k in ("1", "2"):
+        monkeypatch.setenv("IPCR_SEED_BLOOM_K", k)
+        for cfgd, pairs, seq in cases:
+            _check(oracle, cfgd, pairs, seq, jit=3)
+    monkeypatch.delenv("IPCR_SEED_BLOOM_K")
+
+
 def test_dirty_window_overflow_path(oracle, monkeypatch):
     """> 16 orientations share the k-mers of one dirty seed window (k_seed_dirty_probe gives up
     on it and k_seed_dirty_expand verifies every orientation there)."""
