@@ -66,7 +66,8 @@ struct SeedIndex {
     std::vector<uint32_t> bloom;
     // second level, L2-resident: one bit per k-mer value (2S <= 28: exact) or per hashed k-mer
     std::vector<uint32_t> bitmap2;
-    uint32_t bitmap2_mul = 1, bitmap2_shift = 0;  // bit index = (k-mer * mul) >> shift
+    // h = k-mer * mul (32-bit wrap): word = h >> shift, bit = h & 31.  Exact (mul 1, shift 5) when 2S <= 28.
+    uint32_t bitmap2_mul = 1, bitmap2_shift = 5;
     bool use_bloom = false;
     int bloom_k = 1;  // bits per k-mer
     uint64_t n_entries = 0;
@@ -191,8 +192,8 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
     ix.bloom_k = best_k;
     {
         const int bits2 = std::max(10, std::min(2 * ix.S, 28));
-        if (2 * ix.S <= 28) { ix.bitmap2_mul = 1u; ix.bitmap2_shift = 0u; }
-        else { ix.bitmap2_mul = kSeedHashMul; ix.bitmap2_shift = 32u - (uint32_t)bits2; }
+        if (2 * ix.S <= 28) { ix.bitmap2_mul = 1u; ix.bitmap2_shift = 5u; }
+        else { ix.bitmap2_mul = kSeedHashMul; ix.bitmap2_shift = 32u - (uint32_t)(bits2 - 5); }
         ix.bitmap2.assign((size_t)1 << (bits2 - 5), 0u);
     }
     if (const char *e = getenv("IPCR_SEED_BLOOM_K")) ix.bloom_k = std::max(1, std::min(atoi(e), 2));
@@ -203,8 +204,8 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
         uint32_t m;
         const uint32_t w = seed_bloom_word(e.first, ix.S, ix.bloom_k, m);
         ix.bloom[w] |= m;
-        const uint32_t i2 = (uint32_t)(e.first * ix.bitmap2_mul) >> ix.bitmap2_shift;
-        ix.bitmap2[i2 >> 5] |= 1u << (i2 & 31u);
+        const uint32_t h2 = e.first * ix.bitmap2_mul;
+        ix.bitmap2[h2 >> ix.bitmap2_shift] |= 1u << (h2 & 31u);
     }
     uint64_t bits_set = 0;
     for (uint32_t w : ix.bloom) bits_set += (uint64_t)__builtin_popcount(w);
@@ -235,8 +236,8 @@ inline void seed_eval(const Panel &h, const SeedIndex &ix, const uint8_t *seq, u
                 const uint32_t w = seed_bloom_word(kmer, ix.S, ix.bloom_k, m);
                 if ((ix.bloom[w] & m) != m) continue;
             }
-            const uint32_t i2 = (uint32_t)(kmer * ix.bitmap2_mul) >> ix.bitmap2_shift;
-            if (!((ix.bitmap2[i2 >> 5] >> (i2 & 31u)) & 1u)) continue;
+            const uint32_t h2 = kmer * ix.bitmap2_mul;
+            if (!((ix.bitmap2[h2 >> ix.bitmap2_shift] >> (h2 & 31u)) & 1u)) continue;
             for (uint32_t hh = (uint32_t)(kmer * kSeedHashMul) >> (32 - ix.table_bits); ix.slots[hh]; hh = (hh + 1) & tmask) {
                 const uint64_t slot = ix.slots[hh];
                 const uint64_t c = (slot >> 48) & 0xFF;
@@ -259,8 +260,8 @@ inline void seed_eval(const Panel &h, const SeedIndex &ix, const uint8_t *seq, u
             for (uint32_t combo = 0; !overflow && combo < (1u << (2 * pos.size())); combo++) {
                 uint32_t km = base;
                 for (size_t u = 0; u < pos.size(); u++) km |= ((combo >> (2 * u)) & 3u) << (2 * pos[u]);
-                const uint32_t i2 = (uint32_t)(km * ix.bitmap2_mul) >> ix.bitmap2_shift;
-                if (!((ix.bitmap2[i2 >> 5] >> (i2 & 31u)) & 1u)) continue;
+                const uint32_t h2 = km * ix.bitmap2_mul;
+                if (!((ix.bitmap2[h2 >> ix.bitmap2_shift] >> (h2 & 31u)) & 1u)) continue;
                 for (uint32_t hh = (uint32_t)(km * kSeedHashMul) >> (32 - ix.table_bits); ix.slots[hh] && !overflow;
                      hh = (hh + 1) & tmask) {
                     const uint64_t slot = ix.slots[hh];

@@ -141,7 +141,7 @@ struct SeedScanArgs {
     uint32_t bloom_mul;  // kSeedBloomMul << (32 - 2S)
     const uint32_t *bloom;
     const uint32_t *bitmap2;  // second level (global, L2-resident)
-    uint32_t bitmap2_mul, bitmap2_shift;
+    uint32_t bitmap2_mul, bitmap2_shift;  // h = k-mer * mul: word = h >> shift, bit = h & 31
     const unsigned long long *table;
     uint32_t table_shift;  // 32 - table_bits
     uint32_t table_mask;
@@ -290,14 +290,18 @@ k_seed_scan(SeedScanArgs a) {
             // second level for the set bits: one bit per (hashed) k-mer in an L2-resident bitmap;
             // only its hits walk the hash table.  (Keeping 2-4 of these lookups in flight per lane,
             // or moving them to a second, warp-balanced kernel, measured slower: profiles/README.md.)
+            // (The kernel is integer-issue bound, so this loop is written for instruction count: highest
+            // set bit first = one FLO, the funnel shift wraps its amount mod 32, the bitmap word index
+            // and bit position come straight from the hash, the bit test sets a predicate.)
             while (hits) {
-                const int j = __ffs(hits) - 1;
-                hits &= hits - 1u;
-                const uint32_t lo = j < 16 ? w0 : w1, hi = j < 16 ? w1 : w2;
-                const uint32_t kmer = __funnelshift_r(lo, hi, 2 * (j & 15)) & a.kmer_mask;
-                const uint32_t i2 = (kmer * a.bitmap2_mul) >> a.bitmap2_shift;
-                if (__funnelshift_r(ld_u32_policy(a.bitmap2 + (i2 >> 5), keep), 0u, i2) & 1u)
-                    seed_walk(a, kmer, P0 + (uint64_t)(blk * 32 + j), keep);
+                uint32_t j;
+                asm("bfind.u32 %0, %1;" : "=r"(j) : "r"(hits));  // position of the highest set bit
+                hits ^= 1u << j;
+                const uint32_t lo = j < 16u ? w0 : w1, hi = j < 16u ? w1 : w2;
+                const uint32_t kmer = __funnelshift_r(lo, hi, 2u * j) & a.kmer_mask;
+                const uint32_t h2 = kmer * a.bitmap2_mul;
+                if (ld_u32_policy(a.bitmap2 + (h2 >> a.bitmap2_shift), keep) & __funnelshift_l(0u, 1u, h2))
+                    seed_walk(a, kmer, P0 + (uint64_t)(blk * 32) + j, keep);
             }
         }
     }
@@ -357,8 +361,8 @@ k_seed_dirty_probe(SeedDirtyProbeArgs a) {
             for (uint32_t combo = 0; combo < (1u << (2u * t)) && !overflow; combo++) {
                 uint32_t km = base;
                 for (uint32_t u = 0; u < t; u++) km |= ((combo >> (2u * u)) & 3u) << (2u * pos[u]);
-                const uint32_t i2 = (km * a.bitmap2_mul) >> a.bitmap2_shift;
-                if (!((a.bitmap2[i2 >> 5] >> (i2 & 31u)) & 1u)) continue;
+                const uint32_t h2 = km * a.bitmap2_mul;
+                if (!((a.bitmap2[h2 >> a.bitmap2_shift] >> (h2 & 31u)) & 1u)) continue;
                 for (uint32_t h = (km * kSeedHashMulDev) >> a.table_shift;; h = (h + 1u) & a.table_mask) {
                     const unsigned long long slot = a.table[h];
                     if (slot == 0ull) break;
