@@ -11,7 +11,9 @@ from .engine import CompiledPanel, Engine, Product, SimulationScratch, _as_buffe
 
 
 class Genome:
-    """A packed genome resident in HBM (striped one-hot bit-planes + the raw bytes)."""
+    """A packed genome resident in HBM: the raw bytes plus whichever packed format the panel's filter
+    reads (2-bit codes + hard-mismatch bitmap for the seed index, striped one-hot bit-planes for the
+    bit-parallel scan); the other format is packed on demand."""
 
     def __init__(self, handle, n_recs: int, keep=None):
         self._h = handle
