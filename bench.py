@@ -192,16 +192,52 @@ def run_reference(a):
 # clocks
 # --------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  The region is tens of milliseconds
+    long, so NVML is polled from a thread every ~2 ms; `nvidia-smi -lms` is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index=0):
         self.rows = []
         self.proc = None
         self.gpu = gpu_index
+        self.nvml = None
+        self.samples = []   # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self.run = False
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = None
+            try:  # the CUDA device's own PCI address (CUDA and NVML may order devices differently)
+                import torch
+                pr = torch.cuda.get_device_properties(self.gpu)
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.handle = None
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.run = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -211,11 +247,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while self.run:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    why = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    why = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((mhz, why))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.run = False
+            self.t.join(timeout=1.0)
+            sm = sorted(x[0] for x in self.samples)
+            bits = 0
+            for _m, w in self.samples:
+                bits |= w
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(name for bit, name in self.REASONS if bits & bit), "samples": len(sm),
+                    "source": "nvml, polled every ~2 ms inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -235,7 +295,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # dram bytes (read + write) of one launch from the committed `ncu --set full` capture of the
