@@ -198,6 +198,34 @@ def test_seed_index_complete_on_a_multiplex_panel(oracle):
         assert n_true >= 2 * 2 * 36  # both primer sites of (nearly) every planted amplicon, both variants
 
 
+def test_seed_index_high_mismatch_budgets(oracle):
+    """max_mm 4..5 on N-rich sequences: dirty windows with more than four invalid bytes leave the
+    replacement lookups for the verify-everything path; completeness must survive."""
+    rng = random.Random(515)
+    checked = 0
+    for it in range(25):
+        n = rng.randint(150, 260)
+        g = H.random_genome(rng, n, n_frac=rng.choice([0.05, 0.15, 0.3]))
+        mm, tw = rng.choice([4, 5]), rng.choice([0, 2, 3])
+        la, lb = rng.randint(8, 30), rng.randint(8, 30)
+        a, b = H.random_primer(rng, la, rng.choice([0, 0.15])), H.random_primer(rng, lb, 0)
+        for _ in range(3):
+            H.plant_amplicon(rng, g, rng.randint(0, n - la - lb - 10), a, b, la + lb + rng.randint(0, 10),
+                             rng.randint(0, mm), rng.randint(0, mm), tw, revcomp_strand=rng.random() < 0.5)
+        seq = bytes(g)
+        cp = Engine(Config(max_mm=mm, terminal_window=tw)).compile_panel([Pair("x", a, b)])
+        for raw in (False, True):
+            cands, _info = cp.seed_eval(seq, raw)
+            assert len(cands) == len(set(cands))
+            cset = set(cands)
+            for q in range(cp.num_orientations):
+                s, t = cp.orientation(q)
+                for pos in _true_sites(oracle, seq, s, t == "a", mm, tw, raw):
+                    assert (q, pos) in cset, (s, t, mm, tw, raw, pos)
+                    checked += 1
+    assert checked > 100
+
+
 def test_seed_index_dirty_window_overflow(oracle, monkeypatch):
     """More than 16 orientations behind one dirty seed window: the probe gives up on the window
     and every orientation is verified there -- still complete, still duplicate-free."""

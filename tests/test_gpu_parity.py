@@ -346,6 +346,23 @@ def test_both_bitmap_widths(oracle, monkeypatch):
     monkeypatch.delenv("IPCR_SEED_BLOOM_K")
 
 
+def test_high_mismatch_budgets_on_n_rich_input(oracle):
+    """max_mm 4..5 with many N: dirty windows holding more than four invalid bytes (no replacement
+    lookups, every orientation verified) and huge variant sets."""
+    rng = random.Random(515)
+    for it in range(6):
+        n = rng.randint(300, 900)
+        g = H.random_genome(rng, n, n_frac=rng.choice([0.05, 0.15, 0.3]))
+        mm, tw = rng.choice([4, 5]), rng.choice([0, 2, 3])
+        la, lb = rng.randint(8, 30), rng.randint(8, 30)
+        a, b = H.random_primer(rng, la, rng.choice([0, 0.15])), H.random_primer(rng, lb, 0)
+        for _ in range(3):
+            H.plant_amplicon(rng, g, rng.randint(0, n - la - lb - 10), a, b, la + lb + rng.randint(0, 10),
+                             rng.randint(0, mm), rng.randint(0, mm), tw, revcomp_strand=rng.random() < 0.5)
+        cfgd = dict(max_mm=mm, terminal_window=tw, max_len=200, hit_cap=rng.choice([0, 0, 7]))
+        _check(oracle, cfgd, [(a, b, 0, 0)], bytes(g), cap_binds=cfgd["hit_cap"] > 0)
+
+
 def test_dirty_window_overflow_path(oracle, monkeypatch):
     """> 16 orientations share the k-mers of one dirty seed window (k_seed_dirty_probe gives up
     on it and k_seed_dirty_expand verifies every orientation there)."""
