@@ -17,8 +17,8 @@ happens on the GPU through include/ipcr_gpu.h; nothing here computes matches.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
-from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
 
 from . import _capi
 from ._capi import GpuError

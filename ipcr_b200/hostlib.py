@@ -12,11 +12,11 @@ from __future__ import annotations
 
 import ctypes as C
 from collections import OrderedDict
-from dataclasses import dataclass, field
-from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Callable, List, Sequence, Tuple
 
 from . import _capi
-from .engine import CompiledPanel, Config, Engine, Pair, Product, SimulationScratch
+from .engine import Config, Engine, Pair, Product, SimulationScratch
 from .fasta import FastaFile
 
 # ---------------------------------------------------------------- common ----------------
