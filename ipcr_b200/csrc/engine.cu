@@ -905,8 +905,9 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         a.inval = g.inval.as<uint32_t>();
         a.n_chunks = n_chunks;
         a.S = (uint32_t)ix.S;
+        a.d = (uint32_t)(ix.S - ix.S1);
         a.kmer_mask = ix.kmer_mask;
-        a.bloom_mul = seed_bloom_mul(ix.S);
+        a.bloom_mul = seed_bloom_mul(ix.S1);
         a.bloom = t->seed_bloom[variant].as<uint32_t>();
         a.bitmap2 = t->seed_bitmap2[variant].as<uint32_t>();
         a.bitmap2_mul = ix.bitmap2_mul;
@@ -1792,6 +1793,8 @@ int ipcr_gpu_debug_seed_eval(ipcr_panel *p, int raw_mode, const uint8_t *seq, ui
             info[3] = ix.use_bloom ? 1 : 0;
             info[4] = (int32_t)(ix.bloom_fill * 1e6);
             info[5] = ix.bloom_k;
+            info[6] = ix.S1;
+            info[7] = (int32_t)std::min<uint64_t>(ix.n_keys1, 0x7FFFFFFF);
         }
     } catch (const std::exception &) {
         return 1;

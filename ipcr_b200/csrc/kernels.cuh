@@ -244,6 +244,8 @@ k_filter_generic(FilterArgs a) {
 struct VerifyArgs {
     const unsigned long long *cand;
     uint64_t n_cand;
+    // asynchronous chain: the count is still on the device (n = min(*n_cand_ptr, n_cand)); NULL = n_cand
+    const unsigned long long *n_cand_ptr;
     const uint8_t *ascii;
     const SegmentDev *segs;
     uint32_t n_segs;
@@ -312,11 +314,13 @@ __device__ __forceinline__ void compact_site(const VerifyArgs &a, bool ok, const
 __global__ void __launch_bounds__(256)
 k_verify(VerifyArgs a) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_round = (a.n_cand + 31ull) & ~31ull;
+    uint64_t n_cand = a.n_cand;
+    if (a.n_cand_ptr) n_cand = min((uint64_t)*a.n_cand_ptr, n_cand);
+    const uint64_t n_round = (n_cand + 31ull) & ~31ull;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         bool ok = false;
         ipcr_site s;
-        if (i < a.n_cand) {
+        if (i < n_cand) {
             const unsigned long long cw = a.cand[i];
             ok = verify_one(a, (uint32_t)(cw >> kCandPosBits), cw & kCandPosMask, &s);
         }
@@ -402,14 +406,15 @@ __device__ __forceinline__ uint64_t make_prefix(const KeyLayout &kl, uint32_t re
 }
 
 // sort key: ((rec*U + q) << 1 | halo) << pos_bits | pos ; invalid sites sort last
-__global__ void k_site_keys(const ipcr_site *__restrict__ sites, uint64_t n, const OrientDev *__restrict__ orients,
-                            const ipcr_record_info *__restrict__ recs, ScanParams prm, KeyLayout kl,
-                            uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const ipcr_site s = sites[i];
+// rec_reset (optional): per-record flags raised on the device by the pack kernels of the
+// asynchronous chain; OR-ed with the host-supplied recs[].has_reset_byte
+__device__ __forceinline__ uint64_t site_key(const ipcr_site &s, const OrientDev *__restrict__ orients,
+                                             const ipcr_record_info *__restrict__ recs,
+                                             const uint8_t *__restrict__ rec_reset, const ScanParams &prm,
+                                             const KeyLayout &kl) {
     const OrientDev o = orients[s.orient];
-    const bool has_reset = recs[s.rec_idx].has_reset_byte != 0 && prm.max_mm > 0;  // compiled.go:189
+    const bool reset = recs[s.rec_idx].has_reset_byte != 0 || (rec_reset && rec_reset[s.rec_idx] != 0);
+    const bool has_reset = reset && prm.max_mm > 0;  // compiled.go:189
     // rc orientations served by primer.FindMatches are capped BEFORE filterLeftTW
     // (compiled.go:250-257): forced fallback, or an orientation the reference cannot seed
     const bool raw_mode = prm.hit_cap > 0 && o.rc_type && (has_reset || !o.seeded);
@@ -419,7 +424,15 @@ __global__ void k_site_keys(const ipcr_site *__restrict__ sites, uint64_t n, con
     const uint64_t halo = ((s.flags & IPCR_SITE_HALO) && !o.rc_type && o.seeded && has_reset && prm.hit_cap == 0) ? 1u : 0u;
     uint64_t key = (((make_prefix(kl, s.rec_idx, s.orient) << 1) | halo) << kl.pos_bits) | s.pos;
     if (!valid) key = 1ull << kl.key_bits;
-    keys[i] = key;
+    return key;
+}
+
+__global__ void k_site_keys(const ipcr_site *__restrict__ sites, uint64_t n, const OrientDev *__restrict__ orients,
+                            const ipcr_record_info *__restrict__ recs, const uint8_t *__restrict__ rec_reset,
+                            ScanParams prm, KeyLayout kl, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = site_key(sites[i], orients, recs, rec_reset, prm, kl);
     vals[i] = (uint32_t)i;
 }
 
@@ -534,10 +547,7 @@ __device__ __forceinline__ uint64_t flip_mask(uint64_t m, int n) {  // engine.go
 // restatement of one iteration of the outer loops of forEachJoinedProduct
 // (core/engine/engine.go:144-272 / :276-402).  FILL = false counts, true writes.
 template <bool FILL>
-__global__ void __launch_bounds__(128)
-k_join(JoinArgs a) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n_tasks) return;
+__device__ __forceinline__ void join_task(const JoinArgs &a, uint64_t t) {
     const uint64_t n_entries = (uint64_t)a.n_recs * a.n_pairs * 2ull;
     // entry = last e with task_off[e] <= t
     uint64_t lo = 0, hi = n_entries;
@@ -637,6 +647,13 @@ k_join(JoinArgs a) {
         }
     }
     if (!FILL) a.task_cnt[t] = cnt;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_join(JoinArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < a.n_tasks) join_task<FILL>(a, t);
 }
 
 // ---------------------------------------------------------------------------

@@ -60,6 +60,10 @@ inline uint32_t seed_bloom_word(uint32_t kmer, int S, int k, uint32_t &mask) {
 
 struct SeedIndex {
     int S = 0;
+    // first level: the shared-memory bitmap is keyed by the S1 bases at the HIGH end of the S-base seed
+    // window (key1 = k-mer >> 2*(S - S1)).  Fewer free columns => far fewer distinct keys than S-mers
+    // => a sparser bitmap; the exact (or hashed) S-mer test stays in the second level.
+    int S1 = 0;
     uint32_t kmer_mask = 0;
     uint32_t table_bits = 0;
     std::vector<uint64_t> slots;
@@ -71,6 +75,7 @@ struct SeedIndex {
     bool use_bloom = false;
     int bloom_k = 1;  // bits per k-mer
     uint64_t n_entries = 0;
+    uint64_t n_keys1 = 0;     // distinct first-level keys
     double bloom_fill = 0.0;  // fraction of bitmap bits set
     double cand_prob = 0.0;   // expected candidates per genome position
     std::vector<uint16_t> col_off;  // per orientation: site start = k-mer start - col_off
@@ -127,25 +132,48 @@ inline void seed_enumerate(const Orient &o, int S, int max_mm, int tw, bool raw,
     }
 }
 
-// modelled cost of the seed filter per genome position, in units of the scan kernel's fast
-// path (one shared-memory bitmap lookup).  Fitted to B200 measurements on 3 Gbp x 400
-// orientations (profiles/r01_seed_sweep.txt): positions passing the bitmap go through a
-// divergent second-level lookup whose cost grows faster than the pass rate (the warp waits
-// for its busiest lane): ~50 * pass^1.8; a candidate costs ~675 (table walk, atomic append,
-// verify).
-// The second bitmap bit costs ~12 % of the fast path (measured 1.69 vs 1.50 ms per 3 Gbp) and
-// pays for itself only once the bitmap is reasonably full.
-
-inline double seed_pass_rate(double entries, int S, int k) {
-    const double fill = 1.0 - std::exp(-(double)k * entries / (double)kSeedBloomBits);
-    return std::min(1.0, std::pow(fill, k) + entries / std::pow(4.0, S));
+// modelled cost of the seed filter per genome position, in units of the scan kernel's fast path
+// (one shared-memory bitmap lookup).  Positions passing the first-level bitmap pay a divergent
+// second-level lookup in L2 (the warp waits for its busiest lane, so the cost grows faster than the
+// pass rate): ~50 * pass^1.8, fitted to B200 sweeps (profiles/r01_seed_sweep.txt, r02_seed_sweep.txt); a
+// candidate costs ~675 (table walk, append, verify).  The second bitmap bit costs ~12 % of the fast path.
+inline double seed_bloom_fp(double keys, int k) {
+    const double fill = 1.0 - std::exp(-(double)k * keys / (double)kSeedBloomBits);
+    return std::pow(fill, k);
 }
 
-inline double seed_cost(double entries, int S, int k) {
+inline double seed_pass_rate(double keys1, int S1, int k) {
+    return std::min(1.0, seed_bloom_fp(keys1, k) + keys1 / std::pow(4.0, S1));
+}
+
+inline double seed_cost(double entries, int S, double keys1, int S1, int k) {
     const double prob = entries / std::pow(4.0, S);
-    const double pass = seed_pass_rate(entries, S, k);
+    const double pass = seed_pass_rate(keys1, S1, k);
     const double walk = pass <= 0.5 ? 50.0 * std::pow(pass, 1.8) : 15.0;  // > 0.5: no bitmap, every position walks
     return (k == 2 ? 1.12 : 1.0) + walk + prob * 675.0;
+}
+
+// variants of the S1 columns at the high end of orientation o's S-column seed window (an upper bound on
+// its distinct first-level keys)
+inline uint64_t seed_key1_count(const Orient &o, int S, int S1, int max_mm, int tw, bool raw) {
+    const uint64_t kSat = 1ull << 40;
+    const int off = seed_col_off(o, S) + (S - S1);
+    std::vector<uint64_t> ways((size_t)max_mm + 1, 0);
+    ways[0] = 1;
+    for (int j = 0; j < S1; j++) {
+        const uint64_t km = (uint64_t)class_popcount(o.cls[off + j]);
+        const uint64_t kx = seed_col_protected(o, off + j, tw, raw) ? 0 : 4 - km;
+        std::vector<uint64_t> nw((size_t)max_mm + 1, 0);
+        for (int m = 0; m <= max_mm; m++) {
+            if (!ways[m]) continue;
+            nw[m] = std::min(kSat, nw[m] + ways[m] * km);
+            if (m + 1 <= max_mm) nw[m + 1] = std::min(kSat, nw[m + 1] + ways[m] * kx);
+        }
+        ways.swap(nw);
+    }
+    uint64_t total = 0;
+    for (uint64_t w : ways) total = std::min(kSat, total + w);
+    return total;
 }
 
 inline SeedIndex seed_build(const Panel &h, int variant) {
@@ -158,21 +186,32 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
         if (o.L > 0) min_len = std::min(min_len, o.L);
     if (min_len == 1 << 30) min_len = 1;
     const int s_max = std::max(1, std::min(kSeedMaxLen, min_len));
-    int best_s = 0, best_k = 2;
+    int best_s = 0, best_s1 = 0, best_k = 2;
     double best_cost = 1e300;
     for (int S = s_max; S >= 1; S--) {
         uint64_t e = 0;
         for (const Orient &o : h.orients)
             if (o.L >= S) e = std::min<uint64_t>(1ull << 40, e + seed_variant_count(o, S, mm, tw, raw));
         if (e > kSeedMaxEntries) continue;
-        for (int k = 1; k <= 2; k++) {
-            const double c = seed_cost((double)e, S, k);
-            if (c < best_cost) { best_cost = c; best_s = S; best_k = k; }
+        for (int S1 = S; S1 >= std::min(S, 3); S1--) {
+            uint64_t k1 = 0;
+            for (const Orient &o : h.orients)
+                if (o.L >= S) k1 = std::min<uint64_t>(1ull << 40, k1 + seed_key1_count(o, S, S1, mm, tw, raw));
+            k1 = std::min<uint64_t>(k1, e);
+            for (int k = 1; k <= 2; k++) {
+                const double c = seed_cost((double)e, S, (double)k1, S1, k);
+                if (c < best_cost) { best_cost = c; best_s = S; best_s1 = S1; best_k = k; }
+            }
         }
     }
-    if (best_s == 0) best_s = std::min(s_max, 6);  // 4^6 x 2048 orientations always fits
-    if (const char *e = getenv("IPCR_SEED_LEN")) best_s = std::max(1, std::min(atoi(e), s_max));
+    if (best_s == 0) best_s = best_s1 = std::min(s_max, 6);  // 4^6 x 2048 orientations always fits
+    if (const char *e = getenv("IPCR_SEED_LEN")) {
+        best_s = std::max(1, std::min(atoi(e), s_max));
+        best_s1 = std::min(best_s1, best_s);
+    }
+    if (const char *e = getenv("IPCR_SEED_LEN1")) best_s1 = std::max(std::min(best_s, 3), std::min(atoi(e), best_s));
     ix.S = best_s;
+    ix.S1 = best_s1;
     ix.kmer_mask = best_s == 16 ? 0xFFFFFFFFu : ((1u << (2 * best_s)) - 1u);
     std::vector<std::pair<uint32_t, uint32_t>> entries;  // (k-mer, orientation)
     std::vector<uint32_t> tmp;
@@ -197,21 +236,32 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
         ix.bitmap2.assign((size_t)1 << (bits2 - 5), 0u);
     }
     if (const char *e = getenv("IPCR_SEED_BLOOM_K")) ix.bloom_k = std::max(1, std::min(atoi(e), 2));
+    const int d2 = 2 * (ix.S - ix.S1);
+    std::vector<uint32_t> keys1;
+    keys1.reserve(entries.size());
     for (const auto &e : entries) {
         uint32_t hh = (uint32_t)(e.first * kSeedHashMul) >> (32 - ix.table_bits);
         while (ix.slots[hh]) hh = (hh + 1) & tmask;
         ix.slots[hh] = seed_slot(e.first, e.second, ix.col_off[e.second]);
-        uint32_t m;
-        const uint32_t w = seed_bloom_word(e.first, ix.S, ix.bloom_k, m);
-        ix.bloom[w] |= m;
+        keys1.push_back(e.first >> d2);
         const uint32_t h2 = e.first * ix.bitmap2_mul;
         ix.bitmap2[h2 >> ix.bitmap2_shift] |= 1u << (h2 & 31u);
+    }
+    std::sort(keys1.begin(), keys1.end());
+    keys1.erase(std::unique(keys1.begin(), keys1.end()), keys1.end());
+    ix.n_keys1 = keys1.size();
+    if (ix.S1 >= 3) {
+        for (uint32_t k1 : keys1) {
+            uint32_t m;
+            const uint32_t w = seed_bloom_word(k1, ix.S1, ix.bloom_k, m);
+            ix.bloom[w] |= m;
+        }
     }
     uint64_t bits_set = 0;
     for (uint32_t w : ix.bloom) bits_set += (uint64_t)__builtin_popcount(w);
     ix.bloom_fill = (double)bits_set / (double)kSeedBloomBits;
-    ix.use_bloom = ix.S >= 3 && seed_pass_rate((double)ix.n_entries, ix.S, ix.bloom_k) <= 0.5;
-    if (const char *e = getenv("IPCR_SEED_BLOOM")) ix.use_bloom = atoi(e) != 0;
+    ix.use_bloom = ix.S1 >= 3 && seed_pass_rate((double)ix.n_keys1, ix.S1, ix.bloom_k) <= 0.5;
+    if (const char *e = getenv("IPCR_SEED_BLOOM")) ix.use_bloom = atoi(e) != 0 && ix.S1 >= 3;
     ix.cand_prob = (double)ix.n_entries / std::pow(4.0, ix.S);
     return ix;
 }
@@ -233,7 +283,7 @@ inline void seed_eval(const Panel &h, const SeedIndex &ix, const uint8_t *seq, u
         if (n_inv == 0) {
             if (ix.use_bloom) {
                 uint32_t m;
-                const uint32_t w = seed_bloom_word(kmer, ix.S, ix.bloom_k, m);
+                const uint32_t w = seed_bloom_word(kmer >> (2 * (ix.S - ix.S1)), ix.S1, ix.bloom_k, m);
                 if ((ix.bloom[w] & m) != m) continue;
             }
             const uint32_t h2 = kmer * ix.bitmap2_mul;

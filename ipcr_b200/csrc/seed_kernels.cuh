@@ -137,8 +137,9 @@ struct SeedScanArgs {
     const uint32_t *inval;
     uint64_t n_chunks;
     uint32_t S;
+    uint32_t d;          // S - S1: the first-level key is the high S1 bases of the seed window
     uint32_t kmer_mask;
-    uint32_t bloom_mul;  // kSeedBloomMul << (32 - 2S)
+    uint32_t bloom_mul;  // kSeedBloomMul << (32 - 2*S1)
     const uint32_t *bloom;
     const uint32_t *bitmap2;  // second level (global, L2-resident)
     uint32_t bitmap2_mul, bitmap2_shift;  // h = k-mer * mul: word = h >> shift, bit = h & 31
@@ -186,10 +187,17 @@ __device__ __forceinline__ uint4 ld_u128_policy(const uint4 *p, uint64_t pol) {
     return v;
 }
 
+// candidates are rare and arrive in divergent code: the lanes that are here together elect a
+// leader and take ONE atomic for all of them (warp-aggregated append)
 __device__ __forceinline__ void seed_emit(const SeedScanArgs &a, unsigned long long slot, uint64_t p) {
     const uint64_t c = (slot >> 48) & 0xFFull;
     if (p >= c) {
-        const unsigned long long i = atomicAdd(a.cand_count, 1ull);
+        const uint32_t peers = __activemask();
+        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+        unsigned long long base = 0ull;
+        if ((threadIdx.x & 31u) == leader) base = atomicAdd(a.cand_count, (unsigned long long)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const unsigned long long i = base + __popc(peers & ((1u << (threadIdx.x & 31u)) - 1u));
         if (i < a.cand_cap) a.cand[i] = (((slot >> 32) & 0xFFFFull) << kCandPosBits) | (p - c);
     }
 }
@@ -220,29 +228,40 @@ k_seed_scan(SeedScanArgs a) {
     const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     const uint64_t keep = l2_policy_keep(), stream = l2_policy_stream();
+    // The first level looks at the S1 bases at position q; a hit means "the S-mer starting at
+    // p = q - d may be in the index" (d = S - S1 >= 0: the first-level key is the HIGH end of the
+    // seed window).  The lane therefore keeps one code word and one bitmap word to the LEFT of its
+    // 128 positions: c[0] / iv[0].
+    const uint32_t d = a.d;
     for (uint64_t ch = warp; ch < a.n_chunks; ch += n_warps) {
         const uint64_t P0 = ch * kSeedChunk + (uint64_t)lane * 128u;
-        uint32_t c[9], iv[5];
+        uint32_t c[10], iv[6];
         {
             const uint4 *cp = reinterpret_cast<const uint4 *>(a.codes + (P0 >> 4));
             const uint4 q0 = ld_u128_policy(cp, stream), q1 = ld_u128_policy(cp + 1, stream);
-            c[0] = q0.x; c[1] = q0.y; c[2] = q0.z; c[3] = q0.w;
-            c[4] = q1.x; c[5] = q1.y; c[6] = q1.z; c[7] = q1.w;
-            c[8] = ld_u32_policy(a.codes + (P0 >> 4) + 8, stream);
+            c[1] = q0.x; c[2] = q0.y; c[3] = q0.z; c[4] = q0.w;
+            c[5] = q1.x; c[6] = q1.y; c[7] = q1.z; c[8] = q1.w;
+            c[9] = ld_u32_policy(a.codes + (P0 >> 4) + 8, stream);
             const uint4 qi = ld_u128_policy(reinterpret_cast<const uint4 *>(a.inval + (P0 >> 5)), stream);
-            iv[0] = qi.x; iv[1] = qi.y; iv[2] = qi.z; iv[3] = qi.w;
-            iv[4] = ld_u32_policy(a.inval + (P0 >> 5) + 4, stream);
+            iv[1] = qi.x; iv[2] = qi.y; iv[3] = qi.z; iv[4] = qi.w;
+            iv[5] = ld_u32_policy(a.inval + (P0 >> 5) + 4, stream);
+            c[0] = 0u;
+            iv[0] = 0xFFFFFFFFu;  // before the buffer: no window starts there
+            if (d != 0u && P0 != 0ull) {
+                c[0] = ld_u32_policy(a.codes + (P0 >> 4) - 1, stream);
+                iv[0] = ld_u32_policy(a.inval + (P0 >> 5) - 1, stream);
+            }
         }
 #pragma unroll
         for (int blk = 0; blk < 4; blk++) {
-            const uint32_t w0 = c[2 * blk], w1 = c[2 * blk + 1], w2 = c[2 * blk + 2];
+            const uint32_t wm = c[2 * blk], w0 = c[2 * blk + 1], w1 = c[2 * blk + 2], w2 = c[2 * blk + 3];
             uint32_t hits = 0u;
             if (BLOOM) {
                 const char *sb = reinterpret_cast<const char *>(sbloom);
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    // x: 32-bit window whose low 2S bits are the k-mer.  The multiplier is pre-shifted
-                    // by 32-2S, so the product ignores the bits above the k-mer: no mask needed.
+                    // x: 32-bit window whose low 2*S1 bits are the first-level key.  The multiplier is
+                    // pre-shifted by 32-2*S1, so the product ignores the bits above the key: no mask needed.
                     const uint32_t x = j < 16 ? __funnelshift_r(w0, w1, 2 * j) : __funnelshift_r(w1, w2, 2 * (j - 16));
                     // The ALU pipe (SHF/LOP3/LEA, half rate) is the busy one: the byte offset and the
                     // second bit position are formed with multiplies on the FMA pipe instead.
@@ -250,7 +269,7 @@ k_seed_scan(SeedScanArgs a) {
                     uint32_t off, b2;
                     off = __umulhi(hw, kSeedBloomWordsDev) * 4u;
                     const uint32_t w = *reinterpret_cast<const uint32_t *>(sb + off);
-                    uint32_t bit = __funnelshift_r(w, 0u, x);  // bit (k-mer & 31)
+                    uint32_t bit = __funnelshift_r(w, 0u, x);  // bit (key & 31)
                     if (BLOOM == 2) {
                         asm("mul.hi.u32 %0, %1, 2097152;" : "=r"(b2) : "r"(hw));  // hw >> 11: hash bits 11..15
                         bit &= __funnelshift_r(w, 0u, b2);
@@ -260,21 +279,21 @@ k_seed_scan(SeedScanArgs a) {
             } else {
                 hits = 0xFFFFFFFFu;
             }
-            const uint32_t ilo = iv[blk], ihi = iv[blk + 1];
-            if ((ilo | ihi) != 0u) {
+            const uint32_t ipr = iv[blk], ilo = iv[blk + 1], ihi = iv[blk + 2];
+            // windows are addressed by their START p.  A lane lists the dirty windows that start in
+            // ITS 128 positions, and masks the hits q whose window p = q - d is not clean.
+            if ((ilo | ihi) != 0u || (d != 0u && (ipr >> (32u - d)) != 0u)) {
                 // rare: a window holding an invalid byte has no k-mer.  Drop it here; if it holds
                 // 1..max_mm of them it may still be a site (genome N = one mismatch): those "dirty"
-                // windows are listed and verified against every orientation (halo.go:47-108).
+                // windows are listed and resolved by k_seed_dirty_probe (halo.go:47-108).
                 const uint64_t v = (uint64_t)ilo | ((uint64_t)ihi << 32);
                 const uint64_t smask = (1ull << a.S) - 1ull;
-                // d: windows [j, j+S) that hold an invalid byte; only those with <= max_mm of them
-                // can still be sites (inside an N run none can)
                 uint64_t spread = 0ull;
                 for (uint32_t k = 0; k < a.S; k++) spread |= v >> k;
-                const uint32_t d = (uint32_t)spread;
+                const uint32_t dr = (uint32_t)spread;  // windows [j, j+S) of this block that hold an invalid byte
                 if (a.max_mm > 0u && ((ilo & ihi) != 0xFFFFFFFFu || a.S <= a.max_mm)) {
-                    uint32_t elig = 0u;  // dirty windows that can still be sites
-                    for (uint32_t todo = d; todo; todo &= todo - 1u) {
+                    uint32_t elig = 0u;  // dirty windows that can still be sites (inside an N run none can)
+                    for (uint32_t todo = dr; todo; todo &= todo - 1u) {
                         const uint32_t j = (uint32_t)(__ffs(todo) - 1);
                         const uint32_t n = (uint32_t)__popcll((v >> j) & smask);
                         if (n <= a.max_mm && P0 + (uint64_t)(blk * 32) + j + a.S <= a.total_len) elig |= 1u << j;
@@ -285,23 +304,30 @@ k_seed_scan(SeedScanArgs a) {
                             if (i < a.dirty_cap) a.dirty[i] = P0 + (uint64_t)(blk * 32) + (uint32_t)(__ffs(elig) - 1);
                     }
                 }
-                hits &= ~d;
+                // hit bit j stands for the window starting d positions earlier
+                uint32_t df = dr;
+                if (d != 0u) {
+                    const uint64_t vf = (v << d) | (uint64_t)(ipr >> (32u - d));
+                    uint64_t sf = 0ull;
+                    for (uint32_t k = 0; k < a.S; k++) sf |= vf >> k;
+                    df = (uint32_t)sf;
+                }
+                hits &= ~df;
             }
-            // second level for the set bits: one bit per (hashed) k-mer in an L2-resident bitmap;
-            // only its hits walk the hash table.  (Keeping 2-4 of these lookups in flight per lane,
-            // or moving them to a second, warp-balanced kernel, measured slower: profiles/README.md.)
-            // (The kernel is integer-issue bound, so this loop is written for instruction count: highest
+            // second level for the set bits: one bit per (hashed) S-mer in an L2-resident bitmap;
+            // only its hits walk the hash table.  The loop is written for instruction count: highest
             // set bit first = one FLO, the funnel shift wraps its amount mod 32, the bitmap word index
-            // and bit position come straight from the hash, the bit test sets a predicate.)
+            // and bit position come straight from the hash, the bit test sets a predicate.
             while (hits) {
                 uint32_t j;
                 asm("bfind.u32 %0, %1;" : "=r"(j) : "r"(hits));  // position of the highest set bit
                 hits ^= 1u << j;
-                const uint32_t lo = j < 16u ? w0 : w1, hi = j < 16u ? w1 : w2;
-                const uint32_t kmer = __funnelshift_r(lo, hi, 2u * j) & a.kmer_mask;
+                const int32_t jp = (int32_t)j - (int32_t)d;  // window start relative to the block: -d .. 31
+                const uint32_t lo = jp < 0 ? wm : (jp < 16 ? w0 : w1), hi = jp < 0 ? w0 : (jp < 16 ? w1 : w2);
+                const uint32_t kmer = __funnelshift_r(lo, hi, 2u * (uint32_t)jp) & a.kmer_mask;
                 const uint32_t h2 = kmer * a.bitmap2_mul;
                 if (ld_u32_policy(a.bitmap2 + (h2 >> a.bitmap2_shift), keep) & __funnelshift_l(0u, 1u, h2))
-                    seed_walk(a, kmer, P0 + (uint64_t)(blk * 32) + j, keep);
+                    seed_walk(a, kmer, P0 + (uint64_t)(blk * 32) + j - d, keep);
             }
         }
     }

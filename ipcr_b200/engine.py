@@ -156,14 +156,14 @@ class CompiledPanel:
         ([(orientation, start)...], info) -- the candidates the seed filter hands to verify."""
         L = _capi.lib()
         n = C.c_uint64()
-        info = (C.c_int32 * 6)()
+        info = (C.c_int32 * 8)()
         L.ipcr_gpu_debug_seed_eval(self._h, 1 if raw_mode else 0, seq, len(seq), None, 0, C.byref(n), info)
         buf = (C.c_uint64 * max(1, n.value))()
         if L.ipcr_gpu_debug_seed_eval(self._h, 1 if raw_mode else 0, seq, len(seq), buf, n.value, C.byref(n), info):
             raise RuntimeError("seed index evaluation failed")
         cands = [(int(buf[i]) >> 44, int(buf[i]) & ((1 << 44) - 1)) for i in range(n.value)]
         return cands, dict(S=info[0], entries=info[1], table_bits=info[2], bloom=bool(info[3]),
-                           bloom_fill=info[4] / 1e6, bloom_k=info[5])
+                           bloom_fill=info[4] / 1e6, bloom_k=info[5], S1=info[6], keys1=info[7])
 
     def jit_source(self, raw_mode: bool = False) -> str:
         need = C.c_size_t()
