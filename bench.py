@@ -14,12 +14,13 @@ One step = one pass of the hot path (ForEachCompiledProduct over every record):
           to the host; device time from CUDA events on the scratch's own stream.
   e2e   : the same through the reference-facing call with HOST buffers (pinned), H2D and
           D2H inside the timed region, wall clock.
-N > 1, --scaling weak (default): the path partitions into independent records, so every rank
-scans its OWN 3 Gbp genome (same layout, different bases) with no data-path collective;
-value = bases of all ranks / max-over-ranks device time.
-N > 1, --scaling strong: ONE 3 Gbp genome is cut into N shards with a primer-length halo,
-every rank runs stage 1 on its shard, sites are gathered (one NCCL all-gather) and paired once
-on rank 0; time = max over ranks of the device time.
+N > 1, --scaling strong (default): ONE 3 Gbp genome is cut into N shards with a 64-base halo;
+every rank runs stage 1 on its shard into a fixed-size site block in device memory, ONE NCCL
+all-gather moves the blocks (sites never visit the host), stage 2 pairs once; time = max over
+ranks of the device time (CUDA events around stage 1 -> all-gather -> stage 2 -> products).
+e2e at N > 1: every rank additionally copies its shard from its own pinned host buffer first.
+N > 1, --scaling weak: every rank scans its OWN 3 Gbp genome (independent records, no
+collective); value = bases of all ranks / max-over-ranks device time.
 --impl reference times the CPU restatement of the reference's seeded Aho-Corasick engine
 (oracle/, Go toolchain absent) on all host cores over a bounded sample of the same workload.
 """
@@ -59,9 +60,9 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--filter", default="auto", choices=["auto", "seed", "bitparallel", "generic"],
                     help="candidate filter: auto = the library's own choice (seed index when selective)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = one whole genome per GPU (independent records, no collective); "
-                         "strong = one genome sharded over the GPUs, sites gathered, paired once")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong = ONE genome sharded over the GPUs, site blocks all-gathered on the device, "
+                         "paired once (north_star); weak = one whole genome per GPU (independent records, no collective)")
     ap.add_argument("--n-per-mbp", type=float, default=0.0,
                     help="scatter this many N bytes per Mbp over the genome (robustness runs; default off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -77,7 +78,8 @@ def workload_config(a, n_gpus, user_pairs, all_pairs, n_orient):
         sharding = (f"{n_gpus} genomes of {a.genome_mbp:g} Mbp, one per GPU (independent records, "
                     "no data-path collective)")
     else:
-        sharding = f"{n_gpus} shards of ONE genome, 64-base halo, sites gathered (one all-gather), paired on rank 0"
+        sharding = (f"{n_gpus} shards of ONE genome, 64-base halo; stage 1 per rank -> one NCCL all-gather of fixed-size "
+                    "site blocks (device-resident) -> stage 2 once")
     return {
         "workload": f"C5 multiplex: {a.genome_mbp:g} Mbp synthetic genome ({a.contigs} contigs), "
                     f"{len(user_pairs)}-pair panel (+self => {len(all_pairs)} pairs, {n_orient} unique orientations), "
@@ -340,7 +342,8 @@ def run_ours(a):
 
     L = _capi.lib()
     err = _capi.errbuf()
-    if L.ipcr_gpu_init(torch.cuda.current_device(), err, len(err)) != 0:
+    # one process per GPU: the thread is bound to its device by torch; one device per call
+    if L.ipcr_gpu_init(1, err, len(err)) != 0:
         raise RuntimeError(err.value.decode())
 
     user_pairs, all_pairs = synth.multiplex_panel(a.pairs, seed=SEED)
@@ -369,12 +372,13 @@ def run_ours(a):
             if c0 < c1:
                 t = torch.frombuffer(bytearray(data[c0 - s0:c1 - s0]), dtype=torch.uint8)
                 buf[c0 - lo:c1 - lo].copy_(t)
-    if a.n_per_mbp > 0:  # scattered ambiguity codes (input generation, untimed)
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(SEED + 17 + rank)
-        k = int(a.n_per_mbp * (piece_end - lo) / 1e6)
-        idx = torch.randint(0, piece_end - lo, (k,), generator=gen, device=dev)
-        buf[idx] = ord("N")
+    if a.n_per_mbp > 0:  # scattered ambiguity codes (input generation, untimed); the same positions on every rank
+        gen = torch.Generator()
+        gen.manual_seed(SEED + 17 + (7919 * rank if weak else 0))
+        k = int(a.n_per_mbp * total / 1e6)
+        idx = torch.randint(0, total, (k,), generator=gen)
+        idx = idx[(idx >= lo) & (idx < piece_end)] - lo
+        buf[idx.to(dev)] = ord("N")
     torch.cuda.synchronize()
 
     segments = [(buf[s0 - lo:s1 - lo], c, rec_off, own)
@@ -386,54 +390,57 @@ def run_ours(a):
         t = sc.timing()
         return n, t["total_ms"], t
 
-    gather_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    # ---- sharded: stage 1 -> all-gather of site blocks -> stage 2, all on the scratch's stream ----
+    ext = torch.cuda.ExternalStream(D.scratch_stream(sc), device=dev)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    blocks = {"cap": 0, "mine": None, "all": None}
+    host_slice = {"t": None}
 
-    def step_multi():
-        # stage 1 decides from the shard's own bytes whether rc orientations must stay raw
-        sites, recs = D.find_sites_device(cp, sc, segments, n_recs, force_raw=False)
-        t = sc.timing()
-        dev_ms = t["total_ms"]
-        launches = t["kernel_launches"]
-        # ONE collective: every rank learns all sites and the merged per-record reset flags
-        gather_ev[0].record()
-        allsites, records = sharding.gather_sites(dist, sites, recs, n_recs, rank, world, device=dev)
-        gather_ev[1].record()
-        gather_ev[1].synchronize()
-        dev_ms += gather_ev[0].elapsed_time(gather_ev[1])
-        # hit-cap parity: if ANY shard saw a reset byte, shards that filtered with the protected
-        # window redo stage 1 raw (never happens on the N-free bench genome); every rank takes
-        # the same decision from the same merged flags
-        redo = a.hit_cap > 0 and a.mm > 0 and a.tw > 0 and any(r[1] for r in records)
-        if redo:
-            if t["plan_variant"] == 0:
-                sites, recs = D.find_sites_device(cp, sc, segments, n_recs, force_raw=True)
-                t2 = sc.timing()
-                dev_ms += t2["total_ms"]
-                launches += t2["kernel_launches"]
-            allsites, records = sharding.gather_sites(dist, sites, recs, n_recs, rank, world, device=dev)
-        n = 0
-        if rank == 0:
-            records = [(lens[i], records[i][1]) for i in range(n_recs)]
-            _out, n = D.pair_sites(cp, sc, allsites, records, raw=True)
-            tp = sc.timing()
-            dev_ms += tp["pair_ms"]
-            launches += tp["kernel_launches"]
-        t = dict(t)
-        t["kernel_launches"] = launches
-        t["gather_ms"] = gather_ev[0].elapsed_time(gather_ev[1])
-        t["find_total_ms"] = t["total_ms"]
-        return n, dev_ms, t
+    def step_multi(from_host=False):
+        launches = 0
+        while True:
+            site_cap = D.scratch_site_cap(sc)
+            if blocks["cap"] != site_cap:
+                bb = D.site_block_bytes(n_recs, site_cap)
+                blocks.update(cap=site_cap, mine=torch.empty(bb, dtype=torch.uint8, device=dev),
+                              all=torch.empty(world * bb, dtype=torch.uint8, device=dev))
+            with torch.cuda.stream(ext):
+                h0 = time.perf_counter()
+                evs[0].record()
+                if from_host:  # this rank's shard from its own pinned host buffer
+                    buf.copy_(host_slice["t"], non_blocking=True)
+                D.find_sites_block(cp, sc, segments, n_recs, blocks["mine"], site_cap)
+                launches += sc.timing()["kernel_launches"]
+                evs[1].record()
+                h1 = time.perf_counter()
+                dist.all_gather_into_tensor(blocks["all"], blocks["mine"])
+                evs[2].record()
+                h2 = time.perf_counter()
+                # every rank pairs: all see the same blocks, so all take the same retry decisions
+                res = D.pair_blocks(cp, sc, blocks["all"], world, site_cap, lens, raw=True)
+                evs[3].record()
+                h3 = time.perf_counter()
+                if os.environ.get("IPCR_BENCH_TRACE") and rank == 0:
+                    print(f"[trace] host ms: find {1e3*(h1-h0):.3f} gather {1e3*(h2-h1):.3f} pair {1e3*(h3-h2):.3f}", file=sys.stderr)
+            if res is not None:
+                break
+        evs[3].synchronize()
+        t = dict(sc.timing())
+        t["kernel_launches"] = launches + 1
+        t["gather_ms"] = evs[1].elapsed_time(evs[2])
+        t["find_total_ms"] = evs[0].elapsed_time(evs[1])
+        return res[1], evs[0].elapsed_time(evs[3]), t
 
     step = step_single if world == 1 or weak else step_multi
 
     for _ in range(max(3, a.warmup)):
         n_prod, _ms, tm = step()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()  # NVML start-up takes tens of ms: before the barrier, or the other ranks wait for it in step 1
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
-        sampler.start()
     wall0 = time.perf_counter()
     dev_ms_sum, launches, filt_ms, last = 0.0, 0, 0.0, None
     for _ in range(a.steps):
@@ -443,9 +450,9 @@ def run_ours(a):
         filt_ms += tm["filter_ms"]
         last = tm
     torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - wall0) * 1e3 / a.steps
     if world > 1:
         dist.barrier()
-    wall_ms = (time.perf_counter() - wall0) * 1e3 / a.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = dev_ms_sum / a.steps
     if world > 1:
@@ -461,7 +468,7 @@ def run_ours(a):
     # genome from pinned host memory (N = 1, or weak scaling); wall clock, max over ranks ----
     e2e, e2e_stage = None, None
     n_units = world if weak else 1
-    if (world == 1 or weak) and not a.no_e2e:
+    if not a.no_e2e and (world == 1 or weak):
         host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
         host.copy_(buf)
         torch.cuda.synchronize()
@@ -489,6 +496,33 @@ def run_ours(a):
                "gbp_per_s": g / (e2e_ms / 1e3), "h2d_bytes_per_step": n_units * total, "d2h_bytes_per_step": d2h,
                "api": "ipcr_gpu_scan_batch(host records) -> products (C ABI; pinned host buffers)"}
         del host, recs
+    elif not a.no_e2e:
+        # sharded: every rank feeds ITS shard from its own pinned host buffer; wall clock between barriers
+        host_slice["t"] = torch.empty(piece_end - lo, dtype=torch.uint8, pin_memory=True)
+        host_slice["t"].copy_(buf)
+        torch.cuda.synchronize()
+        step_multi(from_host=True)  # warm
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        n_e2e = 0
+        for _ in range(max(1, a.e2e_steps)):
+            n_e2e, _ms, te = step_multi(from_host=True)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, a.e2e_steps)
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+        t = torch.tensor([piece_end - lo], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d = int(t[0])
+        e2e_stage = {k: te[k] for k in ("pack_ms", "filter_ms", "verify_ms", "pair_ms", "gather_ms", "find_total_ms")}
+        g = total / 1e9
+        e2e = {"value": g / (e2e_ms / 1e3) * len(user_pairs), "unit": UNIT, "ms_per_step": e2e_ms,
+               "gbp_per_s": g / (e2e_ms / 1e3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n_e2e * 64 * world,
+               "api": "per rank: pinned host shard -> H2D -> ipcr_gpu_find_sites_block -> NCCL all-gather of site blocks "
+                      "-> ipcr_gpu_pair_blocks -> products on the host of every rank (C ABI)"}
+        host_slice["t"] = None
 
     if rank != 0:
         if world > 1:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define IPCR_GPU_ABI_VERSION 1
+#define IPCR_GPU_ABI_VERSION 2
 #define IPCR_GPU_MAX_PRIMER_LEN 64 /* mismatch positions travel as 64-bit masks */
 
 /* replaces engine.Config (core/engine/engine.go:10-19) */
@@ -125,8 +125,21 @@ typedef struct ipcr_genome ipcr_genome;
 int ipcr_gpu_abi_version(void);
 /* number of visible CUDA devices, or 0 (never fails; no device => 0) */
 int ipcr_gpu_device_count(void);
-/* binds the calling thread to `device` and checks it is sm_100. */
-int ipcr_gpu_init(int device, char *err, size_t errlen);
+/* Checks the devices (sm_100) and sets how many of them ONE ipcr_gpu_scan_batch /
+ * ipcr_gpu_scan_fasta call may spread over: 0 = all visible devices, 1 = only the device of
+ * the scratch, n = the scratch's device plus n - 1 others.  Large inputs (>= 256 Mbp) are then
+ * cut into one slice per device (64-base halo), every device pulls its slice from the caller's
+ * host memory over its own PCIe link and finds its primer sites, the site blocks meet on the
+ * scratch's device over NVLink peer copies and are paired once -- same products, same order.
+ * Replaces the chunk worker pool of the Go host for the GPU engine (internal/pipeline/pipeline.go:
+ * 60-125, internal/runutil/runutil.go:20-59).  Does not change the calling thread's device.
+ * The device-side visitors (probe / nested) need the records on one device: a call that was
+ * spread over several devices leaves none resident. */
+int ipcr_gpu_init(int n_devices_or_0, char *err, size_t errlen);
+/* binds the calling thread to `device` (scratches are created on the thread's current device) */
+int ipcr_gpu_set_device(int device, char *err, size_t errlen);
+/* the device budget set by ipcr_gpu_init (1 before the first call) */
+int ipcr_gpu_num_devices(void);
 
 /* ---- panel: engine.CompilePanel (core/engine/compiled.go:96-136) ---------- */
 ipcr_panel *ipcr_gpu_panel_create(const ipcr_cfg *cfg, const ipcr_pair *pairs, size_t n_pairs,
@@ -205,6 +218,31 @@ int ipcr_gpu_find_sites_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segmen
 int ipcr_gpu_pair_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_site *sites, uint64_t n_sites,
                         const ipcr_record_info *recs, size_t n_recs, const ipcr_product **out,
                         uint64_t *n_out, char *err, size_t errlen);
+
+/* ---- split phase, device-resident (multi-process multi-GPU: stage 1 per rank, ONE all-gather
+ * of fixed-size site blocks, stage 2 on every rank -- the host never touches a site) ---------- */
+/* A site block is [64-byte control | n_recs flag bytes, padded to 16 | site_cap sites]. */
+uint64_t ipcr_gpu_site_block_bytes(size_t n_recs, uint64_t site_cap);
+/* sites per block this scratch currently asks for (grows when a call reported lost sites) */
+uint64_t ipcr_gpu_scratch_site_cap(const ipcr_scratch *s);
+/* the scratch's CUDA stream (cudaStream_t): order foreign work, e.g. the collective, against it */
+void *ipcr_gpu_scratch_stream(ipcr_scratch *s);
+/* Stage 1 of device-resident segments (as ipcr_gpu_find_sites_device) into d_block, a device
+ * buffer of ipcr_gpu_site_block_bytes(n_recs, site_cap) bytes.  ASYNCHRONOUS: returns once the
+ * work is queued on the scratch's stream.  Seed-index panels only (the default filter). */
+int ipcr_gpu_find_sites_block(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
+                              size_t n_recs, int force_raw, void *d_block, uint64_t site_cap, char *err,
+                              size_t errlen);
+/* Stage 2 over n_blocks blocks lying back to back in device memory (what the all-gather left),
+ * queued behind whatever the scratch's stream holds; waits once, for the products.
+ * rec_lens[n_recs] = whole-record lengths.  Returns 0 = done, 1 = error, 2 = run stage 1 again on
+ * EVERY rank and call again: a capacity was too small (ipcr_gpu_scratch_site_cap may have grown) or
+ * a record holds a reset byte while some block was scanned with the plain plan variant (hit-cap
+ * parity, core/engine/compiled.go:185-190); every rank sees the same blocks and so takes the same
+ * decision without talking to the others. */
+int ipcr_gpu_pair_blocks(ipcr_panel *p, ipcr_scratch *s, const void *d_blocks, uint32_t n_blocks,
+                         uint64_t site_cap, const uint64_t *rec_lens, size_t n_recs,
+                         const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen);
 
 /* ---- native FASTA feeder (replaces core/fasta for the hot path) ------ */
 /* Reads and normalises a FASTA file exactly like the reference reader (header ID = first

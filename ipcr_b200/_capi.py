@@ -104,7 +104,9 @@ assert C.sizeof(ProductC) == 64 and C.sizeof(SiteC) == 24
 
 # every entry point include/ipcr_gpu.h declares
 SYMBOLS = [
-    "ipcr_gpu_abi_version", "ipcr_gpu_device_count", "ipcr_gpu_init",
+    "ipcr_gpu_abi_version", "ipcr_gpu_device_count", "ipcr_gpu_init", "ipcr_gpu_set_device", "ipcr_gpu_num_devices",
+    "ipcr_gpu_site_block_bytes", "ipcr_gpu_scratch_site_cap", "ipcr_gpu_scratch_stream",
+    "ipcr_gpu_find_sites_block", "ipcr_gpu_pair_blocks",
     "ipcr_gpu_panel_create", "ipcr_gpu_panel_destroy", "ipcr_gpu_panel_num_pairs",
     "ipcr_gpu_panel_num_orientations", "ipcr_gpu_panel_have", "ipcr_gpu_panel_set_jit", "ipcr_gpu_panel_set_filter",
     "ipcr_gpu_scratch_create", "ipcr_gpu_scratch_destroy",
@@ -145,6 +147,13 @@ def lib():
     sig("ipcr_gpu_abi_version", C.c_int)
     sig("ipcr_gpu_device_count", C.c_int)
     sig("ipcr_gpu_init", C.c_int, C.c_int, *ERR)
+    sig("ipcr_gpu_set_device", C.c_int, C.c_int, *ERR)
+    sig("ipcr_gpu_num_devices", C.c_int)
+    sig("ipcr_gpu_site_block_bytes", U64, SZ, U64)
+    sig("ipcr_gpu_scratch_site_cap", U64, V)
+    sig("ipcr_gpu_scratch_stream", V, V)
+    sig("ipcr_gpu_find_sites_block", C.c_int, V, V, P(SegmentC), SZ, SZ, C.c_int, V, U64, *ERR)
+    sig("ipcr_gpu_pair_blocks", C.c_int, V, V, V, C.c_uint32, U64, P(U64), SZ, P(P(ProductC)), P(U64), *ERR)
     sig("ipcr_gpu_panel_create", V, P(Cfg), P(PairC), SZ, *ERR)
     sig("ipcr_gpu_panel_destroy", None, V)
     sig("ipcr_gpu_panel_num_pairs", SZ, V)

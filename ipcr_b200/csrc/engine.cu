@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -19,6 +20,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device_types.cuh"
@@ -29,6 +31,7 @@
 #include "seed.hpp"
 #include "seed_kernels.cuh"
 #include "sortscan.cuh"
+#include "pair_small.cuh"
 
 namespace ipcr {
 
@@ -241,6 +244,7 @@ struct GenomeData {
     std::vector<ipcr_record_info> recs;
     bool any_reset = false;
     uint64_t own_bases = 0;
+    const ipcr_record_info *recs_dev_ptr = nullptr;  // chain: record table uploaded together with the segments
 };
 
 }  // namespace ipcr
@@ -269,6 +273,21 @@ struct ipcr_scratch {
     ipcr::PinBuf h_counts, h_products, h_sites, h_stage, h_reset;
     uint64_t n_cand = 0;
     uint64_t seed_cap_hint = 0, seed_dirty_hint = 0;  // capacities that sufficed last time (no re-scan)
+    // asynchronous chain (pair_small.cuh): stage 1 writes a site block, one CTA pairs, ONE readback
+    ipcr::DevBuf block, rec_reset_dev, gather;  // own site block; merged per-record flags; blocks of all shards / slabs
+    ipcr::PinBuf h_args;                        // pinned staging of the small per-call tables (segments, records)
+    size_t args_used = 0;
+    bool inflight = false;                      // work was enqueued and not yet waited for
+    uint64_t site_cap_hint = 0, task_cap_hint = 0, prod_cap_hint = 0;
+    uint64_t last_copied = 0;                   // products the chain's single readback carried
+    bool raw_hint = false;                      // a record with a reset byte was seen: start with the raw-rc index
+    const ipcr_product *out_ptr = nullptr;      // products of the last call (pinned, scratch-owned)
+    std::vector<ipcr_scratch *> peers;          // one scratch per further device (multi-GPU inside one process)
+    cudaEvent_t done_ev = nullptr;              // peer: its block has arrived on the primary device
+    bool own_laid = false;                      // multi-device retry: the slice is already resident
+    ipcr::DevBuf seg_reset_dummy;
+    std::vector<std::unique_ptr<ipcr::GenomeData>> slab_g;  // streamed slabs: packed codes per slab (all in flight at once)
+    std::vector<cudaEvent_t> slab_t;
     // records of the last scan that are still resident (for the device-side visitors)
     std::vector<uint64_t> last_rec_base, last_rec_len;
     const uint8_t *last_ascii = nullptr;
@@ -282,6 +301,9 @@ struct ipcr_scratch {
             if (e) cudaEventDestroy(e);
         for (auto &e : slab_ev)
             if (e) cudaEventDestroy(e);
+        for (auto &e : slab_t)
+            if (e) cudaEventDestroy(e);
+        if (done_ev) cudaEventDestroy(done_ev);
         for (auto &e : copy_ev)
             if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -330,7 +352,7 @@ static bool prefer_seed(ipcr_panel *p) {
     return (mode == 3 || mode == 1) && !p->host.orients.empty();
 }
 
-static void launch_pack_planes(ipcr_scratch *s, GenomeData &g) {
+static void launch_pack_planes(ipcr_scratch *s, GenomeData &g, uint8_t *rec_reset = nullptr) {
     cudaStream_t st = s->stream;
     g.lay.W = choose_W(g.lay.total_len, s->sm_count);
     g.lay.rows = g.lay.W + kExtRows;
@@ -341,18 +363,18 @@ static void launch_pack_planes(ipcr_scratch *s, GenomeData &g) {
     if ((reinterpret_cast<uintptr_t>(g.ascii) & 15u) == 0 && g.lay.W % 16 == 0) {
         k_pack<<<(unsigned)g.lay.n_tiles, 1024, 0, st>>>(g.ascii, g.lay, g.planes.as<uint4>(),
                                                          g.segs_dev.as<SegmentDev>(), (uint32_t)g.segs.size(),
-                                                         g.seg_reset.as<uint32_t>());
+                                                         g.seg_reset.as<uint32_t>(), rec_reset);
     } else {  // unaligned adopted buffer: byte-wise variant
         dim3 grid((unsigned)g.lay.n_tiles, (g.lay.rows + 31) / 32), block(32, 32);
         k_pack_bytes<<<grid, block, 0, st>>>(g.ascii, g.lay, g.planes.as<uint4>(), g.segs_dev.as<SegmentDev>(),
-                                             (uint32_t)g.segs.size(), g.seg_reset.as<uint32_t>());
+                                             (uint32_t)g.segs.size(), g.seg_reset.as<uint32_t>(), rec_reset);
     }
     check_launch("k_pack");
     s->launches++;
     g.planes_ready = true;
 }
 
-static void launch_pack_codes(ipcr_scratch *s, GenomeData &g) {
+static void launch_pack_codes(ipcr_scratch *s, GenomeData &g, uint8_t *rec_reset = nullptr) {
     cudaStream_t st = s->stream;
     const uint64_t n_chunks = (g.lay.total_len + kSeedChunk - 1) / kSeedChunk;
     g.n_groups = n_chunks * (kSeedChunk / 32u) + 1;  // + one padding group (look-ahead of the last lane)
@@ -367,6 +389,7 @@ static void launch_pack_codes(ipcr_scratch *s, GenomeData &g) {
     a.segs = g.segs_dev.as<SegmentDev>();
     a.n_segs = (uint32_t)g.segs.size();
     a.seg_reset = g.seg_reset.as<uint32_t>();
+    a.rec_reset = rec_reset;
     a.aligned = (reinterpret_cast<uintptr_t>(g.ascii) & 15u) == 0;
     const unsigned grid = (unsigned)std::min<uint64_t>((g.n_groups + 255) / 256, (uint64_t)s->sm_count * 32);
     k_pack2<<<grid, 256, 0, st>>>(a);
@@ -414,13 +437,16 @@ static void ensure_codes(ipcr_scratch *s, GenomeData &g) {
     }
 }
 
-// builds segment / record tables; `device_src` = segment pointers are device memory (adopt)
-static void build_genome(ipcr_scratch *s, GenomeData &g, const ipcr_segment *segs, size_t n_segs, size_t n_recs,
-                         bool device_src) {
+// builds segment / record tables and queues the H2D copy of host segments; `device_src` =
+// segment pointers are device memory (adopt).  Nothing is packed yet.
+static void layout_genome(ipcr_scratch *s, GenomeData &g, const ipcr_segment *segs, size_t n_segs, size_t n_recs,
+                          bool device_src) {
     g.device = s->device;
     g.segs.clear();
     g.recs.assign(n_recs, ipcr_record_info{});
     g.own_bases = 0;
+    g.planes_ready = g.codes_ready = false;
+    g.any_reset = false;
     uint64_t off = 0;
     for (size_t i = 0; i < n_segs; i++) {
         const ipcr_segment &in = segs[i];
@@ -463,8 +489,6 @@ static void build_genome(ipcr_scratch *s, GenomeData &g, const ipcr_segment *seg
                                    cudaMemcpyHostToDevice, st));
     }
     CU(cudaEventRecord(s->ev[1], st));
-    pack_genome(s, g);
-    CU(cudaEventRecord(s->ev[2], st));
     // whole records stay addressable for the device-side visitors
     s->last_valid = true;
     s->last_ascii = g.ascii;
@@ -477,6 +501,15 @@ static void build_genome(ipcr_scratch *s, GenomeData &g, const ipcr_segment *seg
         s->last_rec_base[d.rec_idx] = d.global_off;
         s->last_rec_len[d.rec_idx] = d.len;
     }
+}
+
+// layout + K1 (synchronous: the per-record reset flags are back on the host when it returns)
+static void build_genome(ipcr_scratch *s, GenomeData &g, const ipcr_segment *segs, size_t n_segs, size_t n_recs,
+                         bool device_src) {
+    layout_genome(s, g, segs, n_segs, n_recs, device_src);
+    if (g.lay.total_len == 0) return;
+    pack_genome(s, g);
+    CU(cudaEventRecord(s->ev[2], s->stream));
 }
 
 static uint64_t read_counter(ipcr_scratch *s, int idx) {
@@ -535,6 +568,17 @@ static uint32_t bit_length(uint64_t v) {
     return b;
 }
 
+static KeyLayout key_layout(const Panel &h, const ipcr_record_info *recs, size_t n_recs) {
+    uint64_t max_len = 1;
+    for (size_t r = 0; r < n_recs; r++) max_len = std::max<uint64_t>(max_len, recs[r].len);
+    KeyLayout kl{};
+    kl.pos_bits = std::max(1u, bit_length(max_len));
+    kl.n_orient = (uint32_t)h.orients.size();
+    const uint32_t prefix_bits = std::max(1u, bit_length((uint64_t)n_recs * kl.n_orient));
+    kl.key_bits = kl.pos_bits + 1 + prefix_bits;
+    return kl;
+}
+
 // Stage 2.  d_sites: device site list (any order).  Products end up in s->h_products.
 static uint64_t pair_sites(ipcr_scratch *s, const ipcr_site *d_sites, uint64_t n_sites,
                            const ipcr_record_info *recs, size_t n_recs) {
@@ -543,14 +587,7 @@ static uint64_t pair_sites(ipcr_scratch *s, const ipcr_site *d_sites, uint64_t n
     const size_t n_pairs = h.roles.size();
     if (n_sites == 0 || n_pairs == 0 || n_recs == 0) return 0;
     if (n_sites >= (1ull << 32)) throw Error("too many primer sites for one pairing pass");
-    const uint32_t U = (uint32_t)h.orients.size();
-    uint64_t max_len = 1;
-    for (size_t r = 0; r < n_recs; r++) max_len = std::max<uint64_t>(max_len, recs[r].len);
-    KeyLayout kl{};
-    kl.pos_bits = std::max(1u, bit_length(max_len));
-    kl.n_orient = U;
-    const uint32_t prefix_bits = std::max(1u, bit_length((uint64_t)n_recs * U));
-    kl.key_bits = kl.pos_bits + 1 + prefix_bits;
+    const KeyLayout kl = key_layout(h, recs, n_recs);
     if (kl.key_bits > 62) throw Error("record count x orientations x record length exceeds the 62-bit sort key");
     const uint64_t n_entries = (uint64_t)n_recs * n_pairs * 2ull;
     if (n_entries >= (1ull << 31)) throw Error("records x pairs too large for one pairing pass; use smaller batches");
@@ -575,7 +612,7 @@ static uint64_t pair_sites(ipcr_scratch *s, const ipcr_site *d_sites, uint64_t n
 
     const unsigned gs = (unsigned)((n_sites + 255) / 256);
     k_site_keys<<<gs, 256, 0, st>>>(d_sites, n_sites, s->tables->orients.as<OrientDev>(),
-                                    s->recs_dev.as<ipcr_record_info>(), prm, kl, s->keys0.as<uint64_t>(),
+                                    s->recs_dev.as<ipcr_record_info>(), nullptr, prm, kl, s->keys0.as<uint64_t>(),
                                     s->vals0.as<uint32_t>());
     check_launch("k_site_keys");
     s->launches++;
@@ -649,6 +686,7 @@ static uint64_t pair_sites(ipcr_scratch *s, const ipcr_site *d_sites, uint64_t n
     s->h_products.ensure(n_prod * sizeof(ipcr_product));
     CU(cudaMemcpyAsync(s->h_products.p, s->products.p, n_prod * sizeof(ipcr_product), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    s->out_ptr = s->h_products.as<ipcr_product>();
     return n_prod;
 }
 
@@ -879,6 +917,16 @@ static const SeedIndex &seed_get(ipcr_scratch *s, int variant) {
     return ix;
 }
 
+static void launch_seed_scan(ipcr_scratch *s, const SeedIndex &ix, const SeedScanArgs &a) {
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((a.n_chunks + 31) / 32, (uint64_t)s->sm_count));
+    const size_t smem = kSeedBloomWords * 4;
+    if (!ix.use_bloom) k_seed_scan<0><<<grid, 1024, 0, s->stream>>>(a);
+    else if (ix.bloom_k == 1) k_seed_scan<1><<<grid, 1024, smem, s->stream>>>(a);
+    else k_seed_scan<2><<<grid, 1024, smem, s->stream>>>(a);
+    check_launch("k_seed_scan");
+    s->launches++;
+}
+
 // Seed-index filter + verify.  Returns false (nothing changed) when the input is too dirty for
 // it; on success the verified sites are in s->sites.
 static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs &v, uint64_t &n_sites) {
@@ -923,13 +971,7 @@ static bool seed_filter(ipcr_scratch *s, GenomeData &g, int variant, VerifyArgs 
         a.dirty = s->dirty.as<unsigned long long>();
         a.dirty_count = ctr + 2;
         a.dirty_cap = dirty_cap;
-        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + 31) / 32, (uint64_t)s->sm_count));
-        const size_t smem = kSeedBloomWords * 4;
-        if (!ix.use_bloom) k_seed_scan<0><<<grid, 1024, 0, st>>>(a);
-        else if (ix.bloom_k == 1) k_seed_scan<1><<<grid, 1024, smem, st>>>(a);
-        else k_seed_scan<2><<<grid, 1024, smem, st>>>(a);
-        check_launch("k_seed_scan");
-        s->launches++;
+        launch_seed_scan(s, ix, a);
         CU(cudaMemcpyAsync(s->h_counts.p, s->counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         n_cand = s->h_counts.as<unsigned long long>()[0];
@@ -1136,7 +1178,392 @@ static uint64_t find_sites(ipcr_scratch *s, GenomeData &g, bool force_raw) {
     return n_sites;
 }
 
+
+// =====================================================================================
+// The asynchronous chain (pair_small.cuh).  Stage 1 leaves a SITE BLOCK in device memory,
+// every count stays on the device, stage 2 is one single-CTA kernel over any number of
+// blocks, and the host waits ONCE for [header | products].  Anything the chain cannot take
+// (more than 8192 sites, inputs too dirty for the seed index, ...) is reported in the
+// header and served by the multi-kernel path.
+// =====================================================================================
+constexpr uint64_t kChainMaxEntries = 1ull << 18;  // records x pairs x 2 one CTA walks
+
+static void begin_call(ipcr_scratch *s) {
+    bind(s);
+    if (s->inflight) CU(cudaStreamSynchronize(s->stream));
+    s->inflight = false;
+    s->args_used = 0;
+    s->launches = 0;
+    s->timing = ipcr_timing{};
+}
+
+// small per-call tables travel through pinned staging so that the copy never blocks the host
+static void upload_staged(ipcr_scratch *s, DevBuf &b, const void *src, size_t bytes) {
+    b.ensure(std::max(bytes, (size_t)16));
+    if (!bytes) return;
+    size_t off = (s->args_used + 63) & ~(size_t)63;
+    if (off + bytes > s->h_args.cap) {
+        CU(cudaStreamSynchronize(s->stream));  // nothing reads the old staging buffer any more
+        s->h_args.ensure(std::max<size_t>(2 * (off + bytes), 1 << 16));
+        off = 0;
+    }
+    memcpy(s->h_args.as<uint8_t>() + off, src, bytes);
+    s->args_used = off + bytes;
+    CU(cudaMemcpyAsync(b.p, s->h_args.as<uint8_t>() + off, bytes, cudaMemcpyHostToDevice, s->stream));
+}
+
+static bool raw_possible(const ipcr_cfg &cfg) { return cfg.hit_cap > 0 && cfg.max_mm > 0 && cfg.terminal_window > 0; }
+
+static int chain_variant(ipcr_scratch *s, bool force_raw) {
+    const Panel &h = s->panel->host;
+    bool any_rc_unseeded = false;
+    for (const Orient &o : h.orients)
+        if (o.rc_type && !o.seeded) any_rc_unseeded = true;
+    return raw_possible(h.cfg) && (force_raw || s->raw_hint || any_rc_unseeded) ? 1 : 0;
+}
+
+// can this panel / record set run the chain at all?
+static bool chain_ok(ipcr_scratch *s, const ipcr_record_info *recs, size_t n_recs) {
+    const Panel &h = s->panel->host;
+    if (getenv("IPCR_NO_CHAIN")) return false;
+    if (!prefer_seed(s->panel) || h.roles.empty() || n_recs == 0 || n_recs > 65535) return false;
+    if ((uint64_t)n_recs * h.roles.size() * 2ull > kChainMaxEntries) return false;
+    if (key_layout(h, recs, n_recs).key_bits + 1 + kSortSmallIdxBits > 64) return false;
+    return seed_host(s->panel, 0).S > 0;
+}
+
+// Stage 1 of the chain on a laid-out genome: init -> pack -> seed scan -> dirty windows -> verify,
+// all into `d_block`.  Nothing is waited for.
+static void stage1_async(ipcr_scratch *s, GenomeData &g, int variant, uint8_t *d_block, uint64_t site_cap) {
+    const Panel &h = s->panel->host;
+    const SeedIndex &ix = seed_get(s, variant);
+    cudaStream_t st = s->stream;
+    DevTables *t = s->tables;
+    const size_t n_recs = g.recs.size();
+    {  // ONE small copy: the segment table and, behind it, the record table stage 2 reads
+        const size_t seg_bytes = (g.segs.size() * sizeof(SegmentDev) + 63) & ~(size_t)63;
+        std::vector<uint8_t> tab(seg_bytes + n_recs * sizeof(ipcr_record_info), 0);
+        memcpy(tab.data(), g.segs.data(), g.segs.size() * sizeof(SegmentDev));
+        for (size_t r = 0; r < n_recs; r++) {
+            ipcr_record_info ri{};
+            ri.len = g.recs[r].len;
+            memcpy(tab.data() + seg_bytes + r * sizeof(ipcr_record_info), &ri, sizeof ri);
+        }
+        upload_staged(s, g.segs_dev, tab.data(), tab.size());
+        g.recs_dev_ptr = reinterpret_cast<const ipcr_record_info *>(g.segs_dev.as<uint8_t>() + seg_bytes);
+    }
+    g.seg_reset.ensure(std::max<size_t>(g.segs.size(), 4) * sizeof(uint32_t));
+    uint64_t cap = std::max<uint64_t>(1ull << 16, (uint64_t)(ix.cand_prob * (double)g.lay.total_len * 1.5) + 4096);
+    cap = std::max(std::min<uint64_t>(cap, 1ull << 28), s->seed_cap_hint);
+    const uint64_t dirty_cap = std::max<uint64_t>(1ull << 16, s->seed_dirty_hint);
+    s->cand.ensure(cap * sizeof(unsigned long long));
+    s->dirty.ensure(dirty_cap * sizeof(unsigned long long));
+    Stage1Ctl init{};
+    init.cand_cap = cap;
+    init.dirty_cap = dirty_cap;
+    init.site_cap = site_cap;
+    init.variant = (uint32_t)variant;
+    init.n_recs = (uint32_t)n_recs;
+    Stage1Ctl *ctl = reinterpret_cast<Stage1Ctl *>(d_block);
+    uint8_t *rec_reset = d_block + sizeof(Stage1Ctl);
+    k_block_init<<<1, 256, 0, st>>>(d_block, init, g.seg_reset.as<uint32_t>(), (uint32_t)g.segs.size());
+    check_launch("k_block_init");
+    CU(cudaEventRecord(s->ev[1], st));
+    launch_pack_codes(s, g, rec_reset);
+    CU(cudaEventRecord(s->ev[2], st));
+    CU(cudaEventRecord(s->ev[3], st));
+    const uint64_t n_chunks = (g.lay.total_len + kSeedChunk - 1) / kSeedChunk;
+    SeedScanArgs a{};
+    a.codes = g.codes.as<uint32_t>();
+    a.inval = g.inval.as<uint32_t>();
+    a.n_chunks = n_chunks;
+    a.S = (uint32_t)ix.S;
+    a.d = (uint32_t)(ix.S - ix.S1);
+    a.kmer_mask = ix.kmer_mask;
+    a.bloom_mul = seed_bloom_mul(ix.S1);
+    a.bloom = t->seed_bloom[variant].as<uint32_t>();
+    a.bitmap2 = t->seed_bitmap2[variant].as<uint32_t>();
+    a.bitmap2_mul = ix.bitmap2_mul;
+    a.bitmap2_shift = ix.bitmap2_shift;
+    a.table = t->seed_table[variant].as<unsigned long long>();
+    a.table_shift = 32u - ix.table_bits;
+    a.table_mask = (uint32_t)((1ull << ix.table_bits) - 1);
+    a.cand = s->cand.as<unsigned long long>();
+    a.cand_count = &ctl->n_cand;
+    a.cand_cap = cap;
+    a.total_len = g.lay.total_len;
+    a.max_mm = (uint32_t)std::max(0, h.cfg.max_mm);
+    a.dirty = s->dirty.as<unsigned long long>();
+    a.dirty_count = &ctl->n_dirty;
+    a.dirty_cap = dirty_cap;
+    launch_seed_scan(s, ix, a);
+    CU(cudaEventRecord(s->ev[4], st));
+    VerifyArgs v{};
+    v.ascii = g.ascii;
+    v.segs = g.segs_dev.as<SegmentDev>();
+    v.n_segs = (uint32_t)g.segs.size();
+    v.orients = t->orients.as<OrientDev>();
+    v.cls = t->cls.as<uint8_t>();
+    v.prm.max_mm = h.cfg.max_mm;
+    v.prm.terminal_window = h.cfg.terminal_window;
+    v.prm.hit_cap = h.cfg.hit_cap;
+    v.prm.circular = h.cfg.circular;
+    v.prm.raw_rc = (uint8_t)variant;
+    v.sites = reinterpret_cast<ipcr_site *>(d_block + block_ctl_bytes(n_recs));
+    v.site_count = &ctl->n_sites;
+    v.site_cap = site_cap;
+    if (h.cfg.max_mm > 0) {  // dirty windows exist only with a mismatch budget (halo.go:76-80)
+        SeedDirtyResolveArgs r{};
+        r.p.dirty = s->dirty.as<unsigned long long>();
+        r.p.codes = a.codes;
+        r.p.inval = a.inval;
+        r.p.S = a.S;
+        r.p.kmer_mask = a.kmer_mask;
+        r.p.bitmap2 = a.bitmap2;
+        r.p.bitmap2_mul = a.bitmap2_mul;
+        r.p.bitmap2_shift = a.bitmap2_shift;
+        r.p.table = a.table;
+        r.p.table_shift = a.table_shift;
+        r.p.table_mask = a.table_mask;
+        r.n_dirty_ptr = &ctl->n_dirty;
+        r.dirty_cap = dirty_cap;
+        r.col_off = t->seed_coloff[variant].as<uint16_t>();
+        r.n_orient = (uint32_t)h.orients.size();
+        r.v = v;
+        k_seed_dirty_resolve<<<(unsigned)s->sm_count * 2, 128, 0, st>>>(r);
+        check_launch("k_seed_dirty_resolve");
+        s->launches++;
+    }
+    v.cand = s->cand.as<unsigned long long>();
+    v.n_cand = cap;
+    v.n_cand_ptr = &ctl->n_cand;
+    k_verify<<<(unsigned)s->sm_count * 8, 256, 0, st>>>(v);
+    check_launch("k_verify");
+    CU(cudaEventRecord(s->ev[5], st));
+    s->launches += 2;  // k_block_init, k_verify
+    s->timing.used_jit = kPathSeed;
+    s->timing.plan_variant = (uint32_t)variant;
+    s->inflight = true;
+}
+
+// Stage 2 of the chain over `n_blocks` site blocks + the readback of [header | products].
+static void pair_async(ipcr_scratch *s, const uint8_t *d_blocks, uint32_t n_blocks, uint64_t block_bytes,
+                       uint64_t block_site_cap, const ipcr_record_info *recs, size_t n_recs,
+                       const ipcr_record_info *d_recs = nullptr) {
+    const Panel &h = s->panel->host;
+    cudaStream_t st = s->stream;
+    const size_t n_pairs = h.roles.size();
+    const uint64_t n_entries = (uint64_t)n_recs * n_pairs * 2ull;
+    const uint32_t task_cap = (uint32_t)std::max<uint64_t>(1u << 15, s->task_cap_hint);
+    const uint64_t prod_cap = std::max<uint64_t>(1u << 12, s->prod_cap_hint);
+    if (!d_recs) {
+        upload_staged(s, s->recs_dev, recs, n_recs * sizeof(ipcr_record_info));
+        d_recs = s->recs_dev.as<ipcr_record_info>();
+    }
+    s->rec_reset_dev.ensure(n_recs + 16);
+    s->fs.ensure((size_t)kPairSmallMax * sizeof(FinalSite));
+    s->entry_tasks.ensure(n_entries * 4);
+    s->task_off.ensure((std::max<uint64_t>(n_entries, task_cap) + 1) * 4);  // general mode: entry scan; bucket mode: live tasks
+    s->task_cnt.ensure((size_t)task_cap * 4);
+    s->prod_off.ensure(((size_t)task_cap + 1) * 4);
+    s->products.ensure((prod_cap + 1) * sizeof(ipcr_product));
+    s->h_products.ensure((prod_cap + 1) * sizeof(ipcr_product));
+    PairSmallArgs a{};
+    a.blocks = d_blocks;
+    a.n_blocks = n_blocks;
+    a.block_bytes = block_bytes;
+    a.ctl_bytes = block_ctl_bytes(n_recs);
+    a.block_site_cap = block_site_cap;
+    a.orients = s->tables->orients.as<OrientDev>();
+    a.rec_reset = s->rec_reset_dev.as<uint8_t>();
+    a.j.fs = s->fs.as<FinalSite>();
+    a.j.pairs = s->tables->pairs.as<PairDev>();
+    a.j.n_pairs = (uint32_t)n_pairs;
+    a.j.n_recs = (uint32_t)n_recs;
+    a.j.recs = d_recs;
+    a.j.prm.max_mm = h.cfg.max_mm;
+    a.j.prm.terminal_window = h.cfg.terminal_window;
+    a.j.prm.hit_cap = h.cfg.hit_cap;
+    a.j.prm.circular = h.cfg.circular;
+    a.j.kl = key_layout(h, recs, n_recs);
+    a.j.entry_tasks = s->entry_tasks.as<uint32_t>();
+    a.j.task_off = s->task_off.as<uint32_t>();
+    a.j.task_cnt = s->task_cnt.as<uint32_t>();
+    a.j.prod_off = s->prod_off.as<uint32_t>();
+    a.j.products = s->products.as<ipcr_product>() + 1;  // the header occupies the first 64 bytes
+    a.j.prod_cap = prod_cap;
+    a.task_cap = task_cap;
+    a.header = s->products.as<PairHeader>();
+    // shared memory: 8192 sort words + either the final keys (general mode) or the two bucket tables
+    constexpr size_t kPairSmemMax = 226 * 1024;
+    const size_t words = (size_t)kPairSmallMax * sizeof(unsigned long long);
+    const uint64_t n_buckets = (uint64_t)n_recs * h.orients.size();
+    size_t smem = 2 * words;
+    if (words + 8 * (n_buckets + 1) <= kPairSmemMax && !getenv("IPCR_NO_BUCKETS")) {
+        a.bucket_cap = (uint32_t)n_buckets;
+        smem = std::max(smem, words + 8 * ((size_t)n_buckets + 1));
+    }
+    static std::mutex attr_mu;
+    {
+        std::lock_guard<std::mutex> lock(attr_mu);
+        CU(cudaFuncSetAttribute(k_pair_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemMax));
+    }
+    k_pair_small<<<1, 1024, smem, st>>>(a);
+    check_launch("k_pair_small");
+    s->launches++;
+    CU(cudaEventRecord(s->ev[6], st));
+    // one readback: the header and as many products as the last calls needed (+ slack)
+    const uint64_t n_copy = std::min<uint64_t>(prod_cap, std::max<uint64_t>(256, s->prod_cap_hint));
+    CU(cudaMemcpyAsync(s->h_products.p, s->products.p, (n_copy + 1) * sizeof(ipcr_product), cudaMemcpyDeviceToHost, st));
+    s->last_copied = n_copy;
+    CU(cudaEventRecord(s->ev[7], st));
+    s->inflight = true;
+}
+
+enum ChainResult { kChainDone, kChainRetry, kChainTooDirty };
+
+// Waits for the chain and reads the header.  kChainDone: *n_prod products are at s->out_ptr.
+// kChainRetry: a capacity (or the plan variant) was adjusted; run stage 1 again if *redo_stage1,
+// else only pair_async.  Larger site lists are paired by the multi-kernel path right here.
+static ChainResult chain_finish(ipcr_scratch *s, const uint8_t *d_blocks, uint32_t n_blocks, uint64_t block_bytes,
+                                ipcr_record_info *recs, size_t n_recs, uint64_t *n_prod, bool *redo_stage1) {
+    const Panel &h = s->panel->host;
+    cudaStream_t st = s->stream;
+    CU(cudaStreamSynchronize(st));
+    s->inflight = false;
+    const PairHeader hd0 = *s->h_products.as<PairHeader>();
+    struct { uint64_t n_sites, n_final, n_tasks, n_prod, n_cand, n_dirty; uint32_t flags, min_variant; } hd{
+        hd0.n_sites, hd0.n_final, hd0.n_tasks, hd0.n_prod, hd0.n_cand, hd0.n_dirty, hd0.flags, hd0.min_variant};
+    *redo_stage1 = false;
+    *n_prod = 0;
+    if (getenv("IPCR_CHAIN_DEBUG"))
+        fprintf(stderr, "[chain] sites %llu final %llu tasks %llu prod %llu cand %llu dirty %llu flags %x variant %u | bucket-mode cycles: keys %u sort %u final %u count %u\n",
+                (unsigned long long)hd.n_sites, (unsigned long long)hd.n_final, (unsigned long long)hd.n_tasks,
+                (unsigned long long)hd.n_prod, (unsigned long long)hd.n_cand, (unsigned long long)hd.n_dirty, hd.flags,
+                hd.min_variant, (hd0.pad[0] & 0xFFFFu) * 64u, (hd0.pad[0] >> 16) * 64u, (hd0.pad[1] & 0xFFFFu) * 64u,
+                (hd0.pad[1] >> 16) * 64u);
+    s->timing.candidates = hd.n_cand;
+    s->timing.sites = hd.n_sites;
+    if (hd.n_dirty > seed_dirty_max()) return kChainTooDirty;
+    if (hd.flags & kPairStage1Overflow) {
+        s->seed_cap_hint = std::max(s->seed_cap_hint, hd.n_cand + hd.n_cand / 4 + 1024);
+        s->seed_dirty_hint = std::max(s->seed_dirty_hint, hd.n_dirty + hd.n_dirty / 4 + 1024);
+        if (hd.n_cand * sizeof(unsigned long long) > (32ull << 30))
+            throw Error(fmt("scan produced %llu candidate sites; the panel is too unspecific for this input",
+                            (unsigned long long)hd.n_cand));
+        *redo_stage1 = true;
+        return kChainRetry;
+    }
+    s->seed_cap_hint = std::max(s->seed_cap_hint, hd.n_cand + hd.n_cand / 4);
+    s->seed_dirty_hint = std::max(s->seed_dirty_hint, hd.n_dirty + hd.n_dirty / 4);
+    if ((hd.flags & kPairAnyReset) && raw_possible(h.cfg)) {
+        s->raw_hint = true;  // later calls start with the raw-rc index
+        if (hd.min_variant == 0) {  // hit-cap parity needs raw rc matches from every block
+            *redo_stage1 = true;
+            return kChainRetry;
+        }
+    }
+    if (hd.flags & kPairSitesLost) {
+        s->site_cap_hint = std::max<uint64_t>(s->site_cap_hint, hd.n_sites + hd.n_sites / 4 + 1024);
+        *redo_stage1 = true;
+        return kChainRetry;
+    }
+    if (hd.flags & kPairNotSmall) {  // complete site lists, too long for one CTA: multi-kernel stage 2
+        if (hd.n_sites >= (1ull << 32)) throw Error("too many primer sites for one pairing pass");
+        const uint64_t ctl_bytes = block_ctl_bytes(n_recs);
+        const ipcr_site *d_sites = reinterpret_cast<const ipcr_site *>(d_blocks + ctl_bytes);
+        if (n_blocks > 1) {
+            s->sites.ensure(hd.n_sites * sizeof(ipcr_site));
+            UnpackArgs u{d_blocks, n_blocks, block_bytes, ctl_bytes, s->sites.as<ipcr_site>(), hd.n_sites};
+            k_unpack_blocks<<<(unsigned)s->sm_count, 256, 0, st>>>(u);
+            check_launch("k_unpack_blocks");
+            s->launches++;
+            d_sites = s->sites.as<ipcr_site>();
+        }
+        s->h_reset.ensure(n_recs + 16);
+        CU(cudaMemcpyAsync(s->h_reset.p, s->rec_reset_dev.p, n_recs, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (size_t r = 0; r < n_recs; r++) recs[r].has_reset_byte = s->h_reset.as<uint8_t>()[r] ? 1 : 0;
+        *n_prod = pair_sites(s, d_sites, hd.n_sites, recs, n_recs);
+        if (*n_prod == 0) CU(cudaEventRecord(s->ev[6], st));
+        CU(cudaEventRecord(s->ev[7], st));
+        CU(cudaStreamSynchronize(st));
+        return kChainDone;
+    }
+    if (hd.flags & (kPairTaskOverflow | kPairProdOverflow)) {
+        s->task_cap_hint = std::max<uint64_t>(s->task_cap_hint, hd.n_tasks + hd.n_tasks / 4 + 1024);
+        s->prod_cap_hint = std::max<uint64_t>(s->prod_cap_hint, hd.n_prod + hd.n_prod / 4 + 1024);
+        if (hd.n_tasks >= (1ull << 31) || hd.n_prod >= (1ull << 31)) throw Error("too many products for one pairing pass");
+        return kChainRetry;
+    }
+    const uint64_t copied = s->last_copied;
+    if (hd.n_prod > copied) {  // the rest of the products
+        CU(cudaMemcpyAsync(s->h_products.as<ipcr_product>() + 1 + copied, s->products.as<ipcr_product>() + 1 + copied,
+                           (hd.n_prod - copied) * sizeof(ipcr_product), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    s->prod_cap_hint = std::max<uint64_t>(s->prod_cap_hint, hd.n_prod + hd.n_prod / 4);
+    s->task_cap_hint = std::max<uint64_t>(s->task_cap_hint, hd.n_tasks + hd.n_tasks / 4);
+    s->out_ptr = s->h_products.as<ipcr_product>() + 1;
+    *n_prod = hd.n_prod;
+    return kChainDone;
+}
+
+static void chain_timing(ipcr_scratch *s, uint64_t n_prod, bool had_h2d) {
+    ipcr_timing &t = s->timing;
+    t.h2d_ms = had_h2d ? ev_ms(s->ev[0], s->ev[1]) : 0.f;
+    t.pack_ms = ev_ms(s->ev[1], s->ev[2]);
+    t.filter_ms = ev_ms(s->ev[3], s->ev[4]);
+    t.verify_ms = ev_ms(s->ev[4], s->ev[5]);
+    t.pair_ms = ev_ms(s->ev[5], s->ev[6]);
+    t.d2h_ms = ev_ms(s->ev[6], s->ev[7]);
+    t.total_ms = ev_ms(had_h2d ? s->ev[0] : s->ev[1], s->ev[7]);
+    t.products = n_prod;
+    t.kernel_launches = s->launches;
+}
+
+// One laid-out genome through the chain.  false: the input is too dirty for the seed index.
+static bool scan_chain(ipcr_scratch *s, GenomeData &g, bool had_h2d, uint64_t *n_prod) {
+    const size_t n_recs = g.recs.size();
+    for (int attempt = 0; attempt < 6; attempt++) {
+        const uint64_t site_cap = std::max<uint64_t>(kPairSmallMax, s->site_cap_hint);
+        const uint64_t bb = block_bytes_for(n_recs, site_cap);
+        s->block.ensure(bb);
+        stage1_async(s, g, chain_variant(s, false), s->block.as<uint8_t>(), site_cap);
+        for (int again = 0; again < 4; again++) {
+            pair_async(s, s->block.as<uint8_t>(), 1, bb, site_cap, g.recs.data(), n_recs, g.recs_dev_ptr);
+            bool redo = false;
+            const ChainResult r = chain_finish(s, s->block.as<uint8_t>(), 1, bb, g.recs.data(), n_recs, n_prod, &redo);
+            if (r == kChainTooDirty) return false;
+            if (r == kChainDone) {
+                chain_timing(s, *n_prod, had_h2d);
+                return true;
+            }
+            if (redo) break;
+        }
+    }
+    throw Error("the asynchronous scan chain did not converge");
+}
+
+// a laid-out genome (ASCII resident or on its way) -> products: the chain when it applies,
+// else pack (synchronous) -> find -> pair
+static uint64_t scan_laidout(ipcr_scratch *s, GenomeData &g, bool had_h2d) {
+    if (!s->inflight) s->args_used = 0;
+    if (g.lay.total_len == 0) {
+        s->out_ptr = s->h_products.as<ipcr_product>();
+        return 0;
+    }
+    if (chain_ok(s, g.recs.data(), g.recs.size())) {
+        uint64_t n = 0;
+        if (scan_chain(s, g, had_h2d, &n)) return n;
+    }
+    pack_genome(s, g);
+    CU(cudaEventRecord(s->ev[2], s->stream));
+    return scan_genome_impl(s, g, true);
+}
 }  // namespace ipcr
+
+#include "multi.hpp"
 
 using namespace ipcr;
 
@@ -1165,7 +1592,7 @@ int ipcr_gpu_device_count(void) {
     return n;
 }
 
-int ipcr_gpu_init(int device, char *err, size_t errlen) {
+int ipcr_gpu_init(int n_devices_or_0, char *err, size_t errlen) {
     ABI_TRY
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -1173,17 +1600,35 @@ int ipcr_gpu_init(int device, char *err, size_t errlen) {
         cudaGetLastError();
         throw Error("no CUDA device visible: the ipcr GPU engine has no CPU fallback");
     }
+    if (n_devices_or_0 < 0 || n_devices_or_0 > n)
+        throw Error(fmt("%d devices requested, %d visible", n_devices_or_0, n));
+    const int use = n_devices_or_0 == 0 ? n : n_devices_or_0;
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    check_device(cur);
+    for (int d = 0; d < n && use > 1; d++) check_device(d);
+    CU(cudaFree(0));
+    g_n_devices.store(use);
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_set_device(int device, char *err, size_t errlen) {
+    ABI_TRY
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        throw Error("no CUDA device visible: the ipcr GPU engine has no CPU fallback");
+    }
     if (device < 0 || device >= n) throw Error(fmt("device %d out of range (0..%d)", device, n - 1));
     CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        throw Error(fmt("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
-                        prop.minor));
+    check_device(device);
     CU(cudaFree(0));
     return 0;
     ABI_CATCH(1)
 }
+
+int ipcr_gpu_num_devices(void) { return g_n_devices.load(); }
 
 ipcr_panel *ipcr_gpu_panel_create(const ipcr_cfg *cfg, const ipcr_pair *pairs, size_t n_pairs, char *err,
                                   size_t errlen) {
@@ -1221,31 +1666,24 @@ ipcr_scratch *ipcr_gpu_scratch_create(ipcr_panel *p, char *err, size_t errlen) {
         cudaGetLastError();
         throw Error("no CUDA device visible: the ipcr GPU engine has no CPU fallback");
     }
-    auto s = std::make_unique<ipcr_scratch>();
-    s->panel = p;
-    CU(cudaGetDevice(&s->device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, s->device));
-    if (prop.major != 10)
-        throw Error(fmt("device %d is sm_%d%d; this library is built for sm_100a (B200) only", s->device,
-                        prop.major, prop.minor));
-    s->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-    for (auto &e : s->ev) CU(cudaEventCreate(&e));
-    for (auto &e : s->copy_ev) CU(cudaEventCreate(&e));
-    s->counters.ensure(8 * sizeof(unsigned long long));
-    s->h_counts.ensure(8 * sizeof(unsigned long long));
-    s->tables = tables_for(p, s->device, s->stream);
-    return s.release();
+    int device = 0;
+    CU(cudaGetDevice(&device));
+    return make_scratch(p, device);
     ABI_CATCH(nullptr)
 }
 
 void ipcr_gpu_scratch_destroy(ipcr_scratch *s) {
     if (!s) return;
+    for (ipcr_scratch *q : s->peers) {
+        cudaSetDevice(q->device);
+        delete q;
+    }
+    s->peers.clear();
     cudaSetDevice(s->device);
     delete s;
 }
+
+void *ipcr_gpu_scratch_stream(ipcr_scratch *s) { return s ? (void *)s->stream : nullptr; }
 
 struct ipcr_fasta {
     std::vector<ipcr::FastaRecord> recs;
@@ -1274,15 +1712,22 @@ static uint64_t scan_records(ipcr_scratch *s, const ipcr_seq *recs, size_t n_rec
     }
     uint64_t total = 0;
     for (size_t i = 0; i < n_recs; i++) total += recs[i].len;
+    if (!s->inflight) s->args_used = 0;
+    std::vector<ipcr_record_info> rinfo(n_recs, ipcr_record_info{});
+    for (size_t i = 0; i < n_recs; i++) rinfo[i].len = recs[i].len;
+    const bool chain = total < (1ull << kCandPosBits) && chain_ok(s, rinfo.data(), n_recs);
+    uint64_t n = 0;
+    // several devices: one slice each (every device pulls its slice over its own PCIe link)
+    if (chain && g_n_devices.load() > 1 && total >= multi_min_bases() && scan_multi_device(s, recs, n_recs, &n)) return n;
     // large inputs: overlap the PCIe copy with the scan, slab by slab
     int n_slabs = (int)std::min<uint64_t>(5, total / (640ull << 20));
     if (const char *e = getenv("IPCR_STREAM_SLABS")) n_slabs = atoi(e);
-    uint64_t n;
     if (n_slabs >= 2 && total < (1ull << kCandPosBits) && n_recs <= 65535) {
+        if (chain && n_slabs <= (int)kPairMaxBlocks && scan_streamed_chain(s, recs, n_recs, n_slabs, &n)) return n;
         n = scan_batch_streamed(s, recs, n_recs, n_slabs);
     } else {
-        build_genome(s, s->own, segs.data(), n_recs, n_recs, false);
-        n = scan_genome_impl(s, s->own, s->own.lay.total_len > 0);
+        layout_genome(s, s->own, segs.data(), n_recs, n_recs, false);
+        n = scan_laidout(s, s->own, true);
     }
     return n;
 }
@@ -1293,11 +1738,9 @@ int ipcr_gpu_scan_batch(ipcr_panel *p, ipcr_scratch *s, const ipcr_seq *recs, si
     if (!p || !s || s->panel != p) throw Error("scratch does not belong to this panel");
     if (out) *out = nullptr;
     if (n_out) *n_out = 0;
-    bind(s);
-    s->launches = 0;
-    s->timing = ipcr_timing{};
+    begin_call(s);
     const uint64_t n = scan_records(s, recs, n_recs);
-    if (out) *out = s->h_products.as<ipcr_product>();
+    if (out) *out = s->out_ptr;
     if (n_out) *n_out = n;
     return 0;
     ABI_CATCH(1)
@@ -1348,9 +1791,7 @@ int ipcr_gpu_scan_fasta(ipcr_panel *p, ipcr_scratch *s, ipcr_fasta *f, const ipc
     if (!p || !s || !f || s->panel != p) throw Error("bad panel/scratch/fasta");
     if (out) *out = nullptr;
     if (n_out) *n_out = 0;
-    bind(s);
-    s->launches = 0;
-    s->timing = ipcr_timing{};
+    begin_call(s);
     f->products.clear();
     ipcr_timing acc{};
     // batches: <= 60000 records and < 2^43 bases per launch chain (sort-key / candidate-word budgets)
@@ -1366,7 +1807,7 @@ int ipcr_gpu_scan_fasta(ipcr_panel *p, ipcr_scratch *s, ipcr_fasta *f, const ipc
         }
         if (batch.empty()) throw Error("a single FASTA record is too large for one device pass");
         const uint64_t n = scan_records(s, batch.data(), batch.size());
-        const ipcr_product *pr = s->h_products.as<ipcr_product>();
+        const ipcr_product *pr = s->out_ptr;
         for (uint64_t k = 0; k < n; k++) {
             ipcr_product q = pr[k];
             q.rec_idx += (uint32_t)base;
@@ -1393,13 +1834,11 @@ int ipcr_gpu_scan_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *seg
     if (!p || !s || s->panel != p) throw Error("scratch does not belong to this panel");
     if (out) *out = nullptr;
     if (n_out) *n_out = 0;
-    bind(s);
-    s->launches = 0;
-    s->timing = ipcr_timing{};
+    begin_call(s);
     CU(cudaEventRecord(s->ev[0], s->stream));
-    build_genome(s, s->own, segs, n_segs, n_recs, true);
-    const uint64_t n = scan_genome_impl(s, s->own, s->own.lay.total_len > 0);
-    if (out) *out = s->h_products.as<ipcr_product>();
+    layout_genome(s, s->own, segs, n_segs, n_recs, true);
+    const uint64_t n = scan_laidout(s, s->own, true);
+    if (out) *out = s->out_ptr;
     if (n_out) *n_out = n;
     return 0;
     ABI_CATCH(1)
@@ -1454,12 +1893,10 @@ int ipcr_gpu_scan_genome(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g, c
     if (g->g.device != s->device) throw Error("genome lives on another device than the scratch");
     if (out) *out = nullptr;
     if (n_out) *n_out = 0;
-    bind(s);
-    s->launches = 0;
-    s->timing = ipcr_timing{};
+    begin_call(s);
     // the handle is logically const: packing the other format on demand is cached state (pack_mu)
     const uint64_t n = scan_genome_impl(s, const_cast<GenomeData &>(g->g), false);
-    if (out) *out = s->h_products.as<ipcr_product>();
+    if (out) *out = s->out_ptr;
     if (n_out) *n_out = n;
     return 0;
     ABI_CATCH(1)
@@ -1470,9 +1907,7 @@ int ipcr_gpu_find_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_genome *g, co
     ABI_TRY
     if (!p || !s || !g || s->panel != p) throw Error("bad panel/scratch/genome");
     if (g->g.device != s->device) throw Error("genome lives on another device than the scratch");
-    bind(s);
-    s->launches = 0;
-    s->timing = ipcr_timing{};
+    begin_call(s);
     for (int i = 0; i < 8; i++) CU(cudaEventRecord(s->ev[i], s->stream));
     const uint64_t n = find_sites(s, const_cast<GenomeData &>(g->g), true);
     if (n) {
@@ -1496,9 +1931,7 @@ int ipcr_gpu_find_sites_device(ipcr_panel *p, ipcr_scratch *s, const ipcr_segmen
                                ipcr_record_info *recs_out, char *err, size_t errlen) {
     ABI_TRY
     if (!p || !s || s->panel != p) throw Error("bad panel/scratch");
-    bind(s);
-    s->launches = 0;
-    s->timing = ipcr_timing{};
+    begin_call(s);
     for (int i = 0; i < 8; i++) CU(cudaEventRecord(s->ev[i], s->stream));
     build_genome(s, s->own, segs, n_segs, n_recs, true);
     const uint64_t n = find_sites(s, s->own, force_raw != 0);
@@ -1546,9 +1979,77 @@ int ipcr_gpu_pair_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_site *sites, 
     s->timing.pair_ms = ev_ms(s->ev[5], s->ev[7]);
     s->timing.products = n;
     s->timing.kernel_launches = s->launches;
-    if (out) *out = s->h_products.as<ipcr_product>();
+    if (out) *out = s->out_ptr;
     if (n_out) *n_out = n;
     return 0;
+    ABI_CATCH(1)
+}
+
+uint64_t ipcr_gpu_site_block_bytes(size_t n_recs, uint64_t site_cap) { return block_bytes_for(n_recs, site_cap); }
+
+uint64_t ipcr_gpu_scratch_site_cap(const ipcr_scratch *s) {
+    return std::max<uint64_t>(4096, s ? s->site_cap_hint : 0);
+}
+
+int ipcr_gpu_find_sites_block(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs, size_t n_recs,
+                              int force_raw, void *d_block, uint64_t site_cap, char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || s->panel != p || !d_block) throw Error("bad panel/scratch/block");
+    begin_call(s);
+    layout_genome(s, s->own, segs, n_segs, n_recs, true);
+    s->last_valid = false;
+    std::vector<ipcr_record_info> rinfo(n_recs, ipcr_record_info{});
+    for (size_t r = 0; r < n_recs; r++) rinfo[r].len = std::max<uint64_t>(1, s->own.recs[r].len);
+    if (!chain_ok(s, rinfo.data(), n_recs))
+        throw Error("ipcr_gpu_find_sites_block needs a seed-index panel; use ipcr_gpu_find_sites_device");
+    if (s->own.lay.total_len == 0) {
+        Stage1Ctl init{};
+        init.site_cap = site_cap;
+        init.variant = (uint32_t)chain_variant(s, force_raw != 0);
+        init.n_recs = (uint32_t)n_recs;
+        s->seg_reset_dummy.ensure(16);
+        for (int i = 1; i <= 5; i++) CU(cudaEventRecord(s->ev[i], s->stream));
+        k_block_init<<<1, 256, 0, s->stream>>>(static_cast<uint8_t *>(d_block), init, s->seg_reset_dummy.as<uint32_t>(), 0);
+        check_launch("k_block_init");
+        s->inflight = true;
+    } else {
+        stage1_async(s, s->own, chain_variant(s, force_raw != 0), static_cast<uint8_t *>(d_block), site_cap);
+    }
+    s->timing.kernel_launches = s->launches;
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_pair_blocks(ipcr_panel *p, ipcr_scratch *s, const void *d_blocks, uint32_t n_blocks, uint64_t site_cap,
+                         const uint64_t *rec_lens, size_t n_recs, const ipcr_product **out, uint64_t *n_out,
+                         char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || s->panel != p || !d_blocks || (!rec_lens && n_recs)) throw Error("bad panel/scratch/blocks");
+    if (n_blocks == 0 || n_blocks > kPairMaxBlocks) throw Error(fmt("1..%u blocks per pairing pass", kPairMaxBlocks));
+    if (out) *out = nullptr;
+    if (n_out) *n_out = 0;
+    bind(s);  // no begin_call: the blocks may still be on their way on this stream
+    std::vector<ipcr_record_info> rinfo(n_recs, ipcr_record_info{});
+    for (size_t r = 0; r < n_recs; r++) rinfo[r].len = rec_lens[r];
+    if (!chain_ok(s, rinfo.data(), n_recs)) throw Error("ipcr_gpu_pair_blocks needs a seed-index panel");
+    const uint64_t bb = block_bytes_for(n_recs, site_cap);
+    const uint8_t *blocks = static_cast<const uint8_t *>(d_blocks);
+    for (int again = 0; again < 4; again++) {
+        pair_async(s, blocks, n_blocks, bb, site_cap, rinfo.data(), n_recs);
+        bool redo = false;
+        uint64_t n = 0;
+        const ChainResult r = chain_finish(s, blocks, n_blocks, bb, rinfo.data(), n_recs, &n, &redo);
+        if (r == kChainTooDirty)
+            throw Error("input too dirty for the seed index: use the host-gathered split phase (ipcr_gpu_find_sites_device)");
+        if (r == kChainDone) {
+            chain_timing(s, n, false);
+            if (out) *out = s->out_ptr;
+            if (n_out) *n_out = n;
+            return 0;
+        }
+        if (redo) return 2;
+    }
+    throw Error("stage 2 did not converge");
     ABI_CATCH(1)
 }
 
@@ -1682,7 +2183,7 @@ int ipcr_gpu_nested(ipcr_scratch *outer, const ipcr_product *products, uint64_t 
         std::vector<ipcr_seq> recs;
         for (uint64_t i = b0; i < b1; i++) recs.push_back(ipcr_seq{amp + offs[i], offs[i + 1] - offs[i]});
         const uint64_t np = scan_records(inner, recs.data(), recs.size());
-        const ipcr_product *pr = inner->h_products.as<ipcr_product>();
+        const ipcr_product *pr = inner->out_ptr;
         for (uint64_t k = 0; k < np; k++) {
             ipcr_product &cur = best[b0 + pr[k].rec_idx];
             if (cur.length < 0 || better(pr[k], cur)) {

@@ -33,7 +33,8 @@ __device__ __forceinline__ uint32_t find_segment(const SegmentDev *segs, uint32_
 
 __global__ void __launch_bounds__(1024)
 k_pack_bytes(const uint8_t *__restrict__ ascii, GenomeLayout lay, uint4 *__restrict__ planes,
-       const SegmentDev *__restrict__ segs, uint32_t n_segs, uint32_t *__restrict__ seg_reset) {
+       const SegmentDev *__restrict__ segs, uint32_t n_segs, uint32_t *__restrict__ seg_reset,
+       uint8_t *__restrict__ rec_reset) {
     __shared__ uint4 tile[32][33];
     const uint64_t t = blockIdx.x;
     const uint32_t r = blockIdx.y * 32u + threadIdx.x;
@@ -59,7 +60,10 @@ k_pack_bytes(const uint8_t *__restrict__ ascii, GenomeLayout lay, uint4 *__restr
                 if (!((rs >> i) & 1u)) continue;
                 const uint64_t P = (stripe0 + i) * lay.W + r;
                 const uint32_t s = find_segment(segs, n_segs, P);
-                if (P - segs[s].global_off < segs[s].len) seg_reset[s] = 1u;
+                if (P - segs[s].global_off < segs[s].len) {
+                    seg_reset[s] = 1u;
+                    if (rec_reset) rec_reset[segs[s].rec_idx] = 1u;
+                }
             }
         }
     }
@@ -79,7 +83,8 @@ k_pack_bytes(const uint8_t *__restrict__ ascii, GenomeLayout lay, uint4 *__restr
 // written out as 8 KB fully coalesced.
 __global__ void __launch_bounds__(1024)
 k_pack(const uint8_t *__restrict__ ascii, GenomeLayout lay, uint4 *__restrict__ planes,
-       const SegmentDev *__restrict__ segs, uint32_t n_segs, uint32_t *__restrict__ seg_reset) {
+       const SegmentDev *__restrict__ segs, uint32_t n_segs, uint32_t *__restrict__ seg_reset,
+       uint8_t *__restrict__ rec_reset) {
     __shared__ uint4 stage[2][16][32];
     const uint64_t t = blockIdx.x;
     const uint32_t i = threadIdx.x & 31u, y = threadIdx.x >> 5;
@@ -113,7 +118,10 @@ k_pack(const uint8_t *__restrict__ ascii, GenomeLayout lay, uint4 *__restrict__ 
                 const uint64_t P = P0 + k;
                 if (!acgt && P < lay.total_len && c * 16u + k < lay.W) {
                     const uint32_t s = find_segment(segs, n_segs, P);
-                    if (P - segs[s].global_off < segs[s].len) seg_reset[s] = 1u;
+                    if (P - segs[s].global_off < segs[s].len) {
+                        seg_reset[s] = 1u;
+                        if (rec_reset) rec_reset[segs[s].rec_idx] = 1u;
+                    }
                 }
             }
         }
@@ -522,19 +530,22 @@ __global__ void k_join_entries(JoinArgs a) {
     a.entry_tasks[e] = (uint32_t)(en - b);
 }
 
+// Partner lists are rc-type orientations: never halo-flagged, so inside their segment the sort
+// keys ascend with the position held in their low pos_bits -- the searches read the 8-byte keys
+// (shared memory in the single-CTA pairing kernel), not the 24-byte site records.
 // first index in [b, e) with pos >= v  (lowerBoundMatchPos, engine.go:87-89)
-__device__ __forceinline__ int64_t lb_pos(const FinalSite *fs, int64_t b, int64_t e, int64_t v) {
+__device__ __forceinline__ int64_t lb_pos(const uint64_t *fkeys, uint64_t pos_mask, int64_t b, int64_t e, int64_t v) {
     while (b < e) {
         const int64_t mid = b + ((e - b) >> 1);
-        if ((int64_t)fs[mid].pos >= v) e = mid; else b = mid + 1;
+        if ((int64_t)(fkeys[mid] & pos_mask) >= v) e = mid; else b = mid + 1;
     }
     return b;
 }
 // first index in [b, e) with pos > v  (upperBoundMatchPos, engine.go:91-93)
-__device__ __forceinline__ int64_t ub_pos(const FinalSite *fs, int64_t b, int64_t e, int64_t v) {
+__device__ __forceinline__ int64_t ub_pos(const uint64_t *fkeys, uint64_t pos_mask, int64_t b, int64_t e, int64_t v) {
     while (b < e) {
         const int64_t mid = b + ((e - b) >> 1);
-        if ((int64_t)fs[mid].pos > v) e = mid; else b = mid + 1;
+        if ((int64_t)(fkeys[mid] & pos_mask) > v) e = mid; else b = mid + 1;
     }
     return b;
 }
@@ -543,39 +554,30 @@ __device__ __forceinline__ uint64_t flip_mask(uint64_t m, int n) {  // engine.go
     return n <= 0 ? 0ull : (__brevll(m) >> (64 - n));
 }
 
-// One thread per forward site of one (record, pair, direction): a verbatim
+// One forward site of one (record, pair, direction) against its partner list [pb, pe): a verbatim
 // restatement of one iteration of the outer loops of forEachJoinedProduct
-// (core/engine/engine.go:144-272 / :276-402).  FILL = false counts, true writes.
+// (core/engine/engine.go:144-272 / :276-402).  FILL = false counts, true writes from products[out].
+// fidx = index of the forward site in the final (sorted, capped) list.  Returns the product count.
 template <bool FILL>
-__device__ __forceinline__ void join_task(const JoinArgs &a, uint64_t t) {
-    const uint64_t n_entries = (uint64_t)a.n_recs * a.n_pairs * 2ull;
-    // entry = last e with task_off[e] <= t
-    uint64_t lo = 0, hi = n_entries;
-    while (lo + 1 < hi) {
-        const uint64_t mid = (lo + hi) >> 1;
-        if ((uint64_t)a.task_off[mid] <= t) lo = mid; else hi = mid;
-    }
-    const uint64_t e = lo;
-    const uint32_t k = (uint32_t)(t - a.task_off[e]);
-    const uint32_t blk = (uint32_t)(e & 1ull);
-    const uint32_t pair = (uint32_t)((e >> 1) % a.n_pairs);
-    const uint32_t rec = (uint32_t)((e >> 1) / a.n_pairs);
-    const PairDev p = a.pairs[pair];
+__device__ __forceinline__ uint32_t join_core(const JoinArgs &a, uint32_t rec, uint32_t pair, uint32_t blk,
+                                              const PairDev &p, uint64_t fidx, int64_t pb, int64_t pe, uint64_t out) {
     const int64_t seq_len = (int64_t)a.recs[rec].len;
     const int64_t minL = p.min_len, maxL = p.max_len;
     const int64_t plen = blk == 0 ? p.blen : p.alen;  // partner primer length
-    uint64_t fb, fe, pb64, pe64;
-    segment_of(a, rec, blk == 0 ? p.fwdA : p.fwdB, fb, fe);
-    segment_of(a, rec, blk == 0 ? p.rcB : p.rcA, pb64, pe64);
-    const int64_t pb = (int64_t)pb64, pe = (int64_t)pe64;
-    const FinalSite ma = a.fs[fb + k];
-    const int64_t apos = (int64_t)ma.pos;
+    const uint64_t pos_mask = (1ull << a.kl.pos_bits) - 1ull;
+    const int64_t apos = (int64_t)(a.fkeys[fidx] & pos_mask);
     uint32_t cnt = 0;
-    uint64_t out = FILL ? a.prod_off[t] : 0;
+    FinalSite ma;
+    bool have_ma = false;
 
-    auto emit = [&](const FinalSite &mb, int64_t end, int64_t length) {
+    auto emit = [&](int64_t j, int64_t end, int64_t length) {
         if (FILL) {
             if (out < a.prod_cap) {
+                if (!have_ma) {
+                    ma = a.fs[fidx];
+                    have_ma = true;
+                }
+                const FinalSite mb = a.fs[j];
                 ipcr_product pr;
                 pr.start = apos;
                 pr.end = end;
@@ -609,14 +611,13 @@ __device__ __forceinline__ void join_task(const JoinArgs &a, uint64_t t) {
             if (hi2 > last) hi2 = last;
         }
         if (hi2 >= lo2) {
-            const int64_t iMin = lb_pos(a.fs, pb, pe, lo2);
-            const int64_t iMax = ub_pos(a.fs, pb, pe, hi2) - 1;
+            const int64_t iMin = lb_pos(a.fkeys, pos_mask, pb, pe, lo2);
+            const int64_t iMax = ub_pos(a.fkeys, pos_mask, pb, pe, hi2) - 1;
             for (int64_t j = iMax; j >= iMin; j--) {
-                const FinalSite mb = a.fs[j];
-                const int64_t end = (int64_t)mb.pos + plen;
+                const int64_t end = (int64_t)(a.fkeys[j] & pos_mask) + plen;
                 const int64_t length = end - apos;
                 if ((minL != 0 && length < minL) || (maxL != 0 && length > maxL)) continue;
-                emit(mb, end, length);
+                emit(j, end, length);
             }
         }
     }
@@ -634,18 +635,42 @@ __device__ __forceinline__ void join_task(const JoinArgs &a, uint64_t t) {
             if (allowed < hiW) hiW = allowed;
         }
         if (hiW >= loW) {
-            const int64_t iMinW = lb_pos(a.fs, pb, pe, loW);
-            const int64_t iMaxW = ub_pos(a.fs, pb, pe, hiW) - 1;
+            const int64_t iMinW = lb_pos(a.fkeys, pos_mask, pb, pe, loW);
+            const int64_t iMaxW = ub_pos(a.fkeys, pos_mask, pb, pe, hiW) - 1;
             for (int64_t j = iMaxW; j >= iMinW; j--) {
-                const FinalSite mb = a.fs[j];
-                if ((int64_t)mb.pos >= apos) continue;
-                const int64_t end = (int64_t)mb.pos + plen;
+                const int64_t mpos = (int64_t)(a.fkeys[j] & pos_mask);
+                if (mpos >= apos) continue;
+                const int64_t end = mpos + plen;
                 const int64_t length = X + end;
                 if ((minL != 0 && length < minL) || (maxL != 0 && length > maxL)) continue;
-                emit(mb, end, length);
+                emit(j, end, length);
             }
         }
     }
+    return cnt;
+}
+
+// task t -> (entry, forward site) through the scanned entry sizes
+template <bool FILL>
+__device__ __forceinline__ void join_task(const JoinArgs &a, uint64_t t) {
+    const uint64_t n_entries = (uint64_t)a.n_recs * a.n_pairs * 2ull;
+    // entry = last e with task_off[e] <= t
+    uint64_t lo = 0, hi = n_entries;
+    while (lo + 1 < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if ((uint64_t)a.task_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint64_t e = lo;
+    const uint32_t k = (uint32_t)(t - a.task_off[e]);
+    const uint32_t blk = (uint32_t)(e & 1ull);
+    const uint32_t pair = (uint32_t)((e >> 1) % a.n_pairs);
+    const uint32_t rec = (uint32_t)((e >> 1) / a.n_pairs);
+    const PairDev p = a.pairs[pair];
+    uint64_t fb, fe, pb64, pe64;
+    segment_of(a, rec, blk == 0 ? p.fwdA : p.fwdB, fb, fe);
+    segment_of(a, rec, blk == 0 ? p.rcB : p.rcA, pb64, pe64);
+    const uint32_t cnt = join_core<FILL>(a, rec, pair, blk, p, fb + k, (int64_t)pb64, (int64_t)pe64,
+                                         FILL ? a.prod_off[t] : 0);
     if (!FILL) a.task_cnt[t] = cnt;
 }
 

@@ -1,0 +1,566 @@
+// pair_small.cuh -- the asynchronous chain: stage-1 site blocks and stage 2 (hit cap, sort,
+// amplicon pairing) in ONE single-CTA launch.
+//
+// A scan usually leaves a few thousand primer sites.  The multi-kernel stage 2 (k_site_keys ->
+// sort -> keep -> scan -> compact -> entries -> scan -> join<count> -> scan -> join<fill>) costs
+// nine launches and three host round trips for ~20 us of work.  Here stage 1 writes its sites,
+// counters and per-record reset flags into a SITE BLOCK in device memory, and one CTA of 1024
+// threads does all of stage 2 out of shared memory over any number of such blocks (one per GPU
+// shard or per streamed slab): it reads every count from the DEVICE, so the host never waits
+// between kernels, and leaves a header the host reads once, together with the products.
+// Same arithmetic and same emission order as the multi-kernel path: it calls the same device
+// functions (site_key, join_task).  Replaces matchCollector's cap, sortMatchesByPos, filterLeftTW
+// and forEachJoinedProduct (/root/reference/core/engine/hit_collect.go:73-98, engine.go:53-76,
+// engine.go:108-404).
+#pragma once
+
+#include "kernels.cuh"
+#include "sortscan.cuh"
+
+namespace ipcr {
+
+constexpr uint32_t kPairSmallMax = kSortSmallMax;  // 8192 sites
+constexpr uint32_t kPairMaxBlocks = 64;
+
+// ---- site block: what stage 1 leaves behind and what multi-GPU shards exchange -------------
+// block = [Stage1Ctl | rec_reset bytes, padded to 16 | sites]; all blocks of a call have one size.
+struct Stage1Ctl {
+    unsigned long long n_sites;     // sites this shard found (may exceed site_cap: then some are lost)
+    unsigned long long n_cand, n_dirty;
+    unsigned long long cand_cap, dirty_cap, site_cap;
+    uint32_t variant;               // plan variant stage 1 ran with
+    uint32_t n_recs;
+    unsigned long long pad[1];
+};
+static_assert(sizeof(Stage1Ctl) == 64, "Stage1Ctl is one 64-byte block");
+
+__host__ __device__ __forceinline__ uint64_t block_ctl_bytes(uint64_t n_recs) {
+    return sizeof(Stage1Ctl) + ((n_recs + 15ull) & ~15ull);
+}
+__host__ __device__ __forceinline__ uint64_t block_bytes_for(uint64_t n_recs, uint64_t site_cap) {
+    return (block_ctl_bytes(n_recs) + site_cap * sizeof(ipcr_site) + 15ull) & ~15ull;
+}
+
+// first kernel of the chain: clears the counters and flags, records the capacities
+__global__ void __launch_bounds__(256)
+k_block_init(uint8_t *block, Stage1Ctl init, uint32_t *seg_reset, uint32_t n_segs) {
+    if (threadIdx.x == 0) *reinterpret_cast<Stage1Ctl *>(block) = init;
+    uint8_t *rr = block + sizeof(Stage1Ctl);
+    const uint32_t rr_bytes = (uint32_t)(block_ctl_bytes(init.n_recs) - sizeof(Stage1Ctl));
+    for (uint32_t i = threadIdx.x; i < rr_bytes; i += blockDim.x) rr[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < n_segs; i += blockDim.x) seg_reset[i] = 0u;
+}
+
+// flags of PairHeader.flags
+constexpr uint32_t kPairNotSmall = 1u;        // more than kPairSmallMax sites: run the multi-kernel path
+constexpr uint32_t kPairSitesLost = 2u;       // a block's stage 1 produced more sites than the block holds
+constexpr uint32_t kPairTaskOverflow = 4u;    // task_cap too small (n_tasks is valid)
+constexpr uint32_t kPairProdOverflow = 8u;    // prod_cap too small (n_prod is valid)
+constexpr uint32_t kPairStage1Overflow = 16u; // a block's candidate or dirty-window list overflowed
+constexpr uint32_t kPairAnyReset = 32u;       // some record holds a reset byte
+constexpr uint32_t kPairMixedVariant = 64u;   // blocks ran different plan variants (informational)
+
+struct PairHeader {
+    unsigned long long n_sites, n_final, n_tasks, n_prod;
+    unsigned long long n_cand, n_dirty;  // largest per-block counts (capacity hints)
+    uint32_t flags;
+    uint32_t min_variant;                // smallest plan variant among the blocks
+    uint32_t pad[2];
+};
+static_assert(sizeof(PairHeader) == 64, "PairHeader is read back as one 64-byte block");
+static_assert(sizeof(PairHeader) == sizeof(ipcr_product), "products follow the header in one buffer");
+
+struct PairSmallArgs {
+    const uint8_t *blocks;
+    uint32_t n_blocks;
+    uint64_t block_bytes, ctl_bytes, block_site_cap;
+    const OrientDev *orients;
+    uint8_t *rec_reset;  // [n_recs] scratch: OR of the blocks' per-record flags
+    JoinArgs j;  // pairs, recs, prm, kl; fs / entry_tasks / task_off / task_cnt / prod_off / products are scratch
+    uint32_t task_cap;
+    uint32_t bucket_cap;  // (record, orientation) buckets the dynamic shared memory has room for (0 = general mode only)
+    PairHeader *header;
+};
+
+// exclusive scan of in[0, n) -> out[0, n], out[n] = total, by one CTA of 1024 threads; returns the total
+// to every thread.  in and out may not alias.  wsum: 33 words of shared memory.
+__device__ __forceinline__ uint32_t cta_scan_global(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *wsum) {
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
+    uint32_t tsum = 0;
+    for (uint32_t i = b; i < e; i++) tsum += in[i];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t x = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    __syncthreads();  // wsum may still be read by a previous call
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < (blockDim.x >> 5) ? wsum[lane] : 0u;
+        uint32_t xi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xi, d);
+            if (lane >= (uint32_t)d) xi += y;
+        }
+        wsum[lane] = xi - w;
+        if (lane == 31) wsum[32] = xi;
+    }
+    __syncthreads();
+    uint32_t run = x - tsum + wsum[warp];
+    for (uint32_t i = b; i < e; i++) {
+        const uint32_t v = in[i];
+        out[i] = run;
+        run += v;
+    }
+    const uint32_t total = wsum[32];
+    if (threadIdx.x == 0) out[n] = total;
+    __syncthreads();
+    return total;
+}
+
+// block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive prefix, *total to all
+__device__ __forceinline__ uint32_t cta_scan_value(uint32_t v, uint32_t *wsum, uint32_t *total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = wsum[lane];
+        uint32_t xi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xi, d);
+            if (lane >= (uint32_t)d) xi += y;
+        }
+        wsum[lane] = xi - w;
+        if (lane == 31) wsum[32] = xi;
+    }
+    __syncthreads();
+    *total = wsum[32];
+    return x - v + wsum[warp];
+}
+
+// in-place exclusive scan of arr[0, n) in shared memory, arr[n] = total; returns the total
+__device__ __forceinline__ uint32_t cta_scan_inplace(uint32_t *arr, uint32_t n, uint32_t *wsum) {
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
+    uint32_t tsum = 0;
+    for (uint32_t i = b; i < e; i++) tsum += arr[i];
+    uint32_t total;
+    uint32_t run = cta_scan_value(tsum, wsum, &total);
+    for (uint32_t i = b; i < e; i++) {
+        const uint32_t v = arr[i];
+        arr[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == 0) arr[n] = total;
+    __syncthreads();
+    return total;
+}
+
+constexpr uint32_t kBucketMaxSize = 64;  // larger (record, orientation) lists go through the general mode
+constexpr int kPairPerThread = kPairSmallMax / 1024;
+
+// BUCKET MODE.  Sites fall into (record, orientation) buckets that are tiny in a sparse scan, so the
+// sort is a counting sort over the buckets plus a rank inside each bucket, the scanned bucket sizes ARE
+// the segment table of the join (no binary searches), and every thread walks a contiguous range of
+// (record, pair, direction) entries -- counting, then writing products in the reference's order with
+// no per-entry or per-task arrays.  Shared memory: sk[8192] words, off[nb + 1], foff[nb + 1].
+// Returns false (nothing written) when a bucket holds more than kBucketMaxSize sites.
+__device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArgs j, PairHeader &h, uint32_t n,
+                                                 unsigned long long *sk, const unsigned long long *s_boff, uint32_t *wsum) {
+    const KeyLayout kl = j.kl;
+    const uint32_t nb = j.n_recs * kl.n_orient;
+    uint32_t *off = reinterpret_cast<uint32_t *>(sk + kPairSmallMax);
+    uint32_t *foff = off + nb + 1;
+    __shared__ uint32_t s_max, s_tasks;
+    const long long t0 = clock64();
+    auto stamp = [&](int slot) {  // debug: cycles / 64 since the mode began, four 16-bit slots in the header pad
+        const uint32_t v = (uint32_t)min((long long)0xFFFF, (clock64() - t0) >> 6);
+        h.pad[slot >> 1] |= v << (16 * (slot & 1));
+    };
+    for (uint32_t i = threadIdx.x; i <= nb; i += blockDim.x) off[i] = foff[i] = 0u;
+    if (threadIdx.x == 0) s_max = s_tasks = 0u;
+    __syncthreads();
+    auto site_at = [&](uint32_t i) -> const ipcr_site & {
+        uint32_t b = 0;
+        while (b + 1 < a.n_blocks && (unsigned long long)i >= s_boff[b + 1]) b++;
+        return reinterpret_cast<const ipcr_site *>(a.blocks + (uint64_t)b * a.block_bytes + a.ctl_bytes)[i - (uint32_t)s_boff[b]];
+    };
+    // ---- 1. keys; slot inside the bucket (arrival order, fixed by the rank pass below) ----
+    unsigned long long word[kPairPerThread];
+    uint32_t slot[kPairPerThread];
+#pragma unroll
+    for (int c = 0; c < kPairPerThread; c++) {
+        const uint32_t i = threadIdx.x + 1024u * c;
+        word[c] = ~0ull;
+        slot[c] = 0u;
+        if (i < n) {
+            const ipcr_site &s = site_at(i);
+            const uint64_t key = site_key(s, a.orients, j.recs, a.rec_reset, j.prm, kl);
+            if (key < (1ull << kl.key_bits)) {  // invalid sites never count
+                word[c] = (key << 14) | ((unsigned long long)i << 1) | ((s.flags & IPCR_SITE_TWVIOL) ? 1ull : 0ull);
+                slot[c] = atomicAdd(&off[(uint32_t)(key >> (kl.pos_bits + 1))], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    stamp(0);
+    {  // largest bucket
+        uint32_t mx = 0;
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) mx = max(mx, off[i]);
+        mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+        if ((threadIdx.x & 31u) == 0u) atomicMax(&s_max, mx);
+    }
+    __syncthreads();
+    if (s_max > kBucketMaxSize) return false;
+    const uint32_t n_valid = cta_scan_inplace(off, nb, wsum);
+    // ---- 2. scatter into bucket order, then rank inside each bucket ----
+#pragma unroll
+    for (int c = 0; c < kPairPerThread; c++)
+        if (word[c] != ~0ull) sk[off[(uint32_t)(word[c] >> (14 + kl.pos_bits + 1))] + slot[c]] = word[c];
+    __syncthreads();
+    uint32_t bk[kPairPerThread], rank[kPairPerThread];
+#pragma unroll
+    for (int c = 0; c < kPairPerThread; c++) {
+        const uint32_t k = threadIdx.x + 1024u * c;
+        word[c] = ~0ull;
+        if (k < n_valid) {
+            const unsigned long long w = sk[k];
+            const uint32_t b = (uint32_t)(w >> (14 + kl.pos_bits + 1));
+            uint32_t r = 0;
+            for (uint32_t x = off[b]; x < off[b + 1]; x++) r += sk[x] < w ? 1u : 0u;
+            word[c] = w;
+            bk[c] = b;
+            rank[c] = r;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < kPairPerThread; c++)
+        if (word[c] != ~0ull) sk[off[bk[c]] + rank[c]] = word[c];
+    __syncthreads();
+    stamp(1);
+    // ---- 3. hit cap (rank in the sorted bucket) + left-window filter; final position of the kept ones ----
+    uint32_t prior[kPairPerThread];
+    const uint64_t cap = j.prm.hit_cap > 0 ? (uint64_t)j.prm.hit_cap : ~0ull;
+#pragma unroll
+    for (int c = 0; c < kPairPerThread; c++) {
+        const uint32_t k = threadIdx.x + 1024u * c;
+        word[c] = ~0ull;
+        if (k < n_valid) {
+            const unsigned long long w = sk[k];
+            const uint32_t b = (uint32_t)(w >> (14 + kl.pos_bits + 1));
+            const uint32_t b0 = off[b];
+            if ((w & 1ull) == 0ull && (uint64_t)(k - b0) < cap) {
+                uint32_t pr = 0;
+                for (uint32_t x = b0; x < k; x++) pr += (sk[x] & 1ull) ? 0u : 1u;  // x - b0 < k - b0 < cap
+                word[c] = w;
+                bk[c] = b;
+                prior[c] = pr;
+                atomicAdd(&foff[b], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n_final = cta_scan_inplace(foff, nb, wsum);
+    h.n_final = n_final;
+    j.n_sites = n_final;
+    if (n_final == 0u) return true;
+    {
+        FinalSite *fs = const_cast<FinalSite *>(j.fs);
+#pragma unroll
+        for (int c = 0; c < kPairPerThread; c++) {
+            if (word[c] == ~0ull) continue;
+            const uint32_t dst = foff[bk[c]] + prior[c];
+            const ipcr_site s = site_at((uint32_t)(word[c] >> 1) & (kPairSmallMax - 1u));
+            sk[dst] = word[c] >> 14;  // every word was read into registers before the scan's barriers
+            FinalSite f;
+            f.pos = s.pos;
+            f.mask = s.mm_mask;
+            f.mm = s.mm;
+            f.pad = 0;
+            fs[dst] = f;
+        }
+    }
+    __syncthreads();
+    j.fkeys = reinterpret_cast<const uint64_t *>(sk);
+    stamp(2);
+    // ---- 4. join.  Live tasks = forward sites of entries whose partner list is not empty (few in a
+    // sparse scan).  A thread owns a contiguous range of entries and lists its live tasks in entry
+    // order; then one thread per task counts, the counts are scanned, one thread per task fills. ----
+    const uint32_t n_entries = j.n_recs * j.n_pairs * 2u;
+    const uint32_t per = (n_entries + blockDim.x - 1) / blockDim.x;
+    const uint32_t e0 = min(n_entries, threadIdx.x * per), e1 = min(n_entries, e0 + per);
+    uint32_t my_live = 0, my_tasks = 0;
+    for (uint32_t en = e0; en < e1; en++) {
+        const uint32_t blk = en & 1u, pair = (en >> 1) % j.n_pairs, rec = (en >> 1) / j.n_pairs;
+        const PairDev p = j.pairs[pair];
+        const uint32_t bf = rec * kl.n_orient + (blk == 0 ? p.fwdA : p.fwdB), bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
+        const uint32_t nf = foff[bf + 1] - foff[bf];
+        my_tasks += nf;
+        if (foff[bp + 1] != foff[bp]) my_live += nf;
+    }
+    if (my_tasks) atomicAdd(&s_tasks, my_tasks);
+    uint32_t n_live;
+    uint32_t lbase = cta_scan_value(my_live, wsum, &n_live);
+    h.n_tasks = s_tasks;
+    stamp(3);
+    if (n_live == 0u) return true;
+    if (n_live > a.task_cap) {
+        h.n_tasks = n_live;
+        h.flags |= kPairTaskOverflow;
+        return true;
+    }
+    uint32_t *tasks = const_cast<uint32_t *>(j.task_off);  // scratch: entry << 13 | forward site index
+    if (my_live) {
+        for (uint32_t en = e0; en < e1; en++) {
+            const uint32_t blk = en & 1u, pair = (en >> 1) % j.n_pairs, rec = (en >> 1) / j.n_pairs;
+            const PairDev p = j.pairs[pair];
+            const uint32_t bf = rec * kl.n_orient + (blk == 0 ? p.fwdA : p.fwdB), bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
+            if (foff[bp + 1] == foff[bp]) continue;
+            for (uint32_t f = foff[bf]; f < foff[bf + 1]; f++) tasks[lbase++] = (en << 13) | f;
+        }
+    }
+    __syncthreads();
+    auto run_task = [&](uint32_t t, bool fill, uint64_t out) -> uint32_t {
+        const uint32_t tk = tasks[t], en = tk >> 13, f = tk & (kPairSmallMax - 1u);
+        const uint32_t blk = en & 1u, pair = (en >> 1) % j.n_pairs, rec = (en >> 1) / j.n_pairs;
+        const PairDev p = j.pairs[pair];
+        const uint32_t bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
+        return fill ? join_core<true>(j, rec, pair, blk, p, f, foff[bp], foff[bp + 1], out)
+                    : join_core<false>(j, rec, pair, blk, p, f, foff[bp], foff[bp + 1], 0);
+    };
+    for (uint32_t t = threadIdx.x; t < n_live; t += blockDim.x) j.task_cnt[t] = run_task(t, false, 0);
+    __syncthreads();
+    uint32_t *poff = const_cast<uint32_t *>(j.prod_off);
+    const uint32_t n_prod = cta_scan_global(j.task_cnt, poff, n_live, wsum);
+    h.n_prod = n_prod;
+    if ((uint64_t)n_prod > j.prod_cap) {
+        h.flags |= kPairProdOverflow;
+        return true;
+    }
+    for (uint32_t t = threadIdx.x; t < n_live; t += blockDim.x)
+        if (j.task_cnt[t]) run_task(t, true, poff[t]);
+    return true;
+}
+
+// dynamic shared memory: m sort words (key << 13 | index), then kPairSmallMax final keys
+__global__ void __launch_bounds__(1024)
+k_pair_small(PairSmallArgs a) {
+    extern __shared__ unsigned long long sk[];
+    __shared__ uint32_t wsum[33];
+    __shared__ uint32_t s_total, s_flags, s_minvar;
+    __shared__ unsigned long long s_boff[kPairMaxBlocks + 1], s_ncand, s_ndirty;
+    JoinArgs j = a.j;
+    // ---- block headers: counts, overflow flags, merged per-record reset flags ----
+    if (threadIdx.x == 0) {
+        unsigned long long off = 0ull, nc = 0ull, nd = 0ull;
+        uint32_t fl = 0u, vmin = 0xFFFFFFFFu, vmax = 0u;
+        for (uint32_t b = 0; b < a.n_blocks; b++) {
+            const Stage1Ctl *ctl = reinterpret_cast<const Stage1Ctl *>(a.blocks + (uint64_t)b * a.block_bytes);
+            s_boff[b] = off;
+            off += ctl->n_sites;
+            if (ctl->n_sites > a.block_site_cap || ctl->n_sites > ctl->site_cap) fl |= kPairSitesLost;
+            if (ctl->n_cand > ctl->cand_cap || ctl->n_dirty > ctl->dirty_cap) fl |= kPairStage1Overflow;
+            nc = max(nc, ctl->n_cand);
+            nd = max(nd, ctl->n_dirty);
+            vmin = min(vmin, ctl->variant);
+            vmax = max(vmax, ctl->variant);
+        }
+        s_boff[a.n_blocks] = off;
+        if (vmin != vmax) fl |= kPairMixedVariant;
+        s_flags = fl;
+        s_minvar = a.n_blocks ? vmin : 0u;
+        s_ncand = nc;
+        s_ndirty = nd;
+    }
+    uint32_t my_reset = 0u;
+    for (uint32_t r = threadIdx.x; r < j.n_recs; r += blockDim.x) {
+        uint8_t v = 0u;
+        for (uint32_t b = 0; b < a.n_blocks; b++) v |= a.blocks[(uint64_t)b * a.block_bytes + sizeof(Stage1Ctl) + r];
+        a.rec_reset[r] = v;
+        my_reset |= v;
+    }
+    const int any_reset = __syncthreads_or((int)my_reset);
+    PairHeader h;
+    h.n_sites = s_boff[a.n_blocks];
+    h.n_final = h.n_tasks = h.n_prod = 0ull;
+    h.n_cand = s_ncand;
+    h.n_dirty = s_ndirty;
+    h.flags = s_flags | (any_reset ? kPairAnyReset : 0u);
+    h.min_variant = s_minvar;
+    h.pad[0] = h.pad[1] = 0u;
+    if (!(h.flags & (kPairSitesLost | kPairStage1Overflow)) && h.n_sites > kPairSmallMax) h.flags |= kPairNotSmall;
+    const uint32_t n = (uint32_t)h.n_sites;
+    if ((h.flags & (kPairSitesLost | kPairStage1Overflow | kPairNotSmall)) != 0u || n == 0u) {
+        if (threadIdx.x == 0) *a.header = h;
+        return;
+    }
+    if (j.n_recs * j.kl.n_orient <= a.bucket_cap) {
+        if (pair_bucket_mode(a, j, h, n, sk, s_boff, wsum)) {
+            if (threadIdx.x == 0) *a.header = h;
+            return;
+        }
+        __syncthreads();
+    }
+    auto site_at = [&](uint32_t i) -> const ipcr_site & {
+        uint32_t b = 0;
+        while (b + 1 < a.n_blocks && (unsigned long long)i >= s_boff[b + 1]) b++;
+        return reinterpret_cast<const ipcr_site *>(a.blocks + (uint64_t)b * a.block_bytes + a.ctl_bytes)[i - (uint32_t)s_boff[b]];
+    };
+    const KeyLayout kl = j.kl;
+    uint32_t m = 2;
+    while (m < n) m <<= 1;
+    unsigned long long *fk = sk + m;  // final keys (shared memory), read by the join through a generic pointer
+    // ---- keys + bitonic sort of (key << 13 | index): equal keys keep their input order ----
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+        sk[i] = i < n ? ((site_key(site_at(i), a.orients, j.recs, a.rec_reset, j.prm, kl) << kSortSmallIdxBits) | i) : ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= m; k <<= 1) {
+        for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+                const uint32_t lo = ((t & ~(jj - 1u)) << 1) | (t & (jj - 1u)), hi = lo + jj;
+                const unsigned long long x = sk[lo], y = sk[hi];
+                if ((x > y) == ((lo & k) == 0u)) {
+                    sk[lo] = y;
+                    sk[hi] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- hit cap + left-window filter: thread t owns the sorted run [t*per, t*per + per) ----
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;  // <= 8
+    const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
+    uint32_t keepbits = 0u, kept = 0u;
+    for (uint32_t k = b; k < e; k++) {
+        const uint64_t key = sk[k] >> kSortSmallIdxBits;
+        if (key >= (1ull << kl.key_bits)) continue;  // invalid sites sort last
+        const uint64_t first_key = (key >> (kl.pos_bits + 1)) << (kl.pos_bits + 1);
+        uint32_t lo = 0, hi = k;  // first sorted index whose key >= first_key
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((sk[mid] >> kSortSmallIdxBits) < first_key) lo = mid + 1; else hi = mid;
+        }
+        const uint32_t rank = k - lo;
+        bool kp = true;
+        if (j.prm.hit_cap > 0 && (uint64_t)rank >= (uint64_t)j.prm.hit_cap) kp = false;
+        if (kp && (site_at((uint32_t)sk[k] & ((1u << kSortSmallIdxBits) - 1u)).flags & IPCR_SITE_TWVIOL)) kp = false;
+        if (kp) {
+            keepbits |= 1u << (k - b);
+            kept++;
+        }
+    }
+    {  // block-wide exclusive scan of `kept`
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        uint32_t x = kept;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= (uint32_t)d) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = wsum[lane];
+            uint32_t xi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xi, d);
+                if (lane >= (uint32_t)d) xi += y;
+            }
+            wsum[lane] = xi - w;
+            if (lane == 31) s_total = xi;
+        }
+        __syncthreads();
+        uint32_t dst = x - kept + wsum[warp];
+        FinalSite *fs = const_cast<FinalSite *>(j.fs);
+        for (uint32_t k = b; k < e; k++) {
+            if (!((keepbits >> (k - b)) & 1u)) continue;
+            const ipcr_site s = site_at((uint32_t)sk[k] & ((1u << kSortSmallIdxBits) - 1u));
+            fk[dst] = sk[k] >> kSortSmallIdxBits;
+            FinalSite f;
+            f.pos = s.pos;
+            f.mask = s.mm_mask;
+            f.mm = s.mm;
+            f.pad = 0;
+            fs[dst] = f;
+            dst++;
+        }
+    }
+    __syncthreads();
+    h.n_final = s_total;
+    j.n_sites = s_total;
+    j.fkeys = reinterpret_cast<const uint64_t *>(fk);
+    if (s_total == 0u) {
+        if (threadIdx.x == 0) *a.header = h;
+        return;
+    }
+    // ---- forward sites per (record, pair, direction), then one task per forward site ----
+    const uint32_t n_entries = j.n_recs * j.n_pairs * 2u;
+    for (uint32_t en = threadIdx.x; en < n_entries; en += blockDim.x) {
+        const uint32_t blk = en & 1u, pair = (en >> 1) % j.n_pairs, rec = (en >> 1) / j.n_pairs;
+        const PairDev p = j.pairs[pair];
+        uint64_t sb, se;
+        segment_of(j, rec, blk == 0 ? p.fwdA : p.fwdB, sb, se);
+        j.entry_tasks[en] = (uint32_t)(se - sb);
+    }
+    __syncthreads();
+    const uint32_t n_tasks = cta_scan_global(j.entry_tasks, const_cast<uint32_t *>(j.task_off), n_entries, wsum);
+    h.n_tasks = n_tasks;
+    j.n_tasks = n_tasks;
+
+    if (n_tasks > a.task_cap) h.flags |= kPairTaskOverflow;
+    if (n_tasks == 0u || n_tasks > a.task_cap) {
+        if (threadIdx.x == 0) *a.header = h;
+        return;
+    }
+    for (uint32_t t = threadIdx.x; t < n_tasks; t += blockDim.x) join_task<false>(j, t);
+    __syncthreads();
+    const uint32_t n_prod = cta_scan_global(j.task_cnt, const_cast<uint32_t *>(j.prod_off), n_tasks, wsum);
+    h.n_prod = n_prod;
+    if ((uint64_t)n_prod > j.prod_cap) {
+        h.flags |= kPairProdOverflow;
+        if (threadIdx.x == 0) *a.header = h;
+        return;
+    }
+    for (uint32_t t = threadIdx.x; t < n_tasks; t += blockDim.x) join_task<true>(j, t);
+    if (threadIdx.x == 0) *a.header = h;
+}
+
+// the multi-kernel stage 2 wants one contiguous site list: copies the blocks' sites back to back
+struct UnpackArgs {
+    const uint8_t *blocks;
+    uint32_t n_blocks;
+    uint64_t block_bytes, ctl_bytes;
+    ipcr_site *sites;
+    uint64_t site_cap;
+};
+
+__global__ void __launch_bounds__(256)
+k_unpack_blocks(UnpackArgs a) {
+    unsigned long long off = 0ull;
+    for (uint32_t bk = 0; bk < a.n_blocks; bk++) {
+        const uint8_t *blk = a.blocks + (uint64_t)bk * a.block_bytes;
+        const unsigned long long n = reinterpret_cast<const Stage1Ctl *>(blk)->n_sites;
+        const ipcr_site *ss = reinterpret_cast<const ipcr_site *>(blk + a.ctl_bytes);
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+             i += (unsigned long long)gridDim.x * blockDim.x)
+            if (off + i < a.site_cap) a.sites[off + i] = ss[i];
+        off += n;
+    }
+}
+
+}  // namespace ipcr

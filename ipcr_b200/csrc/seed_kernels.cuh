@@ -44,6 +44,7 @@ struct Pack2Args {
     const SegmentDev *segs;
     uint32_t n_segs;
     uint32_t *seg_reset;
+    uint8_t *rec_reset;  // optional: per-record flag, raised here so that the asynchronous chain never reads seg_reset on the host
     uint32_t aligned;   // ascii is 16-byte aligned
 };
 
@@ -85,7 +86,10 @@ k_pack2(Pack2Args a) {
             if (first < 32u) {
                 const uint32_t s0 = find_segment(a.segs, a.n_segs, P0 + first);
                 const uint64_t seg_end = a.segs[s0].global_off + a.segs[s0].len;
-                if (P0 + first < seg_end && a.seg_reset[s0] == 0u) a.seg_reset[s0] = 1u;
+                if (P0 + first < seg_end && a.seg_reset[s0] == 0u) {
+                    a.seg_reset[s0] = 1u;
+                    if (a.rec_reset) a.rec_reset[a.segs[s0].rec_idx] = 1u;
+                }
                 if (seg_end < P0 + 32u) {  // the group straddles a segment boundary: look at every byte
                     for (uint32_t k = first + 1; k < 32u; k++) {
                         if (!((inv >> k) & 1u) || P0 + k >= a.total_len) continue;
@@ -93,7 +97,10 @@ k_pack2(Pack2Args a) {
                         const uint32_t x = (b | 0x20u) - 'a';
                         if (x < 32u && ((0x00080045u >> x) & 1u)) continue;
                         const uint32_t s1 = find_segment(a.segs, a.n_segs, P0 + k);
-                        if (P0 + k - a.segs[s1].global_off < a.segs[s1].len) a.seg_reset[s1] = 1u;
+                        if (P0 + k - a.segs[s1].global_off < a.segs[s1].len) {
+                            a.seg_reset[s1] = 1u;
+                            if (a.rec_reset) a.rec_reset[a.segs[s1].rec_idx] = 1u;
+                        }
                     }
                 }
             }
@@ -411,6 +418,84 @@ k_seed_dirty_probe(SeedDirtyProbeArgs a) {
             if (p < c) continue;
             const unsigned long long idx = atomicAdd(a.cand_count, 1ull);
             if (idx < a.cand_cap) a.cand[idx] = ((unsigned long long)(seen[k] & 0xFFFFu) << kCandPosBits) | (p - c);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2r.  Dirty windows, resolved in ONE launch of the asynchronous chain: the replacement
+// lookups of k_seed_dirty_probe, followed directly by the exact verify of every distinct
+// (orientation, seed offset) hit; windows the probe cannot resolve are verified against every
+// orientation.  The window count is read from the device, so the host never waits for it.
+// ---------------------------------------------------------------------------
+struct SeedDirtyResolveArgs {
+    SeedDirtyProbeArgs p;              // cand/over fields unused
+    const unsigned long long *n_dirty_ptr;
+    uint64_t dirty_cap;
+    const uint16_t *col_off;
+    uint32_t n_orient;
+    VerifyArgs v;                      // cand fields unused
+};
+
+__device__ __forceinline__ void dirty_verify_emit(const VerifyArgs &v, uint32_t q, uint64_t start) {
+    ipcr_site s;
+    if (verify_one(v, q, start, &s)) {
+        const unsigned long long dst = atomicAdd(v.site_count, 1ull);
+        if (dst < v.site_cap) v.sites[dst] = s;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_seed_dirty_resolve(SeedDirtyResolveArgs r) {
+    const SeedDirtyProbeArgs &a = r.p;
+    const uint64_t n_dirty = min((uint64_t)*r.n_dirty_ptr, r.dirty_cap);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dirty; i += stride) {
+        const uint64_t p = a.dirty[i];
+        const uint32_t sh = (uint32_t)p & 15u;
+        const uint32_t kmer0 = __funnelshift_r(a.codes[p >> 4], a.codes[(p >> 4) + 1], 2u * sh) & a.kmer_mask;
+        const uint64_t ivw = (uint64_t)a.inval[p >> 5] | ((uint64_t)a.inval[(p >> 5) + 1] << 32);
+        uint32_t iv = (uint32_t)(ivw >> (p & 31u)) & ((1u << a.S) - 1u);  // S <= 16
+        const uint32_t t = __popc(iv);
+        bool overflow = t > kDirtyMaxInvalid;
+        uint32_t seen[kDirtySeen];
+        int n_seen = 0;
+        if (!overflow) {
+            uint32_t pos[kDirtyMaxInvalid] = {0u, 0u, 0u, 0u};
+            uint32_t base = kmer0;
+            for (uint32_t u = 0; u < t; u++) {
+                pos[u] = (uint32_t)(__ffs(iv) - 1);
+                iv &= iv - 1u;
+                base &= ~(3u << (2u * pos[u]));
+            }
+            for (uint32_t combo = 0; combo < (1u << (2u * t)) && !overflow; combo++) {
+                uint32_t km = base;
+                for (uint32_t u = 0; u < t; u++) km |= ((combo >> (2u * u)) & 3u) << (2u * pos[u]);
+                const uint32_t h2 = km * a.bitmap2_mul;
+                if (!((a.bitmap2[h2 >> a.bitmap2_shift] >> (h2 & 31u)) & 1u)) continue;
+                for (uint32_t h = (km * kSeedHashMulDev) >> a.table_shift;; h = (h + 1u) & a.table_mask) {
+                    const unsigned long long slot = a.table[h];
+                    if (slot == 0ull) break;
+                    if ((uint32_t)slot != km) continue;
+                    const uint32_t key = (uint32_t)(slot >> 32) & 0x00FFFFFFu;  // orientation | seed offset << 16
+                    bool dup = false;
+                    for (int k = 0; k < n_seen; k++) dup |= seen[k] == key;
+                    if (dup) continue;
+                    if (n_seen == kDirtySeen) { overflow = true; break; }
+                    seen[n_seen++] = key;
+                }
+            }
+        }
+        if (overflow) {  // rare: every orientation whose seed window can sit here
+            for (uint32_t q = 0; q < r.n_orient; q++) {
+                const uint32_t c = r.col_off[q];
+                if (r.v.orients[q].L >= a.S && p >= c) dirty_verify_emit(r.v, q, p - c);
+            }
+            continue;
+        }
+        for (int k = 0; k < n_seen; k++) {
+            const uint64_t c = seen[k] >> 16;
+            if (p >= c) dirty_verify_emit(r.v, seen[k] & 0xFFFFu, p - c);
         }
     }
 }

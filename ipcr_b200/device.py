@@ -218,6 +218,49 @@ def pair_sites(cp: CompiledPanel, scratch: SimulationScratch, sites, records: Se
     return _products(out, n.value, cp, seq_ids)
 
 
+def site_block_bytes(n_recs: int, site_cap: int) -> int:
+    return int(_capi.lib().ipcr_gpu_site_block_bytes(n_recs, site_cap))
+
+
+def scratch_site_cap(scratch: SimulationScratch) -> int:
+    return int(_capi.lib().ipcr_gpu_scratch_site_cap(scratch._h))
+
+
+def scratch_stream(scratch: SimulationScratch) -> int:
+    """The scratch's cudaStream_t as an integer (torch.cuda.ExternalStream(...) orders NCCL against it)."""
+    return int(_capi.lib().ipcr_gpu_scratch_stream(scratch._h) or 0)
+
+
+def find_sites_block(cp: CompiledPanel, scratch: SimulationScratch, segments: Sequence[Tuple], n_recs: int,
+                     block, site_cap: int, force_raw: bool = False) -> None:
+    """Stage 1 of device-resident shards into `block` (device uint8 tensor of site_block_bytes);
+    asynchronous on the scratch's stream: nothing is waited for."""
+    arr, keep, _nr = Genome._segments(segments)
+    err = _capi.errbuf()
+    _capi.check(_capi.lib().ipcr_gpu_find_sites_block(cp._h, scratch._h, arr, len(segments), n_recs,
+                                                      1 if force_raw else 0, int(block.data_ptr()), site_cap,
+                                                      err, len(err)), err)
+
+
+def pair_blocks(cp: CompiledPanel, scratch: SimulationScratch, blocks, n_blocks: int, site_cap: int,
+                rec_lens: Sequence[int], seq_ids=None, raw: bool = False):
+    """Stage 2 over gathered blocks (device uint8 tensor).  Returns None when stage 1 has to run
+    again on every rank (capacity grown / raw plan variant needed), else the products."""
+    L = _capi.lib()
+    lens = (C.c_uint64 * max(1, len(rec_lens)))(*rec_lens)
+    out = C.POINTER(_capi.ProductC)()
+    n = C.c_uint64()
+    err = _capi.errbuf()
+    rc = L.ipcr_gpu_pair_blocks(cp._h, scratch._h, int(blocks.data_ptr()), n_blocks, site_cap, lens, len(rec_lens),
+                                C.byref(out), C.byref(n), err, len(err))
+    if rc == 2:
+        return None
+    _capi.check(rc, err)
+    if raw:
+        return out, n.value
+    return _products(out, n.value, cp, seq_ids)
+
+
 def synth_fill(scratch: SimulationScratch, tensor, first_pos: int, seed: int) -> None:
     """Fill a device uint8 tensor with the deterministic synthetic genome (bench input)."""
     err = _capi.errbuf()

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_capi.SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.ipcr_gpu_abi_version() == 1
+    assert L.ipcr_gpu_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

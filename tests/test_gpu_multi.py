@@ -1,0 +1,185 @@
+"""Multi-piece paths of the scan, all through the C ABI and all against the CPU oracle:
+  * the device-resident split phase (ipcr_gpu_find_sites_block -> blocks -> ipcr_gpu_pair_blocks),
+    which is what a multi-process multi-GPU run exchanges with ONE all-gather;
+  * several devices inside one process (ipcr_gpu_init(0) + ipcr_gpu_scan_batch), skipped on a
+    single-GPU box;
+  * the reference's worker protocol: many host threads, one scratch each, one shared panel
+    (/root/reference/internal/pipeline/pipeline.go:62-125,
+    internal/pipeline/pipeline_engine_contract_test.go:213-325).
+"""
+import random
+import threading
+
+import pytest
+
+import ipcr_test_helpers as H
+from ipcr_b200 import Config, Engine, Pair, _capi
+from ipcr_b200 import device as D
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+A27F, B1492R = "AGAGTTTGATCMTGGCTCAG", "TACGGYTACCTTGTTAYGACTT"
+PAIRS = [Pair("16S", A27F, B1492R), Pair("16S+A:self", A27F, A27F), Pair("16S+B:self", B1492R, B1492R)]
+RAW = [(p.forward, p.reverse, 0, 0) for p in PAIRS]
+
+
+def _tuple(p):
+    return (p.experiment_id, p.type, p.start, p.end, p.length, p.fwd_mm, p.rev_mm,
+            tuple(p.fwd_mismatch_idx), tuple(p.rev_mismatch_idx))
+
+
+def _otuple(t):
+    return (PAIRS[t[0]].id,) + tuple(t[1:])
+
+
+def _records(rng, lens, with_n=True):
+    recs = []
+    for n in lens:
+        g = H.random_genome(rng, n)
+        for k in range(max(1, n // 20000)):
+            H.plant_amplicon(rng, g, 200 + k * 18000 if n > 20000 else 10, A27F, B1492R, 300 + k, rng.randint(0, 2),
+                             rng.randint(0, 2), 3, revcomp_strand=k % 2 == 1)
+        recs.append(g)
+    if with_n:
+        recs[-1][len(recs[-1]) // 2] = ord("N")  # a reset byte only in the last piece
+    return recs
+
+
+def _plant_across_cuts(recs, lens, pieces):
+    total = sum(lens)
+    for c in [(total * k // pieces) & ~15 for k in range(1, pieces)]:
+        off = 0
+        for ri, n in enumerate(lens):
+            if off + 30 <= c < off + n - 30:
+                recs[ri][c - off - 9:c - off + 11] = A27F.replace("M", "C").encode()
+            off += n
+
+
+CFGS = (dict(max_mm=2, terminal_window=3, max_len=2000, hit_cap=0),
+        dict(max_mm=2, terminal_window=3, max_len=2000, hit_cap=10000),
+        dict(max_mm=1, terminal_window=0, max_len=0, hit_cap=3, circular=True))
+
+
+def _oracle_rows(oracle, cfgd, seqs):
+    want = []
+    for ri, sq in enumerate(seqs):
+        want += [(f"r{ri}",) + _otuple(t) for t in oracle.simulate_compiled(oracle.make_cfg(**cfgd), RAW, sq)]
+    return want
+
+
+def test_block_split_phase_equals_oracle(oracle):
+    """4 shards on one device: every shard leaves a site block, stage 2 pairs over the blocks.  The
+    reset byte sits in the last shard only, so with a hit cap the first round (plain plan variant)
+    must be refused (return code 2) and the second round run raw."""
+    rng = random.Random(5)
+    lens = [90000, 500, 140000, 70000]
+    recs = _records(rng, lens)
+    shards = 4
+    _plant_across_cuts(recs, lens, shards)
+    seqs = [bytes(g) for g in recs]
+    cat = b"".join(seqs)
+    total = len(cat)
+    dev = torch.frombuffer(bytearray(cat), dtype=torch.uint8).cuda()
+    offs = [0]
+    for n in lens:
+        offs.append(offs[-1] + n)
+    for cfgd in CFGS:
+        eng = Engine(Config(**cfgd))
+        cp = eng.compile_panel(PAIRS)
+        sc = eng.new_simulation_scratch(cp)
+        want = _oracle_rows(oracle, cfgd, seqs)
+        rounds = 0
+        while True:
+            rounds += 1
+            assert rounds <= 4
+            cap = D.scratch_site_cap(sc)
+            bb = D.site_block_bytes(len(lens), cap)
+            allb = torch.zeros(shards * bb, dtype=torch.uint8, device="cuda")
+            for k in range(shards):
+                lo, hi = total * k // shards, total * (k + 1) // shards
+                end = min(total, hi + 64)
+                segs = []
+                for c in range(len(lens)):
+                    s0, s1, own1 = max(offs[c], lo), min(offs[c + 1], end), min(offs[c + 1], hi)
+                    if s0 < s1 and own1 > s0:
+                        segs.append((dev[s0:s1], c, s0 - offs[c], own1 - s0))
+                D.find_sites_block(cp, sc, segs, len(lens), allb[k * bb:(k + 1) * bb], cap)
+            got = D.pair_blocks(cp, sc, allb, shards, cap, lens, seq_ids=[f"r{i}" for i in range(len(lens))])
+            if got is not None:
+                break
+        if cfgd["hit_cap"] > 0 and cfgd["terminal_window"] > 0:
+            assert rounds == 2  # the raw-rc redo
+        assert [(p.sequence_id,) + _tuple(p) for p in got] == want, cfgd
+
+
+def test_multi_device_scan_batch_equals_single(oracle, monkeypatch):
+    L = _capi.lib()
+    if L.ipcr_gpu_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    err = _capi.errbuf()
+    rng = random.Random(9)
+    lens = [90000, 500, 140000, 70000, 3]
+    n_dev = L.ipcr_gpu_device_count()
+    recs = _records(rng, lens)
+    _plant_across_cuts(recs, lens, n_dev)
+    seqs = [bytes(g) for g in recs]
+    ids = [f"r{i}" for i in range(len(lens))]
+    monkeypatch.setenv("IPCR_MULTI_MIN_BP", "1")
+    try:
+        for cfgd in CFGS:
+            want = _oracle_rows(oracle, cfgd, seqs)
+            eng = Engine(Config(**cfgd))
+            cp = eng.compile_panel(PAIRS)
+            sc = eng.new_simulation_scratch(cp)
+            assert L.ipcr_gpu_init(1, err, len(err)) == 0, err.value
+            single = [(p.sequence_id,) + _tuple(p) for p in D.scan_batch(cp, sc, seqs, seq_ids=ids)]
+            assert single == want
+            assert L.ipcr_gpu_init(0, err, len(err)) == 0, err.value
+            assert L.ipcr_gpu_num_devices() == n_dev
+            for _ in range(2):  # second call: warm peers, sticky raw variant
+                multi = [(p.sequence_id,) + _tuple(p) for p in D.scan_batch(cp, sc, seqs, seq_ids=ids)]
+                assert multi == want, cfgd
+    finally:
+        L.ipcr_gpu_init(1, err, len(err))
+
+
+def test_concurrent_workers_share_one_panel(oracle):
+    """8 host threads, own scratch each, one shared panel, different records; the first calls race
+    the lazy seed-index build and the per-device table upload.  Results equal the serial ones."""
+    rng = random.Random(21)
+    n_workers, per_worker = 8, 3
+    seqs = []
+    for w in range(n_workers * per_worker):
+        n = rng.choice([3000, 40000, 120000])
+        g = H.random_genome(rng, n, n_frac=0.0005 if w % 2 else 0.0)
+        for k in range(1 + n // 40000):
+            H.plant_amplicon(rng, g, 100 + k * 30000, A27F, B1492R, 400 + w, rng.randint(0, 2), rng.randint(0, 2), 3,
+                             revcomp_strand=(w + k) % 2 == 1)
+        seqs.append(bytes(g))
+    cfgd = dict(max_mm=2, terminal_window=3, max_len=2000, hit_cap=10000)
+    want = [[_otuple(t) for t in oracle.simulate_compiled(oracle.make_cfg(**cfgd), RAW, sq)] for sq in seqs]
+    for mode in (3, 2):  # seed index (asynchronous chain), NVRTC-specialised bit-parallel
+        eng = Engine(Config(**cfgd))
+        cp = eng.compile_panel(PAIRS)  # fresh panel: nothing built yet
+        cp.set_jit(mode)
+        got = [None] * len(seqs)
+        errors = []
+        gate = threading.Barrier(n_workers)
+
+        def worker(w):
+            try:
+                sc = eng.new_simulation_scratch(cp)
+                gate.wait()
+                for i in range(w, len(seqs), n_workers):
+                    got[i] = [_tuple(p) for p in eng.simulate_compiled_with_scratch(f"s{i}", seqs[i], cp, sc)]
+            except Exception as ex:  # noqa: BLE001
+                errors.append(repr(ex))
+
+        th = [threading.Thread(target=worker, args=(w,)) for w in range(n_workers)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errors, errors
+        assert got == want, mode

@@ -5,6 +5,7 @@ same EMISSION ORDER as the reference's production path (oracle layer 2,
 compiled.go:162-267); additionally equal as a multiset to the reference's own
 brute-force oracle (bruteforce.go:11-38) whenever the hit cap does not bind.
 """
+import os
 import random
 
 import numpy as np
@@ -39,11 +40,20 @@ def _check(oracle, cfgd, raw_pairs, seq, jit=0, cap_binds=False):
     cp = eng.compile_panel(pairs)
     ocfg = oracle.make_cfg(**cfgd)
     want = [_otuple(pairs, t) for t in oracle.simulate_compiled(ocfg, [tuple(p) for p in raw_pairs], seq)]
-    # every case runs through the requested bit-parallel filter AND through the seed index (3)
+    # every case runs through the requested bit-parallel filter AND through the seed index (3); the
+    # seed index through all three stage-2 forms: the asynchronous chain in bucket mode (default), the
+    # chain's general (bitonic) mode, and the multi-kernel path
     for mode in dict.fromkeys((jit, 3)):
         cp.set_jit(mode)
-        got = [_tuple(p) for p in eng.simulate_compiled("seq", seq, cp)]
-        assert got == want, (mode, cfgd, raw_pairs, bytes(seq)[:80])
+        for env in ((None,) if mode != 3 else (None, "IPCR_NO_BUCKETS", "IPCR_NO_CHAIN")):
+            if env:
+                os.environ[env] = "1"
+            try:
+                got = [_tuple(p) for p in eng.simulate_compiled("seq", seq, cp)]
+            finally:
+                if env:
+                    del os.environ[env]
+            assert got == want, (mode, env, cfgd, raw_pairs, bytes(seq)[:80])
     if not cap_binds:
         brute = [_otuple(pairs, t) for t in oracle.simulate_bruteforce(ocfg, [tuple(p) for p in raw_pairs], seq)]
         assert H.multiset(got) == H.multiset(brute)
