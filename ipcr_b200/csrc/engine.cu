@@ -109,7 +109,7 @@ struct PlanTables {
 };
 
 struct DevTables {
-    DevBuf orients, cls, pairs;
+    DevBuf orients, cls, pairs, oplanes;
     PlanTables plan[2];
     JitKernel jit[2];
     bool jit_tried[2] = {false, false};
@@ -183,6 +183,19 @@ static DevTables *tables_for(ipcr_panel *p, int device, cudaStream_t st) {
         d.max_len = r.max_len;
         pd.push_back(d);
     }
+    std::vector<uint64_t> oplanes;  // [orientation][A, C, G, T]: columns whose class accepts the base
+    for (const Orient &o : h.orients) {
+        uint64_t pl[4] = {0, 0, 0, 0};
+        for (int j = 0; j < o.L && j < 64; j++) {
+            const uint8_t c = o.cls[(size_t)j];
+            if (c & 1u) pl[0] |= 1ull << j;
+            if (c & 2u) pl[1] |= 1ull << j;
+            if (c & 4u) pl[2] |= 1ull << j;
+            if (c & 8u) pl[3] |= 1ull << j;
+        }
+        oplanes.insert(oplanes.end(), pl, pl + 4);
+    }
+    upload(t->oplanes, oplanes.data(), oplanes.size() * sizeof(uint64_t), st);
     upload(t->orients, od.data(), od.size() * sizeof(OrientDev), st);
     upload(t->cls, cls.data(), cls.size(), st);
     upload(t->pairs, pd.data(), pd.size() * sizeof(PairDev), st);
@@ -1312,6 +1325,11 @@ static void stage1_async(ipcr_scratch *s, GenomeData &g, int variant, uint8_t *d
     v.sites = reinterpret_cast<ipcr_site *>(d_block + block_ctl_bytes(n_recs));
     v.site_count = &ctl->n_sites;
     v.site_cap = site_cap;
+    if (!getenv("IPCR_VERIFY_ASCII")) {
+        v.codes = g.codes.as<uint32_t>();
+        v.inval = g.inval.as<uint32_t>();
+        v.oplanes = t->oplanes.as<uint64_t>();
+    }
     if (h.cfg.max_mm > 0) {  // dirty windows exist only with a mismatch budget (halo.go:76-80)
         SeedDirtyResolveArgs r{};
         r.p.dirty = s->dirty.as<unsigned long long>();

@@ -263,14 +263,86 @@ struct VerifyArgs {
     ipcr_site *sites;
     unsigned long long *site_count;
     uint64_t site_cap;
+    // packed genome (seed-index path): when set, the window is compared 64 columns at a time against
+    // the orientation's four acceptance masks instead of byte by byte on the ASCII
+    const uint32_t *codes;     // 2-bit codes, 16 bases per word (A 0, C 1, T 2, G 3)
+    const uint32_t *inval;     // bit = byte is not an uppercase A/C/G/T
+    const uint64_t *oplanes;   // [orientation][4]: columns accepting A, C, G, T
 };
 
 __device__ __forceinline__ uint32_t onehot_of(uint32_t b) {
     return b == 'A' ? 1u : b == 'C' ? 2u : b == 'G' ? 4u : b == 'T' ? 8u : 0u;
 }
 
+// bits 0, 2, 4, .. of x packed into the low 32 bits
+__device__ __forceinline__ uint32_t even_bits(uint64_t x) {
+    x &= 0x5555555555555555ull;
+    x = (x | (x >> 1)) & 0x3333333333333333ull;
+    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x >> 16)) & 0x00000000FFFFFFFFull;
+    return (uint32_t)x;
+}
+
+// The same predicate on the packed genome: the 64 bases from `start` become two bit planes (low / high
+// code bit) and an invalid mask; column j mismatches iff its byte is invalid or the primer's class at j
+// does not accept the base.  ~10 word loads on 2-3 cache lines instead of 2 byte loads per column.
+__device__ __forceinline__ bool verify_one_codes(const VerifyArgs &a, uint32_t q, uint64_t start, ipcr_site *s) {
+    const uint32_t si = find_segment(a.segs, a.n_segs, start);
+    const SegmentDev seg = a.segs[si];
+    const OrientDev o = a.orients[q];
+    const uint64_t local = start - seg.global_off;
+    if (o.L == 0) return false;  // match.go:32-34
+    if (!(start >= seg.global_off && local + o.L <= seg.len && local < seg.own_len)) return false;
+    const uint32_t *cw = a.codes + (start >> 4);
+    const uint32_t sh = 2u * ((uint32_t)start & 15u);
+    const uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2], w3 = cw[3], w4 = cw[4];
+    const uint64_t c01 = (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+    const uint64_t c23 = (uint64_t)__funnelshift_r(w2, w3, sh) | ((uint64_t)__funnelshift_r(w3, w4, sh) << 32);
+    const uint64_t lo = (uint64_t)even_bits(c01) | ((uint64_t)even_bits(c23) << 32);
+    const uint64_t hi = (uint64_t)even_bits(c01 >> 1) | ((uint64_t)even_bits(c23 >> 1) << 32);
+    const uint32_t *iw = a.inval + (start >> 5);
+    const uint32_t ish = (uint32_t)start & 31u;
+    const uint32_t i0 = iw[0], i1 = iw[1], i2 = iw[2];
+    const uint64_t inv = (uint64_t)__funnelshift_r(i0, i1, ish) | ((uint64_t)__funnelshift_r(i1, i2, ish) << 32);
+    const uint64_t *pl = a.oplanes + 4u * q;
+    const uint64_t match = (~hi & ~lo & pl[0]) | (~hi & lo & pl[1]) | (hi & lo & pl[2]) | (hi & ~lo & pl[3]);
+    const uint64_t lenmask = o.L >= 64 ? ~0ull : ((1ull << o.L) - 1ull);
+    const uint64_t mask = (~match | inv) & lenmask;
+    const int mm = __popcll(mask);
+    if (mm > a.prm.max_mm) return false;
+    const bool viol = (mask & o.prot_mask) != 0;
+    if (viol && !(a.prm.raw_rc && o.rc_type)) return false;
+    uint32_t flags = viol ? IPCR_SITE_TWVIOL : 0u;
+    if (o.seeded) {  // would the reference's AC pass have missed it? (ac.go:159-162)
+        const uint64_t seedmask = (o.seed_len >= 64 ? ~0ull : ((1ull << o.seed_len) - 1ull)) << o.seed_off;
+        uint64_t bad = inv & seedmask & lenmask;
+        if (bad) {
+            if (a.ascii) {  // lowercase acgt are invalid bases but do not reset the automaton (ac.go:25-28)
+                bool reset = false;
+                for (; bad; bad &= bad - 1ull) {
+                    const uint32_t u = a.ascii[start + (uint32_t)(__ffsll((long long)bad) - 1)] & 0xDFu;
+                    if (!(u == 'A' || u == 'C' || u == 'G' || u == 'T')) reset = true;
+                }
+                if (reset) flags |= IPCR_SITE_HALO;
+            } else {
+                flags |= IPCR_SITE_HALO;
+            }
+        }
+    }
+    s->pos = seg.rec_off + local;
+    s->mm_mask = mask;
+    s->rec_idx = seg.rec_idx;
+    s->orient = (uint16_t)q;
+    s->mm = (uint8_t)mm;
+    s->flags = (uint8_t)flags;
+    return true;
+}
+
 // exact check of orientation q at global start `start`; true => *s is a site
 __device__ __forceinline__ bool verify_one(const VerifyArgs &a, uint32_t q, uint64_t start, ipcr_site *s) {
+    if (a.codes) return verify_one_codes(a, q, start, s);
     const uint32_t si = find_segment(a.segs, a.n_segs, start);
     const SegmentDev seg = a.segs[si];
     const OrientDev o = a.orients[q];
