@@ -109,7 +109,7 @@ struct PlanTables {
 };
 
 struct DevTables {
-    DevBuf orients, cls, pairs, oplanes;
+    DevBuf orients, cls, pairs, oplanes, use_off, use_list;
     PlanTables plan[2];
     JitKernel jit[2];
     bool jit_tried[2] = {false, false};
@@ -196,6 +196,21 @@ static DevTables *tables_for(ipcr_panel *p, int device, cudaStream_t st) {
         oplanes.insert(oplanes.end(), pl, pl + 4);
     }
     upload(t->oplanes, oplanes.data(), oplanes.size() * sizeof(uint64_t), st);
+    // (pair, direction) slots per forward orientation, pair-major inside an orientation
+    std::vector<uint32_t> use_off(h.orients.size() + 1, 0), use_list;
+    {
+        std::vector<std::vector<uint32_t>> uses(h.orients.size());
+        for (size_t pi = 0; pi < h.roles.size(); pi++) {
+            uses[(size_t)h.roles[pi].fwdA].push_back((uint32_t)(pi << 1));
+            uses[(size_t)h.roles[pi].fwdB].push_back((uint32_t)(pi << 1) | 1u);
+        }
+        for (size_t q = 0; q < uses.size(); q++) {
+            use_off[q + 1] = use_off[q] + (uint32_t)uses[q].size();
+            use_list.insert(use_list.end(), uses[q].begin(), uses[q].end());
+        }
+    }
+    upload(t->use_off, use_off.data(), use_off.size() * sizeof(uint32_t), st);
+    upload(t->use_list, use_list.data(), use_list.size() * sizeof(uint32_t), st);
     upload(t->orients, od.data(), od.size() * sizeof(OrientDev), st);
     upload(t->cls, cls.data(), cls.size(), st);
     upload(t->pairs, pd.data(), pd.size() * sizeof(PairDev), st);
@@ -1380,7 +1395,7 @@ static void pair_async(ipcr_scratch *s, const uint8_t *d_blocks, uint32_t n_bloc
     }
     s->rec_reset_dev.ensure(n_recs + 16);
     s->fs.ensure((size_t)kPairSmallMax * sizeof(FinalSite));
-    s->entry_tasks.ensure(n_entries * 4);
+    s->entry_tasks.ensure(std::max<uint64_t>(n_entries * 4, (uint64_t)kPairMaxProductive * 8));
     s->task_off.ensure((std::max<uint64_t>(n_entries, task_cap) + 1) * 4);  // general mode: entry scan; bucket mode: live tasks
     s->task_cnt.ensure((size_t)task_cap * 4);
     s->prod_off.ensure(((size_t)task_cap + 1) * 4);
@@ -1411,6 +1426,8 @@ static void pair_async(ipcr_scratch *s, const uint8_t *d_blocks, uint32_t n_bloc
     a.j.products = s->products.as<ipcr_product>() + 1;  // the header occupies the first 64 bytes
     a.j.prod_cap = prod_cap;
     a.task_cap = task_cap;
+    a.use_off = s->tables->use_off.as<uint32_t>();
+    a.use_list = s->tables->use_list.as<uint32_t>();
     a.header = s->products.as<PairHeader>();
     // shared memory: 8192 sort words + either the final keys (general mode) or the two bucket tables
     constexpr size_t kPairSmemMax = 226 * 1024;

@@ -77,6 +77,8 @@ struct PairSmallArgs {
     const OrientDev *orients;
     uint8_t *rec_reset;  // [n_recs] scratch: OR of the blocks' per-record flags
     JoinArgs j;  // pairs, recs, prm, kl; fs / entry_tasks / task_off / task_cnt / prod_off / products are scratch
+    const uint32_t *use_off;   // [n_orient + 1]: (pair, direction) slots in which an orientation is the forward primer
+    const uint32_t *use_list;  // pair << 1 | direction
     uint32_t task_cap;
     uint32_t bucket_cap;  // (record, orientation) buckets the dynamic shared memory has room for (0 = general mode only)
     PairHeader *header;
@@ -169,6 +171,7 @@ __device__ __forceinline__ uint32_t cta_scan_inplace(uint32_t *arr, uint32_t n, 
     return total;
 }
 
+constexpr uint32_t kPairMaxProductive = 1024;  // tasks with products the bucket mode ranks (one per thread)
 constexpr uint32_t kBucketMaxSize = 64;  // larger (record, orientation) lists go through the general mode
 constexpr int kPairPerThread = kPairSmallMax / 1024;
 
@@ -297,62 +300,71 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
     __syncthreads();
     j.fkeys = reinterpret_cast<const uint64_t *>(sk);
     stamp(2);
-    // ---- 4. join.  Live tasks = forward sites of entries whose partner list is not empty (few in a
-    // sparse scan).  A thread owns a contiguous range of entries and lists its live tasks in entry
-    // order; then one thread per task counts, the counts are scanned, one thread per task fills. ----
-    const uint32_t n_entries = j.n_recs * j.n_pairs * 2u;
-    const uint32_t per = (n_entries + blockDim.x - 1) / blockDim.x;
-    const uint32_t e0 = min(n_entries, threadIdx.x * per), e1 = min(n_entries, e0 + per);
-    uint32_t my_live = 0, my_tasks = 0;
-    for (uint32_t en = e0; en < e1; en++) {
-        const uint32_t blk = en & 1u, pair = (en >> 1) % j.n_pairs, rec = (en >> 1) / j.n_pairs;
-        const PairDev p = j.pairs[pair];
-        const uint32_t bf = rec * kl.n_orient + (blk == 0 ? p.fwdA : p.fwdB), bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
-        const uint32_t nf = foff[bf + 1] - foff[bf];
-        my_tasks += nf;
-        if (foff[bp + 1] != foff[bp]) my_live += nf;
-    }
-    if (my_tasks) atomicAdd(&s_tasks, my_tasks);
-    uint32_t n_live;
-    uint32_t lbase = cta_scan_value(my_live, wsum, &n_live);
-    h.n_tasks = s_tasks;
-    stamp(3);
-    if (n_live == 0u) return true;
-    if (n_live > a.task_cap) {
-        h.n_tasks = n_live;
-        h.flags |= kPairTaskOverflow;
-        return true;
-    }
-    uint32_t *tasks = const_cast<uint32_t *>(j.task_off);  // scratch: entry << 13 | forward site index
-    if (my_live) {
-        for (uint32_t en = e0; en < e1; en++) {
-            const uint32_t blk = en & 1u, pair = (en >> 1) % j.n_pairs, rec = (en >> 1) / j.n_pairs;
+    // ---- 4. join, driven by the sites instead of the (record, pair, direction) entries: a final site of
+    // orientation q is a forward site of every (pair, direction) that uses q (use_off / use_list, built
+    // with the panel).  One thread per site counts its products per use; the few PRODUCTIVE tasks are
+    // ranked by (entry, forward site) = the reference's emission order, their counts scanned in that
+    // order, and one thread per productive task writes its products.  No per-entry arrays, no walk over
+    // the (mostly empty) entries. ----
+    __shared__ uint32_t s_npt;
+    if (threadIdx.x == 0) s_npt = 0u;
+    __syncthreads();
+    unsigned long long *pt_key = reinterpret_cast<unsigned long long *>(j.entry_tasks);  // [kPairMaxProductive] scratch
+    uint32_t *pt_cnt = j.task_cnt, *pt_off = const_cast<uint32_t *>(j.prod_off);
+    uint32_t my_tasks = 0;
+    for (uint32_t f = threadIdx.x; f < n_final; f += blockDim.x) {
+        const uint32_t prefix = (uint32_t)(sk[f] >> (kl.pos_bits + 1));
+        const uint32_t rec = prefix / kl.n_orient, q = prefix - rec * kl.n_orient;
+        for (uint32_t u = a.use_off[q]; u < a.use_off[q + 1]; u++) {
+            const uint32_t use = a.use_list[u], pair = use >> 1, blk = use & 1u;
             const PairDev p = j.pairs[pair];
-            const uint32_t bf = rec * kl.n_orient + (blk == 0 ? p.fwdA : p.fwdB), bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
-            if (foff[bp + 1] == foff[bp]) continue;
-            for (uint32_t f = foff[bf]; f < foff[bf + 1]; f++) tasks[lbase++] = (en << 13) | f;
+            const uint32_t bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
+            my_tasks++;
+            const int64_t pb = foff[bp], pe = foff[bp + 1];
+            if (pb == pe) continue;
+            const uint32_t cnt = join_core<false>(j, rec, pair, blk, p, f, pb, pe, 0);
+            if (cnt == 0u) continue;
+            const uint32_t slot = atomicAdd(&s_npt, 1u);
+            if (slot < kPairMaxProductive) {
+                pt_key[slot] = ((unsigned long long)((rec * j.n_pairs + pair) * 2u + blk) << 13) | f;
+                pt_cnt[slot] = cnt;
+            }
         }
     }
+    if (my_tasks) atomicAdd(&s_tasks, my_tasks);
     __syncthreads();
-    auto run_task = [&](uint32_t t, bool fill, uint64_t out) -> uint32_t {
-        const uint32_t tk = tasks[t], en = tk >> 13, f = tk & (kPairSmallMax - 1u);
-        const uint32_t blk = en & 1u, pair = (en >> 1) % j.n_pairs, rec = (en >> 1) / j.n_pairs;
-        const PairDev p = j.pairs[pair];
-        const uint32_t bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
-        return fill ? join_core<true>(j, rec, pair, blk, p, f, foff[bp], foff[bp + 1], out)
-                    : join_core<false>(j, rec, pair, blk, p, f, foff[bp], foff[bp + 1], 0);
-    };
-    for (uint32_t t = threadIdx.x; t < n_live; t += blockDim.x) j.task_cnt[t] = run_task(t, false, 0);
+    h.n_tasks = s_tasks;
+    const uint32_t n_pt = s_npt;
+    stamp(3);
+    if (n_pt == 0u) return true;
+    if (n_pt > kPairMaxProductive) return false;  // dense output: the general mode scales with it
+    // rank = number of productive tasks with a smaller key; the counts land in rank order and are scanned
+    uint32_t my_rank = 0, my_cnt = 0;
+    unsigned long long my_key = 0ull;
+    if (threadIdx.x < n_pt) {
+        my_key = pt_key[threadIdx.x];
+        my_cnt = pt_cnt[threadIdx.x];
+        for (uint32_t x = 0; x < n_pt; x++) my_rank += pt_key[x] < my_key ? 1u : 0u;
+    }
     __syncthreads();
-    uint32_t *poff = const_cast<uint32_t *>(j.prod_off);
-    const uint32_t n_prod = cta_scan_global(j.task_cnt, poff, n_live, wsum);
+    if (threadIdx.x < n_pt) pt_off[my_rank] = my_cnt;
+    __syncthreads();
+    uint32_t v = threadIdx.x < n_pt ? pt_off[threadIdx.x] : 0u, n_prod;
+    const uint32_t excl = cta_scan_value(v, wsum, &n_prod);
     h.n_prod = n_prod;
     if ((uint64_t)n_prod > j.prod_cap) {
         h.flags |= kPairProdOverflow;
         return true;
     }
-    for (uint32_t t = threadIdx.x; t < n_live; t += blockDim.x)
-        if (j.task_cnt[t]) run_task(t, true, poff[t]);
+    if (threadIdx.x < n_pt) pt_off[threadIdx.x] = excl;  // offset of the task with rank = threadIdx.x
+    __syncthreads();
+    if (threadIdx.x < n_pt) {
+        const uint32_t f = (uint32_t)my_key & (kPairSmallMax - 1u), en = (uint32_t)(my_key >> 13);
+        const uint32_t blk = en & 1u, pair = (en >> 1) % j.n_pairs, rec = (en >> 1) / j.n_pairs;
+        const PairDev p = j.pairs[pair];
+        const uint32_t bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
+        join_core<true>(j, rec, pair, blk, p, f, foff[bp], foff[bp + 1], pt_off[my_rank]);
+    }
     return true;
 }
 

@@ -28,7 +28,7 @@ def read_fasta(data: bytes):
                     break
             rid, seq = hdr.decode("latin-1"), bytearray()
         elif rid != "":
-            seq += bytes(c - 32 if 97 <= c <= 122 else c for c in frag.strip(SPACE))
+            seq += frag.strip(SPACE).upper()  # bytes.upper() maps a-z only: normalize.go:5-14
     if rid != "":
         recs.append((rid, bytes(seq)))
     return recs
