@@ -394,7 +394,7 @@ def run_ours(a):
     ext = torch.cuda.ExternalStream(D.scratch_stream(sc), device=dev)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     blocks = {"cap": 0, "mine": None, "all": None}
-    host_slice = {"t": None}
+    host_slice = {}
 
     def step_multi(from_host=False):
         launches = 0
@@ -407,9 +407,13 @@ def run_ours(a):
             with torch.cuda.stream(ext):
                 h0 = time.perf_counter()
                 evs[0].record()
-                if from_host:  # this rank's shard from its own pinned host buffer
-                    buf.copy_(host_slice["t"], non_blocking=True)
-                D.find_sites_block(cp, sc, segments, n_recs, blocks["mine"], site_cap)
+                if from_host:  # this rank's shard, packed, from its own pinned host buffers
+                    host_slice["dcodes"].copy_(host_slice["codes"], non_blocking=True)
+                    host_slice["dinval"].copy_(host_slice["inval"], non_blocking=True)
+                    D.find_sites_block_packed(cp, sc, host_slice["dcodes"], host_slice["dinval"], host_slice["n"],
+                                              host_slice["segs"], n_recs, blocks["mine"], site_cap)
+                else:
+                    D.find_sites_block(cp, sc, segments, n_recs, blocks["mine"], site_cap)
                 launches += sc.timing()["kernel_launches"]
                 evs[1].record()
                 h1 = time.perf_counter()
@@ -473,16 +477,35 @@ def run_ours(a):
         host.copy_(buf)
         torch.cuda.synchronize()
         recs = [host[offs[c]:offs[c + 1]] for c in range(n_recs)]
+        # (a) plain reference-facing call: ASCII records, 1 B/bp over PCIe
         D.scan_batch(cp, sc, recs)  # warm (buffer growth)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(max(1, a.e2e_steps)):
+            prods = D.scan_batch(cp, sc, recs)
+        ascii_ms = (time.perf_counter() - t0) * 1e3 / max(1, a.e2e_steps)
+        ascii_stage = {k: sc.timing()[k] for k in ("h2d_ms", "filter_ms", "pair_ms", "total_ms")}
+        assert len(prods) == n_prod or weak
+        # (b) the native feeder's packed output (0.375 B/bp, produced once when the FASTA is read): the
+        # records are handed to the feeder untimed, every timed step ships the packed form and scans it
+        from ipcr_b200.fasta import FastaFile
+        tp0 = time.perf_counter()
+        ff = FastaFile.from_memory(recs, pin=False, pack=True)
+        feeder_pack_s = time.perf_counter() - tp0
+        ff.scan_raw(cp, sc)  # warm
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         d2h = 0
         for _ in range(max(1, a.e2e_steps)):
-            prods = D.scan_batch(cp, sc, recs)
-            d2h = len(prods) * 64
+            _out, n_e = ff.scan_raw(cp, sc)
+            d2h = n_e * 64
         e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, a.e2e_steps)
         te = sc.timing()
+        if not weak and n_e != n_prod:
+            raise RuntimeError(f"packed e2e path returned {n_e} products, device-resident path {n_prod}")
+        ff.close()
         if world > 1:
             t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -492,15 +515,31 @@ def run_ours(a):
             d2h = int(t[0])
         e2e_stage = {k: te[k] for k in ("h2d_ms", "pack_ms", "filter_ms", "verify_ms", "pair_ms", "total_ms")}
         g = n_units * total / 1e9
+        packed_bytes = n_units * ((total + 4095) // 4096 * 4096 // 32 + 1) * 12
         e2e = {"value": g / (e2e_ms / 1e3) * len(user_pairs), "unit": UNIT, "ms_per_step": e2e_ms,
-               "gbp_per_s": g / (e2e_ms / 1e3), "h2d_bytes_per_step": n_units * total, "d2h_bytes_per_step": d2h,
-               "api": "ipcr_gpu_scan_batch(host records) -> products (C ABI; pinned host buffers)"}
+               "gbp_per_s": g / (e2e_ms / 1e3), "h2d_bytes_per_step": packed_bytes, "d2h_bytes_per_step": d2h,
+               "api": "ipcr_gpu_scan_fasta(feeder handle holding the packed records in pinned host memory) -> products "
+                      "(C ABI): H2D of 2-bit codes + hard-mismatch bitmap in slabs under the scan, verify on the codes",
+               "feeder_pack_s_untimed": feeder_pack_s,
+               "ascii": {"value": g / (ascii_ms / 1e3) * len(user_pairs), "ms_per_step": ascii_ms,
+                         "h2d_bytes_per_step": n_units * total, "stage_ms": ascii_stage,
+                         "api": "ipcr_gpu_scan_batch(ASCII host records, pinned) -> products: 1 B/bp over PCIe"}}
         del host, recs
     elif not a.no_e2e:
         # sharded: every rank feeds ITS shard from its own pinned host buffer; wall clock between barriers
-        host_slice["t"] = torch.empty(piece_end - lo, dtype=torch.uint8, pin_memory=True)
-        host_slice["t"].copy_(buf)
+        hs = torch.empty(piece_end - lo, dtype=torch.uint8, pin_memory=True)
+        hs.copy_(buf)
         torch.cuda.synchronize()
+        # this rank's shard as the feeder leaves it: packed, pinned (untimed); record flags from the bytes
+        hc, hi_ = D.pack_host(hs)
+        psegs = []
+        for (s0, s1, c, rec_off, own) in sharding.shard_segments(lens, shards, shard_rank):
+            seg = hs[s0 - lo:s1 - lo]
+            bad = bool(((seg != 65) & (seg != 67) & (seg != 71) & (seg != 84) & (seg != 97) & (seg != 99)
+                        & (seg != 103) & (seg != 116)).any())
+            psegs.append((s0 - lo, s1 - s0, own, rec_off, c, bad))
+        host_slice.update(t=hs, codes=hc, inval=hi_, dcodes=torch.empty_like(hc, device=dev),
+                          dinval=torch.empty_like(hi_, device=dev), segs=psegs, n=piece_end - lo)
         step_multi(from_host=True)  # warm
         torch.cuda.synchronize()
         dist.barrier()
@@ -513,16 +552,18 @@ def run_ours(a):
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0])
-        t = torch.tensor([piece_end - lo], dtype=torch.int64, device=dev)
+        t = torch.tensor([(host_slice["codes"].numel() + host_slice["inval"].numel()) * 4], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         h2d = int(t[0])
         e2e_stage = {k: te[k] for k in ("pack_ms", "filter_ms", "verify_ms", "pair_ms", "gather_ms", "find_total_ms")}
         g = total / 1e9
         e2e = {"value": g / (e2e_ms / 1e3) * len(user_pairs), "unit": UNIT, "ms_per_step": e2e_ms,
                "gbp_per_s": g / (e2e_ms / 1e3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n_e2e * 64 * world,
-               "api": "per rank: pinned host shard -> H2D -> ipcr_gpu_find_sites_block -> NCCL all-gather of site blocks "
-                      "-> ipcr_gpu_pair_blocks -> products on the host of every rank (C ABI)"}
-        host_slice["t"] = None
+               "api": "per rank: packed shard (2-bit codes + bitmap, pinned host) -> H2D -> ipcr_gpu_find_sites_block_packed "
+                      "-> NCCL all-gather of site blocks -> ipcr_gpu_pair_blocks -> products on the host of every rank (C ABI)"}
+        if n_e2e != n_prod:
+            raise RuntimeError(f"packed sharded e2e returned {n_e2e} products, device-resident path {n_prod}")
+        host_slice.clear()
 
     if rank != 0:
         if world > 1:

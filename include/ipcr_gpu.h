@@ -233,6 +233,17 @@ void *ipcr_gpu_scratch_stream(ipcr_scratch *s);
 int ipcr_gpu_find_sites_block(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs,
                               size_t n_recs, int force_raw, void *d_block, uint64_t site_cap, char *err,
                               size_t errlen);
+/* The same from a PACKED device buffer (ipcr_gpu_pack_host output copied to the device as is): segments
+ * are base offsets into it.  has_reset_byte: the caller saw the bytes (the packed form cannot tell a
+ * lowercase acgt from N; inputs normalised by the reader have no lowercase). */
+typedef struct ipcr_packed_segment {
+    uint64_t off, len, own_len, rec_off;
+    uint32_t rec_idx;
+    uint32_t has_reset_byte;
+} ipcr_packed_segment;
+int ipcr_gpu_find_sites_block_packed(ipcr_panel *p, ipcr_scratch *s, const uint32_t *d_codes, const uint32_t *d_inval,
+                                     uint64_t n_bases, const ipcr_packed_segment *segs, size_t n_segs, size_t n_recs,
+                                     int force_raw, void *d_block, uint64_t site_cap, char *err, size_t errlen);
 /* Stage 2 over n_blocks blocks lying back to back in device memory (what the all-gather left),
  * queued behind whatever the scratch's stream holds; waits once, for the products.
  * rec_lens[n_recs] = whole-record lengths.  Returns 0 = done, 1 = error, 2 = run stage 1 again on
@@ -250,7 +261,20 @@ int ipcr_gpu_pair_blocks(ipcr_panel *p, ipcr_scratch *s, const void *d_blocks, u
  * normalize.go, stream.go:125-131, open.go) into ONE host buffer, multi-threaded.
  * pin != 0 asks for page-locked memory (faster H2D, slower to allocate). */
 typedef struct ipcr_fasta ipcr_fasta;
+#define IPCR_FASTA_PIN 1  /* page-locked sequence buffer */
+#define IPCR_FASTA_PACK 2 /* also keep the PACKED form (2-bit codes + hard-mismatch bitmap, 0.375 B/bp, pinned):
+                             ipcr_gpu_scan_fasta then ships that over PCIe, skips the pack kernel and verifies on
+                             the codes; the device-side visitors need the ASCII path */
+/* pin: IPCR_FASTA_* flags */
 ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *err, size_t errlen);
+/* the same handle from records already in host memory (copied, a-z upper-cased like the reader does) */
+ipcr_fasta *ipcr_gpu_fasta_from_memory(const ipcr_seq *recs, const char *const *ids, size_t n_recs, int threads,
+                                       int flags, char *err, size_t errlen);
+int ipcr_gpu_fasta_is_packed(const ipcr_fasta *f);
+/* the host packer the feeder applies (bit-for-bit what the device pack kernel writes):
+ * codes[*code_words], inval[*inval_words] for n_bases bases, padding included */
+void ipcr_gpu_packed_words(uint64_t n_bases, uint64_t *code_words, uint64_t *inval_words);
+int ipcr_gpu_pack_host(const uint8_t *ascii, uint64_t n_bases, uint32_t *codes, uint32_t *inval, int threads);
 void ipcr_gpu_fasta_close(ipcr_fasta *f);
 size_t ipcr_gpu_fasta_num_records(const ipcr_fasta *f);
 uint64_t ipcr_gpu_fasta_total_bases(const ipcr_fasta *f);

@@ -53,6 +53,17 @@ class SegmentC(C.Structure):
     ]
 
 
+class PackedSegmentC(C.Structure):
+    _fields_ = [
+        ("off", C.c_uint64),
+        ("len", C.c_uint64),
+        ("own_len", C.c_uint64),
+        ("rec_off", C.c_uint64),
+        ("rec_idx", C.c_uint32),
+        ("has_reset_byte", C.c_uint32),
+    ]
+
+
 class ProductC(C.Structure):
     _fields_ = [
         ("start", C.c_int64),
@@ -106,7 +117,8 @@ assert C.sizeof(ProductC) == 64 and C.sizeof(SiteC) == 24
 SYMBOLS = [
     "ipcr_gpu_abi_version", "ipcr_gpu_device_count", "ipcr_gpu_init", "ipcr_gpu_set_device", "ipcr_gpu_num_devices",
     "ipcr_gpu_site_block_bytes", "ipcr_gpu_scratch_site_cap", "ipcr_gpu_scratch_stream",
-    "ipcr_gpu_find_sites_block", "ipcr_gpu_pair_blocks",
+    "ipcr_gpu_find_sites_block", "ipcr_gpu_pair_blocks", "ipcr_gpu_find_sites_block_packed",
+    "ipcr_gpu_fasta_from_memory", "ipcr_gpu_fasta_is_packed", "ipcr_gpu_packed_words", "ipcr_gpu_pack_host",
     "ipcr_gpu_panel_create", "ipcr_gpu_panel_destroy", "ipcr_gpu_panel_num_pairs",
     "ipcr_gpu_panel_num_orientations", "ipcr_gpu_panel_have", "ipcr_gpu_panel_set_jit", "ipcr_gpu_panel_set_filter",
     "ipcr_gpu_scratch_create", "ipcr_gpu_scratch_destroy",
@@ -177,6 +189,11 @@ def lib():
         P(RecordInfoC), *ERR)
     sig("ipcr_gpu_pair_sites", C.c_int, V, V, P(SiteC), U64, P(RecordInfoC), SZ, P(P(ProductC)), P(U64), *ERR)
     sig("ipcr_gpu_fasta_open", V, C.c_char_p, C.c_int, C.c_int, *ERR)
+    sig("ipcr_gpu_fasta_from_memory", V, P(SeqC), P(C.c_char_p), SZ, C.c_int, C.c_int, *ERR)
+    sig("ipcr_gpu_fasta_is_packed", C.c_int, V)
+    sig("ipcr_gpu_packed_words", None, U64, P(U64), P(U64))
+    sig("ipcr_gpu_pack_host", C.c_int, V, U64, V, V, C.c_int)
+    sig("ipcr_gpu_find_sites_block_packed", C.c_int, V, V, V, V, U64, P(PackedSegmentC), SZ, SZ, C.c_int, V, U64, *ERR)
     sig("ipcr_gpu_fasta_close", None, V)
     sig("ipcr_gpu_fasta_num_records", SZ, V)
     sig("ipcr_gpu_fasta_total_bases", U64, V)

@@ -25,6 +25,7 @@
 
 #include "device_types.cuh"
 #include "fasta_host.hpp"
+#include "pack_host.hpp"
 #include "jit.hpp"
 #include "kernels.cuh"
 #include "plan.hpp"
@@ -273,6 +274,8 @@ struct GenomeData {
     bool any_reset = false;
     uint64_t own_bases = 0;
     const ipcr_record_info *recs_dev_ptr = nullptr;  // chain: record table uploaded together with the segments
+    // packed input (host-packed codes + bitmap already in device memory): nothing to pack, no ASCII
+    const uint32_t *codes_ext = nullptr, *inval_ext = nullptr;
 };
 
 }  // namespace ipcr
@@ -687,6 +690,16 @@ static uint64_t pair_sites(ipcr_scratch *s, const ipcr_site *d_sites, uint64_t n
                        sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     const uint64_t n_tasks = *reinterpret_cast<uint32_t *>(s->h_counts.as<unsigned long long>() + 3);
+    {  // the scans are 32-bit: one orientation can serve many pairs, so tasks can outnumber the sites
+        uint64_t max_uses = 1;
+        std::vector<uint32_t> uses(h.orients.size(), 0);
+        for (const PairRoles &r : h.roles) {
+            max_uses = std::max<uint64_t>(max_uses, ++uses[(size_t)r.fwdA]);
+            max_uses = std::max<uint64_t>(max_uses, ++uses[(size_t)r.fwdB]);
+        }
+        if ((uint64_t)n_final * max_uses >= (1ull << 32))
+            throw Error("too many forward sites x pairs for one pairing pass; use smaller batches");
+    }
     if (n_tasks == 0) return 0;
     ja.n_tasks = n_tasks;
     s->task_cnt.ensure(n_tasks * 4);
@@ -699,10 +712,21 @@ static uint64_t pair_sites(ipcr_scratch *s, const ipcr_site *d_sites, uint64_t n
     check_launch("k_join<count>");
     s->launches++;
     exclusive_scan(st, ja.task_cnt, s->prod_off.as<uint32_t>(), n_tasks, s->tmp.as<uint32_t>(), &s->launches);
+    // the true total in 64 bits beside the 32-bit scan: a wrapped scan must fail, not truncate
+    CU(cudaMemsetAsync(s->counters.as<unsigned long long>() + 6, 0, sizeof(unsigned long long), st));
+    k_sum_u32<<<(unsigned)std::min<uint64_t>((n_tasks + 255) / 256, 1024), 256, 0, st>>>(
+        ja.task_cnt, n_tasks, s->counters.as<unsigned long long>() + 6);
+    check_launch("k_sum_u32");
+    s->launches++;
     CU(cudaMemcpyAsync(s->h_counts.as<unsigned long long>() + 4, s->prod_off.as<uint32_t>() + n_tasks,
                        sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s->h_counts.as<unsigned long long>() + 6, s->counters.as<unsigned long long>() + 6,
+                       sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     const uint64_t n_prod = *reinterpret_cast<uint32_t *>(s->h_counts.as<unsigned long long>() + 4);
+    if (s->h_counts.as<unsigned long long>()[6] != n_prod)
+        throw Error(fmt("%llu products do not fit one pairing pass; use smaller batches or a hit cap",
+                        (unsigned long long)s->h_counts.as<unsigned long long>()[6]));
     if (n_prod == 0) return 0;
     s->products.ensure(n_prod * sizeof(ipcr_product));
     ja.products = s->products.as<ipcr_product>();
@@ -821,7 +845,6 @@ static uint64_t scan_batch_streamed(ipcr_scratch *s, const ipcr_seq *recs, size_
             g.segs.push_back(d);
         }
         if (g.segs.empty()) continue;
-        // the first segment must start at 0 for find_segment(); pad with a dummy otherwise
         g.lay.total_len = end - lo;
         g.ascii = base + lo;
         g.own_bases = hi - lo;
@@ -1268,17 +1291,22 @@ static void stage1_async(ipcr_scratch *s, GenomeData &g, int variant, uint8_t *d
     cudaStream_t st = s->stream;
     DevTables *t = s->tables;
     const size_t n_recs = g.recs.size();
-    {  // ONE small copy: the segment table and, behind it, the record table stage 2 reads
+    const bool packed = g.codes_ext != nullptr;
+    const uint8_t *rr_init = nullptr;
+    {  // ONE small copy: the segment table and, behind it, the record table stage 2 reads (+ record flags)
         const size_t seg_bytes = (g.segs.size() * sizeof(SegmentDev) + 63) & ~(size_t)63;
-        std::vector<uint8_t> tab(seg_bytes + n_recs * sizeof(ipcr_record_info), 0);
+        const size_t rec_bytes = n_recs * sizeof(ipcr_record_info);
+        std::vector<uint8_t> tab(seg_bytes + rec_bytes + (packed ? n_recs : 0), 0);
         memcpy(tab.data(), g.segs.data(), g.segs.size() * sizeof(SegmentDev));
         for (size_t r = 0; r < n_recs; r++) {
             ipcr_record_info ri{};
             ri.len = g.recs[r].len;
             memcpy(tab.data() + seg_bytes + r * sizeof(ipcr_record_info), &ri, sizeof ri);
+            if (packed) tab[seg_bytes + rec_bytes + r] = g.recs[r].has_reset_byte ? 1 : 0;
         }
         upload_staged(s, g.segs_dev, tab.data(), tab.size());
         g.recs_dev_ptr = reinterpret_cast<const ipcr_record_info *>(g.segs_dev.as<uint8_t>() + seg_bytes);
+        if (packed) rr_init = g.segs_dev.as<uint8_t>() + seg_bytes + rec_bytes;
     }
     g.seg_reset.ensure(std::max<size_t>(g.segs.size(), 4) * sizeof(uint32_t));
     uint64_t cap = std::max<uint64_t>(1ull << 16, (uint64_t)(ix.cand_prob * (double)g.lay.total_len * 1.5) + 4096);
@@ -1294,16 +1322,18 @@ static void stage1_async(ipcr_scratch *s, GenomeData &g, int variant, uint8_t *d
     init.n_recs = (uint32_t)n_recs;
     Stage1Ctl *ctl = reinterpret_cast<Stage1Ctl *>(d_block);
     uint8_t *rec_reset = d_block + sizeof(Stage1Ctl);
-    k_block_init<<<1, 256, 0, st>>>(d_block, init, g.seg_reset.as<uint32_t>(), (uint32_t)g.segs.size());
+    k_block_init<<<1, 256, 0, st>>>(d_block, init, g.seg_reset.as<uint32_t>(), (uint32_t)g.segs.size(), rr_init);
     check_launch("k_block_init");
     CU(cudaEventRecord(s->ev[1], st));
-    launch_pack_codes(s, g, rec_reset);
+    if (!packed) launch_pack_codes(s, g, rec_reset);
     CU(cudaEventRecord(s->ev[2], st));
+    const uint32_t *d_codes = packed ? g.codes_ext : g.codes.as<uint32_t>();
+    const uint32_t *d_inval = packed ? g.inval_ext : g.inval.as<uint32_t>();
     CU(cudaEventRecord(s->ev[3], st));
     const uint64_t n_chunks = (g.lay.total_len + kSeedChunk - 1) / kSeedChunk;
     SeedScanArgs a{};
-    a.codes = g.codes.as<uint32_t>();
-    a.inval = g.inval.as<uint32_t>();
+    a.codes = d_codes;
+    a.inval = d_inval;
     a.n_chunks = n_chunks;
     a.S = (uint32_t)ix.S;
     a.d = (uint32_t)(ix.S - ix.S1);
@@ -1340,9 +1370,9 @@ static void stage1_async(ipcr_scratch *s, GenomeData &g, int variant, uint8_t *d
     v.sites = reinterpret_cast<ipcr_site *>(d_block + block_ctl_bytes(n_recs));
     v.site_count = &ctl->n_sites;
     v.site_cap = site_cap;
-    if (!getenv("IPCR_VERIFY_ASCII")) {
-        v.codes = g.codes.as<uint32_t>();
-        v.inval = g.inval.as<uint32_t>();
+    if (packed || !getenv("IPCR_VERIFY_ASCII")) {
+        v.codes = d_codes;
+        v.inval = d_inval;
         v.oplanes = t->oplanes.as<uint64_t>();
     }
     if (h.cfg.max_mm > 0) {  // dirty windows exist only with a mismatch budget (halo.go:76-80)
@@ -1725,14 +1755,33 @@ struct ipcr_fasta {
     uint8_t *seq = nullptr;
     uint64_t total = 0;
     bool pinned = false;
+    // packed form of the whole sequence buffer (IPCR_FASTA_PACK): codes + hard-mismatch bitmap, pinned
+    uint32_t *codes = nullptr, *inval = nullptr;
+    std::vector<uint8_t> rec_reset;  // per record: holds a non-ACGT byte (the feeder upper-cased a-z already)
     std::vector<ipcr_product> products;
     ~ipcr_fasta() {
         if (seq) {
             if (pinned) cudaFreeHost(seq);
             else free(seq);
         }
+        if (codes) cudaFreeHost(codes);
+        if (inval) cudaFreeHost(inval);
     }
 };
+
+// the feeder's second output: the packed form of its sequence buffer, in pinned memory
+static void fasta_pack(ipcr_fasta *f, int threads) {
+    const uint64_t groups = packed_groups(f->total);
+    void *c = nullptr, *i = nullptr;
+    CU(cudaMallocHost(&c, groups * 8 + 64));
+    f->codes = static_cast<uint32_t *>(c);
+    CU(cudaMallocHost(&i, groups * 4 + 64));
+    f->inval = static_cast<uint32_t *>(i);
+    pack_host(f->seq, f->total, f->codes, f->inval, threads);
+    f->rec_reset.assign(f->recs.size(), 0);
+    for (size_t r = 0; r < f->recs.size(); r++)
+        f->rec_reset[r] = packed_any_invalid(f->inval, f->recs[r].off, f->recs[r].off + f->recs[r].len) ? 1 : 0;
+}
 
 // host records -> products in s->h_products (shared by scan_batch and scan_fasta)
 static uint64_t scan_records(ipcr_scratch *s, const ipcr_seq *recs, size_t n_recs) {
@@ -1789,6 +1838,8 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
     fasta_read_file(path, fb);
     if (threads <= 0) threads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
     ipcr_fasta *fp = f.get();
+    const bool want_pack = (pin & IPCR_FASTA_PACK) != 0;
+    pin &= IPCR_FASTA_PIN;
     fasta_parse(fb.data, fb.size, threads, f->recs, f->total, [&](uint64_t total) -> uint8_t * {
         const size_t bytes = (size_t)std::max<uint64_t>(total, 1) + 64;
         if (pin) {
@@ -1804,8 +1855,74 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
         if (!fp->seq) throw Error("out of host memory for the FASTA records");
         return fp->seq;
     });
+    if (want_pack) fasta_pack(fp, threads);
     return f.release();
     ABI_CATCH(nullptr)
+}
+
+ipcr_fasta *ipcr_gpu_fasta_from_memory(const ipcr_seq *recs, const char *const *ids, size_t n_recs, int threads,
+                                       int flags, char *err, size_t errlen) {
+    ABI_TRY
+    if (n_recs && !recs) throw Error("recs is NULL");
+    auto f = std::make_unique<ipcr_fasta>();
+    if (threads <= 0) threads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    uint64_t total = 0;
+    for (size_t r = 0; r < n_recs; r++) {
+        FastaRecord fr;
+        fr.id = ids && ids[r] ? ids[r] : std::to_string(r);
+        fr.off = total;
+        fr.len = recs[r].len;
+        total += recs[r].len;
+        f->recs.push_back(std::move(fr));
+    }
+    f->total = total;
+    const size_t bytes = (size_t)std::max<uint64_t>(total, 1) + 64;
+    if (flags & IPCR_FASTA_PIN) {
+        void *q = nullptr;
+        if (cudaMallocHost(&q, bytes) == cudaSuccess) {
+            f->pinned = true;
+            f->seq = static_cast<uint8_t *>(q);
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (!f->seq) f->seq = static_cast<uint8_t *>(malloc(bytes));
+    if (!f->seq) throw Error("out of host memory for the records");
+    {  // the reader's normalisation (a-z upper-cased, normalize.go:5-14), one thread per slice of records
+        std::vector<std::thread> th;
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            for (size_t r = next++; r < n_recs; r = next++) {
+                const uint8_t *src = recs[r].seq;
+                uint8_t *dst = f->seq + f->recs[r].off;
+                for (uint64_t i = 0; i < recs[r].len; i++) {
+                    const uint8_t c = src[i];
+                    dst[i] = (uint8_t)(c - (((uint8_t)(c - 'a') < 26u) ? 32u : 0u));
+                }
+            }
+        };
+        for (int t = 1; t < threads && (size_t)t < n_recs; t++) th.emplace_back(work);
+        work();
+        for (auto &x : th) x.join();
+    }
+    if (flags & IPCR_FASTA_PACK) fasta_pack(f.get(), threads);
+    return f.release();
+    ABI_CATCH(nullptr)
+}
+
+int ipcr_gpu_fasta_is_packed(const ipcr_fasta *f) { return f && f->codes ? 1 : 0; }
+
+void ipcr_gpu_packed_words(uint64_t n_bases, uint64_t *code_words, uint64_t *inval_words) {
+    const uint64_t g = packed_groups(n_bases);
+    if (code_words) *code_words = 2 * g;
+    if (inval_words) *inval_words = g;
+}
+
+int ipcr_gpu_pack_host(const uint8_t *ascii, uint64_t n_bases, uint32_t *codes, uint32_t *inval, int threads) {
+    if ((!ascii && n_bases) || !codes || !inval) return 1;
+    if (threads <= 0) threads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    pack_host(ascii, n_bases, codes, inval, threads);
+    return 0;
 }
 
 void ipcr_gpu_fasta_close(ipcr_fasta *f) { delete f; }
@@ -1828,6 +1945,28 @@ int ipcr_gpu_scan_fasta(ipcr_panel *p, ipcr_scratch *s, ipcr_fasta *f, const ipc
     if (n_out) *n_out = 0;
     begin_call(s);
     f->products.clear();
+    // the packed form goes over PCIe when the whole file fits one launch chain
+    if (f->codes && f->recs.size() <= 60000 && f->total < (1ull << 43) && f->total > 0 && !getenv("IPCR_NO_PACKED")) {
+        std::vector<ipcr_record_info> rinfo(f->recs.size(), ipcr_record_info{});
+        std::vector<uint64_t> roff(f->recs.size() + 1, 0);
+        for (size_t r = 0; r < f->recs.size(); r++) {
+            rinfo[r].len = f->recs[r].len;
+            rinfo[r].has_reset_byte = f->rec_reset[r];
+            roff[r] = f->recs[r].off;
+        }
+        roff[f->recs.size()] = f->total;
+        if (!s->inflight) s->args_used = 0;
+        if (chain_ok(s, rinfo.data(), rinfo.size())) {
+            PackedHost ph{f->codes, f->inval, f->total};
+            uint64_t n = 0;
+            if (scan_packed_chain(s, ph, rinfo, roff, &n)) {
+                f->products.assign(s->out_ptr, s->out_ptr + n);
+                if (out) *out = f->products.data();
+                if (n_out) *n_out = n;
+                return 0;
+            }
+        }
+    }
     ipcr_timing acc{};
     // batches: <= 60000 records and < 2^43 bases per launch chain (sort-key / candidate-word budgets)
     size_t i = 0;
@@ -2002,6 +2141,10 @@ int ipcr_gpu_pair_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_site *sites, 
     for (uint64_t i = 0; i < n_sites; i++) {
         if (sites[i].rec_idx >= n_recs) throw Error(fmt("site %llu: rec_idx out of range", (unsigned long long)i));
         if (sites[i].orient >= n_orient) throw Error(fmt("site %llu: orientation out of range", (unsigned long long)i));
+        // a position outside its record would spill into the neighbouring bits of the sort key
+        if (sites[i].pos + (uint64_t)p->host.orients[sites[i].orient].L > recs[sites[i].rec_idx].len)
+            throw Error(fmt("site %llu: position %llu + primer length exceeds its record", (unsigned long long)i,
+                            (unsigned long long)sites[i].pos));
     }
     CU(cudaEventRecord(s->ev[5], s->stream));
     if (n_sites) {
@@ -2023,7 +2166,7 @@ int ipcr_gpu_pair_sites(ipcr_panel *p, ipcr_scratch *s, const ipcr_site *sites, 
 uint64_t ipcr_gpu_site_block_bytes(size_t n_recs, uint64_t site_cap) { return block_bytes_for(n_recs, site_cap); }
 
 uint64_t ipcr_gpu_scratch_site_cap(const ipcr_scratch *s) {
-    return std::max<uint64_t>(4096, s ? s->site_cap_hint : 0);
+    return std::max<uint64_t>(1024, s ? s->site_cap_hint : 0);
 }
 
 int ipcr_gpu_find_sites_block(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment *segs, size_t n_segs, size_t n_recs,
@@ -2044,12 +2187,67 @@ int ipcr_gpu_find_sites_block(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment
         init.n_recs = (uint32_t)n_recs;
         s->seg_reset_dummy.ensure(16);
         for (int i = 1; i <= 5; i++) CU(cudaEventRecord(s->ev[i], s->stream));
-        k_block_init<<<1, 256, 0, s->stream>>>(static_cast<uint8_t *>(d_block), init, s->seg_reset_dummy.as<uint32_t>(), 0);
+        k_block_init<<<1, 256, 0, s->stream>>>(static_cast<uint8_t *>(d_block), init, s->seg_reset_dummy.as<uint32_t>(), 0, nullptr);
         check_launch("k_block_init");
         s->inflight = true;
     } else {
         stage1_async(s, s->own, chain_variant(s, force_raw != 0), static_cast<uint8_t *>(d_block), site_cap);
     }
+    s->timing.kernel_launches = s->launches;
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_find_sites_block_packed(ipcr_panel *p, ipcr_scratch *s, const uint32_t *d_codes, const uint32_t *d_inval,
+                                     uint64_t n_bases, const ipcr_packed_segment *segs, size_t n_segs, size_t n_recs,
+                                     int force_raw, void *d_block, uint64_t site_cap, char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || s->panel != p || !d_block || !d_codes || !d_inval) throw Error("bad panel/scratch/block/packed buffers");
+    begin_call(s);
+    GenomeData &g = s->own;
+    g.device = s->device;
+    g.segs.clear();
+    g.recs.assign(n_recs, ipcr_record_info{});
+    g.own_bases = 0;
+    for (size_t i = 0; i < n_segs; i++) {
+        const ipcr_packed_segment &in = segs[i];
+        if (in.rec_idx >= n_recs) throw Error(fmt("segment %zu: rec_idx %u out of range", i, in.rec_idx));
+        if (in.own_len > in.len || in.off + in.len > n_bases) throw Error(fmt("segment %zu out of range", i));
+        if (i > 0 && in.off < segs[i - 1].off + segs[i - 1].len) throw Error("packed segments must be ascending and non-overlapping");
+        SegmentDev d{};
+        d.global_off = in.off;
+        d.len = in.len;
+        d.own_len = in.own_len;
+        d.rec_off = in.rec_off;
+        d.rec_idx = in.rec_idx;
+        g.segs.push_back(d);
+        g.recs[in.rec_idx].len = std::max<uint64_t>(g.recs[in.rec_idx].len, in.rec_off + in.len);
+        g.recs[in.rec_idx].has_reset_byte |= in.has_reset_byte ? 1 : 0;
+        g.own_bases += in.own_len;
+    }
+    g.lay.total_len = n_bases;
+    g.ascii = nullptr;
+    g.codes_ext = d_codes;
+    g.inval_ext = d_inval;
+    s->last_valid = false;
+    std::vector<ipcr_record_info> rinfo(n_recs, ipcr_record_info{});
+    for (size_t r = 0; r < n_recs; r++) rinfo[r].len = std::max<uint64_t>(1, g.recs[r].len);
+    if (!chain_ok(s, rinfo.data(), n_recs)) throw Error("ipcr_gpu_find_sites_block_packed needs a seed-index panel");
+    if (n_bases >= (1ull << kCandPosBits)) throw Error("genome too large for one device buffer");
+    if (n_segs == 0 || n_bases == 0) {
+        Stage1Ctl init{};
+        init.site_cap = site_cap;
+        init.variant = (uint32_t)chain_variant(s, force_raw != 0);
+        init.n_recs = (uint32_t)n_recs;
+        s->seg_reset_dummy.ensure(16);
+        for (int i = 1; i <= 5; i++) CU(cudaEventRecord(s->ev[i], s->stream));
+        k_block_init<<<1, 256, 0, s->stream>>>(static_cast<uint8_t *>(d_block), init, s->seg_reset_dummy.as<uint32_t>(), 0, nullptr);
+        check_launch("k_block_init");
+        s->inflight = true;
+    } else {
+        stage1_async(s, g, chain_variant(s, force_raw != 0), static_cast<uint8_t *>(d_block), site_cap);
+    }
+    g.codes_ext = g.inval_ext = nullptr;  // the scratch's own genome goes back to packing for itself
     s->timing.kernel_launches = s->launches;
     return 0;
     ABI_CATCH(1)

@@ -746,6 +746,15 @@ __device__ __forceinline__ void join_task(const JoinArgs &a, uint64_t t) {
     if (!FILL) a.task_cnt[t] = cnt;
 }
 
+// 64-bit total of a u32 array (guards the 32-bit product scan against wrap-around)
+__global__ void __launch_bounds__(256)
+k_sum_u32(const uint32_t *__restrict__ v, uint64_t n, unsigned long long *__restrict__ out) {
+    unsigned long long acc = 0ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += v[i];
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d);
+    if ((threadIdx.x & 31u) == 0u && acc) atomicAdd(out, acc);
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_join(JoinArgs a) {

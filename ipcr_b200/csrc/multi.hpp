@@ -89,7 +89,7 @@ static bool scan_streamed_chain(ipcr_scratch *s, const ipcr_seq *recs, size_t n_
     // 2. stage 1 per slab into its block, stage 2 once; capacities / plan variant may ask for a second round
     bool done = false;
     for (int attempt = 0; attempt < 6 && !done; attempt++) {
-        const uint64_t site_cap = std::max<uint64_t>(4096, s->site_cap_hint);
+        const uint64_t site_cap = std::max<uint64_t>(1024, s->site_cap_hint);
         const uint64_t bb = block_bytes_for(n_recs, site_cap);
         s->gather.ensure((size_t)n_slabs * bb);
         const int variant = chain_variant(s, false);
@@ -104,6 +104,7 @@ static bool scan_streamed_chain(ipcr_scratch *s, const ipcr_seq *recs, size_t n_
             g.recs = rinfo;
             g.lay.total_len = std::min(c.total, hi + kPieceHalo) - lo;
             g.ascii = base + lo;
+            g.codes_ext = g.inval_ext = nullptr;
             g.own_bases = hi - lo;
             g.planes_ready = g.codes_ready = false;
             if (attempt == 0) CU(cudaStreamWaitEvent(st, s->slab_ev[k], 0));
@@ -145,6 +146,129 @@ static bool scan_streamed_chain(ipcr_scratch *s, const ipcr_seq *recs, size_t n_
     t.h2d_ms = ev_ms(s->copy_ev[0], s->copy_ev[1]);
     t.pack_ms = 0.f;
     t.filter_ms = stage1;  // pack + scan + verify of every slab (the chain does not time them apart here)
+    t.verify_ms = 0.f;
+    t.pair_ms = ev_ms(s->ev[5], s->ev[6]);
+    t.d2h_ms = ev_ms(s->ev[6], s->ev[7]);
+    t.total_ms = ev_ms(s->ev[0], s->ev[7]);
+    t.products = *n_prod;
+    t.kernel_launches = s->launches;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// Packed host genome (pack_host.hpp: what the native feeder leaves in pinned memory) -> products.
+// 0.375 B/bp cross PCIe instead of 1 B/bp, there is no pack kernel, and the exact verify reads the
+// same codes.  Slabs are cut on 4096-base boundaries so that every slab is a whole number of packed
+// words; the copy of slab k+1.. runs under stage 1 of slab k.
+// ---------------------------------------------------------------------------------------
+struct PackedHost {
+    const uint32_t *codes = nullptr;  // [2 * packed_groups(total)]
+    const uint32_t *inval = nullptr;  // [packed_groups(total)]
+    uint64_t total = 0;               // bases in the concatenated buffer
+};
+
+static bool scan_packed_chain(ipcr_scratch *s, const PackedHost &ph, const std::vector<ipcr_record_info> &rinfo,
+                              const std::vector<uint64_t> &rec_off, uint64_t *n_prod) {
+    cudaStream_t st = s->stream, cs = s->copy_stream;
+    const size_t n_recs = rinfo.size();
+    const uint64_t total = ph.total, groups = packed_groups(total);
+    int n_slabs = (int)std::min<uint64_t>(8, std::max<uint64_t>(1, total / (256ull << 20)));
+    if (const char *e = getenv("IPCR_STREAM_SLABS")) n_slabs = std::max(1, atoi(e));
+    n_slabs = std::min<int>(n_slabs, (int)kPairMaxBlocks);
+    PieceCut c;
+    c.roff = rec_off;  // n_recs + 1 entries
+    c.total = total;
+    c.cut.resize((size_t)n_slabs + 1);
+    for (int k = 0; k <= n_slabs; k++)
+        c.cut[k] = k == n_slabs ? total : ((total * (uint64_t)k / (uint64_t)n_slabs) & ~(kPackChunk - 1));
+    GenomeData &own = s->own;
+    own.device = s->device;
+    own.codes.ensure((size_t)groups * 8 + 64);
+    own.inval.ensure((size_t)groups * 4 + 64);
+    while ((int)s->slab_ev.size() < n_slabs) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->slab_ev.push_back(e);
+    }
+    while ((int)s->slab_g.size() < n_slabs) s->slab_g.emplace_back(new GenomeData());
+    while ((int)s->slab_t.size() < 2 * n_slabs) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        s->slab_t.push_back(e);
+    }
+    // 1. copies: slab k is ready once every group its scan may touch is resident
+    //    (its chunks, the halo's chunk and one look-ahead group)
+    CU(cudaEventRecord(s->ev[0], st));
+    CU(cudaEventRecord(s->copy_ev[0], cs));
+    uint64_t g_done = 0;
+    for (int k = 0; k < n_slabs; k++) {
+        const uint64_t end = std::min(total, c.cut[k + 1] + kPieceHalo);
+        const uint64_t g_want = std::min(groups, (end + kPackChunk - 1) / kPackChunk * (kPackChunk / 32u) + 1);
+        if (g_want > g_done) {
+            CU(cudaMemcpyAsync(own.codes.as<uint32_t>() + 2 * g_done, ph.codes + 2 * g_done, (g_want - g_done) * 8,
+                               cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(own.inval.as<uint32_t>() + g_done, ph.inval + g_done, (g_want - g_done) * 4,
+                               cudaMemcpyHostToDevice, cs));
+            g_done = g_want;
+        }
+        CU(cudaEventRecord(s->slab_ev[k], cs));
+    }
+    CU(cudaEventRecord(s->copy_ev[1], cs));
+    bool done = false;
+    for (int attempt = 0; attempt < 6 && !done; attempt++) {
+        const uint64_t site_cap = std::max<uint64_t>(1024, s->site_cap_hint);
+        const uint64_t bb = block_bytes_for(n_recs, site_cap);
+        s->gather.ensure((size_t)n_slabs * bb);
+        const int variant = chain_variant(s, false);
+        uint32_t n_blocks = 0;
+        for (int k = 0; k < n_slabs; k++) {
+            const uint64_t lo = c.cut[k], hi = c.cut[k + 1];
+            if (lo >= hi) continue;
+            GenomeData &g = *s->slab_g[k];
+            g.device = s->device;
+            piece_segments(c, n_recs, lo, hi, g.segs);
+            if (g.segs.empty()) continue;
+            g.recs = rinfo;
+            g.lay.total_len = std::min(total, hi + kPieceHalo) - lo;
+            g.ascii = nullptr;
+            g.codes_ext = own.codes.as<uint32_t>() + lo / 16;
+            g.inval_ext = own.inval.as<uint32_t>() + lo / 32;
+            g.own_bases = hi - lo;
+            if (attempt == 0) CU(cudaStreamWaitEvent(st, s->slab_ev[k], 0));
+            CU(cudaEventRecord(s->slab_t[2 * k], st));
+            stage1_async(s, g, variant, s->gather.as<uint8_t>() + (size_t)n_blocks * bb, site_cap);
+            CU(cudaEventRecord(s->slab_t[2 * k + 1], st));
+            n_blocks++;
+        }
+        if (n_blocks == 0) {
+            *n_prod = 0;
+            s->out_ptr = s->h_products.as<ipcr_product>();
+            done = true;
+            break;
+        }
+        for (int again = 0; again < 4 && !done; again++) {
+            std::vector<ipcr_record_info> ri = rinfo;
+            pair_async(s, s->gather.as<uint8_t>(), n_blocks, bb, site_cap, ri.data(), n_recs);
+            bool redo = false;
+            const ChainResult r = chain_finish(s, s->gather.as<uint8_t>(), n_blocks, bb, ri.data(), n_recs, n_prod, &redo);
+            if (r == kChainTooDirty) {
+                CU(cudaStreamSynchronize(cs));
+                return false;
+            }
+            if (r == kChainDone) done = true;
+            else if (redo) break;
+        }
+    }
+    if (!done) throw Error("the packed scan chain did not converge");
+    CU(cudaStreamSynchronize(cs));
+    s->last_valid = false;  // no ASCII on the device: the visitors need ipcr_gpu_scan / _scan_batch
+    ipcr_timing &t = s->timing;
+    float stage1 = 0.f;
+    for (int k = 0; k < n_slabs; k++)
+        if (c.cut[k] < c.cut[k + 1]) stage1 += ev_ms(s->slab_t[2 * k], s->slab_t[2 * k + 1]);
+    t.h2d_ms = ev_ms(s->copy_ev[0], s->copy_ev[1]);
+    t.pack_ms = 0.f;
+    t.filter_ms = stage1;  // scan + verify of every slab
     t.verify_ms = 0.f;
     t.pair_ms = ev_ms(s->ev[5], s->ev[6]);
     t.d2h_ms = ev_ms(s->ev[6], s->ev[7]);
@@ -232,7 +356,7 @@ static bool scan_multi_device(ipcr_scratch *s, const ipcr_seq *recs, size_t n_re
     CU(cudaEventRecord(s->ev[0], st));
     bool done = false;
     for (int attempt = 0; attempt < 6 && !done; attempt++) {
-        const uint64_t site_cap = std::max<uint64_t>(4096, s->site_cap_hint);
+        const uint64_t site_cap = std::max<uint64_t>(1024, s->site_cap_hint);
         const uint64_t bb = block_bytes_for(n_recs, site_cap);
         s->gather.ensure((size_t)n_dev * bb);
         const int variant = chain_variant(s, false);
@@ -273,7 +397,7 @@ static bool scan_multi_device(ipcr_scratch *s, const ipcr_seq *recs, size_t n_re
                     q->block.ensure(bb);
                     uint8_t *blk = k == 0 ? dst : q->block.as<uint8_t>();
                     q->seg_reset_dummy.ensure(16);
-                    k_block_init<<<1, 256, 0, q->stream>>>(blk, init, q->seg_reset_dummy.as<uint32_t>(), 0);
+                    k_block_init<<<1, 256, 0, q->stream>>>(blk, init, q->seg_reset_dummy.as<uint32_t>(), 0, nullptr);
                     check_launch("k_block_init");
                 } else if (k == 0) {
                     stage1_async(q, q->own, variant, dst, site_cap);

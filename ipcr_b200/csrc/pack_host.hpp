@@ -1,0 +1,90 @@
+// pack_host.hpp -- the host side of the packed genome format: ASCII -> 2-bit codes (16 bases per
+// word: A 0, C 1, T 2, G 3 = (byte >> 1) & 3) + hard-mismatch bitmap (32 bases per word: bit = the
+// byte is not an uppercase A/C/G/T, /root/reference/core/primer/iupac.go:62-67).  Bit-for-bit what
+// k_pack2 (seed_kernels.cuh) writes on the device, produced by the native FASTA feeder so that
+// 0.375 B/bp cross PCIe instead of 1 B/bp.  Padding bytes count as 0x00: code 0, invalid.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace ipcr {
+
+constexpr uint64_t kPackChunk = 4096;  // = kSeedChunk: positions one scan warp takes at a time
+
+// 32-base groups the scan kernels may touch for n bases: whole chunks + one look-ahead group
+inline uint64_t packed_groups(uint64_t n_bases) {
+    const uint64_t n_chunks = (n_bases + kPackChunk - 1) / kPackChunk;
+    return n_chunks * (kPackChunk / 32u) + 1;
+}
+
+// four bytes -> 8 code bits + 4 invalid bits (the arithmetic of pack4 in seed_kernels.cuh)
+inline void pack4_host(uint32_t w, uint32_t &code8, uint32_t &inv4) {
+    const uint32_t t = (w >> 1) & 0x03030303u;
+    code8 = (t * 0x01041040u) >> 24;
+    const uint32_t e2 = (t >> 1) & ~t & 0x01010101u;
+    const uint32_t expect = 0x41414141u + 2u * t + 15u * e2;
+    const uint32_t d = expect ^ w;
+    const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+    inv4 = ((nz >> 7) * 0x10204080u) >> 28;
+}
+
+// groups [g0, g1) of a buffer of n bases; returns true if any byte of [32*g0, min(n, 32*g1)) is invalid
+inline bool pack_groups_host(const uint8_t *ascii, uint64_t n, uint64_t g0, uint64_t g1, uint32_t *codes, uint32_t *inval) {
+    uint32_t any = 0;
+    for (uint64_t g = g0; g < g1; g++) {
+        const uint64_t P0 = g * 32ull;
+        uint32_t w[8];
+        if (P0 + 32ull <= n) {
+            memcpy(w, ascii + P0, 32);
+        } else {
+            memset(w, 0, sizeof w);
+            if (P0 < n) memcpy(w, ascii + P0, (size_t)(n - P0));
+        }
+        uint32_t c0 = 0, c1 = 0, inv = 0;
+        for (int k = 0; k < 8; k++) {
+            uint32_t c8, i4;
+            pack4_host(w[k], c8, i4);
+            if (k < 4) c0 |= c8 << (8 * k); else c1 |= c8 << (8 * (k - 4));
+            inv |= i4 << (4 * k);
+        }
+        codes[2 * g] = c0;
+        codes[2 * g + 1] = c1;
+        inval[g] = inv;
+        if (P0 + 32ull <= n) any |= inv;
+        else if (P0 < n) any |= inv & ((1u << (uint32_t)(n - P0)) - 1u);
+    }
+    return any != 0;
+}
+
+// whole buffer, multi-threaded; codes[2 * packed_groups(n)], inval[packed_groups(n)]
+inline void pack_host(const uint8_t *ascii, uint64_t n, uint32_t *codes, uint32_t *inval, int threads) {
+    const uint64_t groups = packed_groups(n);
+    if (threads < 1) threads = 1;
+    if (groups < (1u << 16)) threads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) {
+        const uint64_t g0 = groups * (uint64_t)t / (uint64_t)threads, g1 = groups * (uint64_t)(t + 1) / (uint64_t)threads;
+        if (t + 1 < threads) th.emplace_back([=] { pack_groups_host(ascii, n, g0, g1, codes, inval); });
+        else pack_groups_host(ascii, n, g0, g1, codes, inval);
+    }
+    for (auto &x : th) x.join();
+}
+
+// does [a, b) hold an invalid base?  (per-record reset flags of the feeder: it upper-cases a-z, so an
+// invalid byte IS a reset byte, core/engine/ac.go:141-148)
+inline bool packed_any_invalid(const uint32_t *inval, uint64_t a, uint64_t b) {
+    if (a >= b) return false;
+    uint64_t w0 = a >> 5, w1 = (b - 1) >> 5;
+    for (uint64_t w = w0; w <= w1; w++) {
+        uint32_t m = 0xFFFFFFFFu;
+        if (w == w0) m &= 0xFFFFFFFFu << (a & 31u);
+        if (w == w1 && ((b & 31u) != 0)) m &= (1u << (b & 31u)) - 1u;
+        if (inval[w] & m) return true;
+    }
+    return false;
+}
+
+}  // namespace ipcr

@@ -43,11 +43,12 @@ __host__ __device__ __forceinline__ uint64_t block_bytes_for(uint64_t n_recs, ui
 
 // first kernel of the chain: clears the counters and flags, records the capacities
 __global__ void __launch_bounds__(256)
-k_block_init(uint8_t *block, Stage1Ctl init, uint32_t *seg_reset, uint32_t n_segs) {
+k_block_init(uint8_t *block, Stage1Ctl init, uint32_t *seg_reset, uint32_t n_segs, const uint8_t *rr_init) {
     if (threadIdx.x == 0) *reinterpret_cast<Stage1Ctl *>(block) = init;
     uint8_t *rr = block + sizeof(Stage1Ctl);
     const uint32_t rr_bytes = (uint32_t)(block_ctl_bytes(init.n_recs) - sizeof(Stage1Ctl));
-    for (uint32_t i = threadIdx.x; i < rr_bytes; i += blockDim.x) rr[i] = 0u;
+    // rr_init: per-record flags the host already knows (packed input: the feeder saw every byte)
+    for (uint32_t i = threadIdx.x; i < rr_bytes; i += blockDim.x) rr[i] = (rr_init && i < init.n_recs) ? rr_init[i] : 0u;
     for (uint32_t i = threadIdx.x; i < n_segs; i += blockDim.x) seg_reset[i] = 0u;
 }
 

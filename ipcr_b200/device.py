@@ -242,6 +242,43 @@ def find_sites_block(cp: CompiledPanel, scratch: SimulationScratch, segments: Se
                                                       err, len(err)), err)
 
 
+def pack_host(buf, threads: int = 0):
+    """ipcr_gpu_pack_host on a host buffer (bytes-like or a CPU uint8 tensor): returns (codes, inval) as
+    pinned CPU int32 tensors when torch is importable, else numpy uint32 arrays."""
+    L = _capi.lib()
+    addr, n, keep = _as_buffer(buf)
+    cw, iw = C.c_uint64(), C.c_uint64()
+    L.ipcr_gpu_packed_words(n, C.byref(cw), C.byref(iw))
+    try:
+        import torch
+
+        pin = torch.cuda.is_available()
+        codes = torch.empty(cw.value, dtype=torch.int32, pin_memory=pin)
+        inval = torch.empty(iw.value, dtype=torch.int32, pin_memory=pin)
+        pc, pi = codes.data_ptr(), inval.data_ptr()
+    except ImportError:  # pragma: no cover
+        import numpy as np
+
+        codes = np.empty(cw.value, dtype=np.uint32)
+        inval = np.empty(iw.value, dtype=np.uint32)
+        pc, pi = codes.ctypes.data, inval.ctypes.data
+    if L.ipcr_gpu_pack_host(addr, n, pc, pi, threads):
+        raise _capi.GpuError("ipcr_gpu_pack_host failed")
+    return codes, inval
+
+
+def find_sites_block_packed(cp: CompiledPanel, scratch: SimulationScratch, codes, inval, n_bases: int,
+                            segments: Sequence[Tuple], n_recs: int, block, site_cap: int, force_raw: bool = False):
+    """Stage 1 from a packed DEVICE buffer.  segments: (off, len, own_len, rec_off, rec_idx, has_reset_byte)."""
+    arr = (_capi.PackedSegmentC * max(1, len(segments)))()
+    for i, sg in enumerate(segments):
+        arr[i] = _capi.PackedSegmentC(int(sg[0]), int(sg[1]), int(sg[2]), int(sg[3]), int(sg[4]), 1 if sg[5] else 0)
+    err = _capi.errbuf()
+    _capi.check(_capi.lib().ipcr_gpu_find_sites_block_packed(
+        cp._h, scratch._h, int(codes.data_ptr()), int(inval.data_ptr()), n_bases, arr, len(segments), n_recs,
+        1 if force_raw else 0, int(block.data_ptr()), site_cap, err, len(err)), err)
+
+
 def pair_blocks(cp: CompiledPanel, scratch: SimulationScratch, blocks, n_blocks: int, site_cap: int,
                 rec_lens: Sequence[int], seq_ids=None, raw: bool = False):
     """Stage 2 over gathered blocks (device uint8 tensor).  Returns None when stage 1 has to run

@@ -13,13 +13,54 @@ class FastaFile:
     """All records of a FASTA file, normalised like fasta.StreamChunksPathCtx with chunking off
     (core/fasta/path_ctx.go:40-81)."""
 
-    def __init__(self, path: str, threads: int = 0, pin: bool = False):
+    PIN, PACK = 1, 2  # IPCR_FASTA_* flags
+
+    def __init__(self, path: str, threads: int = 0, pin: bool = False, pack: bool = False):
         err = _capi.errbuf()
-        h = _capi.lib().ipcr_gpu_fasta_open(path.encode(), threads, 1 if pin else 0, err, len(err))
+        flags = (self.PIN if pin else 0) | (self.PACK if pack else 0)
+        h = _capi.lib().ipcr_gpu_fasta_open(path.encode(), threads, flags, err, len(err))
         if not h:
             raise OSError(err.value.decode("utf-8", "replace"))
         self._h = h
         self.path = path
+
+    @classmethod
+    def from_memory(cls, seqs, ids=None, threads: int = 0, pin: bool = True, pack: bool = True):
+        """The feeder's output for records that already sit in host memory (bytes-like, or tensors
+        exposing data_ptr()/numel()): copied, upper-cased, optionally packed."""
+        from .engine import _as_buffer
+
+        arr = (_capi.SeqC * max(1, len(seqs)))()
+        keep = []
+        for i, s_ in enumerate(seqs):
+            addr, n, k = _as_buffer(s_)
+            keep.append(k)
+            arr[i] = _capi.SeqC(addr, n)
+        idarr = None
+        if ids is not None:
+            idarr = (C.c_char_p * max(1, len(ids)))(*[x.encode() for x in ids])
+        err = _capi.errbuf()
+        flags = (cls.PIN if pin else 0) | (cls.PACK if pack else 0)
+        h = _capi.lib().ipcr_gpu_fasta_from_memory(arr, idarr, len(seqs), threads, flags, err, len(err))
+        if not h:
+            raise OSError(err.value.decode("utf-8", "replace"))
+        self = cls.__new__(cls)
+        self._h = h
+        self.path = "<memory>"
+        return self
+
+    @property
+    def packed(self) -> bool:
+        return bool(_capi.lib().ipcr_gpu_fasta_is_packed(self._h))
+
+    def scan_raw(self, cp: CompiledPanel, scratch: SimulationScratch):
+        """ipcr_gpu_scan_fasta without building Product objects: (ctypes product pointer, count)."""
+        out = C.POINTER(_capi.ProductC)()
+        n = C.c_uint64()
+        err = _capi.errbuf()
+        _capi.check(_capi.lib().ipcr_gpu_scan_fasta(cp._h, scratch._h, self._h, C.byref(out), C.byref(n), err,
+                                                    len(err)), err)
+        return out, n.value
 
     def __len__(self) -> int:
         return int(_capi.lib().ipcr_gpu_fasta_num_records(self._h))

@@ -1,0 +1,20 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=${1:-1}
+timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_fasta_feeder.py -x -q -m gpu > gpurun_out/r02_pytest_multi.log 2>&1; echo "pytest multi rc=$?"
+tail -8 gpurun_out/r02_pytest_multi.log
+show() { python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); e=d.get('e2e') or {}
+        print('$1', 'n', d['n_gpus'], d['scaling'], 'ms', round(d['ms_per_step'],4), 'wall', round(d['wall_ms_per_step'],4), {k:round(v,4) for k,v in d['stage_ms'].items()}, d['rank0_ms'], 'prod', d['products'], 'launches', d['gpu_launches'], 'e2e_ms', e.get('ms_per_step'), d.get('e2e_stage_ms'), 'ascii', (e.get('ascii') or {}).get('ms_per_step'), 'pack_s', e.get('feeder_pack_s_untimed'))
+"; }
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-bitparallel 2>gpurun_out/r02_b1.err | tee gpurun_out/r02_bench_n1.json | show n1
+tail -3 gpurun_out/r02_b1.err
+for n in 2 4 8; do
+  if [ $n -le $N ]; then
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 3 2>gpurun_out/r02_b$n.err | tee gpurun_out/r02_bench_strong_n$n.json | show strong
+    grep -v "OMP_NUM\|\*\*\*\*" gpurun_out/r02_b$n.err | tail -3
+  fi
+done

@@ -144,3 +144,35 @@ def test_scan_fasta_matches_per_record_oracle(tmp_path, oracle, monkeypatch):
         got = [(q.sequence_id, q.experiment_id, q.type, q.start, q.end, q.length, q.fwd_mm, q.rev_mm,
                 q.fwd_mismatch_idx, q.rev_mismatch_idx) for q in f.scan(cp, sc)]
         assert got == want and len(got) >= 6
+
+
+def test_host_packer_matches_its_definition():
+    """ipcr_gpu_pack_host: code = (byte >> 1) & 3 (A 0, C 1, T 2, G 3), 16 bases per word; invalid bit =
+    not an uppercase A/C/G/T (core/primer/iupac.go:62-67), 32 per word; padding counts as invalid."""
+    import ctypes as C
+
+    import numpy as np
+
+    from ipcr_b200 import _capi
+
+    L = _capi.lib()
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 31, 32, 33, 4095, 4096, 4097, 70001):
+        a = np.frombuffer(b"ACGTNacgtRYKM*-", dtype=np.uint8)[rng.integers(0, 15, n)].copy()
+        mostly = rng.random(n) < 0.9
+        a[mostly] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(mostly.sum()))]
+        cw, iw = C.c_uint64(), C.c_uint64()
+        L.ipcr_gpu_packed_words(n, C.byref(cw), C.byref(iw))
+        assert cw.value == 2 * iw.value and iw.value * 32 >= n + 32
+        codes = np.full(cw.value, 0xDEADBEEF, dtype=np.uint32)
+        inval = np.full(iw.value, 0xDEADBEEF, dtype=np.uint32)
+        buf = a.tobytes()
+        for threads in (1, 3):
+            assert L.ipcr_gpu_pack_host(buf, n, codes.ctypes.data, inval.ctypes.data, threads) == 0
+            padded = np.zeros(iw.value * 32, dtype=np.uint8)
+            padded[:n] = a
+            want_c = ((padded >> 1) & 3).astype(np.uint64).reshape(-1, 16)
+            want_codes = (want_c << (2 * np.arange(16, dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+            bad = ~np.isin(padded, np.frombuffer(b"ACGT", dtype=np.uint8))
+            want_inval = (bad.reshape(-1, 32).astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+            assert np.array_equal(codes, want_codes) and np.array_equal(inval, want_inval), n

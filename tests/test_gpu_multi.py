@@ -15,6 +15,7 @@ import pytest
 import ipcr_test_helpers as H
 from ipcr_b200 import Config, Engine, Pair, _capi
 from ipcr_b200 import device as D
+from ipcr_b200.fasta import FastaFile
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -183,3 +184,79 @@ def test_concurrent_workers_share_one_panel(oracle):
             t.join()
         assert not errors, errors
         assert got == want, mode
+
+
+def test_packed_feeder_scan_equals_ascii_and_oracle(oracle, monkeypatch):
+    """The feeder's packed output (2-bit codes + hard-mismatch bitmap, 0.375 B/bp over PCIe) through
+    ipcr_gpu_scan_fasta: no pack kernel, verify on the codes, 1..5 streamed slabs -- same products, same
+    order as the ASCII path and the oracle.  Records hold N runs and soft-masked (lowercase) stretches,
+    which the reader upper-cases (core/fasta/normalize.go:5-14) before anything is packed."""
+    rng = random.Random(13)
+    lens = [90000, 500, 140000, 70000, 3]
+    recs = _records(rng, lens)
+    _plant_across_cuts(recs, lens, 4)
+    recs[0][5000:5400] = bytes(recs[0][5000:5400]).lower()
+    recs[2][100:160] = b"N" * 60
+    seqs = [bytes(g) for g in recs]
+    upper = [sq.upper() for sq in seqs]
+    ids = [f"r{i}" for i in range(len(lens))]
+    for cfgd in CFGS:
+        want = _oracle_rows(oracle, cfgd, upper)
+        eng = Engine(Config(**cfgd))
+        cp = eng.compile_panel(PAIRS)
+        sc = eng.new_simulation_scratch(cp)
+        packed = FastaFile.from_memory(seqs, ids=ids, pack=True)
+        plain = FastaFile.from_memory(seqs, ids=ids, pack=False)
+        assert packed.packed and not plain.packed
+        assert packed.records() == list(zip(ids, upper))
+        for slabs in ("1", "3", "5"):
+            monkeypatch.setenv("IPCR_STREAM_SLABS", slabs)
+            got = [(p.sequence_id,) + _tuple(p) for p in packed.scan(cp, sc)]
+            assert got == want, (cfgd, slabs)
+        monkeypatch.delenv("IPCR_STREAM_SLABS")
+        assert [(p.sequence_id,) + _tuple(p) for p in plain.scan(cp, sc)] == want
+        packed.close()
+        plain.close()
+
+
+def test_block_split_phase_packed_equals_oracle(oracle):
+    """Shards that receive the PACKED form (what a multi-process run copies to each GPU): stage 1 from
+    device-resident codes + bitmap into site blocks, stage 2 over the blocks."""
+    rng = random.Random(17)
+    lens = [90000, 500, 140000, 70000]
+    recs = _records(rng, lens)
+    shards = 3
+    _plant_across_cuts(recs, lens, shards)
+    seqs = [bytes(g) for g in recs]
+    cat = b"".join(seqs)
+    total = len(cat)
+    offs = [0]
+    for n in lens:
+        offs.append(offs[-1] + n)
+    reset = [any(c not in b"ACGTacgt" for c in sq) for sq in seqs]
+    for cfgd in CFGS:
+        eng = Engine(Config(**cfgd))
+        cp = eng.compile_panel(PAIRS)
+        sc = eng.new_simulation_scratch(cp)
+        want = _oracle_rows(oracle, cfgd, seqs)
+        pieces = []
+        for k in range(shards):
+            lo, hi = (total * k // shards) & ~4095, ((total * (k + 1) // shards) & ~4095) if k + 1 < shards else total
+            end = min(total, hi + 64)
+            codes, inval = D.pack_host(cat[lo:end])
+            segs = []
+            for c in range(len(lens)):
+                s0, s1, own1 = max(offs[c], lo), min(offs[c + 1], end), min(offs[c + 1], hi)
+                if s0 < s1 and own1 > s0:
+                    segs.append((s0 - lo, s1 - s0, own1 - s0, s0 - offs[c], c, reset[c]))
+            pieces.append((codes.cuda(), inval.cuda(), end - lo, segs))
+        while True:
+            cap = D.scratch_site_cap(sc)
+            bb = D.site_block_bytes(len(lens), cap)
+            allb = torch.zeros(shards * bb, dtype=torch.uint8, device="cuda")
+            for k, (codes, inval, n, segs) in enumerate(pieces):
+                D.find_sites_block_packed(cp, sc, codes, inval, n, segs, len(lens), allb[k * bb:(k + 1) * bb], cap)
+            got = D.pair_blocks(cp, sc, allb, shards, cap, lens, seq_ids=[f"r{i}" for i in range(len(lens))])
+            if got is not None:
+                break
+        assert [(p.sequence_id,) + _tuple(p) for p in got] == want, cfgd
