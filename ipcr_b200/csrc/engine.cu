@@ -316,7 +316,7 @@ struct ipcr_scratch {
     std::vector<ipcr_scratch *> peers;          // one scratch per further device (multi-GPU inside one process)
     cudaEvent_t done_ev = nullptr;              // peer: its block has arrived on the primary device
     bool own_laid = false;                      // multi-device retry: the slice is already resident
-    ipcr::DevBuf seg_reset_dummy;
+    ipcr::DevBuf seg_reset_dummy, chunk_ctr;
     std::vector<std::unique_ptr<ipcr::GenomeData>> slab_g;  // streamed slabs: packed codes per slab (all in flight at once)
     std::vector<cudaEvent_t> slab_t;
     // records of the last scan that are still resident (for the device-side visitors)
@@ -961,18 +961,34 @@ static const SeedIndex &seed_get(ipcr_scratch *s, int variant) {
         CU(cudaStreamSynchronize(s->stream));
         static std::mutex attr_mu;
         std::lock_guard<std::mutex> l2(attr_mu);
-        for (auto fn : {k_seed_scan<1>, k_seed_scan<2>})
+        for (auto fn : {k_seed_scan<1>, k_seed_scan<2>, k_seed_scan<2, 1>, k_seed_scan<2, 2>, k_seed_scan<2, 3>, k_seed_scan<2, 4>,
+                        k_seed_scan<2, 5>, k_seed_scan<2, 6>, k_seed_scan<2, 7>})
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSeedBloomWords * 4)));
         t->seed_ready[variant] = true;
     }
     return ix;
 }
 
-static void launch_seed_scan(ipcr_scratch *s, const SeedIndex &ix, const SeedScanArgs &a) {
+static void launch_seed_scan(ipcr_scratch *s, const SeedIndex &ix, const SeedScanArgs &a0) {
+    SeedScanArgs a = a0;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((a.n_chunks + 31) / 32, (uint64_t)s->sm_count));
     const size_t smem = kSeedBloomWords * 4;
+    int var = 0;
+    if (const char *e = getenv("IPCR_SEED_VAR")) var = atoi(e) & 7;
+    if (var & 4) {
+        s->chunk_ctr.ensure(64);
+        CU(cudaMemsetAsync(s->chunk_ctr.p, 0, 8, s->stream));
+        a.chunk_counter = s->chunk_ctr.as<unsigned long long>();
+    }
     if (!ix.use_bloom) k_seed_scan<0><<<grid, 1024, 0, s->stream>>>(a);
     else if (ix.bloom_k == 1) k_seed_scan<1><<<grid, 1024, smem, s->stream>>>(a);
+    else if (var == 1) k_seed_scan<2, 1><<<grid, 1024, smem, s->stream>>>(a);
+    else if (var == 2) k_seed_scan<2, 2><<<grid, 1024, smem, s->stream>>>(a);
+    else if (var == 3) k_seed_scan<2, 3><<<grid, 1024, smem, s->stream>>>(a);
+    else if (var == 4) k_seed_scan<2, 4><<<grid, 1024, smem, s->stream>>>(a);
+    else if (var == 5) k_seed_scan<2, 5><<<grid, 1024, smem, s->stream>>>(a);
+    else if (var == 6) k_seed_scan<2, 6><<<grid, 1024, smem, s->stream>>>(a);
+    else if (var == 7) k_seed_scan<2, 7><<<grid, 1024, smem, s->stream>>>(a);
     else k_seed_scan<2><<<grid, 1024, smem, s->stream>>>(a);
     check_launch("k_seed_scan");
     s->launches++;

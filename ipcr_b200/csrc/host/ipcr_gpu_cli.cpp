@@ -344,7 +344,10 @@ int main(int argc, char **argv) {
 
     // ---- engine (core.go:108-117) ----
     Gpu g;
-    if (ipcr_gpu_init(0, g.err, sizeof g.err) != 0) die(3, g.err);
+    // probe / nested visitors read amplicons from the records resident on ONE device; plain runs may spread a
+    // chromosome-sized record over every visible GPU behind the ABI
+    const int n_dev = (o.mode == "probe" || o.mode == "nested") ? 1 : 0;
+    if (ipcr_gpu_init(n_dev, g.err, sizeof g.err) != 0) die(3, g.err);
     g.panel = make_panel(o, pairs, false, g.err);
     g.scratch = ipcr_gpu_scratch_create(g.panel, g.err, sizeof g.err);
     if (!g.scratch) die(3, g.err);

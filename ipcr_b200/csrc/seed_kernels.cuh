@@ -162,6 +162,7 @@ struct SeedScanArgs {
     unsigned long long *dirty;
     unsigned long long *dirty_count;
     uint64_t dirty_cap;
+    unsigned long long *chunk_counter;  // VAR & 4: next unclaimed chunk (zeroed before the launch)
 };
 
 // L2 residency: the second-level bitmap (<= 32 MB) and the hash table are hit at random by
@@ -221,7 +222,11 @@ __device__ __forceinline__ void seed_walk(const SeedScanArgs &a, uint32_t kmer, 
 
 // BLOOM: 0 = no shared-memory bitmap (every position goes to the second level), k = 1..2 bits
 // per k-mer, both in the same word.
-template <int BLOOM>
+// VAR (tuning switches, measured on B200 -- profiles/README.md): 1 = the look-ahead / look-behind words
+// come from the neighbouring lane by shuffle instead of five extra strided loads per chunk; 2 = the bitmap
+// address is formed by a multiply-add (FMA pipe) instead of LEA (ALU pipe); 4 = warps claim chunks from a
+// global counter (no tail, no imbalance between SMs) instead of a static stride.
+template <int BLOOM, int VAR = 0>
 __global__ void __launch_bounds__(1024, 1)
 k_seed_scan(SeedScanArgs a) {
     extern __shared__ uint32_t sbloom[];
@@ -240,7 +245,12 @@ k_seed_scan(SeedScanArgs a) {
     // seed window).  The lane therefore keeps one code word and one bitmap word to the LEFT of its
     // 128 positions: c[0] / iv[0].
     const uint32_t d = a.d;
-    for (uint64_t ch = warp; ch < a.n_chunks; ch += n_warps) {
+    uint64_t ch = warp;
+    if (VAR & 4) {
+        if (lane == 0) ch = atomicAdd(a.chunk_counter, 1ull);
+        ch = __shfl_sync(0xFFFFFFFFu, ch, 0);
+    }
+    while (ch < a.n_chunks) {
         const uint64_t P0 = ch * kSeedChunk + (uint64_t)lane * 128u;
         uint32_t c[10], iv[6];
         {
@@ -248,15 +258,36 @@ k_seed_scan(SeedScanArgs a) {
             const uint4 q0 = ld_u128_policy(cp, stream), q1 = ld_u128_policy(cp + 1, stream);
             c[1] = q0.x; c[2] = q0.y; c[3] = q0.z; c[4] = q0.w;
             c[5] = q1.x; c[6] = q1.y; c[7] = q1.z; c[8] = q1.w;
-            c[9] = ld_u32_policy(a.codes + (P0 >> 4) + 8, stream);
             const uint4 qi = ld_u128_policy(reinterpret_cast<const uint4 *>(a.inval + (P0 >> 5)), stream);
             iv[1] = qi.x; iv[2] = qi.y; iv[3] = qi.z; iv[4] = qi.w;
-            iv[5] = ld_u32_policy(a.inval + (P0 >> 5) + 4, stream);
             c[0] = 0u;
             iv[0] = 0xFFFFFFFFu;  // before the buffer: no window starts there
-            if (d != 0u && P0 != 0ull) {
-                c[0] = ld_u32_policy(a.codes + (P0 >> 4) - 1, stream);
-                iv[0] = ld_u32_policy(a.inval + (P0 >> 5) - 1, stream);
+            if (VAR & 1) {
+                // lane l's look-ahead word is lane l+1's first word, its look-behind word lane l-1's last:
+                // four shuffles, and real loads only at the two ends of the warp's 4096 positions
+                c[9] = __shfl_down_sync(0xFFFFFFFFu, c[1], 1);
+                iv[5] = __shfl_down_sync(0xFFFFFFFFu, iv[1], 1);
+                const uint32_t cb = __shfl_up_sync(0xFFFFFFFFu, c[8], 1), ib = __shfl_up_sync(0xFFFFFFFFu, iv[4], 1);
+                if (lane == 31u) {
+                    c[9] = ld_u32_policy(a.codes + (P0 >> 4) + 8, stream);
+                    iv[5] = ld_u32_policy(a.inval + (P0 >> 5) + 4, stream);
+                }
+                if (d != 0u) {
+                    if (lane != 0u) {
+                        c[0] = cb;
+                        iv[0] = ib;
+                    } else if (P0 != 0ull) {
+                        c[0] = ld_u32_policy(a.codes + (P0 >> 4) - 1, stream);
+                        iv[0] = ld_u32_policy(a.inval + (P0 >> 5) - 1, stream);
+                    }
+                }
+            } else {
+                c[9] = ld_u32_policy(a.codes + (P0 >> 4) + 8, stream);
+                iv[5] = ld_u32_policy(a.inval + (P0 >> 5) + 4, stream);
+                if (d != 0u && P0 != 0ull) {
+                    c[0] = ld_u32_policy(a.codes + (P0 >> 4) - 1, stream);
+                    iv[0] = ld_u32_policy(a.inval + (P0 >> 5) - 1, stream);
+                }
             }
         }
 #pragma unroll
@@ -274,7 +305,12 @@ k_seed_scan(SeedScanArgs a) {
                     // second bit position are formed with multiplies on the FMA pipe instead.
                     const uint32_t hw = x * a.bloom_mul;
                     uint32_t off, b2;
-                    off = __umulhi(hw, kSeedBloomWordsDev) * 4u;
+                    if (VAR & 2) {
+                        const uint32_t widx = __umulhi(hw, kSeedBloomWordsDev);
+                        asm("mad.lo.u32 %0, %1, 4, 0;" : "=r"(off) : "r"(widx));
+                    } else {
+                        off = __umulhi(hw, kSeedBloomWordsDev) * 4u;
+                    }
                     const uint32_t w = *reinterpret_cast<const uint32_t *>(sb + off);
                     uint32_t bit = __funnelshift_r(w, 0u, x);  // bit (key & 31)
                     if (BLOOM == 2) {
@@ -336,6 +372,12 @@ k_seed_scan(SeedScanArgs a) {
                 if (ld_u32_policy(a.bitmap2 + (h2 >> a.bitmap2_shift), keep) & __funnelshift_l(0u, 1u, h2))
                     seed_walk(a, kmer, P0 + (uint64_t)(blk * 32) + j - d, keep);
             }
+        }
+        if (VAR & 4) {
+            if (lane == 0) ch = atomicAdd(a.chunk_counter, 1ull);
+            ch = __shfl_sync(0xFFFFFFFFu, ch, 0);
+        } else {
+            ch += n_warps;
         }
     }
 }

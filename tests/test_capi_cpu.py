@@ -265,3 +265,18 @@ def test_seed_index_shape_on_the_benchmark_panel():
     assert cp1.seed_eval(g)[1]["bloom_k"] == 1  # a sparse bitmap does not need the second bit
     assert info["entries"] < 1 << 20
     assert len(cands) < 400  # ~ entries / 4^S per position
+
+
+def test_primer_length_limit_is_an_error_not_a_truncation():
+    """The GPU engine carries mismatch positions as 64-bit masks: primers up to 64 nt compile, longer ones
+    are refused at panel creation with a message naming the limit (the reference stores up to 65 535 nt,
+    core/engine/compiled.go:43-48; documented difference)."""
+    eng = Engine(Config(max_mm=1, terminal_window=3))
+    ok = eng.compile_panel([Pair("edge", "ACGT" * 16, "TTGACCGTAAGC")])
+    assert ok.num_orientations == 4
+    with pytest.raises(Exception) as ei:
+        eng.compile_panel([Pair("long", "ACGT" * 16 + "A", "TTGACCGTAAGC")])
+    assert "longer than 64" in str(ei.value)
+    with pytest.raises(Exception) as ei:
+        eng.compile_panel([Pair("long", "TTGACCGTAAGC", "ACGT" * 17)])
+    assert "longer than 64" in str(ei.value)
