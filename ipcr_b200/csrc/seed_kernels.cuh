@@ -319,6 +319,21 @@ k_seed_scan(SeedScanArgs a) {
                     }
                     hits = __funnelshift_r(hits, bit, 1);
                 }
+            } else if (d == 0u) {
+                // No first level (the panel's keys saturate any bitmap that fits shared memory, e.g. mm 3 x 400
+                // orientations): EVERY position asks the L2-resident second-level bitmap.  The 32 lookups of a
+                // block are independent: issued back to back they overlap their L2 latency instead of paying it
+                // one by one in the walk loop below, which then only sees the ~1.5 % that pass.
+                uint32_t wd[32], sh[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t x = j < 16 ? __funnelshift_r(w0, w1, 2 * j) : __funnelshift_r(w1, w2, 2 * (j - 16));
+                    const uint32_t h2 = (x & a.kmer_mask) * a.bitmap2_mul;
+                    sh[j] = h2;
+                    wd[j] = ld_u32_policy(a.bitmap2 + (h2 >> a.bitmap2_shift), keep);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j++) hits = __funnelshift_r(hits, __funnelshift_r(wd[j], 0u, sh[j]), 1);
             } else {
                 hits = 0xFFFFFFFFu;
             }
@@ -369,7 +384,8 @@ k_seed_scan(SeedScanArgs a) {
                 const uint32_t lo = jp < 0 ? wm : (jp < 16 ? w0 : w1), hi = jp < 0 ? w0 : (jp < 16 ? w1 : w2);
                 const uint32_t kmer = __funnelshift_r(lo, hi, 2u * (uint32_t)jp) & a.kmer_mask;
                 const uint32_t h2 = kmer * a.bitmap2_mul;
-                if (ld_u32_policy(a.bitmap2 + (h2 >> a.bitmap2_shift), keep) & __funnelshift_l(0u, 1u, h2))
+                if ((BLOOM == 0 && d == 0u) ||  // already tested above
+                    (ld_u32_policy(a.bitmap2 + (h2 >> a.bitmap2_shift), keep) & __funnelshift_l(0u, 1u, h2)))
                     seed_walk(a, kmer, P0 + (uint64_t)(blk * 32) + j - d, keep);
             }
         }
