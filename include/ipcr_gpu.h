@@ -313,6 +313,19 @@ int ipcr_gpu_nested(ipcr_scratch *outer_scratch, const ipcr_product *products, u
                     ipcr_panel *inner_panel, ipcr_scratch *inner_scratch, const char *const *inner_ids,
                     ipcr_product *best, char *err, size_t errlen);
 
+/* ---- --sort on the device (internal/common/sort.go:34-74) ----------------
+ * Sorts n products (host array, IN PLACE) into common.LessProduct order:
+ *   (SourceFile, base SequenceID) -> rec_rank[rec_idx] ; Start + off ; End + off ; Length ; Type ;
+ *   ExperimentID -> pair_rank[pair_idx] ; FwdMM ; RevMM
+ * The strings enter as ranks the caller computes once (equal strings, equal rank); rec_off[rec_idx] is the
+ * chunk offset the collector adds (NULL = 0; it is NOT added to the products).  The sort is stable.
+ * tie_out (optional, n bytes): tie_out[i] = 1 when sorted product i equals product i - 1 on every key above --
+ * only possible between pairs that share one experiment ID or duplicated records; LessProduct then goes on
+ * to the mismatch lists, SequenceID and Seq, which the caller settles inside those (tiny) runs. */
+int ipcr_gpu_sort_products(ipcr_scratch *s, ipcr_product *products, uint64_t n, const uint32_t *rec_rank,
+                           const int64_t *rec_off, size_t n_recs, const uint32_t *pair_rank, size_t n_pairs,
+                           uint8_t *tie_out, char *err, size_t errlen);
+
 /* ---- helpers ---------------------------------------------------------------- */
 /* which: 0 = FwdMismatchIdx (ascending), 1 = RevMismatchIdx (reference order:
  * flipped, hence descending).  Returns the count written (<= cap). */

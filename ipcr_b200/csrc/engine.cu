@@ -33,6 +33,7 @@
 #include "seed_kernels.cuh"
 #include "sortscan.cuh"
 #include "pair_small.cuh"
+#include "sort_products.cuh"
 
 namespace ipcr {
 
@@ -317,6 +318,7 @@ struct ipcr_scratch {
     cudaEvent_t done_ev = nullptr;              // peer: its block has arrived on the primary device
     bool own_laid = false;                      // multi-device retry: the slice is already resident
     ipcr::DevBuf seg_reset_dummy, chunk_ctr;
+    ipcr::DevBuf sp_in, sp_out, sp_k[4], sp_ka, sp_kb, sp_ia, sp_ib, sp_tie, sp_rr, sp_ro, sp_pr;  // ipcr_gpu_sort_products
     std::vector<std::unique_ptr<ipcr::GenomeData>> slab_g;  // streamed slabs: packed codes per slab (all in flight at once)
     std::vector<cudaEvent_t> slab_t;
     // records of the last scan that are still resident (for the device-side visitors)
@@ -2299,6 +2301,86 @@ int ipcr_gpu_pair_blocks(ipcr_panel *p, ipcr_scratch *s, const void *d_blocks, u
         if (redo) return 2;
     }
     throw Error("stage 2 did not converge");
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_sort_products(ipcr_scratch *s, ipcr_product *products, uint64_t n, const uint32_t *rec_rank,
+                           const int64_t *rec_off, size_t n_recs, const uint32_t *pair_rank, size_t n_pairs,
+                           uint8_t *tie_out, char *err, size_t errlen) {
+    ABI_TRY
+    if (!s) throw Error("scratch is NULL");
+    if (n == 0) return 0;
+    if (!products || !rec_rank || !pair_rank) throw Error("products / rank tables are NULL");
+    if (n >= (1ull << 32)) throw Error("too many products for one sort");
+    uint32_t max_rr = 0, max_pr = 0;
+    for (size_t r = 0; r < n_recs; r++) max_rr = std::max(max_rr, rec_rank[r]);
+    for (size_t q = 0; q < n_pairs; q++) max_pr = std::max(max_pr, pair_rank[q]);
+    if (max_rr >= (1u << 20) || max_pr >= (1u << 19)) throw Error("rank tables exceed the sort key (2^20 sequences, 2^19 experiments)");
+    for (uint64_t i = 0; i < n; i++) {
+        const ipcr_product &p = products[i];
+        if (p.rec_idx >= n_recs || p.pair_idx >= n_pairs) throw Error(fmt("product %llu: index out of range", (unsigned long long)i));
+        const long long off = rec_off ? rec_off[p.rec_idx] : 0;
+        if (p.start + off < 0 || p.end + off < 0 || p.length < 0 || ((uint64_t)(p.start + off) >> 44) || ((uint64_t)(p.end + off) >> 44) ||
+            ((uint64_t)p.length >> 44) || p.fwd_mm > 255 || p.rev_mm > 255 || p.type > 1)
+            throw Error(fmt("product %llu does not fit the sort key", (unsigned long long)i));
+    }
+    begin_call(s);
+    cudaStream_t st = s->stream;
+    s->sp_in.ensure(n * sizeof(ipcr_product));
+    s->sp_out.ensure(n * sizeof(ipcr_product));
+    for (auto &b : s->sp_k) b.ensure(n * 8);
+    s->sp_ka.ensure(n * 8);
+    s->sp_kb.ensure(n * 8);
+    s->sp_ia.ensure(n * 4);
+    s->sp_ib.ensure(n * 4);
+    s->sp_tie.ensure(n);
+    s->tmp.ensure(std::max(sort_tmp_words(n), scan_tmp_words(n)) * 4);
+    CU(cudaMemcpyAsync(s->sp_in.p, products, n * sizeof(ipcr_product), cudaMemcpyHostToDevice, st));
+    upload(s->sp_rr, rec_rank, n_recs * 4, st);
+    upload(s->sp_pr, pair_rank, n_pairs * 4, st);
+    if (rec_off) upload(s->sp_ro, rec_off, n_recs * 8, st);
+    ProductKeyArgs ka{};
+    ka.products = s->sp_in.as<ipcr_product>();
+    ka.n = n;
+    ka.rec_rank = s->sp_rr.as<uint32_t>();
+    ka.rec_off = rec_off ? s->sp_ro.as<long long>() : nullptr;
+    ka.pair_rank = s->sp_pr.as<uint32_t>();
+    ka.k1 = s->sp_k[0].as<uint64_t>();
+    ka.k2 = s->sp_k[1].as<uint64_t>();
+    ka.k3 = s->sp_k[2].as<uint64_t>();
+    ka.k4 = s->sp_k[3].as<uint64_t>();
+    ka.idx = s->sp_ia.as<uint32_t>();
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    k_product_keys<<<grid, 256, 0, st>>>(ka);
+    check_launch("k_product_keys");
+    s->launches++;
+    // least significant key first; every pass is a stable sort of (key[idx], idx)
+    const uint32_t bits[4] = {44u + bit_length(max_rr), 44u, 64u, 16u};
+    uint32_t *idx = s->sp_ia.as<uint32_t>(), *idx_alt = s->sp_ib.as<uint32_t>();
+    for (int k = 3; k >= 0; k--) {
+        k_gather_u64<<<grid, 256, 0, st>>>(s->sp_k[k].as<uint64_t>(), idx, n, s->sp_ka.as<uint64_t>());
+        check_launch("k_gather_u64");
+        s->launches++;
+        const int where = radix_sort(st, s->sp_ka.as<uint64_t>(), idx, s->sp_kb.as<uint64_t>(), idx_alt, n, bits[k],
+                                     s->tmp.as<uint32_t>(), &s->launches);
+        check_launch("radix_sort");
+        if (where) std::swap(idx, idx_alt);
+    }
+    k_gather_products<<<grid, 256, 0, st>>>(s->sp_in.as<ipcr_product>(), idx, n, s->sp_out.as<ipcr_product>(),
+                                           s->sp_tie.as<uint8_t>(), ka.k1, ka.k2, ka.k3, ka.k4);
+    check_launch("k_gather_products");
+    s->launches++;
+    CU(cudaMemcpyAsync(products, s->sp_out.p, n * sizeof(ipcr_product), cudaMemcpyDeviceToHost, st));
+    std::vector<uint8_t> tie_local;
+    uint8_t *tie = tie_out;
+    if (!tie) {
+        tie_local.resize(n);
+        tie = tie_local.data();
+    }
+    CU(cudaMemcpyAsync(tie, s->sp_tie.p, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    s->timing.kernel_launches = s->launches;
+    return 0;
     ABI_CATCH(1)
 }
 

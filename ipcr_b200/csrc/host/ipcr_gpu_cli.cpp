@@ -12,6 +12,7 @@
 // Everything that matches, annotates or pairs runs on the GPU; this file is policy, ordering
 // and formatting.  Exit codes follow appcore.Run (0 ok, 2 usage, 3 runtime, --no-match-exit-code).
 #include <algorithm>
+#include <chrono>
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
@@ -217,6 +218,78 @@ struct LRU {  // runutil.LRUSet (lru_set.go:8-38)
     }
 };
 
+// The same LRU over integer keys: plain runs (ipcr / multiplex) keep products as POD records and never
+// build a string per product.  Equal strings were interned to equal integers, so key equality is the same.
+struct PodKey {
+    uint64_t a, b, c;
+    bool operator==(const PodKey &o) const { return a == o.a && b == o.b && c == o.c; }
+};
+struct PodKeyHash {
+    size_t operator()(const PodKey &k) const {
+        uint64_t h = k.a * 0x9E3779B97F4A7C15ull;
+        h ^= (k.b + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+        h ^= (k.c + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+        return (size_t)h;
+    }
+};
+struct PodLRU {  // runutil.LRUSet (lru_set.go:8-38)
+    size_t cap;
+    std::list<PodKey> ll;
+    std::unordered_map<PodKey, std::list<PodKey>::iterator, PodKeyHash> m;
+    explicit PodLRU(long long c) : cap(c > 0 ? (size_t)c : 200000) {}
+    bool add(const PodKey &k) {
+        auto it = m.find(k);
+        if (it != m.end()) {
+            ll.splice(ll.begin(), ll, it->second);
+            return true;
+        }
+        ll.push_front(k);
+        m[k] = ll.begin();
+        if (ll.size() > cap) {
+            m.erase(ll.back());
+            ll.pop_back();
+        }
+        return false;
+    }
+};
+
+struct JobMeta {  // one scanned record / chunk
+    std::string id, base;  // SequenceID as scanned; ID without the chunk suffix
+    long long off = 0;     // chunk offset (0 when the ID carries no suffix)
+    bool chunked = false;
+    uint32_t file = 0, base_intern = 0;
+};
+
+static void append_int(std::string &s, long long v) {
+    char buf[24];
+    char *e = buf + sizeof buf, *p = e;
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { *--p = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) *--p = '-';
+    s.append(p, (size_t)(e - p));
+}
+
+// FwdMismatchIdx ascending, RevMismatchIdx in the reference's (flipped, hence descending) order
+// (core/engine/engine.go:127-136) -- the same lists ipcr_gpu_product_mismatch_idx returns
+static void append_idx_csv(std::string &s, const ipcr_product &pc, int which) {
+    bool first = true;
+    if (which == 0) {
+        for (uint64_t m = pc.fwd_mm_mask; m; m &= m - 1) {
+            if (!first) s += ',';
+            first = false;
+            append_int(s, __builtin_ctzll(m));
+        }
+    } else {
+        for (uint64_t m = pc.rev_mm_mask; m;) {
+            const int j = 63 - __builtin_clzll(m);
+            m &= ~(1ull << j);
+            if (!first) s += ',';
+            first = false;
+            append_int(s, j);
+        }
+    }
+}
+
 struct Gpu {
     ipcr_panel *panel = nullptr;
     ipcr_scratch *scratch = nullptr;
@@ -364,9 +437,26 @@ int main(int argc, char **argv) {
 
     std::vector<Product> rows;
     LRU seen(o.dedupe_cap);
+    // phase clocks for IPCR_CLI_TIMING=1 (stderr): where a dense-hit run spends its time
+    using Clock = std::chrono::steady_clock;
+    double t_open = 0, t_scan = 0, t_collect = 0, t_sort = 0, t_write = 0;
+    auto secs = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    uint64_t n_raw = 0;
+    // plain runs: POD rows (rec_idx rewritten to a global job number), integer dedupe keys, device sort
+    const bool plain = o.mode != "probe" && o.mode != "nested";
+    std::vector<ipcr_product> pod;
+    std::vector<JobMeta> metas;
+    PodLRU seen_pod(o.dedupe_cap);
+    std::unordered_map<std::string, uint32_t> base_ids, exp_ids;
+    std::vector<uint32_t> pair_exp(pairs.size());
+    for (size_t i = 0; i < pairs.size(); i++) pair_exp[i] = exp_ids.emplace(pairs[i].id, (uint32_t)exp_ids.size()).first->second;
+    uint32_t file_no = 0;
     for (const std::string &fa : o.files) {
+        const uint32_t this_file = file_no++;
+        const auto tf0 = Clock::now();
         ipcr_fasta *ff = ipcr_gpu_fasta_open(fa.c_str(), 0, 1, g.err, sizeof g.err);
         if (!ff) die(3, g.err);
+        t_open += secs(tf0, Clock::now());
         const size_t nrec = ipcr_gpu_fasta_num_records(ff);
         // jobs = records or rolling chunks (path_ctx.go:83-179), scanned in batches of <= 4096
         struct Job { std::string id; const uint8_t *seq; uint64_t len; };
@@ -394,8 +484,39 @@ int main(int argc, char **argv) {
             for (size_t j = j0; j < j1; j++) recs.push_back(ipcr_seq{jobs[j].seq, jobs[j].len});
             const ipcr_product *out = nullptr;
             uint64_t n = 0;
+            const auto ts0 = Clock::now();
             g.check(ipcr_gpu_scan_batch(g.panel, g.scratch, recs.data(), recs.size(), &out, &n, g.err, sizeof g.err));
+            const auto ts1 = Clock::now();
+            t_scan += secs(ts0, ts1);
+            n_raw += n;
+            struct CollectClock {
+                double &acc; Clock::time_point t0;
+                ~CollectClock() { acc += std::chrono::duration<double>(Clock::now() - t0).count(); }
+            } collect_clock{t_collect, ts1};
             if (n == 0) continue;
+            if (plain) {
+                const size_t meta_base = metas.size();
+                for (size_t j = j0; j < j1; j++) {
+                    JobMeta m;
+                    m.id = jobs[j].id;
+                    m.chunked = split_chunk_suffix(m.id, m.base, m.off);
+                    if (!m.chunked) { m.base = m.id; m.off = 0; }
+                    m.file = this_file;
+                    m.base_intern = base_ids.emplace(m.base, (uint32_t)base_ids.size()).first->second;
+                    metas.push_back(std::move(m));
+                }
+                for (uint64_t i = 0; i < n; i++) {
+                    ipcr_product pc = out[i];
+                    const JobMeta &m = metas[meta_base + pc.rec_idx];
+                    // collector key (pipeline.go:26-30,146-149): base, file, global start / end, type, experiment
+                    const PodKey key{((uint64_t)m.file << 32) | m.base_intern, (uint64_t)(pc.start + m.off),
+                                     ((uint64_t)(pc.end + m.off) << 20) | ((uint64_t)pc.type << 19) | pair_exp[pc.pair_idx]};
+                    if (seen_pod.add(key)) continue;
+                    pc.rec_idx = (uint32_t)(meta_base + pc.rec_idx);
+                    pod.push_back(pc);
+                }
+                continue;
+            }
             std::vector<ipcr_product> raw(out, out + n);  // the visitors reuse the scratch's buffers
             // collector: global coordinates + LRU dedupe (pipeline.go:134-161)
             std::vector<ipcr_product> kept;
@@ -473,7 +594,65 @@ int main(int argc, char **argv) {
         }
         ipcr_gpu_fasta_close(ff);
     }
+    const auto tq0 = Clock::now();
     if (o.sort) std::stable_sort(rows.begin(), rows.end(), less_product);
+    if (plain && o.sort && pod.size() > 1) {
+        // common.LessProduct (sort.go:34-74) with the strings as ranks; the integer part runs on the device
+        std::vector<uint32_t> job_rank(metas.size()), pair_rank(pairs.size());
+        {
+            std::vector<std::pair<std::string, std::string>> keys;  // (file, base)
+            for (const JobMeta &m : metas) keys.emplace_back(o.files[m.file], m.base);
+            std::vector<std::pair<std::string, std::string>> uniq(keys);
+            std::sort(uniq.begin(), uniq.end());
+            uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+            for (size_t j = 0; j < metas.size(); j++)
+                job_rank[j] = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), keys[j]) - uniq.begin());
+            std::vector<std::string> ue;
+            for (const Pair &p : pairs) ue.push_back(p.id);
+            std::sort(ue.begin(), ue.end());
+            ue.erase(std::unique(ue.begin(), ue.end()), ue.end());
+            for (size_t i = 0; i < pairs.size(); i++)
+                pair_rank[i] = (uint32_t)(std::lower_bound(ue.begin(), ue.end(), pairs[i].id) - ue.begin());
+        }
+        std::vector<int64_t> job_off(metas.size());
+        for (size_t j = 0; j < metas.size(); j++) job_off[j] = metas[j].off;
+        auto tail_less = [&](const ipcr_product &a, const ipcr_product &b) {  // what LessProduct looks at after RevMM
+            std::string x, y;
+            append_idx_csv(x, a, 0); append_idx_csv(y, b, 0);
+            if (x != y) return x < y;
+            x.clear(); y.clear();
+            append_idx_csv(x, a, 1); append_idx_csv(y, b, 1);
+            if (x != y) return x < y;
+            const JobMeta &ma = metas[a.rec_idx], &mb = metas[b.rec_idx];
+            return (ma.chunked ? ma.base : ma.id) < (mb.chunked ? mb.base : mb.id);
+        };
+        if (metas.size() < (1u << 20) && pairs.size() < (1u << 19)) {
+            std::vector<uint8_t> tie(pod.size());
+            g.check(ipcr_gpu_sort_products(g.scratch, pod.data(), pod.size(), job_rank.data(), job_off.data(), metas.size(),
+                                           pair_rank.data(), pairs.size(), tie.data(), g.err, sizeof g.err));
+            for (size_t i = 0; i < pod.size();) {  // runs equal on every integer key (rare): finish on the host
+                size_t j = i + 1;
+                while (j < pod.size() && tie[j]) j++;
+                if (j - i > 1) std::stable_sort(pod.begin() + (long)i, pod.begin() + (long)j, tail_less);
+                i = j;
+            }
+        } else {
+            std::stable_sort(pod.begin(), pod.end(), [&](const ipcr_product &a, const ipcr_product &b) {
+                const JobMeta &ma = metas[a.rec_idx], &mb = metas[b.rec_idx];
+                if (job_rank[a.rec_idx] != job_rank[b.rec_idx]) return job_rank[a.rec_idx] < job_rank[b.rec_idx];
+                if (a.start + ma.off != b.start + mb.off) return a.start + ma.off < b.start + mb.off;
+                if (a.end + ma.off != b.end + mb.off) return a.end + ma.off < b.end + mb.off;
+                if (a.length != b.length) return a.length < b.length;
+                if (a.type != b.type) return a.type < b.type;
+                if (pair_rank[a.pair_idx] != pair_rank[b.pair_idx]) return pair_rank[a.pair_idx] < pair_rank[b.pair_idx];
+                if (a.fwd_mm != b.fwd_mm) return a.fwd_mm < b.fwd_mm;
+                if (a.rev_mm != b.rev_mm) return a.rev_mm < b.rev_mm;
+                return tail_less(a, b);
+            });
+        }
+    }
+    t_sort = secs(tq0, Clock::now());
+    const auto tw0 = Clock::now();
 
     // ---- writers ----
     std::string out;
@@ -484,6 +663,32 @@ int main(int argc, char **argv) {
             out += "source_file\tsequence_id\touter_experiment_id\touter_start\touter_end\touter_length\touter_type\t"
                    "inner_experiment_id\tinner_found\tinner_start\tinner_end\tinner_length\tinner_type\tinner_fwd_mm\tinner_rev_mm\n";
         else out += std::string(kHeader) + "\n";
+    }
+    if (plain) {  // output.FormatBaseRowTSV (rows.go:22-30) straight from the POD records
+        out.reserve(out.size() + pod.size() * 96);
+        for (const ipcr_product &pc : pod) {
+            const JobMeta &m = metas[pc.rec_idx];
+            out += o.files[m.file];
+            out += '\t';
+            out += m.chunked ? m.base : m.id;
+            out += '\t';
+            out += pairs[pc.pair_idx].id;
+            out += '\t';
+            append_int(out, pc.start + m.off);
+            out += '\t';
+            append_int(out, pc.end + m.off);
+            out += '\t';
+            append_int(out, pc.length);
+            out += pc.type == 0 ? "\tforward\t" : "\trevcomp\t";
+            append_int(out, pc.fwd_mm);
+            out += '\t';
+            append_int(out, pc.rev_mm);
+            out += '\t';
+            append_idx_csv(out, pc, 0);
+            out += '\t';
+            append_idx_csv(out, pc, 1);
+            out += '\n';
+        }
     }
     for (const Product &p : rows) {
         if (o.mode == "probe") {
@@ -503,9 +708,14 @@ int main(int argc, char **argv) {
         }
     }
     fwrite(out.data(), 1, out.size(), stdout);
+    t_write = secs(tw0, Clock::now());
+    if (getenv("IPCR_CLI_TIMING"))
+        fprintf(stderr, "[ipcr_gpu_cli] feeder %.3f s | scan (H2D + device + D2H) %.3f s | collect (coordinates, dedupe, rows; visitors) "
+                        "%.3f s | sort %.3f s | format + write %.3f s | %llu products from the device, %zu rows, %zu bytes\n",
+                t_open, t_scan, t_collect, t_sort, t_write, (unsigned long long)n_raw, plain ? pod.size() : rows.size(), out.size());
     if (gi.scratch) ipcr_gpu_scratch_destroy(gi.scratch);
     if (gi.panel) ipcr_gpu_panel_destroy(gi.panel);
     ipcr_gpu_scratch_destroy(g.scratch);
     ipcr_gpu_panel_destroy(g.panel);
-    return rows.empty() ? o.no_match_exit : 0;
+    return (plain ? pod.empty() : rows.empty()) ? o.no_match_exit : 0;
 }

@@ -298,6 +298,21 @@ def pair_blocks(cp: CompiledPanel, scratch: SimulationScratch, blocks, n_blocks:
     return _products(out, n.value, cp, seq_ids)
 
 
+def sort_products(scratch: SimulationScratch, raw, n: int, rec_rank: Sequence[int], pair_rank: Sequence[int],
+                  rec_off: Optional[Sequence[int]] = None):
+    """`--sort` on the device: orders the ctypes product array `raw` (n entries, in place) like
+    common.LessProduct given the string ranks; returns the tie flags (bytes)."""
+    L = _capi.lib()
+    rr = (C.c_uint32 * max(1, len(rec_rank)))(*rec_rank)
+    pr = (C.c_uint32 * max(1, len(pair_rank)))(*pair_rank)
+    ro = (C.c_int64 * max(1, len(rec_rank)))(*rec_off) if rec_off is not None else None
+    tie = (C.c_uint8 * max(1, n))()
+    err = _capi.errbuf()
+    _capi.check(L.ipcr_gpu_sort_products(scratch._h, raw, n, rr, ro, len(rec_rank), pr, len(pair_rank), tie, err,
+                                         len(err)), err)
+    return bytes(tie[:n])
+
+
 def synth_fill(scratch: SimulationScratch, tensor, first_pos: int, seed: int) -> None:
     """Fill a device uint8 tensor with the deterministic synthetic genome (bench input)."""
     err = _capi.errbuf()

@@ -260,3 +260,65 @@ def test_block_split_phase_packed_equals_oracle(oracle):
             if got is not None:
                 break
         assert [(p.sequence_id,) + _tuple(p) for p in got] == want, cfgd
+
+
+def test_device_sort_equals_less_product(oracle):
+    """ipcr_gpu_sort_products against common.LessProduct (hostlib.less_key restates internal/common/sort.go:34-74)
+    on a dense product list: several records whose IDs sort differently from their file order, chunk-style
+    offsets, circular wrap products, two pairs sharing one experiment ID (ties the device reports)."""
+    import ctypes as C
+
+    from ipcr_b200 import hostlib as HL
+    from ipcr_b200.engine import Engine as E
+
+    rng = random.Random(33)
+    # the two "alpha" pairs differ in two forward columns: a site one mismatch away from both ties on every
+    # integer key and differs only in its mismatch list -- the tie-break the device leaves to the caller
+    pairs = [Pair("zeta", "GATTAC", "TTGACC"), Pair("alpha", "ACGTTG", "CCATGG"), Pair("alpha", "ACCTTC", "CCATGG"),
+             Pair("mid", "TTGACC", "GATTAC")]
+    ids = ["chr10", "chr2", "chrX:100-900", "chr1", "b"]
+    lens = [30000, 21000, 800, 25000, 12000]
+    seqs = [bytes(H.random_genome(rng, n)) for n in lens]
+    eng = Engine(Config(max_mm=1, terminal_window=0, max_len=600, hit_cap=0, circular=True))
+    cp = eng.compile_panel(pairs)
+    sc = eng.new_simulation_scratch(cp)
+    arr = (_capi.SeqC * len(seqs))()
+    keep = []
+    for i, sq in enumerate(seqs):
+        b = C.create_string_buffer(sq, len(sq))
+        keep.append(b)
+        arr[i] = _capi.SeqC(C.cast(b, C.c_void_p).value, len(sq))
+    out = C.POINTER(_capi.ProductC)()
+    n = C.c_uint64()
+    err = _capi.errbuf()
+    _capi.check(_capi.lib().ipcr_gpu_scan_batch(cp._h, sc._h, arr, len(seqs), C.byref(out), C.byref(n), err, len(err)), err)
+    n = n.value
+    assert n > 5000
+    raw = (_capi.ProductC * n)()
+    C.memmove(raw, out, n * C.sizeof(_capi.ProductC))
+    prods = [E._product(raw[i], ids[raw[i].rec_idx], cp, None) for i in range(n)]
+    for p in prods:
+        p.source_file = "f.fa"
+    want = sorted(prods, key=HL.less_key)
+    # ranks of the strings, offsets of the chunk-style ID
+    split = [HL.split_chunk_suffix(x) for x in ids]
+    bases = [b if ok else x for (b, _o, ok), x in zip(split, ids)]
+    offs = [o if ok else 0 for (_b, o, ok) in split]
+    ub, up = sorted(set(bases)), sorted(set(p.id for p in pairs))
+    tie = D.sort_products(sc, raw, n, [ub.index(b) for b in bases], [up.index(p.id) for p in pairs], offs)
+    got = [E._product(raw[i], ids[raw[i].rec_idx], cp, None) for i in range(n)]
+    for p in got:
+        p.source_file = "f.fa"
+    # settle the reported ties like the caller has to
+    i = 0
+    while i < n:
+        j = i + 1
+        while j < n and tie[j]:
+            j += 1
+        if j - i > 1:
+            got[i:j] = sorted(got[i:j], key=HL.less_key)
+        i = j
+    key = lambda p: (p.sequence_id, p.experiment_id, p.type, p.start, p.end, p.length, p.fwd_mm, p.rev_mm,
+                     tuple(p.fwd_mismatch_idx), tuple(p.rev_mismatch_idx))
+    assert [key(p) for p in got] == [key(p) for p in want]
+    assert any(tie)
