@@ -68,6 +68,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bitparallel", action="store_true", help="skip the bit-parallel comparison pass")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1, sharded: how the site blocks meet -- peer = CUDA IPC peer memory read by the pairing kernel "
+                         "itself (falls back to nccl if the mapping fails), nccl = one all-gather")
     ap.add_argument("--no-e2e-fasta", action="store_true", help="skip the FASTA-on-disk -> sorted TSV measurement (N = 1)")
     ap.add_argument("--no-n-variant", action="store_true", help="skip the second value on a genome with scattered N (N = 1)")
     return ap.parse_args()
@@ -474,7 +477,54 @@ def run_ours(a):
     blocks = {"cap": 0, "mine": None, "all": None}
     host_slice = {}
 
+    # the exchange: peer memory (the pairing kernel reads every rank's block in place) or one NCCL all-gather
+    peer = {"x": None, "why": None}
+    last_raw = {"p": None}
+    if world > 1 and not weak and a.exchange == "peer":
+        try:
+            peer["x"] = D.PeerExchange(dist, sc, n_recs, rank, world, dev)
+        except Exception as ex:  # e.g. CUDA IPC not permitted in this container
+            peer["why"] = str(ex)
+        ok = torch.tensor([1 if peer["x"] is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok[0]) == 0:
+            peer["x"] = None
+
+    def step_peer(from_host=False):
+        launches = 0
+        while True:
+            if D.scratch_site_cap(sc) != peer["x"].site_cap:  # a block overflowed: bigger blocks, new mappings
+                peer["x"].close()
+                peer["x"] = D.PeerExchange(dist, sc, n_recs, rank, world, dev)
+            with torch.cuda.stream(ext):
+                evs[0].record()
+                blk = peer["x"].begin_step()
+                if from_host:
+                    host_slice["dcodes"].copy_(host_slice["codes"], non_blocking=True)
+                    host_slice["dinval"].copy_(host_slice["inval"], non_blocking=True)
+                    D.find_sites_block_packed(cp, sc, host_slice["dcodes"], host_slice["dinval"], host_slice["n"],
+                                              host_slice["segs"], n_recs, blk, peer["x"].site_cap)
+                else:
+                    D.find_sites_block(cp, sc, segments, n_recs, blk, peer["x"].site_cap)
+                peer["x"].publish()
+                launches += sc.timing()["kernel_launches"] + 1
+                evs[1].record()
+                evs[2].record()
+                res = peer["x"].pair(cp, lens)
+                evs[3].record()
+            if res is not None:
+                break
+        evs[3].synchronize()
+        t = dict(sc.timing())
+        t["kernel_launches"] = launches + 1
+        t["gather_ms"] = 0.0
+        t["find_total_ms"] = evs[0].elapsed_time(evs[1])
+        last_raw["p"] = res[0]
+        return res[1], evs[0].elapsed_time(evs[3]), t
+
     def step_multi(from_host=False):
+        if peer["x"] is not None:
+            return step_peer(from_host)
         launches = 0
         while True:
             site_cap = D.scratch_site_cap(sc)
@@ -511,12 +561,23 @@ def run_ours(a):
         t["kernel_launches"] = launches + 1
         t["gather_ms"] = evs[1].elapsed_time(evs[2])
         t["find_total_ms"] = evs[0].elapsed_time(evs[1])
+        last_raw["p"] = res[0]
         return res[1], evs[0].elapsed_time(evs[3]), t
 
     step = step_single if world == 1 or weak else step_multi
 
     for _ in range(max(3, a.warmup)):
         n_prod, _ms, tm = step()
+    if peer["x"] is not None:  # the two exchanges must hand stage 2 the same sites: identical product bytes
+        import ctypes
+        n_a, _ms, _t = step()
+        bytes_peer = ctypes.string_at(last_raw["p"], n_a * 64)
+        px, peer["x"] = peer["x"], None
+        n_b, _ms, _t = step()
+        bytes_nccl = ctypes.string_at(last_raw["p"], n_b * 64)
+        peer["x"] = px
+        if bytes_peer != bytes_nccl:
+            raise RuntimeError(f"peer exchange and NCCL all-gather disagree ({n_a} vs {n_b} products)")
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()  # NVML start-up takes tens of ms: before the barrier, or the other ranks wait for it in step 1
@@ -696,6 +757,10 @@ def run_ours(a):
         "stage_ms": {k: last[k] for k in ("pack_ms", "filter_ms", "verify_ms", "pair_ms", "d2h_ms")} if last else None,
         "candidates": last["candidates"] if last else None, "sites": last["sites"] if last else None,
         "rank0_ms": ({k: last.get(k) for k in ("find_total_ms", "gather_ms")} if last and world > 1 else None),
+        "exchange": (None if world == 1 or weak else
+                     ("peer memory: every rank's pairing kernel reads the other ranks' site blocks in place (CUDA IPC over "
+                      "NVLink, release/acquire on a step counter); no collective on the data path" if peer["x"] is not None
+                      else "one NCCL all-gather of the site blocks" + (f" (peer mapping failed: {peer['why']})" if peer["why"] else ""))),
         "filter_path": {0: "table-driven bit-parallel", 1: "NVRTC bit-parallel", 2: "seed index"}.get(path),
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }

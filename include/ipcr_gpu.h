@@ -255,6 +255,29 @@ int ipcr_gpu_pair_blocks(ipcr_panel *p, ipcr_scratch *s, const void *d_blocks, u
                          uint64_t site_cap, const uint64_t *rec_lens, size_t n_recs,
                          const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen);
 
+/* ---- peer exchange: the same split phase with the collective FUSED into the pairing kernel ------------
+ * One process per GPU.  Every rank owns a double-buffered site block in its own device memory and exports it
+ * through CUDA IPC; the other ranks map it (NVLink peer access).  A step is
+ *   d_block = ipcr_gpu_peer_begin_step(s);  ipcr_gpu_find_sites_block[_packed](.., d_block, site_cap);
+ *   ipcr_gpu_peer_publish(s);  ipcr_gpu_pair_peers(..)
+ * on EVERY rank: stage 1 ends by publishing the step number in the block's control word (st.release.sys), the
+ * pairing kernel of every rank waits for all step numbers (ld.acquire.sys) and reads the peers' sites straight
+ * out of their memories -- no collective library, no copy, no host between stage 1 and stage 2.  Double buffering
+ * makes the exchange safe without a barrier: a rank can only overwrite a block two steps later, which needs its
+ * own pairing of the step in between, which needs every peer's NEXT publication, which follows their pairing of
+ * this step.  A rank that never publishes makes the others fail after 4 s instead of hanging.
+ * handle_out / handles: IPCR_GPU_PEER_HANDLE_BYTES per rank, exchanged by the caller (any transport). */
+#define IPCR_GPU_PEER_HANDLE_BYTES 64
+int ipcr_gpu_peer_create(ipcr_scratch *s, size_t n_recs, uint64_t site_cap, void *handle_out, char *err, size_t errlen);
+int ipcr_gpu_peer_open(ipcr_scratch *s, const void *handles, uint32_t n_ranks, uint32_t my_rank, char *err, size_t errlen);
+void *ipcr_gpu_peer_begin_step(ipcr_scratch *s);
+int ipcr_gpu_peer_publish(ipcr_scratch *s, char *err, size_t errlen);
+/* like ipcr_gpu_pair_blocks (0 done / 1 error / 2 run the step again on every rank; when
+ * ipcr_gpu_scratch_site_cap grew, create + exchange + open again first) */
+int ipcr_gpu_pair_peers(ipcr_panel *p, ipcr_scratch *s, const uint64_t *rec_lens, size_t n_recs,
+                        const ipcr_product **out, uint64_t *n_out, char *err, size_t errlen);
+void ipcr_gpu_peer_close(ipcr_scratch *s);
+
 /* ---- native FASTA feeder (replaces core/fasta for the hot path) ------ */
 /* Reads and normalises a FASTA file exactly like the reference reader (header ID = first
  * token, TrimSpace per line, a-z upper-cased, gzip by magic/suffix; core/fasta/scan.go,

@@ -118,7 +118,9 @@ SYMBOLS = [
     "ipcr_gpu_abi_version", "ipcr_gpu_device_count", "ipcr_gpu_init", "ipcr_gpu_set_device", "ipcr_gpu_num_devices",
     "ipcr_gpu_site_block_bytes", "ipcr_gpu_scratch_site_cap", "ipcr_gpu_scratch_stream",
     "ipcr_gpu_find_sites_block", "ipcr_gpu_pair_blocks", "ipcr_gpu_find_sites_block_packed",
-    "ipcr_gpu_sort_products", "ipcr_gpu_fasta_from_memory", "ipcr_gpu_fasta_is_packed", "ipcr_gpu_packed_words", "ipcr_gpu_pack_host",
+    "ipcr_gpu_sort_products", "ipcr_gpu_fasta_from_memory",
+    "ipcr_gpu_peer_create", "ipcr_gpu_peer_open", "ipcr_gpu_peer_begin_step", "ipcr_gpu_peer_publish",
+    "ipcr_gpu_pair_peers", "ipcr_gpu_peer_close", "ipcr_gpu_fasta_is_packed", "ipcr_gpu_packed_words", "ipcr_gpu_pack_host",
     "ipcr_gpu_panel_create", "ipcr_gpu_panel_destroy", "ipcr_gpu_panel_num_pairs",
     "ipcr_gpu_panel_num_orientations", "ipcr_gpu_panel_have", "ipcr_gpu_panel_set_jit", "ipcr_gpu_panel_set_filter",
     "ipcr_gpu_scratch_create", "ipcr_gpu_scratch_destroy",
@@ -194,6 +196,12 @@ def lib():
     sig("ipcr_gpu_packed_words", None, U64, P(U64), P(U64))
     sig("ipcr_gpu_pack_host", C.c_int, V, U64, V, V, C.c_int)
     sig("ipcr_gpu_find_sites_block_packed", C.c_int, V, V, V, V, U64, P(PackedSegmentC), SZ, SZ, C.c_int, V, U64, *ERR)
+    sig("ipcr_gpu_peer_create", C.c_int, V, SZ, U64, V, *ERR)
+    sig("ipcr_gpu_peer_open", C.c_int, V, V, C.c_uint32, C.c_uint32, *ERR)
+    sig("ipcr_gpu_peer_begin_step", V, V)
+    sig("ipcr_gpu_peer_publish", C.c_int, V, *ERR)
+    sig("ipcr_gpu_pair_peers", C.c_int, V, V, P(U64), SZ, P(P(ProductC)), P(U64), *ERR)
+    sig("ipcr_gpu_peer_close", None, V)
     sig("ipcr_gpu_sort_products", C.c_int, V, P(ProductC), U64, P(C.c_uint32), P(C.c_int64), SZ, P(C.c_uint32), SZ,
         P(C.c_uint8), *ERR)
     sig("ipcr_gpu_fasta_close", None, V)

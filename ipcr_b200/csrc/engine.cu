@@ -318,6 +318,12 @@ struct ipcr_scratch {
     cudaEvent_t done_ev = nullptr;              // peer: its block has arrived on the primary device
     bool own_laid = false;                      // multi-device retry: the slice is already resident
     ipcr::DevBuf seg_reset_dummy, chunk_ctr;
+    // peer exchange (one process per GPU): own double-buffered block, exported through CUDA IPC; the peers' mappings
+    ipcr::DevBuf peer_buf, peer_tab[2];
+    std::vector<void *> peer_map;  // cudaIpcOpenMemHandle results (NULL for this rank)
+    uint32_t peer_n = 0, peer_rank = 0;
+    uint64_t peer_step = 0, peer_cap = 0, peer_bb = 0;
+    size_t peer_recs = 0;
     ipcr::DevBuf sp_in, sp_out, sp_k[4], sp_ka, sp_kb, sp_ia, sp_ib, sp_tie, sp_rr, sp_ro, sp_pr;  // ipcr_gpu_sort_products
     std::vector<std::unique_ptr<ipcr::GenomeData>> slab_g;  // streamed slabs: packed codes per slab (all in flight at once)
     std::vector<cudaEvent_t> slab_t;
@@ -1430,7 +1436,8 @@ static void stage1_async(ipcr_scratch *s, GenomeData &g, int variant, uint8_t *d
 // Stage 2 of the chain over `n_blocks` site blocks + the readback of [header | products].
 static void pair_async(ipcr_scratch *s, const uint8_t *d_blocks, uint32_t n_blocks, uint64_t block_bytes,
                        uint64_t block_site_cap, const ipcr_record_info *recs, size_t n_recs,
-                       const ipcr_record_info *d_recs = nullptr) {
+                       const ipcr_record_info *d_recs = nullptr, const uint8_t *const *d_peer_blocks = nullptr,
+                       uint64_t wait_seq = 0) {
     const Panel &h = s->panel->host;
     cudaStream_t st = s->stream;
     const size_t n_pairs = h.roles.size();
@@ -1451,6 +1458,12 @@ static void pair_async(ipcr_scratch *s, const uint8_t *d_blocks, uint32_t n_bloc
     s->h_products.ensure((prod_cap + 1) * sizeof(ipcr_product));
     PairSmallArgs a{};
     a.blocks = d_blocks;
+    a.peer_blocks = d_peer_blocks;
+    a.wait_seq = wait_seq;
+    if (d_peer_blocks) {
+        s->gather.ensure((size_t)n_blocks * block_bytes + 64);
+        a.stage = s->gather.as<uint8_t>();
+    }
     a.n_blocks = n_blocks;
     a.block_bytes = block_bytes;
     a.ctl_bytes = block_ctl_bytes(n_recs);
@@ -1478,7 +1491,7 @@ static void pair_async(ipcr_scratch *s, const uint8_t *d_blocks, uint32_t n_bloc
     a.use_list = s->tables->use_list.as<uint32_t>();
     a.header = s->products.as<PairHeader>();
     // shared memory: 8192 sort words + either the final keys (general mode) or the two bucket tables
-    constexpr size_t kPairSmemMax = 226 * 1024;
+    constexpr size_t kPairSmemMax = 222 * 1024;  // + ~1.5 KB of static shared memory in the kernel: 227 KB per CTA at most
     const size_t words = (size_t)kPairSmallMax * sizeof(unsigned long long);
     const uint64_t n_buckets = (uint64_t)n_recs * h.orients.size();
     size_t smem = 2 * words;
@@ -1509,7 +1522,8 @@ enum ChainResult { kChainDone, kChainRetry, kChainTooDirty };
 // kChainRetry: a capacity (or the plan variant) was adjusted; run stage 1 again if *redo_stage1,
 // else only pair_async.  Larger site lists are paired by the multi-kernel path right here.
 static ChainResult chain_finish(ipcr_scratch *s, const uint8_t *d_blocks, uint32_t n_blocks, uint64_t block_bytes,
-                                ipcr_record_info *recs, size_t n_recs, uint64_t *n_prod, bool *redo_stage1) {
+                                ipcr_record_info *recs, size_t n_recs, uint64_t *n_prod, bool *redo_stage1,
+                                const uint8_t *const *d_peer_blocks = nullptr) {
     const Panel &h = s->panel->host;
     cudaStream_t st = s->stream;
     CU(cudaStreamSynchronize(st));
@@ -1527,6 +1541,8 @@ static ChainResult chain_finish(ipcr_scratch *s, const uint8_t *d_blocks, uint32
                 (hd0.pad[1] >> 16) * 64u);
     s->timing.candidates = hd.n_cand;
     s->timing.sites = hd.n_sites;
+    if (hd.flags & kPairPeerTimeout)
+        throw Error("peer exchange: a rank did not publish its site block within 4 s (did every rank run stage 1 of this step?)");
     if (hd.n_dirty > seed_dirty_max()) return kChainTooDirty;
     if (hd.flags & kPairStage1Overflow) {
         s->seed_cap_hint = std::max(s->seed_cap_hint, hd.n_cand + hd.n_cand / 4 + 1024);
@@ -1555,9 +1571,9 @@ static ChainResult chain_finish(ipcr_scratch *s, const uint8_t *d_blocks, uint32
         if (hd.n_sites >= (1ull << 32)) throw Error("too many primer sites for one pairing pass");
         const uint64_t ctl_bytes = block_ctl_bytes(n_recs);
         const ipcr_site *d_sites = reinterpret_cast<const ipcr_site *>(d_blocks + ctl_bytes);
-        if (n_blocks > 1) {
+        if (n_blocks > 1 || d_peer_blocks) {
             s->sites.ensure(hd.n_sites * sizeof(ipcr_site));
-            UnpackArgs u{d_blocks, n_blocks, block_bytes, ctl_bytes, s->sites.as<ipcr_site>(), hd.n_sites};
+            UnpackArgs u{d_blocks, d_peer_blocks, n_blocks, block_bytes, ctl_bytes, s->sites.as<ipcr_site>(), hd.n_sites};
             k_unpack_blocks<<<(unsigned)s->sm_count, 256, 0, st>>>(u);
             check_launch("k_unpack_blocks");
             s->launches++;
@@ -1763,6 +1779,8 @@ void ipcr_gpu_scratch_destroy(ipcr_scratch *s) {
     }
     s->peers.clear();
     cudaSetDevice(s->device);
+    for (void *m : s->peer_map)
+        if (m) cudaIpcCloseMemHandle(m);
     delete s;
 }
 
@@ -2302,6 +2320,122 @@ int ipcr_gpu_pair_blocks(ipcr_panel *p, ipcr_scratch *s, const void *d_blocks, u
     }
     throw Error("stage 2 did not converge");
     ABI_CATCH(1)
+}
+
+// ---- peer exchange (one process per GPU; the collective is fused into the pairing kernel) ----
+static void peer_close(ipcr_scratch *s) {
+    for (void *m : s->peer_map)
+        if (m) cudaIpcCloseMemHandle(m);
+    s->peer_map.clear();
+    s->peer_n = 0;
+}
+
+int ipcr_gpu_peer_create(ipcr_scratch *s, size_t n_recs, uint64_t site_cap, void *handle_out, char *err, size_t errlen) {
+    ABI_TRY
+    if (!s || !handle_out) throw Error("scratch / handle is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == IPCR_GPU_PEER_HANDLE_BYTES, "IPC handle size");
+    begin_call(s);
+    peer_close(s);
+    s->peer_recs = n_recs;
+    s->peer_cap = site_cap;
+    s->peer_bb = block_bytes_for(n_recs, site_cap);
+    s->peer_step = 0;
+    s->peer_buf.release();  // a fresh allocation: an exported one cannot be resized under its importers
+    s->peer_buf.ensure(2 * s->peer_bb);
+    CU(cudaMemsetAsync(s->peer_buf.p, 0, 2 * s->peer_bb, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->peer_buf.p));
+    memcpy(handle_out, &h, sizeof h);
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_peer_open(ipcr_scratch *s, const void *handles, uint32_t n_ranks, uint32_t my_rank, char *err, size_t errlen) {
+    ABI_TRY
+    if (!s || !handles || !s->peer_buf.p) throw Error("ipcr_gpu_peer_create first");
+    if (n_ranks == 0 || n_ranks > kPairMaxBlocks || my_rank >= n_ranks) throw Error(fmt("1..%u ranks", kPairMaxBlocks));
+    bind(s);
+    peer_close(s);
+    s->peer_map.assign(n_ranks, nullptr);
+    std::vector<const uint8_t *> tab[2];
+    for (uint32_t r = 0; r < n_ranks; r++) {
+        const uint8_t *base = s->peer_buf.as<uint8_t>();
+        if (r != my_rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, static_cast<const uint8_t *>(handles) + (size_t)r * sizeof h, sizeof h);
+            void *m = nullptr;
+            CU(cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess));
+            s->peer_map[r] = m;
+            base = static_cast<const uint8_t *>(m);
+        }
+        tab[0].push_back(base);
+        tab[1].push_back(base + s->peer_bb);
+    }
+    for (int k = 0; k < 2; k++) upload(s->peer_tab[k], tab[k].data(), tab[k].size() * sizeof(void *), s->stream);
+    CU(cudaStreamSynchronize(s->stream));
+    s->peer_n = n_ranks;
+    s->peer_rank = my_rank;
+    s->peer_step = 0;
+    return 0;
+    ABI_CATCH(1)
+}
+
+void *ipcr_gpu_peer_begin_step(ipcr_scratch *s) {
+    if (!s || !s->peer_n) return nullptr;
+    s->peer_step++;
+    return s->peer_buf.as<uint8_t>() + (s->peer_step & 1ull) * s->peer_bb;
+}
+
+int ipcr_gpu_peer_publish(ipcr_scratch *s, char *err, size_t errlen) {
+    ABI_TRY
+    if (!s || !s->peer_n || s->peer_step == 0) throw Error("no peer step in progress");
+    bind(s);
+    k_block_publish<<<1, 1, 0, s->stream>>>(s->peer_buf.as<uint8_t>() + (s->peer_step & 1ull) * s->peer_bb, s->peer_step);
+    check_launch("k_block_publish");
+    s->launches++;
+    s->inflight = true;
+    return 0;
+    ABI_CATCH(1)
+}
+
+int ipcr_gpu_pair_peers(ipcr_panel *p, ipcr_scratch *s, const uint64_t *rec_lens, size_t n_recs, const ipcr_product **out,
+                        uint64_t *n_out, char *err, size_t errlen) {
+    ABI_TRY
+    if (!p || !s || s->panel != p || (!rec_lens && n_recs)) throw Error("bad panel/scratch");
+    if (!s->peer_n || s->peer_step == 0) throw Error("no peer step in progress");
+    if (n_recs != s->peer_recs) throw Error("record count differs from ipcr_gpu_peer_create");
+    if (out) *out = nullptr;
+    if (n_out) *n_out = 0;
+    bind(s);
+    std::vector<ipcr_record_info> rinfo(n_recs, ipcr_record_info{});
+    for (size_t r = 0; r < n_recs; r++) rinfo[r].len = rec_lens[r];
+    if (!chain_ok(s, rinfo.data(), n_recs)) throw Error("ipcr_gpu_pair_peers needs a seed-index panel");
+    const uint8_t *const *tab = s->peer_tab[s->peer_step & 1ull].as<const uint8_t *>();
+    const uint8_t *own = s->peer_buf.as<uint8_t>() + (s->peer_step & 1ull) * s->peer_bb;
+    for (int again = 0; again < 4; again++) {
+        pair_async(s, own, s->peer_n, s->peer_bb, s->peer_cap, rinfo.data(), n_recs, nullptr, tab, s->peer_step);
+        bool redo = false;
+        uint64_t n = 0;
+        const ChainResult r = chain_finish(s, own, s->peer_n, s->peer_bb, rinfo.data(), n_recs, &n, &redo, tab);
+        if (r == kChainTooDirty)
+            throw Error("input too dirty for the seed index: use the host-gathered split phase (ipcr_gpu_find_sites_device)");
+        if (r == kChainDone) {
+            chain_timing(s, n, false);
+            if (out) *out = s->out_ptr;
+            if (n_out) *n_out = n;
+            return 0;
+        }
+        if (redo) return 2;
+    }
+    throw Error("stage 2 did not converge");
+    ABI_CATCH(1)
+}
+
+void ipcr_gpu_peer_close(ipcr_scratch *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    peer_close(s);
 }
 
 int ipcr_gpu_sort_products(ipcr_scratch *s, ipcr_product *products, uint64_t n, const uint32_t *rec_rank,

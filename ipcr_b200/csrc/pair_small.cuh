@@ -30,7 +30,7 @@ struct Stage1Ctl {
     unsigned long long cand_cap, dirty_cap, site_cap;
     uint32_t variant;               // plan variant stage 1 ran with
     uint32_t n_recs;
-    unsigned long long pad[1];
+    unsigned long long seq;         // peer exchange: step number published once the block is complete
 };
 static_assert(sizeof(Stage1Ctl) == 64, "Stage1Ctl is one 64-byte block");
 
@@ -44,12 +44,30 @@ __host__ __device__ __forceinline__ uint64_t block_bytes_for(uint64_t n_recs, ui
 // first kernel of the chain: clears the counters and flags, records the capacities
 __global__ void __launch_bounds__(256)
 k_block_init(uint8_t *block, Stage1Ctl init, uint32_t *seg_reset, uint32_t n_segs, const uint8_t *rr_init) {
-    if (threadIdx.x == 0) *reinterpret_cast<Stage1Ctl *>(block) = init;
+    if (threadIdx.x == 0) {
+        Stage1Ctl *ctl = reinterpret_cast<Stage1Ctl *>(block);
+        init.seq = ctl->seq;  // the peer exchange's sequence number outlives the re-initialisation
+        *ctl = init;
+    }
     uint8_t *rr = block + sizeof(Stage1Ctl);
     const uint32_t rr_bytes = (uint32_t)(block_ctl_bytes(init.n_recs) - sizeof(Stage1Ctl));
     // rr_init: per-record flags the host already knows (packed input: the feeder saw every byte)
     for (uint32_t i = threadIdx.x; i < rr_bytes; i += blockDim.x) rr[i] = (rr_init && i < init.n_recs) ? rr_init[i] : 0u;
     for (uint32_t i = threadIdx.x; i < n_segs; i += blockDim.x) seg_reset[i] = 0u;
+}
+
+// last kernel of stage 1 in the peer exchange: every write of the chain is complete (stream order); make the
+// block visible system-wide and publish the step number the peers' pairing kernels are spinning on
+__global__ void k_block_publish(uint8_t *block, unsigned long long seq) {
+    __threadfence_system();
+    unsigned long long *p = &reinterpret_cast<Stage1Ctl *>(block)->seq;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(seq) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // flags of PairHeader.flags
@@ -60,6 +78,7 @@ constexpr uint32_t kPairProdOverflow = 8u;    // prod_cap too small (n_prod is v
 constexpr uint32_t kPairStage1Overflow = 16u; // a block's candidate or dirty-window list overflowed
 constexpr uint32_t kPairAnyReset = 32u;       // some record holds a reset byte
 constexpr uint32_t kPairMixedVariant = 64u;   // blocks ran different plan variants (informational)
+constexpr uint32_t kPairPeerTimeout = 128u;   // a peer never published its block (peer exchange)
 
 struct PairHeader {
     unsigned long long n_sites, n_final, n_tasks, n_prod;
@@ -72,7 +91,12 @@ static_assert(sizeof(PairHeader) == 64, "PairHeader is read back as one 64-byte 
 static_assert(sizeof(PairHeader) == sizeof(ipcr_product), "products follow the header in one buffer");
 
 struct PairSmallArgs {
+    // blocks back to back in local memory (blocks + b * block_bytes), or -- peer exchange -- one pointer per rank
+    // into that rank's own device memory (mapped through CUDA IPC / peer access, read over NVLink)
     const uint8_t *blocks;
+    const uint8_t *const *peer_blocks;  // device array of n_blocks pointers, or NULL
+    unsigned long long wait_seq;        // peer exchange: spin until every block's seq == wait_seq (0 = do not wait)
+    uint8_t *stage;                     // peer exchange: local copy of the published blocks (n_blocks * block_bytes)
     uint32_t n_blocks;
     uint64_t block_bytes, ctl_bytes, block_site_cap;
     const OrientDev *orients;
@@ -183,7 +207,8 @@ constexpr int kPairPerThread = kPairSmallMax / 1024;
 // no per-entry or per-task arrays.  Shared memory: sk[8192] words, off[nb + 1], foff[nb + 1].
 // Returns false (nothing written) when a bucket holds more than kBucketMaxSize sites.
 __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArgs j, PairHeader &h, uint32_t n,
-                                                 unsigned long long *sk, const unsigned long long *s_boff, uint32_t *wsum) {
+                                                 unsigned long long *sk, const unsigned long long *s_boff,
+                                                 const uint8_t *const *s_blk, uint32_t *wsum) {
     const KeyLayout kl = j.kl;
     const uint32_t nb = j.n_recs * kl.n_orient;
     uint32_t *off = reinterpret_cast<uint32_t *>(sk + kPairSmallMax);
@@ -200,7 +225,7 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
     auto site_at = [&](uint32_t i) -> const ipcr_site & {
         uint32_t b = 0;
         while (b + 1 < a.n_blocks && (unsigned long long)i >= s_boff[b + 1]) b++;
-        return reinterpret_cast<const ipcr_site *>(a.blocks + (uint64_t)b * a.block_bytes + a.ctl_bytes)[i - (uint32_t)s_boff[b]];
+        return reinterpret_cast<const ipcr_site *>(s_blk[b] + a.ctl_bytes)[i - (uint32_t)s_boff[b]];
     };
     // ---- 1. keys; slot inside the bucket (arrival order, fixed by the rank pass below) ----
     unsigned long long word[kPairPerThread];
@@ -376,13 +401,75 @@ k_pair_small(PairSmallArgs a) {
     __shared__ uint32_t wsum[33];
     __shared__ uint32_t s_total, s_flags, s_minvar;
     __shared__ unsigned long long s_boff[kPairMaxBlocks + 1], s_ncand, s_ndirty;
+    __shared__ const uint8_t *s_blk[kPairMaxBlocks];
+    __shared__ unsigned long long s_ns[kPairMaxBlocks];
+    __shared__ uint32_t s_timeout;
     JoinArgs j = a.j;
+    if (threadIdx.x == 0) s_timeout = 0u;
+    if (threadIdx.x < a.n_blocks)
+        s_blk[threadIdx.x] = a.peer_blocks ? a.peer_blocks[threadIdx.x] : a.blocks + (uint64_t)threadIdx.x * a.block_bytes;
+    __syncthreads();
+    // ---- peer exchange: the collective is fused into this kernel.  Thread b waits until rank b has published
+    // the block of this step (ld.acquire.sys on its control word, over NVLink for a remote rank); everything read
+    // afterwards comes straight out of the owners' memories. ----
+    if (a.wait_seq != 0ull) {
+        if (threadIdx.x < a.n_blocks) {
+            const unsigned long long *p = &reinterpret_cast<const Stage1Ctl *>(s_blk[threadIdx.x])->seq;
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+            while (ld_acquire_sys_u64(p) != a.wait_seq) {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 4000000000ull) {  // 4 s: a peer died or never ran stage 1
+                    atomicOr(&s_timeout, 1u);
+                    break;
+                }
+            }
+            s_ns[threadIdx.x] = reinterpret_cast<const Stage1Ctl *>(s_blk[threadIdx.x])->n_sites;  // every rank in parallel
+        }
+        __syncthreads();
+        if (s_timeout) {
+            if (threadIdx.x == 0) {
+                PairHeader h{};
+                h.flags = kPairPeerTimeout;
+                *a.header = h;
+            }
+            return;
+        }
+        // Pull what was published -- control words, record flags, the sites actually present -- into local
+        // memory with ONE wave of independent 16-byte loads over NVLink (every thread has a few in flight), instead
+        // of paying the remote latency once per dependent access in the phases below.
+        if (a.stage) {
+            __shared__ uint32_t s_words[kPairMaxBlocks + 1];
+            if (threadIdx.x == 0) {
+                uint32_t acc = 0;
+                for (uint32_t b = 0; b < a.n_blocks; b++) {
+                    s_words[b] = acc;
+                    const unsigned long long ns = s_ns[b];
+                    const uint64_t have = ns < a.block_site_cap ? ns : a.block_site_cap;
+                    acc += (uint32_t)((a.ctl_bytes + have * sizeof(ipcr_site) + 15ull) >> 4);
+                }
+                s_words[a.n_blocks] = acc;
+            }
+            __syncthreads();
+            const uint32_t total = s_words[a.n_blocks];
+            for (uint32_t g = threadIdx.x; g < total; g += blockDim.x) {
+                uint32_t b = 0;
+                while (b + 1 < a.n_blocks && g >= s_words[b + 1]) b++;
+                const uint32_t w = g - s_words[b];
+                reinterpret_cast<uint4 *>(a.stage + (uint64_t)b * a.block_bytes)[w] = reinterpret_cast<const uint4 *>(s_blk[b])[w];
+            }
+            __syncthreads();
+            if (threadIdx.x < a.n_blocks) s_blk[threadIdx.x] = a.stage + (uint64_t)threadIdx.x * a.block_bytes;
+            __syncthreads();
+        }
+    }
     // ---- block headers: counts, overflow flags, merged per-record reset flags ----
     if (threadIdx.x == 0) {
         unsigned long long off = 0ull, nc = 0ull, nd = 0ull;
         uint32_t fl = 0u, vmin = 0xFFFFFFFFu, vmax = 0u;
         for (uint32_t b = 0; b < a.n_blocks; b++) {
-            const Stage1Ctl *ctl = reinterpret_cast<const Stage1Ctl *>(a.blocks + (uint64_t)b * a.block_bytes);
+            const Stage1Ctl *ctl = reinterpret_cast<const Stage1Ctl *>(s_blk[b]);
             s_boff[b] = off;
             off += ctl->n_sites;
             if (ctl->n_sites > a.block_site_cap || ctl->n_sites > ctl->site_cap) fl |= kPairSitesLost;
@@ -402,7 +489,7 @@ k_pair_small(PairSmallArgs a) {
     uint32_t my_reset = 0u;
     for (uint32_t r = threadIdx.x; r < j.n_recs; r += blockDim.x) {
         uint8_t v = 0u;
-        for (uint32_t b = 0; b < a.n_blocks; b++) v |= a.blocks[(uint64_t)b * a.block_bytes + sizeof(Stage1Ctl) + r];
+        for (uint32_t b = 0; b < a.n_blocks; b++) v |= s_blk[b][sizeof(Stage1Ctl) + r];
         a.rec_reset[r] = v;
         my_reset |= v;
     }
@@ -422,7 +509,7 @@ k_pair_small(PairSmallArgs a) {
         return;
     }
     if (j.n_recs * j.kl.n_orient <= a.bucket_cap) {
-        if (pair_bucket_mode(a, j, h, n, sk, s_boff, wsum)) {
+        if (pair_bucket_mode(a, j, h, n, sk, s_boff, s_blk, wsum)) {
             if (threadIdx.x == 0) *a.header = h;
             return;
         }
@@ -431,7 +518,7 @@ k_pair_small(PairSmallArgs a) {
     auto site_at = [&](uint32_t i) -> const ipcr_site & {
         uint32_t b = 0;
         while (b + 1 < a.n_blocks && (unsigned long long)i >= s_boff[b + 1]) b++;
-        return reinterpret_cast<const ipcr_site *>(a.blocks + (uint64_t)b * a.block_bytes + a.ctl_bytes)[i - (uint32_t)s_boff[b]];
+        return reinterpret_cast<const ipcr_site *>(s_blk[b] + a.ctl_bytes)[i - (uint32_t)s_boff[b]];
     };
     const KeyLayout kl = j.kl;
     uint32_t m = 2;
@@ -556,6 +643,7 @@ k_pair_small(PairSmallArgs a) {
 // the multi-kernel stage 2 wants one contiguous site list: copies the blocks' sites back to back
 struct UnpackArgs {
     const uint8_t *blocks;
+    const uint8_t *const *peer_blocks;
     uint32_t n_blocks;
     uint64_t block_bytes, ctl_bytes;
     ipcr_site *sites;
@@ -566,7 +654,7 @@ __global__ void __launch_bounds__(256)
 k_unpack_blocks(UnpackArgs a) {
     unsigned long long off = 0ull;
     for (uint32_t bk = 0; bk < a.n_blocks; bk++) {
-        const uint8_t *blk = a.blocks + (uint64_t)bk * a.block_bytes;
+        const uint8_t *blk = a.peer_blocks ? a.peer_blocks[bk] : a.blocks + (uint64_t)bk * a.block_bytes;
         const unsigned long long n = reinterpret_cast<const Stage1Ctl *>(blk)->n_sites;
         const ipcr_site *ss = reinterpret_cast<const ipcr_site *>(blk + a.ctl_bytes);
         for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;

@@ -238,8 +238,61 @@ def find_sites_block(cp: CompiledPanel, scratch: SimulationScratch, segments: Se
     arr, keep, _nr = Genome._segments(segments)
     err = _capi.errbuf()
     _capi.check(_capi.lib().ipcr_gpu_find_sites_block(cp._h, scratch._h, arr, len(segments), n_recs,
-                                                      1 if force_raw else 0, int(block.data_ptr()), site_cap,
+                                                      1 if force_raw else 0, _ptr(block), site_cap,
                                                       err, len(err)), err)
+
+
+def _ptr(x) -> int:
+    """device address of a tensor, or the integer address itself"""
+    return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+
+
+class PeerExchange:
+    """The peer-memory exchange of site blocks (include/ipcr_gpu.h, "peer exchange"): every rank exports its
+    double-buffered block through CUDA IPC, the handles travel once through torch.distributed, and from then on
+    stage 2 reads the peers' blocks straight over NVLink -- no collective on the data path."""
+
+    def __init__(self, dist, scratch: SimulationScratch, n_recs: int, rank: int, world: int, device):
+        import torch
+
+        self.scratch, self.n_recs, self.rank, self.world = scratch, n_recs, rank, world
+        self.site_cap = scratch_site_cap(scratch)
+        L = _capi.lib()
+        handle = C.create_string_buffer(64)
+        err = _capi.errbuf()
+        _capi.check(L.ipcr_gpu_peer_create(scratch._h, n_recs, self.site_cap, handle, err, len(err)), err)
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(device)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine)
+        raw = bytes(allh.cpu().numpy().tobytes())
+        _capi.check(L.ipcr_gpu_peer_open(scratch._h, raw, world, rank, err, len(err)), err)
+        dist.barrier()  # nobody starts a step before every rank has mapped every block
+
+    def begin_step(self) -> int:
+        p = _capi.lib().ipcr_gpu_peer_begin_step(self.scratch._h)
+        if not p:
+            raise _capi.GpuError("peer exchange is not set up")
+        return int(p)
+
+    def publish(self) -> None:
+        err = _capi.errbuf()
+        _capi.check(_capi.lib().ipcr_gpu_peer_publish(self.scratch._h, err, len(err)), err)
+
+    def pair(self, cp: CompiledPanel, rec_lens: Sequence[int]):
+        """(ctypes product pointer, count), or None when the step has to run again on every rank."""
+        L = _capi.lib()
+        lens = (C.c_uint64 * max(1, len(rec_lens)))(*rec_lens)
+        out = C.POINTER(_capi.ProductC)()
+        n = C.c_uint64()
+        err = _capi.errbuf()
+        rc = L.ipcr_gpu_pair_peers(cp._h, self.scratch._h, lens, len(rec_lens), C.byref(out), C.byref(n), err, len(err))
+        if rc == 2:
+            return None
+        _capi.check(rc, err)
+        return out, n.value
+
+    def close(self) -> None:
+        _capi.lib().ipcr_gpu_peer_close(self.scratch._h)
 
 
 def pack_host(buf, threads: int = 0):
@@ -276,7 +329,7 @@ def find_sites_block_packed(cp: CompiledPanel, scratch: SimulationScratch, codes
     err = _capi.errbuf()
     _capi.check(_capi.lib().ipcr_gpu_find_sites_block_packed(
         cp._h, scratch._h, int(codes.data_ptr()), int(inval.data_ptr()), n_bases, arr, len(segments), n_recs,
-        1 if force_raw else 0, int(block.data_ptr()), site_cap, err, len(err)), err)
+        1 if force_raw else 0, _ptr(block), site_cap, err, len(err)), err)
 
 
 def pair_blocks(cp: CompiledPanel, scratch: SimulationScratch, blocks, n_blocks: int, site_cap: int,
