@@ -294,6 +294,9 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
 ipcr_fasta *ipcr_gpu_fasta_from_memory(const ipcr_seq *recs, const char *const *ids, size_t n_recs, int threads,
                                        int flags, char *err, size_t errlen);
 int ipcr_gpu_fasta_is_packed(const ipcr_fasta *f);
+/* the packed form of the handle's whole sequence buffer (records back to back): 2 * n_groups code words,
+ * n_groups bitmap words; owned by the handle */
+int ipcr_gpu_fasta_packed(const ipcr_fasta *f, const uint32_t **codes, const uint32_t **inval, uint64_t *n_groups);
 /* the host packer the feeder applies (bit-for-bit what the device pack kernel writes):
  * codes[*code_words], inval[*inval_words] for n_bases bases, padding included */
 void ipcr_gpu_packed_words(uint64_t n_bases, uint64_t *code_words, uint64_t *inval_words);

@@ -120,7 +120,7 @@ SYMBOLS = [
     "ipcr_gpu_find_sites_block", "ipcr_gpu_pair_blocks", "ipcr_gpu_find_sites_block_packed",
     "ipcr_gpu_sort_products", "ipcr_gpu_fasta_from_memory",
     "ipcr_gpu_peer_create", "ipcr_gpu_peer_open", "ipcr_gpu_peer_begin_step", "ipcr_gpu_peer_publish",
-    "ipcr_gpu_pair_peers", "ipcr_gpu_peer_close", "ipcr_gpu_fasta_is_packed", "ipcr_gpu_packed_words", "ipcr_gpu_pack_host",
+    "ipcr_gpu_pair_peers", "ipcr_gpu_peer_close", "ipcr_gpu_fasta_is_packed", "ipcr_gpu_fasta_packed", "ipcr_gpu_packed_words", "ipcr_gpu_pack_host",
     "ipcr_gpu_panel_create", "ipcr_gpu_panel_destroy", "ipcr_gpu_panel_num_pairs",
     "ipcr_gpu_panel_num_orientations", "ipcr_gpu_panel_have", "ipcr_gpu_panel_set_jit", "ipcr_gpu_panel_set_filter",
     "ipcr_gpu_scratch_create", "ipcr_gpu_scratch_destroy",
@@ -193,6 +193,7 @@ def lib():
     sig("ipcr_gpu_fasta_open", V, C.c_char_p, C.c_int, C.c_int, *ERR)
     sig("ipcr_gpu_fasta_from_memory", V, P(SeqC), P(C.c_char_p), SZ, C.c_int, C.c_int, *ERR)
     sig("ipcr_gpu_fasta_is_packed", C.c_int, V)
+    sig("ipcr_gpu_fasta_packed", C.c_int, V, P(P(C.c_uint32)), P(P(C.c_uint32)), P(U64))
     sig("ipcr_gpu_packed_words", None, U64, P(U64), P(U64))
     sig("ipcr_gpu_pack_host", C.c_int, V, U64, V, V, C.c_int)
     sig("ipcr_gpu_find_sites_block_packed", C.c_int, V, V, V, V, U64, P(PackedSegmentC), SZ, SZ, C.c_int, V, U64, *ERR)

@@ -1876,7 +1876,18 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
     ipcr_fasta *fp = f.get();
     const bool want_pack = (pin & IPCR_FASTA_PACK) != 0;
     pin &= IPCR_FASTA_PIN;
+    FastaPackTarget pk;
     fasta_parse(fb.data, fb.size, threads, f->recs, f->total, [&](uint64_t total) -> uint8_t * {
+        if (want_pack) {  // the packed form is written by the copy pass itself, while its input is still in cache
+            const uint64_t groups = packed_groups(total);
+            void *c = nullptr, *i = nullptr;
+            CU(cudaMallocHost(&c, groups * 8 + 64));
+            fp->codes = static_cast<uint32_t *>(c);
+            CU(cudaMallocHost(&i, groups * 4 + 64));
+            fp->inval = static_cast<uint32_t *>(i);
+            pk.codes = fp->codes;
+            pk.inval = fp->inval;
+        }
         const size_t bytes = (size_t)std::max<uint64_t>(total, 1) + 64;
         if (pin) {
             void *q = nullptr;
@@ -1890,8 +1901,12 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
         fp->seq = static_cast<uint8_t *>(malloc(bytes));
         if (!fp->seq) throw Error("out of host memory for the FASTA records");
         return fp->seq;
-    });
-    if (want_pack) fasta_pack(fp, threads);
+    }, &pk);
+    if (want_pack) {
+        f->rec_reset.assign(f->recs.size(), 0);
+        for (size_t r = 0; r < f->recs.size(); r++)
+            f->rec_reset[r] = packed_any_invalid(f->inval, f->recs[r].off, f->recs[r].off + f->recs[r].len) ? 1 : 0;
+    }
     return f.release();
     ABI_CATCH(nullptr)
 }
@@ -1947,6 +1962,14 @@ ipcr_fasta *ipcr_gpu_fasta_from_memory(const ipcr_seq *recs, const char *const *
 }
 
 int ipcr_gpu_fasta_is_packed(const ipcr_fasta *f) { return f && f->codes ? 1 : 0; }
+
+int ipcr_gpu_fasta_packed(const ipcr_fasta *f, const uint32_t **codes, const uint32_t **inval, uint64_t *n_groups) {
+    if (!f || !f->codes) return 1;
+    if (codes) *codes = f->codes;
+    if (inval) *inval = f->inval;
+    if (n_groups) *n_groups = packed_groups(f->total);
+    return 0;
+}
 
 void ipcr_gpu_packed_words(uint64_t n_bases, uint64_t *code_words, uint64_t *inval_words) {
     const uint64_t g = packed_groups(n_bases);

@@ -12,7 +12,9 @@
 //   * gzip input is detected by magic number or a .gz suffix.
 // (One deliberate difference: the reference hands lines longer than 1 MiB to TrimSpace in
 //  1 MiB fragments; here a line is always trimmed as a whole.)
-// The work is split over threads at line boundaries: pass 1 counts, pass 2 copies.
+// The work is split over threads at line boundaries: pass 1 counts (64-byte SSE2 blocks: a block without '>'
+// or stray white space contributes its size minus its newlines), pass 2 copies and upper-cases and -- when the
+// caller asks for the packed form -- packs every finished 64 KB of output while it is still in cache.
 #pragma once
 
 #include <fcntl.h>
@@ -21,6 +23,8 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <emmintrin.h>
+
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -28,6 +32,8 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#include "pack_host.hpp"
 
 namespace ipcr {
 
@@ -72,9 +78,13 @@ inline void fasta_trim(const uint8_t *d, size_t &a, size_t &b) {
 }
 
 // Parses `n` bytes of FASTA text.  `alloc(total)` must return a buffer for the sequence bytes.
+struct FastaPackTarget {  // optional: the packed form (pack_host.hpp) of the sequence buffer, filled by pass 2
+    uint32_t *codes = nullptr, *inval = nullptr;
+};
+
 template <class Alloc>
 inline void fasta_parse(const uint8_t *d, size_t n, int threads, std::vector<FastaRecord> &recs, uint64_t &total,
-                        Alloc &&alloc) {
+                        Alloc &&alloc, FastaPackTarget *pack = nullptr) {
     recs.clear();
     total = 0;
     if (threads < 1) threads = 1;
@@ -95,15 +105,73 @@ inline void fasta_parse(const uint8_t *d, size_t n, int threads, std::vector<Fas
     auto pass1 = [&](int t) {
         FastaPiece &pc = pieces[t];
         uint64_t *cur = &pc.head_kept;
-        fasta_for_lines(d, n, cut[t], cut[t + 1], [&](size_t a, size_t b) {
-            if (b > a && d[a] == '>') {
-                pc.hdrs.push_back({fasta_header_id(d + a + 1, b - a - 1), 0});
-                cur = &pc.hdrs.back().kept;
-                return;
+        // slow path: line by line (headers, lines with white space at their ends)
+        auto lines = [&](size_t lo, size_t hi) {
+            fasta_for_lines(d, n, lo, hi, [&](size_t a, size_t b) {
+                if (b > a && d[a] == '>') {
+                    pc.hdrs.push_back({fasta_header_id(d + a + 1, b - a - 1), 0});
+                    cur = &pc.hdrs.back().kept;
+                    return;
+                }
+                fasta_trim(d, a, b);
+                *cur += b - a;
+            });
+        };
+        // fast path: whole lines that hold no '>' and no white space except their '\n' keep every other byte.
+        // p always sits at a line start; blocks of 64 bytes are classified with SSE2 compares.
+        size_t p = cut[t];
+        const size_t hi = cut[t + 1];
+        const __m128i v_nl = _mm_set1_epi8('\n'), v_gt = _mm_set1_epi8('>'), v_sp = _mm_set1_epi8(' ');
+        const __m128i v_lo = _mm_set1_epi8((char)(-0x09 - 128)), v_span = _mm_set1_epi8((char)(0x0D - 0x09 + 1 - 128));
+        while (p < hi) {
+            size_t q = p;
+            uint64_t kept = 0;
+            size_t last_nl = p;  // one past the last newline seen in clean blocks
+            bool dirty = false;
+            while (q + 64 <= hi) {
+                uint32_t nl_bits[4];
+                uint32_t bad = 0;
+                for (int k = 0; k < 4; k++) {
+                    const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(d + q + 16 * k));
+                    const uint32_t nl = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, v_nl));
+                    // bytes 0x09..0x0D: (v - 0x09) < 5 unsigned, done as a signed compare after biasing by 128
+                    const __m128i ws = _mm_cmplt_epi8(_mm_add_epi8(v, v_lo), v_span);
+                    const uint32_t other = (uint32_t)_mm_movemask_epi8(
+                        _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(v, v_gt), _mm_cmpeq_epi8(v, v_sp)), ws));
+                    nl_bits[k] = nl;
+                    bad |= other & ~nl;
+                }
+                if (bad) {
+                    dirty = true;
+                    break;
+                }
+                uint32_t cnt = 0;
+                for (int k = 0; k < 4; k++) {
+                    cnt += (uint32_t)__builtin_popcount(nl_bits[k]);
+                    if (nl_bits[k]) last_nl = q + 16 * k + (32 - __builtin_clz(nl_bits[k]));
+                }
+                kept += 64 - cnt;
+                q += 64;
             }
-            fasta_trim(d, a, b);
-            *cur += b - a;
-        });
+            // the clean blocks cover [p, q): whole lines up to last_nl count as they are, the unfinished line
+            // (from last_nl) goes to the slow path together with whatever follows in the dirty block
+            if (last_nl > p) {
+                *cur += kept - (q - last_nl);
+                p = last_nl;
+            }
+            if (!dirty && q + 64 > hi) {  // tail of the range
+                lines(p, hi);
+                break;
+            }
+            // slow path over the lines that start before the end of the dirty block
+            size_t stop = std::min(hi, q + 64);
+            const uint8_t *nl = static_cast<const uint8_t *>(memchr(d + stop - 1, '\n', n - (stop - 1)));
+            stop = nl ? (size_t)(nl - d) + 1 : n;
+            stop = std::min(stop, hi);  // lines START inside [p, hi); fasta_for_lines reads each to its own end
+            lines(p, stop);
+            p = stop;
+            if (stop >= hi) break;
+        }
     };
     {
         std::vector<std::thread> th;
@@ -135,9 +203,14 @@ inline void fasta_parse(const uint8_t *d, size_t n, int threads, std::vector<Fas
             }
         }
     }
-    uint8_t *out = alloc(total);
+    uint8_t *out = alloc(total);  // the callback also allocates the pack target (it knows the total now)
+    const bool do_pack = pack && pack->codes && pack->inval;
+    std::vector<uint64_t> end_off((size_t)threads, 0);
     auto pass2 = [&](int t) {
         uint64_t w = start_off[t];
+        // 32-base groups lying entirely inside this thread's output range are packed here, 64 KB at a time,
+        // right after they were written (still in cache); the groups shared with a neighbour come last
+        uint64_t g_next = (start_off[t] + 31) / 32;
         bool keep = start_open[t] != 0;
         size_t hi = 0;
         fasta_for_lines(d, n, cut[t], cut[t + 1], [&](size_t a, size_t b) {
@@ -155,13 +228,29 @@ inline void fasta_parse(const uint8_t *d, size_t n, int threads, std::vector<Fas
                 dst[i] = (uint8_t)(c - (((uint8_t)(c - 'a') < 26u) ? 32u : 0u));
             }
             w += k;
+            if (do_pack && w / 32 >= g_next + 2048) {
+                pack_groups_host(out, total, g_next, w / 32, pack->codes, pack->inval);
+                g_next = w / 32;
+            }
         });
+        if (do_pack && w / 32 > g_next) pack_groups_host(out, total, g_next, w / 32, pack->codes, pack->inval);
+        end_off[t] = w;
     };
     {
         std::vector<std::thread> th;
         for (int t = 1; t < threads; t++) th.emplace_back(pass2, t);
         pass2(0);
         for (auto &x : th) x.join();
+    }
+    if (do_pack) {  // groups straddling two threads' ranges, the ragged tail and the padding groups
+        const uint64_t groups = packed_groups(total);
+        for (int t = 0; t < threads; t++) {
+            const uint64_t g_lo = start_off[t] / 32, g_first = (start_off[t] + 31) / 32;
+            if (g_first > g_lo) pack_groups_host(out, total, g_lo, std::min(g_first, groups), pack->codes, pack->inval);
+            const uint64_t g_end = end_off[t] / 32;  // first group this thread did not finish
+            const uint64_t g_stop = t + 1 < threads ? (start_off[t + 1] + 31) / 32 : groups;
+            if (g_stop > g_end) pack_groups_host(out, total, g_end, std::min(g_stop, groups), pack->codes, pack->inval);
+        }
     }
 }
 

@@ -36,7 +36,7 @@ def ref_reader(data: bytes):
             seq = bytearray()
         elif rid != "":
             line = frag.strip(SPACE)
-            seq += bytes(c - 32 if 97 <= c <= 122 else c for c in line)
+            seq += line.upper()  # bytes.upper() maps a-z only (normalize.go:5-14)
     flush()
     return recs
 
@@ -176,3 +176,57 @@ def test_host_packer_matches_its_definition():
             bad = ~np.isin(padded, np.frombuffer(b"ACGT", dtype=np.uint8))
             want_inval = (bad.reshape(-1, 32).astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
             assert np.array_equal(codes, want_codes) and np.array_equal(inval, want_inval), n
+
+
+def test_feeder_fast_paths_and_fused_pack(tmp_path):
+    """A 9 MB file (several threads): long clean stretches (the SSE2 counting path), CRLF and padded lines, '>'
+    inside lines, blank lines, lowercase, N runs; records against the restatement of core/fasta, and -- the
+    packing needs pinned memory, i.e. a CUDA driver -- the fused packed output against ipcr_gpu_pack_host of
+    the concatenated records."""
+    import ctypes as C
+
+    import numpy as np
+
+    from ipcr_b200 import _capi
+
+    rng = np.random.default_rng(11)
+    parts, want = [], []
+    for r in range(7):
+        n = int(rng.integers(200_000, 2_500_000))
+        seq = np.frombuffer(b"ACGTacgtNRY", dtype=np.uint8)[rng.choice(11, n, p=[.22, .22, .22, .22, .02, .02, .02, .02, .02, .01, .01])]
+        seq = seq.tobytes()
+        width = [60, 80, 70, 61, 80, 1000, 80][r]
+        lines = [seq[i:i + width] for i in range(0, n, width)]
+        for k in range(0, len(lines), 997):  # sprinkle the odd cases
+            lines[k] = [b"  " + lines[k] + b" \t", lines[k] + b"\r", b"\t" + lines[k], lines[k][:5] + b">" + lines[k][5:]][k % 4]
+        body = b"\n".join(lines)
+        if r == 2:
+            body = body.replace(b"\n", b"\r\n")
+        parts.append(b">rec%d some description\n" % r + body + (b"\n\n" if r % 2 else b"\n"))
+    data = b"".join(parts)
+    assert len(data) > 8 << 20
+    path = tmp_path / "big.fa"
+    path.write_bytes(data)
+    ref = ref_reader(data)
+    L = _capi.lib()
+    for threads in (1, 3, 8):
+        ff = FastaFile(str(path), threads=threads)
+        assert ff.records() == ref
+        ff.close()
+    if L.ipcr_gpu_device_count() == 0:
+        return  # pinned allocations need a driver: the packed half runs on the GPU box
+    cat = b"".join(s_ for _id, s_ in ref)
+    cw, iw = C.c_uint64(), C.c_uint64()
+    L.ipcr_gpu_packed_words(len(cat), C.byref(cw), C.byref(iw))
+    wc = np.zeros(cw.value, dtype=np.uint32)
+    wi = np.zeros(iw.value, dtype=np.uint32)
+    assert L.ipcr_gpu_pack_host(cat, len(cat), wc.ctypes.data, wi.ctypes.data, 2) == 0
+    for threads in (1, 5, 8):
+        ff = FastaFile(str(path), threads=threads, pack=True)
+        pc, pi, ng = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.c_uint64()
+        assert L.ipcr_gpu_fasta_packed(ff._h, C.byref(pc), C.byref(pi), C.byref(ng)) == 0
+        assert ng.value == iw.value
+        got_c = np.ctypeslib.as_array(pc, shape=(2 * ng.value,)).copy()
+        got_i = np.ctypeslib.as_array(pi, shape=(ng.value,)).copy()
+        assert np.array_equal(got_c, wc) and np.array_equal(got_i, wi), threads
+        ff.close()
