@@ -629,7 +629,7 @@ def run_ours(a):
         # records are handed to the feeder untimed, every timed step ships the packed form and scans it
         from ipcr_b200.fasta import FastaFile
         tp0 = time.perf_counter()
-        ff = FastaFile.from_memory(recs, pin=False, pack=True)
+        ff = FastaFile.from_memory(recs, pin=True, pack=True)
         feeder_pack_s = time.perf_counter() - tp0
         ff.scan_raw(cp, sc)  # warm
         torch.cuda.synchronize()

@@ -284,7 +284,8 @@ void ipcr_gpu_peer_close(ipcr_scratch *s);
  * normalize.go, stream.go:125-131, open.go) into ONE host buffer, multi-threaded.
  * pin != 0 asks for page-locked memory (faster H2D, slower to allocate). */
 typedef struct ipcr_fasta ipcr_fasta;
-#define IPCR_FASTA_PIN 1  /* page-locked sequence buffer */
+#define IPCR_FASTA_PIN 1  /* page-locked buffers: faster H2D, but locking costs ~0.5 s per GB -- for handles that are
+                             scanned many times; a one-shot FASTA -> TSV run is faster without */
 #define IPCR_FASTA_PACK 2 /* also keep the PACKED form (2-bit codes + hard-mismatch bitmap, 0.375 B/bp, pinned):
                              ipcr_gpu_scan_fasta then ships that over PCIe, skips the pack kernel and verifies on
                              the codes; the device-side visitors need the ASCII path */

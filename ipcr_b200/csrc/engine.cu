@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1793,26 +1794,44 @@ struct ipcr_fasta {
     bool pinned = false;
     // packed form of the whole sequence buffer (IPCR_FASTA_PACK): codes + hard-mismatch bitmap, pinned
     uint32_t *codes = nullptr, *inval = nullptr;
+    bool packed_pinned = false;  // page-locking costs ~0.5 s per GB: only worth it for handles scanned many times
     std::vector<uint8_t> rec_reset;  // per record: holds a non-ACGT byte (the feeder upper-cased a-z already)
     std::vector<ipcr_product> products;
+    void alloc_packed(uint64_t total, bool pin) {
+        const uint64_t groups = ipcr::packed_groups(total);
+        if (pin) {
+            void *c = nullptr, *i = nullptr;
+            if (cudaMallocHost(&c, groups * 8 + 64) == cudaSuccess && cudaMallocHost(&i, groups * 4 + 64) == cudaSuccess) {
+                codes = static_cast<uint32_t *>(c);
+                inval = static_cast<uint32_t *>(i);
+                packed_pinned = true;
+                return;
+            }
+            cudaGetLastError();
+            if (c) cudaFreeHost(c);
+        }
+        codes = static_cast<uint32_t *>(malloc(groups * 8 + 64));
+        inval = static_cast<uint32_t *>(malloc(groups * 4 + 64));
+        if (!codes || !inval) throw std::runtime_error("out of host memory for the packed records");
+    }
     ~ipcr_fasta() {
         if (seq) {
             if (pinned) cudaFreeHost(seq);
             else free(seq);
         }
-        if (codes) cudaFreeHost(codes);
-        if (inval) cudaFreeHost(inval);
+        if (packed_pinned) {
+            if (codes) cudaFreeHost(codes);
+            if (inval) cudaFreeHost(inval);
+        } else {
+            free(codes);
+            free(inval);
+        }
     }
 };
 
 // the feeder's second output: the packed form of its sequence buffer, in pinned memory
-static void fasta_pack(ipcr_fasta *f, int threads) {
-    const uint64_t groups = packed_groups(f->total);
-    void *c = nullptr, *i = nullptr;
-    CU(cudaMallocHost(&c, groups * 8 + 64));
-    f->codes = static_cast<uint32_t *>(c);
-    CU(cudaMallocHost(&i, groups * 4 + 64));
-    f->inval = static_cast<uint32_t *>(i);
+static void fasta_pack(ipcr_fasta *f, int threads, bool pin) {
+    f->alloc_packed(f->total, pin);
     pack_host(f->seq, f->total, f->codes, f->inval, threads);
     f->rec_reset.assign(f->recs.size(), 0);
     for (size_t r = 0; r < f->recs.size(); r++)
@@ -1877,14 +1896,16 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
     const bool want_pack = (pin & IPCR_FASTA_PACK) != 0;
     pin &= IPCR_FASTA_PIN;
     FastaPackTarget pk;
+    const auto t_begin = std::chrono::steady_clock::now();
+    double alloc_s = 0.0;
     fasta_parse(fb.data, fb.size, threads, f->recs, f->total, [&](uint64_t total) -> uint8_t * {
+        const auto ta = std::chrono::steady_clock::now();
+        struct Stop {
+            double &acc; std::chrono::steady_clock::time_point t0;
+            ~Stop() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+        } stop{alloc_s, ta};
         if (want_pack) {  // the packed form is written by the copy pass itself, while its input is still in cache
-            const uint64_t groups = packed_groups(total);
-            void *c = nullptr, *i = nullptr;
-            CU(cudaMallocHost(&c, groups * 8 + 64));
-            fp->codes = static_cast<uint32_t *>(c);
-            CU(cudaMallocHost(&i, groups * 4 + 64));
-            fp->inval = static_cast<uint32_t *>(i);
+            fp->alloc_packed(total, pin != 0);
             pk.codes = fp->codes;
             pk.inval = fp->inval;
         }
@@ -1902,6 +1923,10 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
         if (!fp->seq) throw Error("out of host memory for the FASTA records");
         return fp->seq;
     }, &pk);
+    if (getenv("IPCR_FEEDER_TIMING"))
+        fprintf(stderr, "[feeder] %zu bytes, %d threads: allocations %.3f s (packed: %s, page-locked: %s), parse + copy + pack %.3f s\n",
+                fb.size, threads, alloc_s, want_pack ? "yes" : "no", pin ? "yes" : "no",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() - alloc_s);
     if (want_pack) {
         f->rec_reset.assign(f->recs.size(), 0);
         for (size_t r = 0; r < f->recs.size(); r++)
@@ -1956,7 +1981,7 @@ ipcr_fasta *ipcr_gpu_fasta_from_memory(const ipcr_seq *recs, const char *const *
         work();
         for (auto &x : th) x.join();
     }
-    if (flags & IPCR_FASTA_PACK) fasta_pack(f.get(), threads);
+    if (flags & IPCR_FASTA_PACK) fasta_pack(f.get(), threads, (flags & IPCR_FASTA_PIN) != 0);
     return f.release();
     ABI_CATCH(nullptr)
 }

@@ -454,9 +454,46 @@ int main(int argc, char **argv) {
     for (const std::string &fa : o.files) {
         const uint32_t this_file = file_no++;
         const auto tf0 = Clock::now();
-        ipcr_fasta *ff = ipcr_gpu_fasta_open(fa.c_str(), 0, 1, g.err, sizeof g.err);
+        // plain unchunked runs take the feeder's packed form through ipcr_gpu_scan_fasta (0.375 B/bp over PCIe, no
+        // pack kernel); nothing is page-locked: locking 1 GB costs more than a one-shot copy from pageable memory saves
+        const bool packed_path = plain && chunk <= 0;
+        ipcr_fasta *ff = ipcr_gpu_fasta_open(fa.c_str(), 0, packed_path ? IPCR_FASTA_PACK : 0, g.err, sizeof g.err);
         if (!ff) die(3, g.err);
         t_open += secs(tf0, Clock::now());
+        if (packed_path) {
+            const size_t nrec = ipcr_gpu_fasta_num_records(ff);
+            const size_t meta_base = metas.size();
+            for (size_t r = 0; r < nrec; r++) {
+                const char *id; const uint8_t *seq; uint64_t len;
+                ipcr_gpu_fasta_record(ff, r, &id, &seq, &len);
+                JobMeta m;
+                m.id = id;
+                m.chunked = split_chunk_suffix(m.id, m.base, m.off);  // the collector strips ANY :a-b suffix (pipeline.go:140-156)
+                if (!m.chunked) { m.base = m.id; m.off = 0; }
+                m.file = this_file;
+                m.base_intern = base_ids.emplace(m.base, (uint32_t)base_ids.size()).first->second;
+                metas.push_back(std::move(m));
+            }
+            const ipcr_product *out = nullptr;
+            uint64_t n = 0;
+            const auto ts0 = Clock::now();
+            g.check(ipcr_gpu_scan_fasta(g.panel, g.scratch, ff, &out, &n, g.err, sizeof g.err));
+            const auto ts1 = Clock::now();
+            t_scan += secs(ts0, ts1);
+            n_raw += n;
+            for (uint64_t i = 0; i < n; i++) {
+                ipcr_product pc = out[i];
+                const JobMeta &m = metas[meta_base + pc.rec_idx];
+                const PodKey key{((uint64_t)m.file << 32) | m.base_intern, (uint64_t)(pc.start + m.off),
+                                 ((uint64_t)(pc.end + m.off) << 20) | ((uint64_t)pc.type << 19) | pair_exp[pc.pair_idx]};
+                if (seen_pod.add(key)) continue;
+                pc.rec_idx = (uint32_t)(meta_base + pc.rec_idx);
+                pod.push_back(pc);
+            }
+            t_collect += secs(ts1, Clock::now());
+            ipcr_gpu_fasta_close(ff);
+            continue;
+        }
         const size_t nrec = ipcr_gpu_fasta_num_records(ff);
         // jobs = records or rolling chunks (path_ctx.go:83-179), scanned in batches of <= 4096
         struct Job { std::string id; const uint8_t *seq; uint64_t len; };
