@@ -453,11 +453,24 @@ k_pair_small(PairSmallArgs a) {
             }
             __syncthreads();
             const uint32_t total = s_words[a.n_blocks];
-            for (uint32_t g = threadIdx.x; g < total; g += blockDim.x) {
-                uint32_t b = 0;
-                while (b + 1 < a.n_blocks && g >= s_words[b + 1]) b++;
-                const uint32_t w = g - s_words[b];
-                reinterpret_cast<uint4 *>(a.stage + (uint64_t)b * a.block_bytes)[w] = reinterpret_cast<const uint4 *>(s_blk[b])[w];
+            for (uint32_t base = 0; base < total; base += 8u * blockDim.x) {  // eight remote loads in flight per thread
+                uint4 v[8];
+                uint4 *dst[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t g = base + (uint32_t)k * blockDim.x + threadIdx.x;
+                    dst[k] = nullptr;
+                    if (g < total) {
+                        uint32_t b = 0;
+                        while (b + 1 < a.n_blocks && g >= s_words[b + 1]) b++;
+                        const uint32_t w = g - s_words[b];
+                        dst[k] = reinterpret_cast<uint4 *>(a.stage + (uint64_t)b * a.block_bytes) + w;
+                        v[k] = reinterpret_cast<const uint4 *>(s_blk[b])[w];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (dst[k]) *dst[k] = v[k];
             }
             __syncthreads();
             if (threadIdx.x < a.n_blocks) s_blk[threadIdx.x] = a.stage + (uint64_t)threadIdx.x * a.block_bytes;
