@@ -253,6 +253,8 @@ class PeerExchange:
     stage 2 reads the peers' blocks straight over NVLink -- no collective on the data path."""
 
     def __init__(self, dist, scratch: SimulationScratch, n_recs: int, rank: int, world: int, device):
+        """Collective: every rank must call it.  Raises on EVERY rank if any rank cannot export or map a
+        block (each phase ends with an agreement), so a caller can fall back to a collective library."""
         import torch
 
         self.scratch, self.n_recs, self.rank, self.world = scratch, n_recs, rank, world
@@ -260,13 +262,21 @@ class PeerExchange:
         L = _capi.lib()
         handle = C.create_string_buffer(64)
         err = _capi.errbuf()
-        _capi.check(L.ipcr_gpu_peer_create(scratch._h, n_recs, self.site_cap, handle, err, len(err)), err)
+
+        def agree(ok: bool, what: str):
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t[0]) == 0:
+                raise _capi.GpuError(f"peer exchange unavailable: {what} failed on "
+                                     + ("this rank: " + err.value.decode("utf-8", "replace") if not ok else "another rank"))
+
+        agree(L.ipcr_gpu_peer_create(scratch._h, n_recs, self.site_cap, handle, err, len(err)) == 0, "exporting the block")
         mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(device)
         allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(allh, mine)
         raw = bytes(allh.cpu().numpy().tobytes())
-        _capi.check(L.ipcr_gpu_peer_open(scratch._h, raw, world, rank, err, len(err)), err)
-        dist.barrier()  # nobody starts a step before every rank has mapped every block
+        agree(L.ipcr_gpu_peer_open(scratch._h, raw, world, rank, err, len(err)) == 0, "mapping the peers' blocks")
+        # nobody starts a step before every rank has mapped every block (the agreement is a barrier)
 
     def begin_step(self) -> int:
         p = _capi.lib().ipcr_gpu_peer_begin_step(self.scratch._h)
