@@ -276,6 +276,7 @@ struct GenomeData {
     bool any_reset = false;
     uint64_t own_bases = 0;
     const ipcr_record_info *recs_dev_ptr = nullptr;  // chain: record table uploaded together with the segments
+    std::vector<uint8_t> last_tab;                   // what segs_dev holds (skip the copy when nothing changed)
     // packed input (host-packed codes + bitmap already in device memory): nothing to pack, no ASCII
     const uint32_t *codes_ext = nullptr, *inval_ext = nullptr;
 };
@@ -318,7 +319,8 @@ struct ipcr_scratch {
     std::vector<ipcr_scratch *> peers;          // one scratch per further device (multi-GPU inside one process)
     cudaEvent_t done_ev = nullptr;              // peer: its block has arrived on the primary device
     bool own_laid = false;                      // multi-device retry: the slice is already resident
-    ipcr::DevBuf seg_reset_dummy, chunk_ctr;
+    ipcr::DevBuf seg_reset_dummy, chunk_ctr, verify_done;
+    uint64_t pending_publish = 0;  // peer exchange: step number the next stage 1 publishes from inside k_verify
     // peer exchange (one process per GPU): own double-buffered block, exported through CUDA IPC; the peers' mappings
     ipcr::DevBuf peer_buf, peer_tab[2];
     std::vector<void *> peer_map;  // cudaIpcOpenMemHandle results (NULL for this rank)
@@ -441,6 +443,7 @@ static void launch_pack_codes(ipcr_scratch *s, GenomeData &g, uint8_t *rec_reset
 // K1 on the genome's concatenated ASCII buffer, in the format the panel's filter reads
 static void pack_genome(ipcr_scratch *s, GenomeData &g) {
     cudaStream_t st = s->stream;
+    g.last_tab.clear();  // segs_dev is rewritten below in the multi-kernel path's own layout
     g.planes_ready = g.codes_ready = false;
     upload(g.segs_dev, g.segs.data(), g.segs.size() * sizeof(SegmentDev), st);
     g.seg_reset.ensure(g.segs.size() * sizeof(uint32_t));
@@ -1310,7 +1313,8 @@ static bool chain_ok(ipcr_scratch *s, const ipcr_record_info *recs, size_t n_rec
 
 // Stage 1 of the chain on a laid-out genome: init -> pack -> seed scan -> dirty windows -> verify,
 // all into `d_block`.  Nothing is waited for.
-static void stage1_async(ipcr_scratch *s, GenomeData &g, int variant, uint8_t *d_block, uint64_t site_cap) {
+static void stage1_async(ipcr_scratch *s, GenomeData &g, int variant, uint8_t *d_block, uint64_t site_cap,
+                         uint64_t publish_seq = 0) {
     const Panel &h = s->panel->host;
     const SeedIndex &ix = seed_get(s, variant);
     cudaStream_t st = s->stream;
@@ -1329,7 +1333,10 @@ static void stage1_async(ipcr_scratch *s, GenomeData &g, int variant, uint8_t *d
             memcpy(tab.data() + seg_bytes + r * sizeof(ipcr_record_info), &ri, sizeof ri);
             if (packed) tab[seg_bytes + rec_bytes + r] = g.recs[r].has_reset_byte ? 1 : 0;
         }
-        upload_staged(s, g.segs_dev, tab.data(), tab.size());
+        if (tab != g.last_tab || !g.segs_dev.p) {  // unchanged tables (same shards every call) are already there
+            upload_staged(s, g.segs_dev, tab.data(), tab.size());
+            g.last_tab = tab;
+        }
         g.recs_dev_ptr = reinterpret_cast<const ipcr_record_info *>(g.segs_dev.as<uint8_t>() + seg_bytes);
         if (packed) rr_init = g.segs_dev.as<uint8_t>() + seg_bytes + rec_bytes;
     }
@@ -1425,6 +1432,15 @@ static void stage1_async(ipcr_scratch *s, GenomeData &g, int variant, uint8_t *d
     v.cand = s->cand.as<unsigned long long>();
     v.n_cand = cap;
     v.n_cand_ptr = &ctl->n_cand;
+    if (publish_seq) {  // peer exchange: k_verify's last block publishes the finished block
+        if (!s->verify_done.p) {
+            s->verify_done.ensure(64);
+            CU(cudaMemsetAsync(s->verify_done.p, 0, 64, st));
+        }
+        v.publish_seq_ptr = &ctl->seq;
+        v.publish_seq = publish_seq;
+        v.blocks_done = s->verify_done.as<unsigned int>();
+    }
     k_verify<<<(unsigned)s->sm_count * 8, 256, 0, st>>>(v);
     check_launch("k_verify");
     CU(cudaEventRecord(s->ev[5], st));
@@ -2275,7 +2291,8 @@ int ipcr_gpu_find_sites_block(ipcr_panel *p, ipcr_scratch *s, const ipcr_segment
         check_launch("k_block_init");
         s->inflight = true;
     } else {
-        stage1_async(s, s->own, chain_variant(s, force_raw != 0), static_cast<uint8_t *>(d_block), site_cap);
+        stage1_async(s, s->own, chain_variant(s, force_raw != 0), static_cast<uint8_t *>(d_block), site_cap, s->pending_publish);
+        s->pending_publish = 0;  // k_verify's last block publishes: ipcr_gpu_peer_publish has nothing left to do
     }
     s->timing.kernel_launches = s->launches;
     return 0;
@@ -2329,7 +2346,8 @@ int ipcr_gpu_find_sites_block_packed(ipcr_panel *p, ipcr_scratch *s, const uint3
         check_launch("k_block_init");
         s->inflight = true;
     } else {
-        stage1_async(s, g, chain_variant(s, force_raw != 0), static_cast<uint8_t *>(d_block), site_cap);
+        stage1_async(s, g, chain_variant(s, force_raw != 0), static_cast<uint8_t *>(d_block), site_cap, s->pending_publish);
+        s->pending_publish = 0;
     }
     g.codes_ext = g.inval_ext = nullptr;  // the scratch's own genome goes back to packing for itself
     s->timing.kernel_launches = s->launches;
@@ -2432,6 +2450,7 @@ int ipcr_gpu_peer_open(ipcr_scratch *s, const void *handles, uint32_t n_ranks, u
 void *ipcr_gpu_peer_begin_step(ipcr_scratch *s) {
     if (!s || !s->peer_n) return nullptr;
     s->peer_step++;
+    s->pending_publish = s->peer_step;
     return s->peer_buf.as<uint8_t>() + (s->peer_step & 1ull) * s->peer_bb;
 }
 
@@ -2439,9 +2458,12 @@ int ipcr_gpu_peer_publish(ipcr_scratch *s, char *err, size_t errlen) {
     ABI_TRY
     if (!s || !s->peer_n || s->peer_step == 0) throw Error("no peer step in progress");
     bind(s);
-    k_block_publish<<<1, 1, 0, s->stream>>>(s->peer_buf.as<uint8_t>() + (s->peer_step & 1ull) * s->peer_bb, s->peer_step);
-    check_launch("k_block_publish");
-    s->launches++;
+    if (s->pending_publish) {  // stage 1 did not publish from inside its verify kernel (empty shard): do it here
+        k_block_publish<<<1, 1, 0, s->stream>>>(s->peer_buf.as<uint8_t>() + (s->peer_step & 1ull) * s->peer_bb, s->peer_step);
+        check_launch("k_block_publish");
+        s->launches++;
+        s->pending_publish = 0;
+    }
     s->inflight = true;
     return 0;
     ABI_CATCH(1)

@@ -265,6 +265,9 @@ struct VerifyArgs {
     uint64_t site_cap;
     // packed genome (seed-index path): when set, the window is compared 64 columns at a time against
     // the orientation's four acceptance masks instead of byte by byte on the ASCII
+    unsigned long long *publish_seq_ptr;  // peer exchange: where the last block stores publish_seq (or NULL)
+    unsigned long long publish_seq;
+    unsigned int *blocks_done;            // zeroed counter of finished blocks
     const uint32_t *codes;     // 2-bit codes, 16 bases per word (A 0, C 1, T 2, G 3)
     const uint32_t *inval;     // bit = byte is not an uppercase A/C/G/T
     const uint64_t *oplanes;   // [orientation][4]: columns accepting A, C, G, T
@@ -405,6 +408,19 @@ k_verify(VerifyArgs a) {
             ok = verify_one(a, (uint32_t)(cw >> kCandPosBits), cw & kCandPosMask, &s);
         }
         compact_site(a, ok, s);
+    }
+    // peer exchange: the LAST block to finish publishes the step number of the (now complete) site block
+    // system-wide -- what would otherwise be one more tiny kernel launch at the end of stage 1
+    if (a.publish_seq_ptr) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(a.blocks_done, 1u) == gridDim.x - 1u) {
+                *a.blocks_done = 0u;  // ready for the next launch (stream-ordered)
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.publish_seq_ptr), "l"(a.publish_seq) : "memory");
+            }
+        }
     }
 }
 
