@@ -319,7 +319,7 @@ struct ipcr_scratch {
     std::vector<ipcr_scratch *> peers;          // one scratch per further device (multi-GPU inside one process)
     cudaEvent_t done_ev = nullptr;              // peer: its block has arrived on the primary device
     bool own_laid = false;                      // multi-device retry: the slice is already resident
-    ipcr::DevBuf seg_reset_dummy, chunk_ctr, verify_done;
+    ipcr::DevBuf seg_reset_dummy, chunk_ctr, verify_done, pair_dbg;
     uint64_t pending_publish = 0;  // peer exchange: step number the next stage 1 publishes from inside k_verify
     // peer exchange (one process per GPU): own double-buffered block, exported through CUDA IPC; the peers' mappings
     ipcr::DevBuf peer_buf, peer_tab[2];
@@ -1515,6 +1515,15 @@ static void pair_async(ipcr_scratch *s, const uint8_t *d_blocks, uint32_t n_bloc
     if (words + 8 * (n_buckets + 1) <= kPairSmemMax && !getenv("IPCR_NO_BUCKETS")) {
         a.bucket_cap = (uint32_t)n_buckets;
         smem = std::max(smem, words + 8 * ((size_t)n_buckets + 1));
+        // + the panel tables of the join (uses, pairs, record lengths) when they still fit
+        const size_t tables = 4 * ((h.orients.size() + 1) + 2 * n_pairs + 8 * n_pairs + 4 * n_recs + 16);
+        if (words + 8 * ((size_t)n_buckets + 1) + tables <= kPairSmemMax) smem = std::max(smem, words + 8 * ((size_t)n_buckets + 1) + tables);
+    }
+    a.smem_words = (uint32_t)(smem / 4);
+    if (getenv("IPCR_CHAIN_DEBUG")) {
+        s->pair_dbg.ensure(32 * 8);
+        CU(cudaMemsetAsync(s->pair_dbg.p, 0, 32 * 8, st));
+        a.dbg = s->pair_dbg.as<unsigned long long>();
     }
     static std::mutex attr_mu;
     {
@@ -1550,6 +1559,14 @@ static ChainResult chain_finish(ipcr_scratch *s, const uint8_t *d_blocks, uint32
         hd0.n_sites, hd0.n_final, hd0.n_tasks, hd0.n_prod, hd0.n_cand, hd0.n_dirty, hd0.flags, hd0.min_variant};
     *redo_stage1 = false;
     *n_prod = 0;
+    if (getenv("IPCR_CHAIN_DEBUG") && s->pair_dbg.p) {
+        unsigned long long d[32];
+        if (cudaMemcpy(d, s->pair_dbg.p, sizeof d, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            fprintf(stderr, "[chain] k_pair_small marks (cycles of thread 0):");
+            for (unsigned long long i = 1; i <= d[0] && i < 32; i++) fprintf(stderr, " %llu", d[i]);
+            fprintf(stderr, "\n");
+        }
+    }
     if (getenv("IPCR_CHAIN_DEBUG"))
         fprintf(stderr, "[chain] sites %llu final %llu tasks %llu prod %llu cand %llu dirty %llu flags %x variant %u | bucket-mode cycles: keys %u sort %u final %u count %u\n",
                 (unsigned long long)hd.n_sites, (unsigned long long)hd.n_final, (unsigned long long)hd.n_tasks,

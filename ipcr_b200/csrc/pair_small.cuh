@@ -105,6 +105,8 @@ struct PairSmallArgs {
     const uint32_t *use_off;   // [n_orient + 1]: (pair, direction) slots in which an orientation is the forward primer
     const uint32_t *use_list;  // pair << 1 | direction
     uint32_t task_cap;
+    uint32_t smem_words;  // dynamic shared memory of this launch, in 32-bit words
+    unsigned long long *dbg;  // optional: 32 clock64 stamps of thread 0 (IPCR_CHAIN_DEBUG)
     uint32_t bucket_cap;  // (record, orientation) buckets the dynamic shared memory has room for (0 = general mode only)
     PairHeader *header;
 };
@@ -219,9 +221,15 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
         const uint32_t v = (uint32_t)min((long long)0xFFFF, (clock64() - t0) >> 6);
         h.pad[slot >> 1] |= v << (16 * (slot & 1));
     };
+    int dbg_n = 0;
+    auto mark = [&]() {  // finer: absolute cycle counts of thread 0 into a.dbg
+        if (a.dbg && threadIdx.x == 0 && dbg_n < 31) a.dbg[1 + dbg_n] = (unsigned long long)(clock64() - t0);
+        dbg_n++;
+    };
     for (uint32_t i = threadIdx.x; i <= nb; i += blockDim.x) off[i] = foff[i] = 0u;
     if (threadIdx.x == 0) s_max = s_tasks = 0u;
     __syncthreads();
+    mark();  // 1 zeroed
     auto site_at = [&](uint32_t i) -> const ipcr_site & {
         uint32_t b = 0;
         while (b + 1 < a.n_blocks && (unsigned long long)i >= s_boff[b + 1]) b++;
@@ -246,6 +254,7 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
     }
     __syncthreads();
     stamp(0);
+    mark();  // 2 keys
     {  // largest bucket
         uint32_t mx = 0;
         for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) mx = max(mx, off[i]);
@@ -254,7 +263,9 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
     }
     __syncthreads();
     if (s_max > kBucketMaxSize) return false;
+    mark();  // 3 max
     const uint32_t n_valid = cta_scan_inplace(off, nb, wsum);
+    mark();  // 4 scan 1
     // ---- 2. scatter into bucket order, then rank inside each bucket ----
 #pragma unroll
     for (int c = 0; c < kPairPerThread; c++)
@@ -281,6 +292,7 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
         if (word[c] != ~0ull) sk[off[bk[c]] + rank[c]] = word[c];
     __syncthreads();
     stamp(1);
+    mark();  // 5 sorted
     // ---- 3. hit cap (rank in the sorted bucket) + left-window filter; final position of the kept ones ----
     uint32_t prior[kPairPerThread];
     const uint64_t cap = j.prm.hit_cap > 0 ? (uint64_t)j.prm.hit_cap : ~0ull;
@@ -303,7 +315,9 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
         }
     }
     __syncthreads();
+    mark();  // 6 keep
     const uint32_t n_final = cta_scan_inplace(foff, nb, wsum);
+    mark();  // 7 scan 2
     h.n_final = n_final;
     j.n_sites = n_final;
     if (n_final == 0u) return true;
@@ -326,6 +340,7 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
     __syncthreads();
     j.fkeys = reinterpret_cast<const uint64_t *>(sk);
     stamp(2);
+    mark();  // 8 final written
     // ---- 4. join, driven by the sites instead of the (record, pair, direction) entries: a final site of
     // orientation q is a forward site of every (pair, direction) that uses q (use_off / use_list, built
     // with the panel).  One thread per site counts its products per use; the few PRODUCTIVE tasks are
@@ -334,34 +349,85 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
     // the (mostly empty) entries. ----
     __shared__ uint32_t s_npt;
     if (threadIdx.x == 0) s_npt = 0u;
+    // The panel tables the join walks (uses per orientation, pairs, record lengths) move into what is left of the
+    // dynamic shared memory when they fit: every task otherwise pays four dependent global loads before it has
+    // looked at a single site.
+    const uint32_t *use_off = a.use_off, *use_list = a.use_list;
+    {
+        const uint32_t n_uses = 2u * j.n_pairs;
+        uint32_t *base = foff + nb + 1;
+        base += ((uintptr_t)base & 15u) ? (16u - ((uintptr_t)base & 15u)) / 4u : 0u;  // 16-byte aligned (PairDev copies)
+        const uint64_t need = (uint64_t)(kl.n_orient + 1) + n_uses + 8ull * j.n_pairs + 4ull * j.n_recs + 8;
+        const uint64_t have = a.smem_words > (uint64_t)(base - reinterpret_cast<uint32_t *>(sk)) ?
+                                  a.smem_words - (uint64_t)(base - reinterpret_cast<uint32_t *>(sk)) : 0;
+        if (need <= have) {
+            PairDev *s_pairs = reinterpret_cast<PairDev *>(base);
+            ipcr_record_info *s_recs = reinterpret_cast<ipcr_record_info *>(base + 8u * j.n_pairs);
+            uint32_t *s_uoff = base + 8u * j.n_pairs + 4u * j.n_recs, *s_ulist = s_uoff + kl.n_orient + 1;
+            for (uint32_t i = threadIdx.x; i < 8u * j.n_pairs; i += blockDim.x) base[i] = reinterpret_cast<const uint32_t *>(j.pairs)[i];
+            for (uint32_t i = threadIdx.x; i < 4u * j.n_recs; i += blockDim.x)
+                reinterpret_cast<uint32_t *>(s_recs)[i] = reinterpret_cast<const uint32_t *>(j.recs)[i];
+            for (uint32_t i = threadIdx.x; i <= kl.n_orient; i += blockDim.x) s_uoff[i] = a.use_off[i];
+            for (uint32_t i = threadIdx.x; i < n_uses; i += blockDim.x) s_ulist[i] = a.use_list[i];
+            j.pairs = s_pairs;
+            j.recs = s_recs;
+            use_off = s_uoff;
+            use_list = s_ulist;
+        }
+    }
     __syncthreads();
+    mark();  // 9 tables staged
     unsigned long long *pt_key = reinterpret_cast<unsigned long long *>(j.entry_tasks);  // [kPairMaxProductive] scratch
     uint32_t *pt_cnt = j.task_cnt, *pt_off = const_cast<uint32_t *>(j.prod_off);
+    // pass A: (site, use) pairs whose partner list is not empty -- a few hundred of several thousand -- are LISTED;
+    // pass B then runs the partner search once per listed task with every lane busy (doing the search inside
+    // pass A made each warp execute it in nearly every iteration for one or two of its lanes)
+    __shared__ uint32_t s_nlive;
+    if (threadIdx.x == 0) s_nlive = 0u;
+    __syncthreads();
+    uint32_t *live = const_cast<uint32_t *>(j.task_off);  // scratch, task_cap entries: site << 19 | use
     uint32_t my_tasks = 0;
     for (uint32_t f = threadIdx.x; f < n_final; f += blockDim.x) {
         const uint32_t prefix = (uint32_t)(sk[f] >> (kl.pos_bits + 1));
         const uint32_t rec = prefix / kl.n_orient, q = prefix - rec * kl.n_orient;
-        for (uint32_t u = a.use_off[q]; u < a.use_off[q + 1]; u++) {
-            const uint32_t use = a.use_list[u], pair = use >> 1, blk = use & 1u;
-            const PairDev p = j.pairs[pair];
-            const uint32_t bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
+        for (uint32_t u = use_off[q]; u < use_off[q + 1]; u++) {
+            const uint32_t use = use_list[u], pair = use >> 1, blk = use & 1u;
+            const uint32_t bp = rec * kl.n_orient + (blk == 0 ? j.pairs[pair].rcB : j.pairs[pair].rcA);
             my_tasks++;
-            const int64_t pb = foff[bp], pe = foff[bp + 1];
-            if (pb == pe) continue;
-            const uint32_t cnt = join_core<false>(j, rec, pair, blk, p, f, pb, pe, 0);
-            if (cnt == 0u) continue;
-            const uint32_t slot = atomicAdd(&s_npt, 1u);
-            if (slot < kPairMaxProductive) {
-                pt_key[slot] = ((unsigned long long)((rec * j.n_pairs + pair) * 2u + blk) << 13) | f;
-                pt_cnt[slot] = cnt;
-            }
+            if (foff[bp] == foff[bp + 1]) continue;
+            const uint32_t slot = atomicAdd(&s_nlive, 1u);
+            if (slot < a.task_cap) live[slot] = (f << 19) | use;
         }
     }
+    __syncthreads();
+    const uint32_t n_live = s_nlive;
+    if (n_live > a.task_cap) {
+        h.n_tasks = n_live;
+        h.flags |= kPairTaskOverflow;
+        return true;
+    }
+    for (uint32_t t = threadIdx.x; t < n_live; t += blockDim.x) {
+        const uint32_t f = live[t] >> 19, use = live[t] & ((1u << 19) - 1u), pair = use >> 1, blk = use & 1u;
+        const uint32_t prefix = (uint32_t)(sk[f] >> (kl.pos_bits + 1));
+        const uint32_t rec = prefix / kl.n_orient;
+        const PairDev p = j.pairs[pair];
+        const uint32_t bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
+        const uint32_t cnt = join_core<false>(j, rec, pair, blk, p, f, foff[bp], foff[bp + 1], 0);
+        if (cnt == 0u) continue;
+        const uint32_t slot = atomicAdd(&s_npt, 1u);
+        if (slot < kPairMaxProductive) {
+            pt_key[slot] = ((unsigned long long)((rec * j.n_pairs + pair) * 2u + blk) << 13) | f;
+            pt_cnt[slot] = cnt;
+        }
+    }
+    my_tasks = __reduce_add_sync(0xFFFFFFFFu, my_tasks);
+    if ((threadIdx.x & 31u) != 0u) my_tasks = 0u;
     if (my_tasks) atomicAdd(&s_tasks, my_tasks);
     __syncthreads();
     h.n_tasks = s_tasks;
     const uint32_t n_pt = s_npt;
     stamp(3);
+    mark();  // 10 counted
     if (n_pt == 0u) return true;
     if (n_pt > kPairMaxProductive) return false;  // dense output: the general mode scales with it
     // rank = number of productive tasks with a smaller key; the counts land in rank order and are scanned
@@ -391,6 +457,8 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
         const uint32_t bp = rec * kl.n_orient + (blk == 0 ? p.rcB : p.rcA);
         join_core<true>(j, rec, pair, blk, p, f, foff[bp], foff[bp + 1], pt_off[my_rank]);
     }
+    mark();  // 11 filled
+    if (a.dbg && threadIdx.x == 0) a.dbg[0] = (unsigned long long)dbg_n;
     return true;
 }
 
