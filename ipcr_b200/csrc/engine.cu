@@ -973,8 +973,7 @@ static const SeedIndex &seed_get(ipcr_scratch *s, int variant) {
         CU(cudaStreamSynchronize(s->stream));
         static std::mutex attr_mu;
         std::lock_guard<std::mutex> l2(attr_mu);
-        for (auto fn : {k_seed_scan<1>, k_seed_scan<2>, k_seed_scan<2, 1>, k_seed_scan<2, 2>, k_seed_scan<2, 3>, k_seed_scan<2, 4>,
-                        k_seed_scan<2, 5>, k_seed_scan<2, 6>, k_seed_scan<2, 7>})
+        for (auto fn : {k_seed_scan<1>, k_seed_scan<2>, k_seed_scan<2, 1>, k_seed_scan<2, 4>, k_seed_scan<2, 5>})
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSeedBloomWords * 4)));
         t->seed_ready[variant] = true;
     }
@@ -986,7 +985,7 @@ static void launch_seed_scan(ipcr_scratch *s, const SeedIndex &ix, const SeedSca
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((a.n_chunks + 31) / 32, (uint64_t)s->sm_count));
     const size_t smem = kSeedBloomWords * 4;
     int var = 0;
-    if (const char *e = getenv("IPCR_SEED_VAR")) var = atoi(e) & 7;
+    if (const char *e = getenv("IPCR_SEED_VAR")) var = atoi(e) & 5;
     if (var & 4) {
         s->chunk_ctr.ensure(64);
         CU(cudaMemsetAsync(s->chunk_ctr.p, 0, 8, s->stream));
@@ -995,12 +994,8 @@ static void launch_seed_scan(ipcr_scratch *s, const SeedIndex &ix, const SeedSca
     if (!ix.use_bloom) k_seed_scan<0><<<grid, 1024, 0, s->stream>>>(a);
     else if (ix.bloom_k == 1) k_seed_scan<1><<<grid, 1024, smem, s->stream>>>(a);
     else if (var == 1) k_seed_scan<2, 1><<<grid, 1024, smem, s->stream>>>(a);
-    else if (var == 2) k_seed_scan<2, 2><<<grid, 1024, smem, s->stream>>>(a);
-    else if (var == 3) k_seed_scan<2, 3><<<grid, 1024, smem, s->stream>>>(a);
     else if (var == 4) k_seed_scan<2, 4><<<grid, 1024, smem, s->stream>>>(a);
     else if (var == 5) k_seed_scan<2, 5><<<grid, 1024, smem, s->stream>>>(a);
-    else if (var == 6) k_seed_scan<2, 6><<<grid, 1024, smem, s->stream>>>(a);
-    else if (var == 7) k_seed_scan<2, 7><<<grid, 1024, smem, s->stream>>>(a);
     else k_seed_scan<2><<<grid, 1024, smem, s->stream>>>(a);
     check_launch("k_seed_scan");
     s->launches++;
@@ -1562,17 +1557,16 @@ static ChainResult chain_finish(ipcr_scratch *s, const uint8_t *d_blocks, uint32
     if (getenv("IPCR_CHAIN_DEBUG") && s->pair_dbg.p) {
         unsigned long long d[32];
         if (cudaMemcpy(d, s->pair_dbg.p, sizeof d, cudaMemcpyDeviceToHost) == cudaSuccess) {
-            fprintf(stderr, "[chain] k_pair_small marks (cycles of thread 0):");
+            fprintf(stderr, "[chain] k_pair_small phase ends (cycles of thread 0: zeroed, keys, max, scan, sorted, keep, scan, final, tables, joined, filled):");
             for (unsigned long long i = 1; i <= d[0] && i < 32; i++) fprintf(stderr, " %llu", d[i]);
             fprintf(stderr, "\n");
         }
     }
     if (getenv("IPCR_CHAIN_DEBUG"))
-        fprintf(stderr, "[chain] sites %llu final %llu tasks %llu prod %llu cand %llu dirty %llu flags %x variant %u | bucket-mode cycles: keys %u sort %u final %u count %u\n",
+        fprintf(stderr, "[chain] sites %llu final %llu tasks %llu prod %llu cand %llu dirty %llu flags %x variant %u\n",
                 (unsigned long long)hd.n_sites, (unsigned long long)hd.n_final, (unsigned long long)hd.n_tasks,
                 (unsigned long long)hd.n_prod, (unsigned long long)hd.n_cand, (unsigned long long)hd.n_dirty, hd.flags,
-                hd.min_variant, (hd0.pad[0] & 0xFFFFu) * 64u, (hd0.pad[0] >> 16) * 64u, (hd0.pad[1] & 0xFFFFu) * 64u,
-                (hd0.pad[1] >> 16) * 64u);
+                hd.min_variant);
     s->timing.candidates = hd.n_cand;
     s->timing.sites = hd.n_sites;
     if (hd.flags & kPairPeerTimeout)

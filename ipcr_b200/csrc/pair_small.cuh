@@ -217,12 +217,8 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
     uint32_t *foff = off + nb + 1;
     __shared__ uint32_t s_max, s_tasks;
     const long long t0 = clock64();
-    auto stamp = [&](int slot) {  // debug: cycles / 64 since the mode began, four 16-bit slots in the header pad
-        const uint32_t v = (uint32_t)min((long long)0xFFFF, (clock64() - t0) >> 6);
-        h.pad[slot >> 1] |= v << (16 * (slot & 1));
-    };
     int dbg_n = 0;
-    auto mark = [&]() {  // finer: absolute cycle counts of thread 0 into a.dbg
+    auto mark = [&]() {  // IPCR_CHAIN_DEBUG: cycle count of thread 0 at the end of every phase, into a.dbg
         if (a.dbg && threadIdx.x == 0 && dbg_n < 31) a.dbg[1 + dbg_n] = (unsigned long long)(clock64() - t0);
         dbg_n++;
     };
@@ -253,7 +249,6 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
         }
     }
     __syncthreads();
-    stamp(0);
     mark();  // 2 keys
     {  // largest bucket
         uint32_t mx = 0;
@@ -291,7 +286,6 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
     for (int c = 0; c < kPairPerThread; c++)
         if (word[c] != ~0ull) sk[off[bk[c]] + rank[c]] = word[c];
     __syncthreads();
-    stamp(1);
     mark();  // 5 sorted
     // ---- 3. hit cap (rank in the sorted bucket) + left-window filter; final position of the kept ones ----
     uint32_t prior[kPairPerThread];
@@ -339,7 +333,6 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
     }
     __syncthreads();
     j.fkeys = reinterpret_cast<const uint64_t *>(sk);
-    stamp(2);
     mark();  // 8 final written
     // ---- 4. join, driven by the sites instead of the (record, pair, direction) entries: a final site of
     // orientation q is a forward site of every (pair, direction) that uses q (use_off / use_list, built
@@ -426,7 +419,6 @@ __device__ __forceinline__ bool pair_bucket_mode(const PairSmallArgs &a, JoinArg
     __syncthreads();
     h.n_tasks = s_tasks;
     const uint32_t n_pt = s_npt;
-    stamp(3);
     mark();  // 10 counted
     if (n_pt == 0u) return true;
     if (n_pt > kPairMaxProductive) return false;  // dense output: the general mode scales with it

@@ -222,10 +222,11 @@ __device__ __forceinline__ void seed_walk(const SeedScanArgs &a, uint32_t kmer, 
 
 // BLOOM: 0 = no shared-memory bitmap (every position goes to the second level), k = 1..2 bits
 // per k-mer, both in the same word.
-// VAR (tuning switches, measured on B200 -- profiles/README.md): 1 = the look-ahead / look-behind words
-// come from the neighbouring lane by shuffle instead of five extra strided loads per chunk; 2 = the bitmap
-// address is formed by a multiply-add (FMA pipe) instead of LEA (ALU pipe); 4 = warps claim chunks from a
-// global counter (no tail, no imbalance between SMs) instead of a static stride.
+// VAR (tuning switches, IPCR_SEED_VAR; measured on B200, profiles/r02_seed_variants.txt: +-0.5 %, default 0):
+// 1 = the look-ahead / look-behind words come from the neighbouring lane by shuffle instead of five extra strided
+// loads per chunk; 4 = warps claim chunks from a global counter (no tail, no imbalance between SMs) instead of a
+// static stride.  (Forming the bitmap address with a multiply-add to move it off the ALU pipe does not survive
+// ptxas: a multiply by 4 becomes LEA again.)
 template <int BLOOM, int VAR = 0>
 __global__ void __launch_bounds__(1024, 1)
 k_seed_scan(SeedScanArgs a) {
@@ -305,12 +306,7 @@ k_seed_scan(SeedScanArgs a) {
                     // second bit position are formed with multiplies on the FMA pipe instead.
                     const uint32_t hw = x * a.bloom_mul;
                     uint32_t off, b2;
-                    if (VAR & 2) {
-                        const uint32_t widx = __umulhi(hw, kSeedBloomWordsDev);
-                        asm("mad.lo.u32 %0, %1, 4, 0;" : "=r"(off) : "r"(widx));
-                    } else {
-                        off = __umulhi(hw, kSeedBloomWordsDev) * 4u;
-                    }
+                    off = __umulhi(hw, kSeedBloomWordsDev) * 4u;
                     const uint32_t w = *reinterpret_cast<const uint32_t *>(sb + off);
                     uint32_t bit = __funnelshift_r(w, 0u, x);  // bit (key & 31)
                     if (BLOOM == 2) {
