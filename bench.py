@@ -486,6 +486,15 @@ def run_ours(a):
         except Exception as ex:  # e.g. CUDA IPC not permitted in this container: one NCCL all-gather instead
             peer["x"], peer["why"] = None, str(ex)
 
+    def feed_packed():
+        """H2D of this rank's packed shard: the codes, and the bitmap as its run list when it has one."""
+        host_slice["dcodes"].copy_(host_slice["codes"], non_blocking=True)
+        if host_slice.get("runs") is not None:
+            runs, n_runs = host_slice["runs"]
+            D.inval_from_runs(sc, host_slice["dinval"], host_slice["n"], runs, n_runs)
+        else:
+            host_slice["dinval"].copy_(host_slice["inval"], non_blocking=True)
+
     def step_peer(from_host=False):
         launches = 0
         while True:
@@ -496,8 +505,7 @@ def run_ours(a):
                 evs[0].record()
                 blk = peer["x"].begin_step()
                 if from_host:
-                    host_slice["dcodes"].copy_(host_slice["codes"], non_blocking=True)
-                    host_slice["dinval"].copy_(host_slice["inval"], non_blocking=True)
+                    feed_packed()
                     D.find_sites_block_packed(cp, sc, host_slice["dcodes"], host_slice["dinval"], host_slice["n"],
                                               host_slice["segs"], n_recs, blk, peer["x"].site_cap)
                 else:
@@ -532,8 +540,7 @@ def run_ours(a):
                 h0 = time.perf_counter()
                 evs[0].record()
                 if from_host:  # this rank's shard, packed, from its own pinned host buffers
-                    host_slice["dcodes"].copy_(host_slice["codes"], non_blocking=True)
-                    host_slice["dinval"].copy_(host_slice["inval"], non_blocking=True)
+                    feed_packed()
                     D.find_sites_block_packed(cp, sc, host_slice["dcodes"], host_slice["dinval"], host_slice["n"],
                                               host_slice["segs"], n_recs, blocks["mine"], site_cap)
                 else:
@@ -650,11 +657,14 @@ def run_ours(a):
             d2h = int(t[0])
         e2e_stage = {k: te[k] for k in ("h2d_ms", "pack_ms", "filter_ms", "verify_ms", "pair_ms", "total_ms")}
         g = n_units * total / 1e9
-        packed_bytes = n_units * ((total + 4095) // 4096 * 4096 // 32 + 1) * 12
+        # 2-bit codes (8 bytes per 32 bases); the hard-mismatch bitmap of this N-free genome travels as a run list
+        # of a few bytes (12 bytes per 32 bases when --n-per-mbp scatters too many runs for that)
+        packed_bytes = n_units * ((total + 4095) // 4096 * 4096 // 32 + 1) * (8 if a.n_per_mbp == 0 else 12)
         e2e = {"value": g / (e2e_ms / 1e3) * len(user_pairs), "unit": UNIT, "ms_per_step": e2e_ms,
                "gbp_per_s": g / (e2e_ms / 1e3), "h2d_bytes_per_step": packed_bytes, "d2h_bytes_per_step": d2h,
                "api": "ipcr_gpu_scan_fasta(feeder handle holding the packed records in pinned host memory) -> products "
-                      "(C ABI): H2D of 2-bit codes + hard-mismatch bitmap in slabs under the scan, verify on the codes",
+                      "(C ABI): H2D of the 2-bit codes in slabs under the scan (the hard-mismatch bitmap as a run list, rebuilt on "
+                      "the device), verify on the codes",
                "feeder_pack_s_untimed": feeder_pack_s,
                "ascii": {"value": g / (ascii_ms / 1e3) * len(user_pairs), "ms_per_step": ascii_ms,
                          "h2d_bytes_per_step": n_units * total, "stage_ms": ascii_stage,
@@ -674,7 +684,8 @@ def run_ours(a):
                         & (seg != 103) & (seg != 116)).any())
             psegs.append((s0 - lo, s1 - s0, own, rec_off, c, bad))
         host_slice.update(t=hs, codes=hc, inval=hi_, dcodes=torch.empty_like(hc, device=dev),
-                          dinval=torch.empty_like(hi_, device=dev), segs=psegs, n=piece_end - lo)
+                          dinval=torch.empty_like(hi_, device=dev), segs=psegs, n=piece_end - lo,
+                          runs=D.packed_runs(hi_, piece_end - lo, max_runs=max(4096, hi_.numel() // 64)))
         step_multi(from_host=True)  # warm
         torch.cuda.synchronize()
         dist.barrier()
@@ -687,14 +698,15 @@ def run_ours(a):
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0])
-        t = torch.tensor([(host_slice["codes"].numel() + host_slice["inval"].numel()) * 4], dtype=torch.int64, device=dev)
+        t = torch.tensor([host_slice["codes"].numel() * 4 + (host_slice["runs"][1] * 16 if host_slice.get("runs") is not None
+                                                              else host_slice["inval"].numel() * 4)], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         h2d = int(t[0])
         e2e_stage = {k: te[k] for k in ("pack_ms", "filter_ms", "verify_ms", "pair_ms", "gather_ms", "find_total_ms")}
         g = total / 1e9
         e2e = {"value": g / (e2e_ms / 1e3) * len(user_pairs), "unit": UNIT, "ms_per_step": e2e_ms,
                "gbp_per_s": g / (e2e_ms / 1e3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n_e2e * 64 * world,
-               "api": "per rank: packed shard (2-bit codes + bitmap, pinned host) -> H2D -> ipcr_gpu_find_sites_block_packed "
+               "api": "per rank: packed shard (2-bit codes + the bitmap's run list, pinned host) -> H2D -> ipcr_gpu_find_sites_block_packed "
                       "-> NCCL all-gather of site blocks -> ipcr_gpu_pair_blocks -> products on the host of every rank (C ABI)"}
         if n_e2e != n_prod:
             raise RuntimeError(f"packed sharded e2e returned {n_e2e} products, device-resident path {n_prod}")

@@ -302,6 +302,14 @@ int ipcr_gpu_fasta_packed(const ipcr_fasta *f, const uint32_t **codes, const uin
  * codes[*code_words], inval[*inval_words] for n_bases bases, padding included */
 void ipcr_gpu_packed_words(uint64_t n_bases, uint64_t *code_words, uint64_t *inval_words);
 int ipcr_gpu_pack_host(const uint8_t *ascii, uint64_t n_bases, uint32_t *codes, uint32_t *inval, int threads);
+/* The bitmap of a real genome is nearly empty (few, long N runs): as a list of runs [runs[2i], runs[2i+1]) of
+ * invalid bases (padding included) it is a few KB instead of 0.125 B/bp.  Returns the number of runs written, or
+ * -1 when there are more than max_runs (ship the bitmap then).  ipcr_gpu_scan_fasta does this by itself. */
+int64_t ipcr_gpu_packed_runs(const uint32_t *inval, uint64_t n_bases, uint64_t *runs, uint64_t max_runs, int threads);
+/* rebuilds the bitmap words of n_bases bases in DEVICE memory from such a run list; queued on the scratch's stream
+ * (call it before ipcr_gpu_find_sites_block_packed of the same step) */
+int ipcr_gpu_inval_from_runs(ipcr_scratch *s, uint32_t *d_inval, uint64_t n_bases, const uint64_t *runs, uint64_t n_runs,
+                             char *err, size_t errlen);
 void ipcr_gpu_fasta_close(ipcr_fasta *f);
 size_t ipcr_gpu_fasta_num_records(const ipcr_fasta *f);
 uint64_t ipcr_gpu_fasta_total_bases(const ipcr_fasta *f);

@@ -121,6 +121,7 @@ SYMBOLS = [
     "ipcr_gpu_sort_products", "ipcr_gpu_fasta_from_memory",
     "ipcr_gpu_peer_create", "ipcr_gpu_peer_open", "ipcr_gpu_peer_begin_step", "ipcr_gpu_peer_publish",
     "ipcr_gpu_pair_peers", "ipcr_gpu_peer_close", "ipcr_gpu_fasta_is_packed", "ipcr_gpu_fasta_packed", "ipcr_gpu_packed_words", "ipcr_gpu_pack_host",
+    "ipcr_gpu_packed_runs", "ipcr_gpu_inval_from_runs",
     "ipcr_gpu_panel_create", "ipcr_gpu_panel_destroy", "ipcr_gpu_panel_num_pairs",
     "ipcr_gpu_panel_num_orientations", "ipcr_gpu_panel_have", "ipcr_gpu_panel_set_jit", "ipcr_gpu_panel_set_filter",
     "ipcr_gpu_scratch_create", "ipcr_gpu_scratch_destroy",
@@ -196,6 +197,8 @@ def lib():
     sig("ipcr_gpu_fasta_packed", C.c_int, V, P(P(C.c_uint32)), P(P(C.c_uint32)), P(U64))
     sig("ipcr_gpu_packed_words", None, U64, P(U64), P(U64))
     sig("ipcr_gpu_pack_host", C.c_int, V, U64, V, V, C.c_int)
+    sig("ipcr_gpu_packed_runs", C.c_int64, V, U64, P(U64), U64, C.c_int)
+    sig("ipcr_gpu_inval_from_runs", C.c_int, V, V, U64, P(U64), U64, *ERR)
     sig("ipcr_gpu_find_sites_block_packed", C.c_int, V, V, V, V, U64, P(PackedSegmentC), SZ, SZ, C.c_int, V, U64, *ERR)
     sig("ipcr_gpu_peer_create", C.c_int, V, SZ, U64, V, *ERR)
     sig("ipcr_gpu_peer_open", C.c_int, V, V, C.c_uint32, C.c_uint32, *ERR)

@@ -319,7 +319,7 @@ struct ipcr_scratch {
     std::vector<ipcr_scratch *> peers;          // one scratch per further device (multi-GPU inside one process)
     cudaEvent_t done_ev = nullptr;              // peer: its block has arrived on the primary device
     bool own_laid = false;                      // multi-device retry: the slice is already resident
-    ipcr::DevBuf seg_reset_dummy, chunk_ctr, verify_done, pair_dbg;
+    ipcr::DevBuf seg_reset_dummy, chunk_ctr, verify_done, pair_dbg, runs_dev;
     uint64_t pending_publish = 0;  // peer exchange: step number the next stage 1 publishes from inside k_verify
     // peer exchange (one process per GPU): own double-buffered block, exported through CUDA IPC; the peers' mappings
     ipcr::DevBuf peer_buf, peer_tab[2];
@@ -1822,6 +1822,34 @@ struct ipcr_fasta {
     // packed form of the whole sequence buffer (IPCR_FASTA_PACK): codes + hard-mismatch bitmap, pinned
     uint32_t *codes = nullptr, *inval = nullptr;
     bool packed_pinned = false;  // page-locking costs ~0.5 s per GB: only worth it for handles scanned many times
+    // the bitmap as a run list (a real genome's N runs are few): shipped instead of the 0.125 B/bp bitmap
+    std::vector<uint64_t> inval_runs;
+    bool runs_ok = false;
+    // per-record reset flags: from the run list when there is one (O(runs log records)), else from the bitmap
+    void find_rec_reset() {
+        rec_reset.assign(recs.size(), 0);
+        if (!runs_ok) {
+            for (size_t r = 0; r < recs.size(); r++)
+                rec_reset[r] = ipcr::packed_any_invalid(inval, recs[r].off, recs[r].off + recs[r].len) ? 1 : 0;
+            return;
+        }
+        for (size_t i = 0; i + 1 < inval_runs.size(); i += 2) {
+            const uint64_t a = inval_runs[i], b = std::min<uint64_t>(inval_runs[i + 1], total);
+            if (a >= b) continue;  // the padding behind the last record
+            size_t lo = 0, hi = recs.size();  // first record whose end lies beyond a
+            while (lo < hi) {
+                const size_t mid = (lo + hi) / 2;
+                if (recs[mid].off + recs[mid].len > a) hi = mid; else lo = mid + 1;
+            }
+            for (size_t r = lo; r < recs.size() && recs[r].off < b; r++)
+                if (recs[r].len) rec_reset[r] = 1;
+        }
+    }
+    void find_runs(int threads) {
+        const uint64_t groups = ipcr::packed_groups(total);
+        runs_ok = ipcr::packed_invalid_runs_mt(inval, groups, std::max<uint64_t>(4096, groups / 64), inval_runs, threads);
+        if (!runs_ok) inval_runs.clear();
+    }
     std::vector<uint8_t> rec_reset;  // per record: holds a non-ACGT byte (the feeder upper-cased a-z already)
     std::vector<ipcr_product> products;
     void alloc_packed(uint64_t total, bool pin) {
@@ -1860,9 +1888,8 @@ struct ipcr_fasta {
 static void fasta_pack(ipcr_fasta *f, int threads, bool pin) {
     f->alloc_packed(f->total, pin);
     pack_host(f->seq, f->total, f->codes, f->inval, threads);
-    f->rec_reset.assign(f->recs.size(), 0);
-    for (size_t r = 0; r < f->recs.size(); r++)
-        f->rec_reset[r] = packed_any_invalid(f->inval, f->recs[r].off, f->recs[r].off + f->recs[r].len) ? 1 : 0;
+    f->find_runs(threads);
+    f->find_rec_reset();
 }
 
 // host records -> products in s->h_products (shared by scan_batch and scan_fasta)
@@ -1955,9 +1982,8 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
                 fb.size, threads, alloc_s, want_pack ? "yes" : "no", pin ? "yes" : "no",
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() - alloc_s);
     if (want_pack) {
-        f->rec_reset.assign(f->recs.size(), 0);
-        for (size_t r = 0; r < f->recs.size(); r++)
-            f->rec_reset[r] = packed_any_invalid(f->inval, f->recs[r].off, f->recs[r].off + f->recs[r].len) ? 1 : 0;
+        f->find_runs(threads);
+        f->find_rec_reset();
     }
     return f.release();
     ABI_CATCH(nullptr)
@@ -2029,6 +2055,38 @@ void ipcr_gpu_packed_words(uint64_t n_bases, uint64_t *code_words, uint64_t *inv
     if (inval_words) *inval_words = g;
 }
 
+int64_t ipcr_gpu_packed_runs(const uint32_t *inval, uint64_t n_bases, uint64_t *runs, uint64_t max_runs, int threads) {
+    if (!inval || (!runs && max_runs)) return -1;
+    if (threads <= 0) threads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    std::vector<uint64_t> r;
+    if (!packed_invalid_runs_mt(inval, packed_groups(n_bases), max_runs, r, threads)) return -1;
+    memcpy(runs, r.data(), r.size() * sizeof(uint64_t));
+    return (int64_t)(r.size() / 2);
+}
+
+int ipcr_gpu_inval_from_runs(ipcr_scratch *s, uint32_t *d_inval, uint64_t n_bases, const uint64_t *runs, uint64_t n_runs,
+                             char *err, size_t errlen) {
+    ABI_TRY
+    if (!s || !d_inval || (!runs && n_runs)) throw Error("scratch / bitmap / runs is NULL");
+    bind(s);
+    if (s->inflight) CU(cudaStreamSynchronize(s->stream));  // the staging buffer below may still be in use
+    s->inflight = false;
+    s->args_used = 0;
+    const uint64_t groups = packed_groups(n_bases);
+    for (uint64_t i = 0; i < n_runs; i++)
+        if (runs[2 * i] > runs[2 * i + 1] || runs[2 * i + 1] > groups * 32ull) throw Error("run outside the packed buffer");
+    CU(cudaMemsetAsync(d_inval, 0, (size_t)groups * 4, s->stream));
+    if (n_runs) {
+        upload_staged(s, s->runs_dev, runs, n_runs * 16);
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_runs * 32 + 255) / 256, (uint64_t)s->sm_count * 8);
+        k_inval_fill<<<grid, 256, 0, s->stream>>>(s->runs_dev.as<unsigned long long>(), n_runs, d_inval);
+        check_launch("k_inval_fill");
+    }
+    s->inflight = true;
+    return 0;
+    ABI_CATCH(1)
+}
+
 int ipcr_gpu_pack_host(const uint8_t *ascii, uint64_t n_bases, uint32_t *codes, uint32_t *inval, int threads) {
     if ((!ascii && n_bases) || !codes || !inval) return 1;
     if (threads <= 0) threads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
@@ -2068,7 +2126,8 @@ int ipcr_gpu_scan_fasta(ipcr_panel *p, ipcr_scratch *s, ipcr_fasta *f, const ipc
         roff[f->recs.size()] = f->total;
         if (!s->inflight) s->args_used = 0;
         if (chain_ok(s, rinfo.data(), rinfo.size())) {
-            PackedHost ph{f->codes, f->inval, f->total};
+            PackedHost ph{f->codes, f->inval, f->total, f->runs_ok && !getenv("IPCR_NO_RUNS") ? f->inval_runs.data() : nullptr,
+                          f->inval_runs.size() / 2};
             uint64_t n = 0;
             if (scan_packed_chain(s, ph, rinfo, roff, &n)) {
                 f->products.assign(s->out_ptr, s->out_ptr + n);

@@ -165,6 +165,8 @@ struct PackedHost {
     const uint32_t *codes = nullptr;  // [2 * packed_groups(total)]
     const uint32_t *inval = nullptr;  // [packed_groups(total)]
     uint64_t total = 0;               // bases in the concatenated buffer
+    const uint64_t *runs = nullptr;   // optional: the bitmap as [start, end) runs (then only the codes cross PCIe)
+    uint64_t n_runs = 0;
 };
 
 static bool scan_packed_chain(ipcr_scratch *s, const PackedHost &ph, const std::vector<ipcr_record_info> &rinfo,
@@ -200,6 +202,17 @@ static bool scan_packed_chain(ipcr_scratch *s, const PackedHost &ph, const std::
     //    (its chunks, the halo's chunk and one look-ahead group)
     CU(cudaEventRecord(s->ev[0], st));
     CU(cudaEventRecord(s->copy_ev[0], cs));
+    const bool by_runs = ph.runs != nullptr;
+    if (by_runs) {  // the bitmap is rebuilt on the device from its run list: 0.25 B/bp cross PCIe instead of 0.375
+        CU(cudaMemsetAsync(own.inval.p, 0, (size_t)groups * 4, st));
+        if (ph.n_runs) {
+            upload(s->runs_dev, ph.runs, ph.n_runs * 16, st);
+            const unsigned grid = (unsigned)std::min<uint64_t>((ph.n_runs * 32 + 255) / 256, (uint64_t)s->sm_count * 8);
+            k_inval_fill<<<grid, 256, 0, st>>>(s->runs_dev.as<unsigned long long>(), ph.n_runs, own.inval.as<uint32_t>());
+            check_launch("k_inval_fill");
+            s->launches++;
+        }
+    }
     uint64_t g_done = 0;
     for (int k = 0; k < n_slabs; k++) {
         const uint64_t end = std::min(total, c.cut[k + 1] + kPieceHalo);
@@ -207,8 +220,9 @@ static bool scan_packed_chain(ipcr_scratch *s, const PackedHost &ph, const std::
         if (g_want > g_done) {
             CU(cudaMemcpyAsync(own.codes.as<uint32_t>() + 2 * g_done, ph.codes + 2 * g_done, (g_want - g_done) * 8,
                                cudaMemcpyHostToDevice, cs));
-            CU(cudaMemcpyAsync(own.inval.as<uint32_t>() + g_done, ph.inval + g_done, (g_want - g_done) * 4,
-                               cudaMemcpyHostToDevice, cs));
+            if (!by_runs)
+                CU(cudaMemcpyAsync(own.inval.as<uint32_t>() + g_done, ph.inval + g_done, (g_want - g_done) * 4,
+                                   cudaMemcpyHostToDevice, cs));
             g_done = g_want;
         }
         CU(cudaEventRecord(s->slab_ev[k], cs));

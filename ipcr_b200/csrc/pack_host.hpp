@@ -73,6 +73,82 @@ inline void pack_host(const uint8_t *ascii, uint64_t n, uint32_t *codes, uint32_
     for (auto &x : th) x.join();
 }
 
+// The bitmap of a real genome is almost empty (N runs are few and long): as a list of runs [start, end) it is
+// a few KB instead of 0.125 B/bp, and the device rebuilds the words (k_inval_fill).  Includes the padding
+// positions behind n (the packer marks them invalid).  Returns false when there are more than max_runs runs
+// (scattered IUPAC codes): the caller then ships the bitmap itself.
+inline bool packed_invalid_runs(const uint32_t *inval, uint64_t groups, uint64_t max_runs, std::vector<uint64_t> &runs) {
+    runs.clear();
+    bool open = false;
+    uint64_t start = 0;
+    for (uint64_t g = 0; g < groups; g++) {
+        const uint32_t w = inval[g];
+        if (w == 0u) {
+            if (open) {
+                runs.push_back(start);
+                runs.push_back(g * 32ull);
+                open = false;
+                if (runs.size() / 2 > max_runs) return false;
+            }
+            continue;
+        }
+        if (w == 0xFFFFFFFFu) {
+            if (!open) {
+                open = true;
+                start = g * 32ull;
+            }
+            continue;
+        }
+        for (uint32_t i = 0; i < 32u; i++) {
+            const bool bad = (w >> i) & 1u;
+            if (bad && !open) {
+                open = true;
+                start = g * 32ull + i;
+            } else if (!bad && open) {
+                runs.push_back(start);
+                runs.push_back(g * 32ull + i);
+                open = false;
+            }
+        }
+        if (runs.size() / 2 > max_runs) return false;
+    }
+    if (open) {
+        runs.push_back(start);
+        runs.push_back(groups * 32ull);
+    }
+    return runs.size() / 2 <= max_runs;
+}
+
+// the same over several threads: each takes a range of groups, runs that touch at a range boundary are merged
+inline bool packed_invalid_runs_mt(const uint32_t *inval, uint64_t groups, uint64_t max_runs, std::vector<uint64_t> &runs,
+                                   int threads) {
+    if (threads < 2 || groups < (1u << 20)) return packed_invalid_runs(inval, groups, max_runs, runs);
+    std::vector<std::vector<uint64_t>> part((size_t)threads);
+    std::vector<char> ok((size_t)threads, 1);
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) {
+        const uint64_t g0 = groups * (uint64_t)t / (uint64_t)threads, g1 = groups * (uint64_t)(t + 1) / (uint64_t)threads;
+        th.emplace_back([&, t, g0, g1] {
+            ok[(size_t)t] = packed_invalid_runs(inval + g0, g1 - g0, max_runs, part[(size_t)t]) ? 1 : 0;
+            for (uint64_t &v : part[(size_t)t]) v += g0 * 32ull;
+        });
+    }
+    for (auto &x : th) x.join();
+    runs.clear();
+    for (int t = 0; t < threads; t++) {
+        if (!ok[(size_t)t]) return false;
+        for (size_t i = 0; i + 1 < part[(size_t)t].size(); i += 2) {
+            if (!runs.empty() && runs.back() == part[(size_t)t][i]) runs.back() = part[(size_t)t][i + 1];
+            else {
+                runs.push_back(part[(size_t)t][i]);
+                runs.push_back(part[(size_t)t][i + 1]);
+            }
+        }
+        if (runs.size() / 2 > max_runs) return false;
+    }
+    return true;
+}
+
 // does [a, b) hold an invalid base?  (per-record reset flags of the feeder: it upper-cases a-z, so an
 // invalid byte IS a reset byte, core/engine/ac.go:141-148)
 inline bool packed_any_invalid(const uint32_t *inval, uint64_t a, uint64_t b) {

@@ -108,6 +108,27 @@ k_pack2(Pack2Args a) {
     }
 }
 
+// The hard-mismatch bitmap from its run list (pack_host.hpp: packed_invalid_runs): one warp per run, the lanes
+// stride over the run's words; partial first / last words are OR-ed in atomically (two runs may share a word).
+// The bitmap was zeroed before.
+__global__ void __launch_bounds__(256)
+k_inval_fill(const unsigned long long *__restrict__ runs, uint64_t n_runs, uint32_t *__restrict__ inval) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n_runs; r += n_warps) {
+        const uint64_t a = runs[2 * r], b = runs[2 * r + 1];  // [a, b)
+        if (a >= b) continue;
+        const uint64_t w0 = a >> 5, w1 = (b - 1) >> 5;
+        for (uint64_t w = w0 + lane; w <= w1; w += 32u) {
+            uint32_t m = 0xFFFFFFFFu;
+            if (w == w0) m &= 0xFFFFFFFFu << (a & 31u);
+            if (w == w1 && (b & 31u) != 0u) m &= (1u << (b & 31u)) - 1u;
+            if (m == 0xFFFFFFFFu) inval[w] = m;  // interior words belong to this run alone
+            else atomicOr(&inval[w], m);
+        }
+    }
+}
+
 struct SeedExpandArgs {
     const unsigned long long *dirty;
     uint64_t n_dirty;

@@ -330,6 +330,19 @@ def pack_host(buf, threads: int = 0):
     return codes, inval
 
 
+def packed_runs(inval, n_bases: int, max_runs: int = 1 << 20, threads: int = 0):
+    """Run list of a host bitmap (ipcr_gpu_packed_runs): ctypes uint64 array of 2 * n entries and n, or None."""
+    runs = (C.c_uint64 * (2 * max_runs + 2))()
+    n = _capi.lib().ipcr_gpu_packed_runs(_ptr(inval), n_bases, runs, max_runs, threads)
+    return (runs, int(n)) if n >= 0 else None
+
+
+def inval_from_runs(scratch: SimulationScratch, d_inval, n_bases: int, runs, n_runs: int) -> None:
+    """Rebuild the device bitmap from a run list, on the scratch's stream."""
+    err = _capi.errbuf()
+    _capi.check(_capi.lib().ipcr_gpu_inval_from_runs(scratch._h, _ptr(d_inval), n_bases, runs, n_runs, err, len(err)), err)
+
+
 def find_sites_block_packed(cp: CompiledPanel, scratch: SimulationScratch, codes, inval, n_bases: int,
                             segments: Sequence[Tuple], n_recs: int, block, site_cap: int, force_raw: bool = False):
     """Stage 1 from a packed DEVICE buffer.  segments: (off, len, own_len, rec_off, rec_idx, has_reset_byte)."""

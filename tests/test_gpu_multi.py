@@ -213,6 +213,10 @@ def test_packed_feeder_scan_equals_ascii_and_oracle(oracle, monkeypatch):
             monkeypatch.setenv("IPCR_STREAM_SLABS", slabs)
             got = [(p.sequence_id,) + _tuple(p) for p in packed.scan(cp, sc)]
             assert got == want, (cfgd, slabs)
+        # the bitmap travels as a run list by default (rebuilt on the device); the same with the bitmap itself
+        monkeypatch.setenv("IPCR_NO_RUNS", "1")
+        assert [(p.sequence_id,) + _tuple(p) for p in packed.scan(cp, sc)] == want, cfgd
+        monkeypatch.delenv("IPCR_NO_RUNS")
         monkeypatch.delenv("IPCR_STREAM_SLABS")
         assert [(p.sequence_id,) + _tuple(p) for p in plain.scan(cp, sc)] == want
         packed.close()
