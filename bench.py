@@ -500,6 +500,7 @@ def run_ours(a):
         while True:
             if D.scratch_site_cap(sc) != peer["x"].site_cap:  # a block overflowed: bigger blocks, new mappings
                 peer["x"].close()
+                dist.barrier()  # every import is closed before any rank frees the block it exported
                 peer["x"] = D.PeerExchange(dist, sc, n_recs, rank, world, dev)
             with torch.cuda.stream(ext):
                 evs[0].record()

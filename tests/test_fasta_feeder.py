@@ -230,3 +230,41 @@ def test_feeder_fast_paths_and_fused_pack(tmp_path):
         got_i = np.ctypeslib.as_array(pi, shape=(ng.value,)).copy()
         assert np.array_equal(got_c, wc) and np.array_equal(got_i, wi), threads
         ff.close()
+
+
+def test_invalid_run_list_round_trips():
+    """ipcr_gpu_packed_runs: the hard-mismatch bitmap as [start, end) runs (what crosses PCIe instead of the bitmap);
+    expanding the runs gives the bitmap back, padding included; too many runs are refused."""
+    import ctypes as C
+
+    import numpy as np
+
+    from ipcr_b200 import _capi
+
+    L = _capi.lib()
+    rng = np.random.default_rng(3)
+    for n in (0, 5, 4096, 70001, 3_000_000):
+        a = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+        for _ in range(min(40, n // 50)):  # N runs of mixed lengths, some adjacent to word boundaries
+            at = int(rng.integers(0, n))
+            a[at:at + int(rng.choice([1, 2, 31, 32, 33, 500, 5000]))] = ord("N")
+        cw, iw = C.c_uint64(), C.c_uint64()
+        L.ipcr_gpu_packed_words(n, C.byref(cw), C.byref(iw))
+        codes = np.zeros(cw.value, dtype=np.uint32)
+        inval = np.zeros(iw.value, dtype=np.uint32)
+        assert L.ipcr_gpu_pack_host(a.tobytes(), n, codes.ctypes.data, inval.ctypes.data, 2) == 0
+        runs = (C.c_uint64 * 400)()
+        for threads in (1, 4):
+            k = L.ipcr_gpu_packed_runs(inval.ctypes.data, n, runs, 199, threads)
+            assert k >= 1  # at least the padding behind the last base
+            bits = np.zeros(iw.value * 32, dtype=np.uint8)
+            prev_end = -1
+            for i in range(k):
+                lo, hi = runs[2 * i], runs[2 * i + 1]
+                assert prev_end < lo < hi <= iw.value * 32  # disjoint, ascending, not touching
+                bits[lo:hi] = 1
+                prev_end = hi
+            back = (bits.reshape(-1, 32).astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+            assert np.array_equal(back, inval), (n, threads)
+        if n >= 70001:
+            assert L.ipcr_gpu_packed_runs(inval.ctypes.data, n, runs, 3, 1) == -1

@@ -253,7 +253,15 @@ def test_block_split_phase_packed_equals_oracle(oracle):
                 s0, s1, own1 = max(offs[c], lo), min(offs[c + 1], end), min(offs[c + 1], hi)
                 if s0 < s1 and own1 > s0:
                     segs.append((s0 - lo, s1 - s0, own1 - s0, s0 - offs[c], c, reset[c]))
-            pieces.append((codes.cuda(), inval.cuda(), end - lo, segs))
+            d_inval = inval.cuda()
+            got_runs = D.packed_runs(inval, end - lo, max_runs=4096)
+            if got_runs is not None and k % 2 == 0:  # every other shard: the bitmap rebuilt on the device from its runs
+                rebuilt = torch.full_like(d_inval, 0x5A5A5A5A)
+                D.inval_from_runs(sc, rebuilt, end - lo, *got_runs)
+                torch.cuda.synchronize()
+                assert torch.equal(rebuilt.cpu(), inval)
+                d_inval = rebuilt
+            pieces.append((codes.cuda(), d_inval, end - lo, segs))
         while True:
             cap = D.scratch_site_cap(sc)
             bb = D.site_block_bytes(len(lens), cap)
