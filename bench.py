@@ -330,7 +330,7 @@ class ClockSampler:
 
 # dram bytes (read + write) of one launch from the committed `ncu --set full` capture of the
 # bench command (profiles/README.md says which file); None until captured
-NCU_TRAFFIC = {"k_seed_scan": 1.1918e9,    # profiles/r01_ncu_full_k_seed_scan.csv (3 Gbp, 400 orientations)
+NCU_TRAFFIC = {"k_seed_scan": 1.1927e9,    # profiles/r02_ncu_full_k_seed_scan.csv (3 Gbp, 400 orientations): 1.1882 GB read + 4.5 MB written
                "ipcr_scan_jit": 1.635e9}   # profiles/r01_ncu_full_scan_jit_and_pack_raw.csv (3 Gbp, one group)
 
 
