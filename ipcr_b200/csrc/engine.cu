@@ -991,7 +991,8 @@ static void launch_seed_scan(ipcr_scratch *s, const SeedIndex &ix, const SeedSca
         CU(cudaMemsetAsync(s->chunk_ctr.p, 0, 8, s->stream));
         a.chunk_counter = s->chunk_ctr.as<unsigned long long>();
     }
-    if (!ix.use_bloom) k_seed_scan<0><<<grid, 1024, 0, s->stream>>>(a);
+    if (ix.pigeon) k_seed_scan<3><<<grid, 1024, kSeedHalfWords * 2 * 4, s->stream>>>(a);
+    else if (!ix.use_bloom) k_seed_scan<0><<<grid, 1024, 0, s->stream>>>(a);
     else if (ix.bloom_k == 1) k_seed_scan<1><<<grid, 1024, smem, s->stream>>>(a);
     else if (var == 1) k_seed_scan<2, 1><<<grid, 1024, smem, s->stream>>>(a);
     else if (var == 4) k_seed_scan<2, 4><<<grid, 1024, smem, s->stream>>>(a);

@@ -32,6 +32,7 @@ namespace ipcr {
 
 constexpr uint32_t kSeedBloomWords = 57344;  // 224 KB of shared memory
 constexpr uint32_t kSeedBloomBits = kSeedBloomWords * 32u;
+constexpr uint32_t kSeedHalfWords = 2048;  // pigeonhole tables: 65536 bits per half window
 constexpr uint32_t kSeedBloomMul = 0x85EBCA6Bu;
 constexpr uint32_t kSeedHashMul = 0x9E3779B1u;
 constexpr int kSeedMaxLen = 16;                    // 2 bits per base in a 32-bit k-mer
@@ -74,6 +75,12 @@ struct SeedIndex {
     uint32_t bitmap2_mul = 1, bitmap2_shift = 5;
     bool use_bloom = false;
     int bloom_k = 1;  // bits per k-mer
+    // PIGEONHOLE first level (S = 16; replaces the bitmap when the panel's keys would saturate it, e.g. mm 3 x 400
+    // orientations): a window with <= m mismatches has <= m / 2 of them in its low or in its high 8 bases.
+    // bloom[0, 2048) = one bit per low 8-mer within m / 2 mismatches of some orientation's low half (protected
+    // columns exact, IUPAC expanded), bloom[2048, 4096) the same for the high halves.  pass = either half hits.
+    bool pigeon = false;
+    double pigeon_pass = 0.0;  // modelled share of positions that go on to the second level
     uint64_t n_entries = 0;
     uint64_t n_keys1 = 0;     // distinct first-level keys
     double bloom_fill = 0.0;  // fraction of bitmap bits set
@@ -128,6 +135,29 @@ inline void seed_enumerate(const Orient &o, int S, int max_mm, int tw, bool raw,
             const bool match = (cls >> b) & 1;
             if (!match && (prot || f.mm >= max_mm)) continue;
             stack.push_back({f.j + 1, f.kmer | (kSeedCodeOfBit[b] << (2 * f.j)), f.mm + (match ? 0 : 1)});
+        }
+    }
+}
+
+// every 8-mer within t mismatches of columns [c0, c0 + 8) of orientation o's S = 16 seed window -> one bit each
+inline void seed_half_enumerate(const Orient &o, int c0, int t, int tw, bool raw, std::vector<uint32_t> &table) {
+    const int off = seed_col_off(o, 16) + c0;
+    struct Frame { int j; uint32_t v; int mm; };
+    std::vector<Frame> stack;
+    stack.push_back({0, 0u, 0});
+    while (!stack.empty()) {
+        const Frame f = stack.back();
+        stack.pop_back();
+        if (f.j == 8) {
+            table[f.v >> 5] |= 1u << (f.v & 31u);
+            continue;
+        }
+        const uint8_t cls = o.cls[off + f.j];
+        const bool prot = seed_col_protected(o, off + f.j, tw, raw);
+        for (int b = 0; b < 4; b++) {
+            const bool match = (cls >> b) & 1;
+            if (!match && (prot || f.mm >= t)) continue;
+            stack.push_back({f.j + 1, f.v | (kSeedCodeOfBit[b] << (2 * f.j)), f.mm + (match ? 0 : 1)});
         }
     }
 }
@@ -262,6 +292,40 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
     ix.bloom_fill = (double)bits_set / (double)kSeedBloomBits;
     ix.use_bloom = ix.S1 >= 3 && seed_pass_rate((double)ix.n_keys1, ix.S1, ix.bloom_k) <= 0.5;
     if (const char *e = getenv("IPCR_SEED_BLOOM")) ix.use_bloom = atoi(e) != 0 && ix.S1 >= 3;
+    // pigeonhole first level: worth it when the bitmap is (nearly) useless and the half-window tables are selective
+    {
+        bool all16 = ix.S == 16;
+        for (const Orient &o : h.orients) all16 = all16 && o.L >= 16;
+        int want = -1;  // -1 = decide by the model
+        if (const char *e = getenv("IPCR_SEED_PIGEON")) want = atoi(e) != 0 ? 1 : 0;
+        if (all16 && want != 0) {
+            std::vector<uint32_t> lo(kSeedHalfWords, 0u), hi(kSeedHalfWords, 0u);
+            const int t = mm / 2;
+            for (const Orient &o : h.orients) {
+                seed_half_enumerate(o, 0, t, tw, raw, lo);
+                seed_half_enumerate(o, 8, t, tw, raw, hi);
+            }
+            uint64_t nlo = 0, nhi = 0;
+            for (uint32_t w : lo) nlo += (uint64_t)__builtin_popcount(w);
+            for (uint32_t w : hi) nhi += (uint64_t)__builtin_popcount(w);
+            const double pass = 1.0 - (1.0 - (double)nlo / 65536.0) * (1.0 - (double)nhi / 65536.0);
+            // fast path costs ~2.2 bitmap lookups (two LDS, more shifts); the second level as in seed_cost()
+            const double prob = (double)ix.n_entries / std::pow(4.0, ix.S);
+            const double cost_pigeon = 2.2 + (pass <= 0.5 ? 50.0 * std::pow(pass, 1.8) : 15.0) + prob * 675.0;
+            const double cost_now = ix.use_bloom ? seed_cost((double)ix.n_entries, ix.S, (double)ix.n_keys1, ix.S1, ix.bloom_k)
+                                                 : 1.0 + 15.0 + prob * 675.0;
+            if (want == 1 || cost_pigeon < cost_now) {
+                ix.pigeon = true;
+                ix.pigeon_pass = pass;
+                ix.use_bloom = true;
+                ix.bloom_k = 3;  // reported by the debug tap: 3 = pigeonhole tables
+                ix.S1 = ix.S;  // the kernel looks at the window where it starts (d = 0)
+                std::fill(ix.bloom.begin(), ix.bloom.end(), 0u);
+                std::copy(lo.begin(), lo.end(), ix.bloom.begin());
+                std::copy(hi.begin(), hi.end(), ix.bloom.begin() + kSeedHalfWords);
+            }
+        }
+    }
     ix.cand_prob = (double)ix.n_entries / std::pow(4.0, ix.S);
     return ix;
 }
@@ -281,7 +345,12 @@ inline void seed_eval(const Panel &h, const SeedIndex &ix, const uint8_t *seq, u
             kmer |= (uint32_t)((b >> 1) & 3u) << (2 * j);
         }
         if (n_inv == 0) {
-            if (ix.use_bloom) {
+            if (ix.pigeon) {
+                const uint32_t lo = kmer & 0xFFFFu, hi = kmer >> 16;
+                const bool in_lo = (ix.bloom[lo >> 5] >> (lo & 31u)) & 1u;
+                const bool in_hi = (ix.bloom[kSeedHalfWords + (hi >> 5)] >> (hi & 31u)) & 1u;
+                if (!in_lo && !in_hi) continue;
+            } else if (ix.use_bloom) {
                 uint32_t m;
                 const uint32_t w = seed_bloom_word(kmer >> (2 * (ix.S - ix.S1)), ix.S1, ix.bloom_k, m);
                 if ((ix.bloom[w] & m) != m) continue;

@@ -15,6 +15,7 @@ namespace ipcr {
 
 constexpr uint32_t kSeedChunk = 4096;  // positions one warp takes at a time (128 per lane)
 constexpr uint32_t kSeedBloomWordsDev = 57344;  // 224 KB
+constexpr uint32_t kSeedHalfWordsDev = 2048;    // pigeonhole first level: one bit per 8-mer, 8 KB per half
 constexpr uint32_t kSeedBloomMulDev = 0x85EBCA6Bu;
 constexpr uint32_t kSeedHashMulDev = 0x9E3779B1u;
 
@@ -241,8 +242,8 @@ __device__ __forceinline__ void seed_walk(const SeedScanArgs &a, uint32_t kmer, 
     }
 }
 
-// BLOOM: 0 = no shared-memory bitmap (every position goes to the second level), k = 1..2 bits
-// per k-mer, both in the same word.
+// BLOOM: 0 = no shared-memory bitmap (every position goes to the second level), k = 1..2 bits per k-mer, both
+// in the same word, 3 = pigeonhole half-window tables (see below).
 // VAR (tuning switches, IPCR_SEED_VAR; measured on B200, profiles/r02_seed_variants.txt: +-0.5 %, default 0):
 // 1 = the look-ahead / look-behind words come from the neighbouring lane by shuffle instead of five extra strided
 // loads per chunk; 4 = warps claim chunks from a global counter (no tail, no imbalance between SMs) instead of a
@@ -255,7 +256,8 @@ k_seed_scan(SeedScanArgs a) {
     if (BLOOM) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.bloom);
         uint4 *dst = reinterpret_cast<uint4 *>(sbloom);
-        for (uint32_t i = threadIdx.x; i < kSeedBloomWordsDev / 4u; i += blockDim.x) dst[i] = __ldg(src + i);
+        const uint32_t n16 = BLOOM == 3 ? kSeedHalfWordsDev * 2u / 4u : kSeedBloomWordsDev / 4u;
+        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
         __syncthreads();
     }
     const uint32_t lane = threadIdx.x & 31u;
@@ -316,7 +318,21 @@ k_seed_scan(SeedScanArgs a) {
         for (int blk = 0; blk < 4; blk++) {
             const uint32_t wm = c[2 * blk], w0 = c[2 * blk + 1], w1 = c[2 * blk + 2], w2 = c[2 * blk + 3];
             uint32_t hits = 0u;
-            if (BLOOM) {
+            if (BLOOM == 3) {
+                // PIGEONHOLE first level (S = 16): the key set of a big panel at mm 3 saturates any bitmap that
+                // fits shared memory, but a window with <= m mismatches has <= m / 2 of them in its low or in its
+                // high 8 bases.  Two exact 64 Kbit tables (8 KB each) hold every 8-mer within m / 2 mismatches of
+                // some orientation's low / high half; a position goes on iff EITHER half is in its table.
+                const char *sb = reinterpret_cast<const char *>(sbloom);
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t x = j < 16 ? __funnelshift_r(w0, w1, 2 * j) : __funnelshift_r(w1, w2, 2 * (j - 16));
+                    const uint32_t wl = *reinterpret_cast<const uint32_t *>(sb + ((x >> 3) & 0x1FFCu));
+                    const uint32_t wh = *reinterpret_cast<const uint32_t *>(sb + kSeedHalfWordsDev * 4u + ((x >> 19) & 0x1FFCu));
+                    const uint32_t bit = __funnelshift_r(wl, 0u, x) | __funnelshift_r(wh, 0u, x >> 16);
+                    hits = __funnelshift_r(hits, bit, 1);
+                }
+            } else if (BLOOM) {
                 const char *sb = reinterpret_cast<const char *>(sbloom);
 #pragma unroll
                 for (int j = 0; j < 32; j++) {

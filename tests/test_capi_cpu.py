@@ -280,3 +280,42 @@ def test_primer_length_limit_is_an_error_not_a_truncation():
     with pytest.raises(Exception) as ei:
         eng.compile_panel([Pair("long", "TTGACCGTAAGC", "ACGT" * 17)])
     assert "longer than 64" in str(ei.value)
+
+
+def test_pigeonhole_first_level_never_loses_a_true_site(oracle, monkeypatch):
+    """The pigeonhole first level of the seed index (two exact 8-mer tables for the low / high half of a 16-base
+    window, each within max_mm / 2 mismatches; chosen by the cost model when a panel's keys would saturate the
+    shared-memory bitmap, e.g. mm 3 x 400 orientations) is forced on small panels here: every start the brute
+    force accepts is still a candidate, none comes twice."""
+    monkeypatch.setenv("IPCR_SEED_PIGEON", "1")
+    rng = random.Random(777)
+    checked = used = 0
+    for it in range(80):
+        n = rng.randint(150, 360)
+        g = H.random_genome(rng, n, n_frac=rng.choice([0, 0.02]), lower_frac=rng.choice([0, 0.03]))
+        mm, tw = rng.randint(0, 3), rng.choice([0, 1, 3, 4])
+        pairs = []
+        for k in range(rng.randint(1, 3)):
+            la, lb = rng.randint(16, 34), rng.randint(16, 34)
+            a = H.random_primer(rng, la, rng.choice([0, 0.15]))
+            b = H.random_primer(rng, lb, rng.choice([0, 0.15]))
+            pairs.append(Pair(f"p{k}", a, b))
+            for _ in range(3):
+                H.plant_amplicon(rng, g, rng.randint(0, max(0, n - la - lb - 10)), a, b, la + lb + rng.randint(0, 10),
+                                 rng.randint(0, mm), rng.randint(0, mm), tw, revcomp_strand=rng.random() < 0.5)
+        seq = bytes(g)
+        cp = Engine(Config(max_mm=mm, terminal_window=tw, hit_cap=rng.choice([0, 5]))).compile_panel(pairs)
+        for raw in (False, True):
+            cands, info = cp.seed_eval(seq, raw)
+            if info["S"] != 16:
+                continue
+            assert info["bloom_k"] == 3  # the debug tap reports the pigeonhole tables as k = 3
+            used += 1
+            assert len(cands) == len(set(cands)), "duplicate candidate"
+            cset = set(cands)
+            for q in range(cp.num_orientations):
+                s, t = cp.orientation(q)
+                for pos in _true_sites(oracle, seq, s, t == "a", mm, tw, raw):
+                    assert (q, pos) in cset, (s, t, mm, tw, raw, pos, info)
+                    checked += 1
+    assert used > 60 and checked > 600
