@@ -67,6 +67,9 @@ def parse_args():
                     help="scatter this many N bytes per Mbp over the genome (robustness runs; default off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--in-process-devices", type=int, default=1,
+                    help="N = 1 only: also time the packed end-to-end call spread over K devices of this ONE process "
+                         "(ipcr_gpu_init(K); what a single Go host process would see)")
     ap.add_argument("--no-bitparallel", action="store_true", help="skip the bit-parallel comparison pass")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1, sharded: how the site blocks meet -- peer = CUDA IPC peer memory read by the pairing kernel "
@@ -648,6 +651,30 @@ def run_ours(a):
         te = sc.timing()
         if not weak and n_e != n_prod:
             raise RuntimeError(f"packed e2e path returned {n_e} products, device-resident path {n_prod}")
+        one_process = None
+        if world == 1 and a.in_process_devices > 1:
+            from ipcr_b200 import _capi
+            L, err = _capi.lib(), _capi.errbuf()
+            if L.ipcr_gpu_init(a.in_process_devices, err, len(err)) != 0:
+                raise RuntimeError(err.value.decode())
+            try:
+                for _ in range(2):
+                    ff.scan_raw(cp, sc)  # warm: peer scratches, tables on every device
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(max(1, a.e2e_steps)):
+                    _out, n_m = ff.scan_raw(cp, sc)
+                mp_ms = (time.perf_counter() - t0) * 1e3 / max(1, a.e2e_steps)
+                tm = sc.timing()
+                if n_m != n_prod:
+                    raise RuntimeError(f"in-process multi-device e2e returned {n_m} products, one device {n_prod}")
+                one_process = {"devices": int(L.ipcr_gpu_num_devices()), "ms_per_step": mp_ms,
+                               "value": total / 1e9 / (mp_ms / 1e3) * len(user_pairs),
+                               "stage_ms": {k: tm[k] for k in ("h2d_ms", "filter_ms", "verify_ms", "pair_ms", "total_ms")},
+                               "api": "the same ipcr_gpu_scan_fasta call after ipcr_gpu_init(K): every device copies its "
+                                      "slice of the codes over its own PCIe link, blocks meet by NVLink peer copies"}
+            finally:
+                L.ipcr_gpu_init(1, err, len(err))
         ff.close()
         if world > 1:
             t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -670,6 +697,8 @@ def run_ours(a):
                "ascii": {"value": g / (ascii_ms / 1e3) * len(user_pairs), "ms_per_step": ascii_ms,
                          "h2d_bytes_per_step": n_units * total, "stage_ms": ascii_stage,
                          "api": "ipcr_gpu_scan_batch(ASCII host records, pinned) -> products: 1 B/bp over PCIe"}}
+        if one_process is not None:
+            e2e["one_process"] = one_process
         del host, recs
     elif not a.no_e2e:
         # sharded: every rank feeds ITS shard from its own pinned host buffer; wall clock between barriers

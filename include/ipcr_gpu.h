@@ -389,7 +389,7 @@ int ipcr_gpu_debug_plan_eval(const ipcr_panel *p, uint32_t orient, const uint8_t
 /* orientation string / type ('A' forward-type, 'a' rc-type) of a unique orientation */
 /* host evaluation of the panel's seed index on one sequence: the (orientation << 44 | start)
  * candidates the seed filter hands to verify; info[8] = {S, entries, table_bits, bloom used,
- * bloom fill ppm, bitmap bits per key, S1 (first-level key length), distinct first-level keys} */
+ * bloom fill ppm, bitmap bits per key | anchor stride << 8, S1 (first-level key length), distinct first-level keys} */
 int ipcr_gpu_debug_seed_eval(ipcr_panel *p, int raw_mode, const uint8_t *seq, uint64_t len, uint64_t *out,
                              uint64_t cap, uint64_t *n, int32_t *info);
 int ipcr_gpu_debug_orientation(const ipcr_panel *p, uint32_t orient, char *buf, size_t buflen,

@@ -973,7 +973,9 @@ static const SeedIndex &seed_get(ipcr_scratch *s, int variant) {
         CU(cudaStreamSynchronize(s->stream));
         static std::mutex attr_mu;
         std::lock_guard<std::mutex> l2(attr_mu);
-        for (auto fn : {k_seed_scan<1>, k_seed_scan<2>, k_seed_scan<2, 1>, k_seed_scan<2, 4>, k_seed_scan<2, 5>})
+        for (auto fn : {k_seed_scan<1>, k_seed_scan<2>, k_seed_scan<2, 1>, k_seed_scan<2, 4>, k_seed_scan<2, 5>,
+                        k_seed_scan<2, 2>, k_seed_scan<2, 8>,
+                        k_seed_scan<1, 0, 2>, k_seed_scan<2, 0, 2>, k_seed_scan<1, 0, 4>, k_seed_scan<2, 0, 4>})
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSeedBloomWords * 4)));
         t->seed_ready[variant] = true;
     }
@@ -985,18 +987,26 @@ static void launch_seed_scan(ipcr_scratch *s, const SeedIndex &ix, const SeedSca
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((a.n_chunks + 31) / 32, (uint64_t)s->sm_count));
     const size_t smem = kSeedBloomWords * 4;
     int var = 0;
-    if (const char *e = getenv("IPCR_SEED_VAR")) var = atoi(e) & 5;
+    if (const char *e = getenv("IPCR_SEED_VAR")) var = atoi(e) & 15;
     if (var & 4) {
         s->chunk_ctr.ensure(64);
         CU(cudaMemsetAsync(s->chunk_ctr.p, 0, 8, s->stream));
         a.chunk_counter = s->chunk_ctr.as<unsigned long long>();
     }
+    a.prefetch = ix.stride > 1 ? 1u : 0u;
+    if (const char *e = getenv("IPCR_SEED_PREFETCH")) a.prefetch = atoi(e) != 0 ? 1u : 0u;
     if (ix.pigeon) k_seed_scan<3><<<grid, 1024, kSeedHalfWords * 2 * 4, s->stream>>>(a);
     else if (!ix.use_bloom) k_seed_scan<0><<<grid, 1024, 0, s->stream>>>(a);
+    else if (ix.stride == 4 && ix.bloom_k == 1) k_seed_scan<1, 0, 4><<<grid, 1024, smem, s->stream>>>(a);
+    else if (ix.stride == 4) k_seed_scan<2, 0, 4><<<grid, 1024, smem, s->stream>>>(a);
+    else if (ix.stride == 2 && ix.bloom_k == 1) k_seed_scan<1, 0, 2><<<grid, 1024, smem, s->stream>>>(a);
+    else if (ix.stride == 2) k_seed_scan<2, 0, 2><<<grid, 1024, smem, s->stream>>>(a);
     else if (ix.bloom_k == 1) k_seed_scan<1><<<grid, 1024, smem, s->stream>>>(a);
     else if (var == 1) k_seed_scan<2, 1><<<grid, 1024, smem, s->stream>>>(a);
     else if (var == 4) k_seed_scan<2, 4><<<grid, 1024, smem, s->stream>>>(a);
     else if (var == 5) k_seed_scan<2, 5><<<grid, 1024, smem, s->stream>>>(a);
+    else if (var == 2) k_seed_scan<2, 2><<<grid, 1024, smem, s->stream>>>(a);
+    else if (var == 8) k_seed_scan<2, 8><<<grid, 1024, smem, s->stream>>>(a);
     else k_seed_scan<2><<<grid, 1024, smem, s->stream>>>(a);
     check_launch("k_seed_scan");
     s->launches++;
@@ -2130,7 +2140,9 @@ int ipcr_gpu_scan_fasta(ipcr_panel *p, ipcr_scratch *s, ipcr_fasta *f, const ipc
             PackedHost ph{f->codes, f->inval, f->total, f->runs_ok && !getenv("IPCR_NO_RUNS") ? f->inval_runs.data() : nullptr,
                           f->inval_runs.size() / 2};
             uint64_t n = 0;
-            if (scan_packed_chain(s, ph, rinfo, roff, &n)) {
+            // ipcr_gpu_init(n > 1): every device takes a slice of the packed arrays over its own PCIe link
+            const bool multi = g_n_devices.load() > 1 && f->total >= multi_min_bases();
+            if ((multi && scan_packed_multi(s, ph, rinfo, roff, &n)) || scan_packed_chain(s, ph, rinfo, roff, &n)) {
                 f->products.assign(s->out_ptr, s->out_ptr + n);
                 if (out) *out = f->products.data();
                 if (n_out) *n_out = n;
@@ -2899,7 +2911,7 @@ int ipcr_gpu_debug_seed_eval(ipcr_panel *p, int raw_mode, const uint8_t *seq, ui
             info[2] = (int32_t)ix.table_bits;
             info[3] = ix.use_bloom ? 1 : 0;
             info[4] = (int32_t)(ix.bloom_fill * 1e6);
-            info[5] = ix.bloom_k;
+            info[5] = ix.bloom_k | (ix.stride << 8);
             info[6] = ix.S1;
             info[7] = (int32_t)std::min<uint64_t>(ix.n_keys1, 0x7FFFFFFF);
         }

@@ -466,4 +466,167 @@ static bool scan_multi_device(ipcr_scratch *s, const ipcr_seq *recs, size_t n_re
     return true;
 }
 
+// ---------------------------------------------------------------------------------------
+// The packed host genome over several devices of ONE process (ipcr_gpu_scan_fasta after
+// ipcr_gpu_init(n)): slices are cut on 4096-base boundaries, so a slice of the packed arrays
+// is a plain pointer offset; every device copies ITS slice of the codes over its own PCIe
+// link (0.25 B/bp in total, the bitmap from the clipped run list), runs stage 1 on it, and
+// peer-copies its site block to the calling scratch's device, where stage 2 runs once.
+// ---------------------------------------------------------------------------------------
+static bool scan_packed_multi(ipcr_scratch *s, const PackedHost &ph, const std::vector<ipcr_record_info> &rinfo,
+                              const std::vector<uint64_t> &rec_off, uint64_t *n_prod) {
+    ensure_peers(s, std::min<int>(g_n_devices.load(), (int)kPairMaxBlocks));
+    const int n_dev = (int)s->peers.size() + 1;
+    if (n_dev < 2) return false;
+    const size_t n_recs = rinfo.size();
+    const uint64_t total = ph.total, groups = packed_groups(total);
+    PieceCut c;
+    c.roff = rec_off;
+    c.total = total;
+    c.cut.resize((size_t)n_dev + 1);
+    for (int k = 0; k <= n_dev; k++)
+        c.cut[k] = k == n_dev ? total : ((total * (uint64_t)k / (uint64_t)n_dev) & ~(kPackChunk - 1));
+    cudaStream_t st = s->stream;
+    CU(cudaEventRecord(s->ev[0], st));
+    const bool by_runs = ph.runs != nullptr;
+    bool done = false;
+    for (int attempt = 0; attempt < 6 && !done; attempt++) {
+        const uint64_t site_cap = std::max<uint64_t>(1024, s->site_cap_hint);
+        const uint64_t bb = block_bytes_for(n_recs, site_cap);
+        s->gather.ensure((size_t)n_dev * bb);
+        const int variant = chain_variant(s, false);
+        std::vector<std::string> errs((size_t)n_dev);
+        auto job = [&](int k) {
+            try {
+                ipcr_scratch *q = k == 0 ? s : s->peers[(size_t)k - 1];
+                CU(cudaSetDevice(q->device));
+                if (k > 0) {
+                    if (q->inflight) CU(cudaStreamSynchronize(q->stream));
+                    q->inflight = false;
+                    q->args_used = 0;
+                    q->launches = 0;
+                    q->seed_cap_hint = s->seed_cap_hint;
+                    q->seed_dirty_hint = s->seed_dirty_hint;
+                }
+                const uint64_t lo = c.cut[k], hi = c.cut[k + 1];
+                uint8_t *dst = s->gather.as<uint8_t>() + (size_t)k * bb;
+                if (q->slab_g.empty()) q->slab_g.emplace_back(new GenomeData());
+                GenomeData &g = *q->slab_g[0];
+                g.device = q->device;
+                if (lo < hi) piece_segments(c, n_recs, lo, hi, g.segs);
+                else g.segs.clear();
+                if (g.segs.empty()) {  // an empty slice still owes an (empty) block
+                    Stage1Ctl init{};
+                    init.site_cap = site_cap;
+                    init.variant = (uint32_t)variant;
+                    init.n_recs = (uint32_t)n_recs;
+                    q->block.ensure(bb);
+                    uint8_t *blk = k == 0 ? dst : q->block.as<uint8_t>();
+                    q->seg_reset_dummy.ensure(16);
+                    k_block_init<<<1, 256, 0, q->stream>>>(blk, init, q->seg_reset_dummy.as<uint32_t>(), 0, nullptr);
+                    check_launch("k_block_init");
+                } else {
+                    // the groups this slice's scan may touch: its chunks, the halo's chunk, one look-ahead group
+                    const uint64_t end = std::min(total, hi + kPieceHalo);
+                    const uint64_t g_lo = lo / 32u;
+                    const uint64_t g_hi = std::min(groups, (end + kPackChunk - 1) / kPackChunk * (kPackChunk / 32u) + 1);
+                    const uint64_t ng = g_hi - g_lo;
+                    GenomeData &own = q->own;
+                    own.device = q->device;
+                    if (attempt == 0 || !q->own_laid) {
+                        own.codes.ensure((size_t)ng * 8 + 64);
+                        own.inval.ensure((size_t)ng * 4 + 64);
+                        CU(cudaMemcpyAsync(own.codes.p, ph.codes + 2 * g_lo, ng * 8, cudaMemcpyHostToDevice, q->stream));
+                        if (!by_runs) {
+                            CU(cudaMemcpyAsync(own.inval.p, ph.inval + g_lo, ng * 4, cudaMemcpyHostToDevice, q->stream));
+                        } else {
+                            CU(cudaMemsetAsync(own.inval.p, 0, (size_t)ng * 4, q->stream));
+                            // the runs that reach into [lo, cov), clipped and moved to slice coordinates
+                            const uint64_t cov = g_hi * 32u;
+                            std::vector<uint64_t> mine;
+                            size_t a = 0, b = (size_t)ph.n_runs;  // first run whose end lies behind lo
+                            while (a < b) {
+                                const size_t m = (a + b) / 2;
+                                if (ph.runs[2 * m + 1] <= lo) a = m + 1;
+                                else b = m;
+                            }
+                            for (size_t r = a; r < (size_t)ph.n_runs && ph.runs[2 * r] < cov; r++) {
+                                mine.push_back(std::max(ph.runs[2 * r], lo) - lo);
+                                mine.push_back(std::min(ph.runs[2 * r + 1], cov) - lo);
+                            }
+                            if (!mine.empty()) {
+                                const uint64_t nr = mine.size() / 2;
+                                upload_staged(q, q->runs_dev, mine.data(), mine.size() * 8);
+                                const unsigned grid =
+                                    (unsigned)std::min<uint64_t>((nr * 32 + 255) / 256, (uint64_t)q->sm_count * 8);
+                                k_inval_fill<<<grid, 256, 0, q->stream>>>(q->runs_dev.as<unsigned long long>(), nr,
+                                                                          own.inval.as<uint32_t>());
+                                check_launch("k_inval_fill");
+                                q->launches++;
+                            }
+                        }
+                        q->own_laid = true;
+                    }
+                    g.recs = rinfo;
+                    g.lay.total_len = end - lo;
+                    g.ascii = nullptr;
+                    g.codes_ext = own.codes.as<uint32_t>();
+                    g.inval_ext = own.inval.as<uint32_t>();
+                    g.own_bases = hi - lo;
+                    if (k == 0) {
+                        stage1_async(q, g, variant, dst, site_cap);
+                    } else {
+                        q->block.ensure(bb);
+                        stage1_async(q, g, variant, q->block.as<uint8_t>(), site_cap);
+                    }
+                }
+                if (k > 0) {
+                    CU(cudaMemcpyPeerAsync(dst, s->device, q->block.p, q->device, bb, q->stream));
+                    CU(cudaEventRecord(q->done_ev, q->stream));
+                    q->inflight = true;
+                }
+            } catch (const std::exception &e) {
+                errs[(size_t)k] = e.what();
+                if (errs[(size_t)k].empty()) errs[(size_t)k] = "unknown error";
+            }
+        };
+        {  // one host thread per further device: the packed arrays are only pinned on request
+            std::vector<std::thread> th;
+            for (int k = 1; k < n_dev; k++) th.emplace_back(job, k);
+            job(0);
+            for (auto &t : th) t.join();
+        }
+        CU(cudaSetDevice(s->device));
+        for (const std::string &e : errs)
+            if (!e.empty()) throw Error(e);
+        for (ipcr_scratch *q : s->peers) CU(cudaStreamWaitEvent(st, q->done_ev, 0));
+        for (int again = 0; again < 4 && !done; again++) {
+            std::vector<ipcr_record_info> ri = rinfo;
+            pair_async(s, s->gather.as<uint8_t>(), (uint32_t)n_dev, bb, site_cap, ri.data(), n_recs);
+            bool redo = false;
+            const ChainResult r = chain_finish(s, s->gather.as<uint8_t>(), (uint32_t)n_dev, bb, ri.data(), n_recs, n_prod, &redo);
+            if (r == kChainTooDirty) {
+                for (ipcr_scratch *q : s->peers) q->own_laid = false;
+                s->own_laid = false;
+                return false;
+            }
+            if (r == kChainDone) done = true;
+            else if (redo) break;
+        }
+    }
+    for (ipcr_scratch *q : s->peers) {
+        q->own_laid = false;
+        q->inflight = false;  // chain_finish waited for the primary stream, which waited for every peer
+        s->launches += q->launches;
+    }
+    s->own_laid = false;
+    if (!done) throw Error("the multi-device packed scan chain did not converge");
+    s->last_valid = false;
+    chain_timing(s, *n_prod, true);
+    s->timing.pack_ms = 0.f;
+    s->timing.total_ms = ev_ms(s->ev[0], s->ev[7]);
+    s->timing.kernel_launches = s->launches;
+    return true;
+}
+
 }  // namespace ipcr

@@ -19,6 +19,7 @@
 // (halo.go:47-108).  Exactness still lives in the verify kernel.
 #pragma once
 
+#include <cstdio>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -65,6 +66,10 @@ struct SeedIndex {
     // window (key1 = k-mer >> 2*(S - S1)).  Fewer free columns => far fewer distinct keys than S-mers
     // => a sparser bitmap; the exact (or hashed) S-mer test stays in the second level.
     int S1 = 0;
+    // anchor stride of the first level (1, 2 or 4; needs S - S1 >= stride - 1): the bitmap holds, per S-mer, its
+    // S1-mers at the window offsets d-stride+1 .. d (d = S - S1), and the kernel looks only at every stride-th
+    // position; a hit there stands for the `stride` windows that hold the anchor at one of those offsets.
+    int stride = 1;
     uint32_t kmer_mask = 0;
     uint32_t table_bits = 0;
     std::vector<uint64_t> slots;
@@ -162,11 +167,19 @@ inline void seed_half_enumerate(const Orient &o, int c0, int t, int tw, bool raw
     }
 }
 
-// modelled cost of the seed filter per genome position, in units of the scan kernel's fast path
-// (one shared-memory bitmap lookup).  Positions passing the first-level bitmap pay a divergent
-// second-level lookup in L2 (the warp waits for its busiest lane, so the cost grows faster than the
-// pass rate): ~50 * pass^1.8, fitted to B200 sweeps (profiles/r01_seed_sweep.txt, r02_seed_sweep.txt); a
-// candidate costs ~675 (table walk, append, verify).  The second bitmap bit costs ~12 % of the fast path.
+// Modelled cost of the seed filter per genome position, in units of the scan kernel's unstrided fast path (one
+// shared-memory bitmap lookup = ~10 warp instructions per 32 positions; 1.29 ms per 3 Gbp on B200).
+//  * fast path at anchor stride t: 0.1 + 0.92 / t (1.05 / t with the second bitmap bit);
+//  * an anchor that passes the first level sends its t windows through a DIVERGENT second-level lookup (an L2 round
+//    trip; the t lookups of one anchor are issued together) while the other lanes of the warp wait: a warp works on
+//    32 lanes x 32 / t anchors at a time and loops max-over-lanes(passing anchors) times, so the cost is
+//    c * E[max of 32 Binomial(32 / t, pass)], c = 0.1 * (1 + (t - 1) * (0.5 + 8 * pass)): linear in `pass` while passes
+//    are rare (a single false positive stalls the whole warp: this is why a strided panel wants the second bitmap
+//    bit), flatter once every lane has some; with a stride the shorter fast path hides less of the round trips, the
+//    more so the more there are.  Fitted to B200 within ~15 %: profiles/r02_seed_sweep.txt (100 pairs, S1 10..16 x
+//    1..2 bits) and profiles/r02_seed_stride.txt (1..100 pairs x stride 1 / 2 / 4).  Beyond pass = 0.08 a stride
+//    lost in every measurement (100 pairs, stride 2: 4.04 ms against 2.26) and is not considered;
+//  * a candidate costs ~675 (table walk, append, verify).
 inline double seed_bloom_fp(double keys, int k) {
     const double fill = 1.0 - std::exp(-(double)k * keys / (double)kSeedBloomBits);
     return std::pow(fill, k);
@@ -176,18 +189,39 @@ inline double seed_pass_rate(double keys1, int S1, int k) {
     return std::min(1.0, seed_bloom_fp(keys1, k) + keys1 / std::pow(4.0, S1));
 }
 
-inline double seed_cost(double entries, int S, double keys1, int S1, int k) {
+// E[max over `lanes` independent Binomial(n, p)], n <= 32
+inline double seed_expected_max(int n, double p, int lanes = 32) {
+    if (p <= 0.0 || n <= 0) return 0.0;
+    if (p >= 1.0) return (double)n;
+    double pmf = std::pow(1.0 - p, n), cdf = 0.0, prev = 0.0, e = 0.0;
+    for (int m = 0; m <= n; m++) {
+        cdf = std::min(1.0, cdf + pmf);
+        const double f = std::pow(cdf, lanes);
+        e += (double)m * (f - prev);
+        prev = f;
+        pmf *= (double)(n - m) / (double)(m + 1) * p / (1.0 - p);
+    }
+    return e;
+}
+
+inline double seed_walk_cost(double pass, int t) {
+    if (pass > 0.5) return 15.0;  // no bitmap: every position asks the second level
+    if (t > 1 && pass > 0.08) return 1e9;
+    return 0.1 * (1.0 + (double)(t - 1) * (0.5 + 8.0 * pass)) * seed_expected_max(32 / t, pass);
+}
+
+inline double seed_cost(double entries, int S, double keys1, int S1, int k, int t = 1) {
     const double prob = entries / std::pow(4.0, S);
     const double pass = seed_pass_rate(keys1, S1, k);
-    const double walk = pass <= 0.5 ? 50.0 * std::pow(pass, 1.8) : 15.0;  // > 0.5: no bitmap, every position walks
-    return (k == 2 ? 1.12 : 1.0) + walk + prob * 675.0;
+    const double fast = 0.1 + (k == 2 ? 1.05 : 0.92) / (double)t;
+    return fast + seed_walk_cost(pass, t) + prob * 675.0;
 }
 
 // variants of the S1 columns at the high end of orientation o's S-column seed window (an upper bound on
 // its distinct first-level keys)
-inline uint64_t seed_key1_count(const Orient &o, int S, int S1, int max_mm, int tw, bool raw) {
+inline uint64_t seed_key1_count(const Orient &o, int S, int S1, int max_mm, int tw, bool raw, int e = -1) {
     const uint64_t kSat = 1ull << 40;
-    const int off = seed_col_off(o, S) + (S - S1);
+    const int off = seed_col_off(o, S) + (e < 0 ? S - S1 : e);  // e: offset of the S1 columns inside the window
     std::vector<uint64_t> ways((size_t)max_mm + 1, 0);
     ways[0] = 1;
     for (int j = 0; j < S1; j++) {
@@ -216,8 +250,10 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
         if (o.L > 0) min_len = std::min(min_len, o.L);
     if (min_len == 1 << 30) min_len = 1;
     const int s_max = std::max(1, std::min(kSeedMaxLen, min_len));
-    int best_s = 0, best_s1 = 0, best_k = 2;
+    int best_s = 0, best_s1 = 0, best_k = 2, best_t = 1;
     double best_cost = 1e300;
+    int max_stride = 4;
+    if (const char *e = getenv("IPCR_SEED_STRIDE")) max_stride = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);
     for (int S = s_max; S >= 1; S--) {
         uint64_t e = 0;
         for (const Orient &o : h.orients)
@@ -225,12 +261,17 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
         if (e > kSeedMaxEntries) continue;
         for (int S1 = S; S1 >= std::min(S, 3); S1--) {
             uint64_t k1 = 0;
-            for (const Orient &o : h.orients)
-                if (o.L >= S) k1 = std::min<uint64_t>(1ull << 40, k1 + seed_key1_count(o, S, S1, mm, tw, raw));
-            k1 = std::min<uint64_t>(k1, e);
-            for (int k = 1; k <= 2; k++) {
-                const double c = seed_cost((double)e, S, (double)k1, S1, k);
-                if (c < best_cost) { best_cost = c; best_s = S; best_s1 = S1; best_k = k; }
+            int offs = 0;  // offsets d, d-1, .. counted so far
+            for (int t = 1; t <= max_stride && S - S1 >= t - 1; t *= 2) {
+                for (; offs < t; offs++)
+                    for (const Orient &o : h.orients)
+                        if (o.L >= S)
+                            k1 = std::min<uint64_t>(1ull << 40, k1 + seed_key1_count(o, S, S1, mm, tw, raw, S - S1 - offs));
+                const uint64_t kk = std::min<uint64_t>(k1, e * (uint64_t)t);
+                for (int k = 1; k <= 2; k++) {
+                    const double c = seed_cost((double)e, S, (double)kk, S1, k, t);
+                    if (c < best_cost) { best_cost = c; best_s = S; best_s1 = S1; best_k = k; best_t = t; }
+                }
             }
         }
     }
@@ -240,8 +281,14 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
         best_s1 = std::min(best_s1, best_s);
     }
     if (const char *e = getenv("IPCR_SEED_LEN1")) best_s1 = std::max(std::min(best_s, 3), std::min(atoi(e), best_s));
+    if (const char *e = getenv("IPCR_SEED_STRIDE_FORCE")) {  // tests: this stride whatever the model says
+        best_t = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);
+        best_s1 = std::max(std::min(best_s, 3), std::min(best_s1, best_s - (best_t - 1)));
+    }
+    while (best_t > 1 && best_s - best_s1 < best_t - 1) best_t /= 2;
     ix.S = best_s;
     ix.S1 = best_s1;
+    ix.stride = best_t;
     ix.kmer_mask = best_s == 16 ? 0xFFFFFFFFu : ((1u << (2 * best_s)) - 1u);
     std::vector<std::pair<uint32_t, uint32_t>> entries;  // (k-mer, orientation)
     std::vector<uint32_t> tmp;
@@ -267,13 +314,14 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
     }
     if (const char *e = getenv("IPCR_SEED_BLOOM_K")) ix.bloom_k = std::max(1, std::min(atoi(e), 2));
     const int d2 = 2 * (ix.S - ix.S1);
+    const uint32_t key1_mask = ix.S1 >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ix.S1)) - 1u);
     std::vector<uint32_t> keys1;
-    keys1.reserve(entries.size());
+    keys1.reserve(entries.size() * (size_t)ix.stride);
     for (const auto &e : entries) {
         uint32_t hh = (uint32_t)(e.first * kSeedHashMul) >> (32 - ix.table_bits);
         while (ix.slots[hh]) hh = (hh + 1) & tmask;
         ix.slots[hh] = seed_slot(e.first, e.second, ix.col_off[e.second]);
-        keys1.push_back(e.first >> d2);
+        for (int i = 0; i < ix.stride; i++) keys1.push_back((e.first >> (d2 - 2 * i)) & key1_mask);
         const uint32_t h2 = e.first * ix.bitmap2_mul;
         ix.bitmap2[h2 >> ix.bitmap2_shift] |= 1u << (h2 & 31u);
     }
@@ -292,6 +340,7 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
     ix.bloom_fill = (double)bits_set / (double)kSeedBloomBits;
     ix.use_bloom = ix.S1 >= 3 && seed_pass_rate((double)ix.n_keys1, ix.S1, ix.bloom_k) <= 0.5;
     if (const char *e = getenv("IPCR_SEED_BLOOM")) ix.use_bloom = atoi(e) != 0 && ix.S1 >= 3;
+    if (!ix.use_bloom) ix.stride = 1;  // without the bitmap every position goes to the second level
     // pigeonhole first level: worth it when the bitmap is (nearly) useless and the half-window tables are selective
     {
         bool all16 = ix.S == 16;
@@ -311,8 +360,8 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
             const double pass = 1.0 - (1.0 - (double)nlo / 65536.0) * (1.0 - (double)nhi / 65536.0);
             // fast path costs ~2.2 bitmap lookups (two LDS, more shifts); the second level as in seed_cost()
             const double prob = (double)ix.n_entries / std::pow(4.0, ix.S);
-            const double cost_pigeon = 2.2 + (pass <= 0.5 ? 50.0 * std::pow(pass, 1.8) : 15.0) + prob * 675.0;
-            const double cost_now = ix.use_bloom ? seed_cost((double)ix.n_entries, ix.S, (double)ix.n_keys1, ix.S1, ix.bloom_k)
+            const double cost_pigeon = 2.2 + seed_walk_cost(pass, 1) + prob * 675.0;
+            const double cost_now = ix.use_bloom ? seed_cost((double)ix.n_entries, ix.S, (double)ix.n_keys1, ix.S1, ix.bloom_k, ix.stride)
                                                  : 1.0 + 15.0 + prob * 675.0;
             if (want == 1 || cost_pigeon < cost_now) {
                 ix.pigeon = true;
@@ -320,6 +369,7 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
                 ix.use_bloom = true;
                 ix.bloom_k = 3;  // reported by the debug tap: 3 = pigeonhole tables
                 ix.S1 = ix.S;  // the kernel looks at the window where it starts (d = 0)
+                ix.stride = 1;
                 std::fill(ix.bloom.begin(), ix.bloom.end(), 0u);
                 std::copy(lo.begin(), lo.end(), ix.bloom.begin());
                 std::copy(hi.begin(), hi.end(), ix.bloom.begin() + kSeedHalfWords);
@@ -327,6 +377,10 @@ inline SeedIndex seed_build(const Panel &h, int variant) {
         }
     }
     ix.cand_prob = (double)ix.n_entries / std::pow(4.0, ix.S);
+    if (getenv("IPCR_SEED_DEBUG"))
+        fprintf(stderr, "seed index[%d]: S=%d S1=%d bits=%d stride=%d entries=%llu keys1=%llu fill=%.4f bloom=%d pigeon=%d\n",
+                variant, ix.S, ix.S1, ix.bloom_k, ix.stride, (unsigned long long)ix.n_entries,
+                (unsigned long long)ix.n_keys1, ix.bloom_fill, ix.use_bloom ? 1 : 0, ix.pigeon ? 1 : 0);
     return ix;
 }
 
@@ -351,8 +405,11 @@ inline void seed_eval(const Panel &h, const SeedIndex &ix, const uint8_t *seq, u
                 const bool in_hi = (ix.bloom[kSeedHalfWords + (hi >> 5)] >> (hi & 31u)) & 1u;
                 if (!in_lo && !in_hi) continue;
             } else if (ix.use_bloom) {
+                // the anchor that answers for window p: the multiple of `stride` in [p + d - stride + 1, p + d]
+                const uint64_t d = (uint64_t)(ix.S - ix.S1), q = (p + d) / (uint64_t)ix.stride * (uint64_t)ix.stride;
+                const uint32_t key = (kmer >> (2 * (q - p))) & (ix.S1 >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ix.S1)) - 1u));
                 uint32_t m;
-                const uint32_t w = seed_bloom_word(kmer >> (2 * (ix.S - ix.S1)), ix.S1, ix.bloom_k, m);
+                const uint32_t w = seed_bloom_word(key, ix.S1, ix.bloom_k, m);
                 if ((ix.bloom[w] & m) != m) continue;
             }
             const uint32_t h2 = kmer * ix.bitmap2_mul;

@@ -185,6 +185,7 @@ struct SeedScanArgs {
     unsigned long long *dirty_count;
     uint64_t dirty_cap;
     unsigned long long *chunk_counter;  // VAR & 4: next unclaimed chunk (zeroed before the launch)
+    uint32_t prefetch;  // != 0: a warp asks L2 for its NEXT chunk's sectors before it works on this one
 };
 
 // L2 residency: the second-level bitmap (<= 32 MB) and the hash table are hit at random by
@@ -249,7 +250,12 @@ __device__ __forceinline__ void seed_walk(const SeedScanArgs &a, uint32_t kmer, 
 // loads per chunk; 4 = warps claim chunks from a global counter (no tail, no imbalance between SMs) instead of a
 // static stride.  (Forming the bitmap address with a multiply-add to move it off the ALU pipe does not survive
 // ptxas: a multiply by 4 becomes LEA again.)
-template <int BLOOM, int VAR = 0>
+// T (BLOOM 1 / 2 only): anchor stride of the first level.  A panel with few keys does not need a lookup per position:
+// the index holds, per S-mer, its S1-mers at the T window offsets d-T+1 .. d, so the S1-mer at every T-th
+// position ("anchor") answers for the T windows that contain it at one of those offsets.  A set anchor bit is
+// then spread over its T windows and the second level sorts them out.  T lookups fewer per T positions; the
+// key set grows T-fold, so seed.hpp's cost model only picks T > 1 while the bitmap stays sparse.
+template <int BLOOM, int VAR = 0, int T = 1>
 __global__ void __launch_bounds__(1024, 1)
 k_seed_scan(SeedScanArgs a) {
     extern __shared__ uint32_t sbloom[];
@@ -277,6 +283,14 @@ k_seed_scan(SeedScanArgs a) {
     while (ch < a.n_chunks) {
         const uint64_t P0 = ch * kSeedChunk + (uint64_t)lane * 128u;
         uint32_t c[10], iv[6];
+        if (!(VAR & 4) && a.prefetch != 0u && ch + n_warps < a.n_chunks) {
+            // a warp's loads and its lookups are one dependent chain per chunk; with a strided first level the
+            // chain is short and the DRAM latency shows.  The next chunk (one lane = one 32-byte sector of codes,
+            // every other lane one sector of the bitmap) is on its way into L2 while this one is worked on.
+            const uint64_t Pn = P0 + n_warps * kSeedChunk;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.codes + (Pn >> 4)));
+            if ((lane & 1u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.inval + (Pn >> 5)));
+        }
         {
             const uint4 *cp = reinterpret_cast<const uint4 *>(a.codes + (P0 >> 4));
             const uint4 q0 = ld_u128_policy(cp, stream), q1 = ld_u128_policy(cp + 1, stream);
@@ -335,7 +349,7 @@ k_seed_scan(SeedScanArgs a) {
             } else if (BLOOM) {
                 const char *sb = reinterpret_cast<const char *>(sbloom);
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
+                for (int j = 0; j < 32; j += T) {
                     // x: 32-bit window whose low 2*S1 bits are the first-level key.  The multiplier is
                     // pre-shifted by 32-2*S1, so the product ignores the bits above the key: no mask needed.
                     const uint32_t x = j < 16 ? __funnelshift_r(w0, w1, 2 * j) : __funnelshift_r(w1, w2, 2 * (j - 16));
@@ -350,7 +364,30 @@ k_seed_scan(SeedScanArgs a) {
                         asm("mul.hi.u32 %0, %1, 2097152;" : "=r"(b2) : "r"(hw));  // hw >> 11: hash bits 11..15
                         bit &= __funnelshift_r(w, 0u, b2);
                     }
-                    hits = __funnelshift_r(hits, bit, 1);
+                    if (T > 1) bit &= 1u;  // T bits enter the hit word per step: only the answer may be set
+                    hits = __funnelshift_r(hits, bit, T);
+                }
+                if (T > 1) {
+                    // anchor bit j answers for the windows whose hit bits are j .. j+T-1 (j + T <= 32).  Their T
+                    // second-level lookups are independent: issued together they cost one L2 round trip, not T
+                    // (this code is divergent, the rest of the warp waits for it).
+                    uint32_t anchors = hits;
+                    hits = 0u;
+                    while (anchors) {
+                        uint32_t j;
+                        asm("bfind.u32 %0, %1;" : "=r"(j) : "r"(anchors));
+                        anchors ^= 1u << j;
+                        uint32_t wd[T], h2[T];
+#pragma unroll
+                        for (int i = 0; i < T; i++) {
+                            const int32_t jp = (int32_t)j + i - (int32_t)d;  // window start relative to the block
+                            const uint32_t lo = jp < 0 ? wm : (jp < 16 ? w0 : w1), hi = jp < 0 ? w0 : (jp < 16 ? w1 : w2);
+                            h2[i] = (__funnelshift_r(lo, hi, 2u * (uint32_t)jp) & a.kmer_mask) * a.bitmap2_mul;
+                            wd[i] = ld_u32_policy(a.bitmap2 + (h2[i] >> a.bitmap2_shift), keep);
+                        }
+#pragma unroll
+                        for (int i = 0; i < T; i++) hits |= (__funnelshift_r(wd[i], 0u, h2[i]) & 1u) << (j + i);
+                    }
                 }
             } else if (d == 0u) {
                 // No first level (the panel's keys saturate any bitmap that fits shared memory, e.g. mm 3 x 400
@@ -409,6 +446,34 @@ k_seed_scan(SeedScanArgs a) {
             // only its hits walk the hash table.  The loop is written for instruction count: highest
             // set bit first = one FLO, the funnel shift wraps its amount mod 32, the bitmap word index
             // and bit position come straight from the hash, the bit test sets a predicate.
+            constexpr int NB = (VAR & 2) ? 2 : ((VAR & 8) ? 3 : 1);
+            if (NB > 1 && T == 1 && !(BLOOM == 0)) {
+                // A lane's passes are a chain of dependent L2 round trips (the warp loops max-over-lanes times and
+                // nothing else of this warp runs meanwhile): NB lookups per trip shorten the chain NB-fold.
+                while (hits) {
+                    uint32_t jj[NB], km[NB], hh[NB], wd[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        jj[b] = 0xFFFFFFFFu;
+                        wd[b] = 0u;
+                        if (hits) {
+                            uint32_t j;
+                            asm("bfind.u32 %0, %1;" : "=r"(j) : "r"(hits));
+                            hits ^= 1u << j;
+                            jj[b] = j;
+                            const int32_t jp = (int32_t)j - (int32_t)d;
+                            const uint32_t lo = jp < 0 ? wm : (jp < 16 ? w0 : w1), hi = jp < 0 ? w0 : (jp < 16 ? w1 : w2);
+                            km[b] = __funnelshift_r(lo, hi, 2u * (uint32_t)jp) & a.kmer_mask;
+                            hh[b] = km[b] * a.bitmap2_mul;
+                            wd[b] = ld_u32_policy(a.bitmap2 + (hh[b] >> a.bitmap2_shift), keep);
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < NB; b++)
+                        if (jj[b] != 0xFFFFFFFFu && (wd[b] & __funnelshift_l(0u, 1u, hh[b])))
+                            seed_walk(a, km[b], P0 + (uint64_t)(blk * 32) + jj[b] - d, keep);
+                }
+            }
             while (hits) {
                 uint32_t j;
                 asm("bfind.u32 %0, %1;" : "=r"(j) : "r"(hits));  // position of the highest set bit
@@ -417,7 +482,7 @@ k_seed_scan(SeedScanArgs a) {
                 const uint32_t lo = jp < 0 ? wm : (jp < 16 ? w0 : w1), hi = jp < 0 ? w0 : (jp < 16 ? w1 : w2);
                 const uint32_t kmer = __funnelshift_r(lo, hi, 2u * (uint32_t)jp) & a.kmer_mask;
                 const uint32_t h2 = kmer * a.bitmap2_mul;
-                if ((BLOOM == 0 && d == 0u) ||  // already tested above
+                if ((BLOOM == 0 && d == 0u) || T > 1 ||  // already tested above
                     (ld_u32_policy(a.bitmap2 + (h2 >> a.bitmap2_shift), keep) & __funnelshift_l(0u, 1u, h2)))
                     seed_walk(a, kmer, P0 + (uint64_t)(blk * 32) + j - d, keep);
             }

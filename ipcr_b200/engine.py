@@ -163,7 +163,7 @@ class CompiledPanel:
             raise RuntimeError("seed index evaluation failed")
         cands = [(int(buf[i]) >> 44, int(buf[i]) & ((1 << 44) - 1)) for i in range(n.value)]
         return cands, dict(S=info[0], entries=info[1], table_bits=info[2], bloom=bool(info[3]),
-                           bloom_fill=info[4] / 1e6, bloom_k=info[5], S1=info[6], keys1=info[7])
+                           bloom_fill=info[4] / 1e6, bloom_k=info[5] & 0xFF, stride=info[5] >> 8, S1=info[6], keys1=info[7])
 
     def jit_source(self, raw_mode: bool = False) -> str:
         need = C.c_size_t()

@@ -261,8 +261,15 @@ def test_seed_index_shape_on_the_benchmark_panel():
     g = bytes(H.random_genome(rng, 50000))
     cands, info = cp.seed_eval(g)
     assert info["S"] >= 12 and info["bloom"] and info["bloom_fill"] < 0.35 and info["bloom_k"] == 2
-    cp1 = Engine(Config(max_mm=1, terminal_window=3)).compile_panel(allp)
-    assert cp1.seed_eval(g)[1]["bloom_k"] == 1  # a sparse bitmap does not need the second bit
+    assert info["stride"] == 1  # 220 k first-level keys: a strided first level would double them (measured: 4.0 vs 2.3 ms)
+    # mm 1: 20 times fewer keys.  The first level looks at every 4th position only (its keys at 4 window offsets)
+    # and takes the second bitmap bit, because a false positive there stalls a whole warp
+    info1 = Engine(Config(max_mm=1, terminal_window=3)).compile_panel(allp).seed_eval(g)[1]
+    assert info1["stride"] == 4 and info1["bloom_k"] == 2 and info1["S"] - info1["S1"] >= 3 and info1["bloom_fill"] < 0.1
+    # one pair, no mismatches: a handful of keys, one bit is enough
+    _, one = synth.multiplex_panel(1, seed=7)
+    info0 = Engine(Config(max_mm=0, terminal_window=3)).compile_panel(one).seed_eval(g)[1]
+    assert info0["stride"] == 4 and info0["bloom_k"] == 1
     assert info["entries"] < 1 << 20
     assert len(cands) < 400  # ~ entries / 4^S per position
 
@@ -319,3 +326,49 @@ def test_pigeonhole_first_level_never_loses_a_true_site(oracle, monkeypatch):
                     assert (q, pos) in cset, (s, t, mm, tw, raw, pos, info)
                     checked += 1
     assert used > 60 and checked > 600
+
+
+@pytest.mark.parametrize("stride", [2, 4])
+def test_strided_first_level_never_loses_a_true_site(oracle, monkeypatch, stride):
+    """Anchor stride of the seed index's first level (small panels: one shared-memory lookup per 2 or 4 positions;
+    the bitmap then holds each seed's first-level keys at `stride` window offsets): with the stride forced, every
+    start the brute force accepts is still a candidate, none comes twice, and the candidate set is the one the
+    unstrided index gives (the first level is only a filter: the second level decides)."""
+    rng = random.Random(4242 + stride)
+    checked = used = 0
+    for it in range(60):
+        n = rng.randint(150, 360)
+        g = H.random_genome(rng, n, n_frac=rng.choice([0, 0.02]), lower_frac=rng.choice([0, 0.03]))
+        mm, tw = rng.randint(0, 3), rng.choice([0, 1, 3, 4])
+        pairs = []
+        for k in range(rng.randint(1, 3)):
+            la, lb = rng.randint(12, 34), rng.randint(12, 34)
+            a = H.random_primer(rng, la, rng.choice([0, 0.15]))
+            b = H.random_primer(rng, lb, rng.choice([0, 0.15]))
+            pairs.append(Pair(f"p{k}", a, b))
+            for _ in range(3):
+                H.plant_amplicon(rng, g, rng.randint(0, max(0, n - la - lb - 10)), a, b, la + lb + rng.randint(0, 10),
+                                 rng.randint(0, mm), rng.randint(0, mm), tw, revcomp_strand=rng.random() < 0.5)
+        seq = bytes(g)
+        cfg = Config(max_mm=mm, terminal_window=tw, hit_cap=rng.choice([0, 5]))
+        plain = Engine(cfg).compile_panel(pairs)
+        cp = Engine(cfg).compile_panel(pairs)
+        for raw in (False, True):
+            monkeypatch.setenv("IPCR_SEED_STRIDE_FORCE", "1")  # the index is built at its first use
+            want, info1 = plain.seed_eval(seq, raw)
+            monkeypatch.setenv("IPCR_SEED_STRIDE_FORCE", str(stride))
+            cands, info = cp.seed_eval(seq, raw)
+            assert info1["stride"] == 1
+            if not info["bloom"] or info["stride"] != stride:
+                continue  # a seed too short to leave `stride - 1` bases beside a 3-base key
+            used += 1
+            assert info["S"] - info["S1"] >= stride - 1
+            assert len(cands) == len(set(cands)), "duplicate candidate"
+            assert sorted(cands) == sorted(want)
+            cset = set(cands)
+            for q in range(cp.num_orientations):
+                s, t = cp.orientation(q)
+                for pos in _true_sites(oracle, seq, s, t == "a", mm, tw, raw):
+                    assert (q, pos) in cset, (s, t, mm, tw, raw, pos, info)
+                    checked += 1
+    assert used > 60 and checked > 400

@@ -47,9 +47,9 @@ def _records(rng, lens, with_n=True):
     return recs
 
 
-def _plant_across_cuts(recs, lens, pieces):
+def _plant_across_cuts(recs, lens, pieces, align=16):
     total = sum(lens)
-    for c in [(total * k // pieces) & ~15 for k in range(1, pieces)]:
+    for c in [(total * k // pieces) & ~(align - 1) for k in range(1, pieces)]:
         off = 0
         for ri, n in enumerate(lens):
             if off + 30 <= c < off + n - 30:
@@ -221,6 +221,55 @@ def test_packed_feeder_scan_equals_ascii_and_oracle(oracle, monkeypatch):
         assert [(p.sequence_id,) + _tuple(p) for p in plain.scan(cp, sc)] == want
         packed.close()
         plain.close()
+
+
+def test_multi_device_packed_scan_fasta_equals_oracle(oracle, monkeypatch):
+    """ipcr_gpu_scan_fasta over the packed form after ipcr_gpu_init(0): every device copies its own
+    4096-base-aligned slice of the codes (the bitmap from the clipped run list, or its slice), the site blocks
+    meet on the calling scratch's device.  Same rows, same order as one device and the oracle; binding
+    sites are planted across every slice boundary, N runs straddle one."""
+    L = _capi.lib()
+    if L.ipcr_gpu_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    err = _capi.errbuf()
+    rng = random.Random(21)
+    lens = [90000, 500, 140000, 70000, 3]
+    n_dev = L.ipcr_gpu_device_count()
+    recs = _records(rng, lens)
+    _plant_across_cuts(recs, lens, n_dev, align=4096)
+    cut1 = (sum(lens) // n_dev) & ~4095  # an N run over the first boundary (inside record 0 or 2)
+    off = 0
+    for ri, n in enumerate(lens):
+        if off + 200 <= cut1 < off + n - 200:
+            recs[ri][cut1 - off + 40:cut1 - off + 90] = b"N" * 50
+            recs[ri][cut1 - off - 120:cut1 - off - 60] = b"N" * 60
+        off += n
+    recs[0][5000:5400] = bytes(recs[0][5000:5400]).lower()
+    seqs = [bytes(g) for g in recs]
+    upper = [sq.upper() for sq in seqs]
+    ids = [f"r{i}" for i in range(len(lens))]
+    monkeypatch.setenv("IPCR_MULTI_MIN_BP", "1")
+    try:
+        for cfgd in CFGS:
+            want = _oracle_rows(oracle, cfgd, upper)
+            eng = Engine(Config(**cfgd))
+            cp = eng.compile_panel(PAIRS)
+            sc = eng.new_simulation_scratch(cp)
+            packed = FastaFile.from_memory(seqs, ids=ids, pack=True)
+            assert L.ipcr_gpu_init(0, err, len(err)) == 0, err.value
+            for runs in (True, False, True):  # third call: warm peers, sticky raw variant
+                if runs:
+                    monkeypatch.delenv("IPCR_NO_RUNS", raising=False)
+                else:
+                    monkeypatch.setenv("IPCR_NO_RUNS", "1")
+                got = [(p.sequence_id,) + _tuple(p) for p in packed.scan(cp, sc)]
+                assert got == want, (cfgd, runs)
+            assert L.ipcr_gpu_init(1, err, len(err)) == 0, err.value
+            assert [(p.sequence_id,) + _tuple(p) for p in packed.scan(cp, sc)] == want
+            packed.close()
+    finally:
+        monkeypatch.delenv("IPCR_NO_RUNS", raising=False)
+        L.ipcr_gpu_init(1, err, len(err))
 
 
 def test_block_split_phase_packed_equals_oracle(oracle):

@@ -54,6 +54,17 @@ def _check(oracle, cfgd, raw_pairs, seq, jit=0, cap_binds=False):
                 if env:
                     del os.environ[env]
             assert got == want, (mode, env, cfgd, raw_pairs, bytes(seq)[:80])
+    # small panels take the strided first level of the seed index (anchor stride 4) by default; the same case
+    # through the stride-1 and stride-2 kernels (the index is built at a panel's first scan, so: fresh panels)
+    for stride in ("1", "2"):
+        os.environ["IPCR_SEED_STRIDE_FORCE"] = stride
+        try:
+            cp2 = eng.compile_panel(pairs)
+            cp2.set_jit(3)
+            got2 = [_tuple(p) for p in eng.simulate_compiled("seq", seq, cp2)]
+        finally:
+            del os.environ["IPCR_SEED_STRIDE_FORCE"]
+        assert got2 == want, ("stride", stride, cfgd, raw_pairs, bytes(seq)[:80])
     if not cap_binds:
         brute = [_otuple(pairs, t) for t in oracle.simulate_bruteforce(ocfg, [tuple(p) for p in raw_pairs], seq)]
         assert H.multiset(got) == H.multiset(brute)
