@@ -289,6 +289,11 @@ typedef struct ipcr_fasta ipcr_fasta;
 #define IPCR_FASTA_PACK 2 /* also keep the PACKED form (2-bit codes + hard-mismatch bitmap, 0.375 B/bp, pinned):
                              ipcr_gpu_scan_fasta then ships that over PCIe, skips the pack kernel and verifies on
                              the codes; the device-side visitors need the ASCII path */
+#define IPCR_FASTA_PACK_ONLY 4 /* ipcr_gpu_fasta_open: ONLY the packed form -- the feeder never writes the 1 B/bp ASCII
+                             buffer (a third of its memory traffic and all of its page faults).  For runs that hand
+                             the handle to ipcr_gpu_scan_fasta and read ids / lengths only.  ipcr_gpu_fasta_record's
+                             `seq` is then rebuilt from the codes on first use, every non-ACGT byte as 'N' (the
+                             same thing to the engine; NOT the file's IUPAC letters) */
 /* pin: IPCR_FASTA_* flags */
 ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *err, size_t errlen);
 /* the same handle from records already in host memory (copied, a-z upper-cased like the reader does) */

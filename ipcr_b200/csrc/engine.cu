@@ -1863,6 +1863,26 @@ struct ipcr_fasta {
     }
     std::vector<uint8_t> rec_reset;  // per record: holds a non-ACGT byte (the feeder upper-cased a-z already)
     std::vector<ipcr_product> products;
+    // IPCR_FASTA_PACK_ONLY: no ASCII was kept.  The paths that need it (ipcr_gpu_fasta_record's seq, the scan of a
+    // handle the packed chain cannot take) rebuild it once from the codes, non-ACGT bytes as 'N'.
+    std::mutex ascii_mu;
+    const uint8_t *ascii(int threads = 0) {
+        std::lock_guard<std::mutex> lock(ascii_mu);
+        if (seq || !codes) return seq;
+        uint8_t *buf = static_cast<uint8_t *>(malloc((size_t)std::max<uint64_t>(total, 1) + 64));
+        if (!buf) throw std::runtime_error("out of host memory for the FASTA records");
+        if (threads <= 0) threads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        if (total < (1u << 22)) threads = 1;
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++) {
+            const uint64_t a = total * (uint64_t)t / (uint64_t)threads, b = total * (uint64_t)(t + 1) / (uint64_t)threads;
+            if (t + 1 < threads) th.emplace_back([=] { ipcr::unpack_host(codes, inval, a, b, buf + a); });
+            else ipcr::unpack_host(codes, inval, a, b, buf + a);
+        }
+        for (auto &x : th) x.join();
+        seq = buf;
+        return seq;
+    }
     void alloc_packed(uint64_t total, bool pin) {
         const uint64_t groups = ipcr::packed_groups(total);
         if (pin) {
@@ -1958,9 +1978,11 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
     fasta_read_file(path, fb);
     if (threads <= 0) threads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
     ipcr_fasta *fp = f.get();
-    const bool want_pack = (pin & IPCR_FASTA_PACK) != 0;
+    const bool pack_only = (pin & IPCR_FASTA_PACK_ONLY) != 0;
+    const bool want_pack = pack_only || (pin & IPCR_FASTA_PACK) != 0;
     pin &= IPCR_FASTA_PIN;
     FastaPackTarget pk;
+    pk.only = pack_only;
     const auto t_begin = std::chrono::steady_clock::now();
     double alloc_s = 0.0;
     fasta_parse(fb.data, fb.size, threads, f->recs, f->total, [&](uint64_t total) -> uint8_t * {
@@ -1974,6 +1996,7 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
             pk.codes = fp->codes;
             pk.inval = fp->inval;
         }
+        if (pack_only) return nullptr;  // no ASCII buffer: pass 2 packs from per-thread staging
         const size_t bytes = (size_t)std::max<uint64_t>(total, 1) + 64;
         if (pin) {
             void *q = nullptr;
@@ -2112,7 +2135,13 @@ uint64_t ipcr_gpu_fasta_total_bases(const ipcr_fasta *f) { return f ? f->total :
 int ipcr_gpu_fasta_record(const ipcr_fasta *f, size_t i, const char **id, const uint8_t **seq, uint64_t *len) {
     if (!f || i >= f->recs.size()) return 1;
     if (id) *id = f->recs[i].id.c_str();
-    if (seq) *seq = f->seq + f->recs[i].off;
+    if (seq) {
+        try {
+            *seq = const_cast<ipcr_fasta *>(f)->ascii() + f->recs[i].off;  // pack-only handles rebuild it on first use
+        } catch (const std::exception &) {
+            return 1;
+        }
+    }
     if (len) *len = f->recs[i].len;
     return 0;
 }
@@ -2158,7 +2187,7 @@ int ipcr_gpu_scan_fasta(ipcr_panel *p, ipcr_scratch *s, ipcr_fasta *f, const ipc
         uint64_t bases = 0;
         const size_t base = i;
         while (i < f->recs.size() && batch.size() < 60000 && bases + f->recs[i].len < (1ull << 43)) {
-            batch.push_back(ipcr_seq{f->seq + f->recs[i].off, f->recs[i].len});
+            batch.push_back(ipcr_seq{f->ascii() + f->recs[i].off, f->recs[i].len});
             bases += f->recs[i].len;
             i++;
         }

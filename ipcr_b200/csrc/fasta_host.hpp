@@ -26,7 +26,10 @@
 #include <emmintrin.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -80,6 +83,56 @@ inline void fasta_trim(const uint8_t *d, size_t &a, size_t &b) {
 // Parses `n` bytes of FASTA text.  `alloc(total)` must return a buffer for the sequence bytes.
 struct FastaPackTarget {  // optional: the packed form (pack_host.hpp) of the sequence buffer, filled by pass 2
     uint32_t *codes = nullptr, *inval = nullptr;
+    // pack-only: no sequence buffer at all (alloc() may return NULL).  Every thread normalises into a 64 KB staging
+    // buffer and packs from there; the (at most two) 32-base groups a thread shares with its neighbours, and the
+    // ragged last group, are assembled in 32-byte edge slots and packed after the join.  Saves writing -- and
+    // page-faulting in -- 1 B/bp of memory nobody reads when the scan takes the packed form.
+    bool only = false;
+};
+
+// pass 2 of the pack-only mode: the normalised bytes of one thread's output range [start, end) -> codes / bitmap
+struct FastaPackStage {
+    static constexpr size_t kCap = 64 * 1024;
+    std::vector<uint8_t> buf;
+    uint64_t A = 0, B = 0;      // interior of the range: whole groups [A / 32, B / 32)
+    uint64_t w = 0;             // next output offset
+    uint64_t base = 0;          // offset of buf[0] (a multiple of 32)
+    size_t fill = 0;
+    uint8_t *head = nullptr, *tail = nullptr;  // edge slots of the groups holding `start` / `end` (when not aligned)
+    uint64_t head_base = 0, tail_base = 0;
+    uint32_t *codes = nullptr, *inval = nullptr;
+
+    static void norm(uint8_t *dst, const uint8_t *src, size_t k) {  // normalize.go:8-10 (auto-vectorised)
+        for (size_t i = 0; i < k; i++) {
+            const uint8_t c = src[i];
+            dst[i] = (uint8_t)(c - (((uint8_t)(c - 'a') < 26u) ? 32u : 0u));
+        }
+    }
+    void flush() {
+        const size_t ng = fill / 32;
+        if (ng) pack_groups_staged(buf.data(), base / 32, ng, codes, inval);
+        const size_t rest = fill - ng * 32;
+        if (rest) memmove(buf.data(), buf.data() + ng * 32, rest);
+        base += (uint64_t)ng * 32;
+        fill = rest;
+    }
+    void put(const uint8_t *src, size_t k) {
+        while (k) {
+            if (w < A) {  // the group shared with the previous thread(s)
+                const size_t m = (size_t)std::min<uint64_t>(k, A - w);
+                norm(head + (w - head_base), src, m);
+                w += m; src += m; k -= m;
+            } else if (w < B) {
+                const size_t m = (size_t)std::min<uint64_t>(std::min<uint64_t>(k, B - w), kCap - fill);
+                norm(buf.data() + fill, src, m);
+                fill += m; w += m; src += m; k -= m;
+                if (fill >= kCap) flush();
+            } else {  // the group shared with the next thread(s), or the ragged last group of the buffer
+                norm(tail + (w - tail_base), src, k);
+                w += k; k = 0;
+            }
+        }
+    }
 };
 
 template <class Alloc>
@@ -88,7 +141,11 @@ inline void fasta_parse(const uint8_t *d, size_t n, int threads, std::vector<Fas
     recs.clear();
     total = 0;
     if (threads < 1) threads = 1;
-    if (n < (size_t)(8u << 20)) threads = 1;
+    {
+        size_t mt_min = (size_t)(8u << 20);  // below this one thread is faster
+        if (const char *e = getenv("IPCR_FEEDER_MT_MIN")) mt_min = (size_t)atoll(e);  // tests: tiny multi-threaded files
+        if (n < mt_min) threads = 1;
+    }
     // range starts snapped to line starts
     std::vector<size_t> cut((size_t)threads + 1, n);
     cut[0] = 0;
@@ -173,12 +230,24 @@ inline void fasta_parse(const uint8_t *d, size_t n, int threads, std::vector<Fas
             if (stop >= hi) break;
         }
     };
+    const bool timing = getenv("IPCR_FEEDER_TIMING") != nullptr;
+    const auto t_p0 = std::chrono::steady_clock::now();
     {
         std::vector<std::thread> th;
         for (int t = 1; t < threads; t++) th.emplace_back(pass1, t);
         pass1(0);
         for (auto &x : th) x.join();
     }
+    const auto t_p1 = std::chrono::steady_clock::now();
+    struct PhaseNote {  // stderr at scope exit: pass 1 (count) / everything after it (allocation, copy or staging, pack)
+        bool on; std::chrono::steady_clock::time_point a, b;
+        ~PhaseNote() {
+            if (on)
+                fprintf(stderr, "[feeder] pass 1 (count) %.3f s, allocation + pass 2 (normalise, pack) %.3f s\n",
+                        std::chrono::duration<double>(b - a).count(),
+                        std::chrono::duration<double>(std::chrono::steady_clock::now() - b).count());
+        }
+    } phase_note{timing, t_p0, t_p1};
     // merge: record table, and for every thread its output cursor and whether the record that
     // is open at its range start is kept (non-empty ID)
     std::vector<uint64_t> start_off((size_t)threads, 0);
@@ -206,6 +275,60 @@ inline void fasta_parse(const uint8_t *d, size_t n, int threads, std::vector<Fas
     uint8_t *out = alloc(total);  // the callback also allocates the pack target (it knows the total now)
     const bool do_pack = pack && pack->codes && pack->inval;
     std::vector<uint64_t> end_off((size_t)threads, 0);
+    if (do_pack && pack->only) {
+        // edge groups: those holding a range boundary that is not group-aligned (several boundaries may share one)
+        std::vector<uint64_t> bound((size_t)threads + 1, total);
+        for (int t = 0; t < threads; t++) bound[t] = start_off[t];
+        std::vector<uint64_t> edge_g;
+        for (int t = 0; t <= threads; t++)
+            if (bound[t] % 32 != 0) edge_g.push_back(bound[t] / 32);
+        std::sort(edge_g.begin(), edge_g.end());
+        edge_g.erase(std::unique(edge_g.begin(), edge_g.end()), edge_g.end());
+        std::vector<uint8_t> edge(edge_g.size() * 32 + 32, 0);
+        auto slot = [&](uint64_t off) -> uint8_t * {
+            const size_t i = (size_t)(std::lower_bound(edge_g.begin(), edge_g.end(), off / 32) - edge_g.begin());
+            return edge.data() + i * 32;
+        };
+        auto pass2p = [&](int t) {
+            FastaPackStage st;
+            const uint64_t start = bound[t], end = bound[t + 1];
+            st.w = start;
+            st.A = std::min(end, (start + 31) / 32 * 32);
+            st.B = std::max(st.A, end / 32 * 32);
+            // a range that lies inside ONE unaligned group has no interior: everything goes to that group's slot
+            if (start / 32 == end / 32 && start % 32 != 0) st.A = st.B = end;
+            st.base = st.A;
+            st.codes = pack->codes;
+            st.inval = pack->inval;
+            if (start % 32 != 0) { st.head = slot(start); st.head_base = start / 32 * 32; }
+            if (end % 32 != 0) { st.tail = slot(end); st.tail_base = end / 32 * 32; }
+            if (st.A == end && start % 32 != 0 && start / 32 == end / 32) { st.tail = st.head; st.tail_base = st.head_base; }
+            st.buf.resize(FastaPackStage::kCap + 64);
+            bool keep = start_open[t] != 0;
+            size_t hi = 0;
+            fasta_for_lines(d, n, cut[t], cut[t + 1], [&](size_t a, size_t b) {
+                if (b > a && d[a] == '>') {
+                    keep = !pieces[t].hdrs[hi++].id.empty();
+                    return;
+                }
+                if (!keep) return;
+                fasta_trim(d, a, b);
+                st.put(d + a, b - a);
+            });
+            st.flush();
+            end_off[t] = st.w;
+        };
+        {
+            std::vector<std::thread> th;
+            for (int t = 1; t < threads; t++) th.emplace_back(pass2p, t);
+            pass2p(0);
+            for (auto &x : th) x.join();
+        }
+        for (size_t i = 0; i < edge_g.size(); i++) pack_groups_staged(edge.data() + i * 32, edge_g[i], 1, pack->codes, pack->inval);
+        // the padding groups behind the last base: 0x00 bytes = code 0, invalid
+        pack_groups_host(nullptr, 0, (total + 31) / 32, packed_groups(total), pack->codes, pack->inval);
+        return;
+    }
     auto pass2 = [&](int t) {
         uint64_t w = start_off[t];
         // 32-base groups lying entirely inside this thread's output range are packed here, 64 KB at a time,

@@ -457,15 +457,16 @@ int main(int argc, char **argv) {
         // plain unchunked runs take the feeder's packed form through ipcr_gpu_scan_fasta (0.375 B/bp over PCIe, no
         // pack kernel); nothing is page-locked: locking 1 GB costs more than a one-shot copy from pageable memory saves
         const bool packed_path = plain && chunk <= 0;
-        ipcr_fasta *ff = ipcr_gpu_fasta_open(fa.c_str(), 0, packed_path ? IPCR_FASTA_PACK : 0, g.err, sizeof g.err);
+        // (and only ids and lengths are read back, so the feeder does not even write the ASCII records: PACK_ONLY)
+        ipcr_fasta *ff = ipcr_gpu_fasta_open(fa.c_str(), 0, packed_path ? IPCR_FASTA_PACK_ONLY : 0, g.err, sizeof g.err);
         if (!ff) die(3, g.err);
         t_open += secs(tf0, Clock::now());
         if (packed_path) {
             const size_t nrec = ipcr_gpu_fasta_num_records(ff);
             const size_t meta_base = metas.size();
             for (size_t r = 0; r < nrec; r++) {
-                const char *id; const uint8_t *seq; uint64_t len;
-                ipcr_gpu_fasta_record(ff, r, &id, &seq, &len);
+                const char *id; uint64_t len;
+                ipcr_gpu_fasta_record(ff, r, &id, nullptr, &len);
                 JobMeta m;
                 m.id = id;
                 m.chunked = split_chunk_suffix(m.id, m.base, m.off);  // the collector strips ANY :a-b suffix (pipeline.go:140-156)

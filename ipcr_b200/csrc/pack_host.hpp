@@ -5,8 +5,14 @@
 // 0.375 B/bp cross PCIe instead of 1 B/bp.  Padding bytes count as 0x00: code 0, invalid.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#if defined(__x86_64__)
+#include <cpuid.h>
+#include <immintrin.h>
+#endif
 #include <thread>
 #include <vector>
 
@@ -31,9 +37,88 @@ inline void pack4_host(uint32_t w, uint32_t &code8, uint32_t &inv4) {
     inv4 = ((nz >> 7) * 0x10204080u) >> 28;
 }
 
+#if defined(__x86_64__)
+// AVX2 + BMI2 form of the same (chosen at run time): a byte is valid iff it equals one of 'A' 'C' 'G' 'T' (four
+// compares, one movemask = the 32 bitmap bits); its code is bits 1..2 of the byte, gathered 8 bytes at a time by PEXT.
+// ~20 instructions per 32 bases instead of ~110.
+__attribute__((target("avx2,bmi2")))
+inline void pack_groups_staged_avx2(const uint8_t *src, uint64_t g0, uint64_t ng, uint32_t *codes, uint32_t *inval) {
+    const __m256i vA = _mm256_set1_epi8('A'), vC = _mm256_set1_epi8('C'), vG = _mm256_set1_epi8('G'), vT = _mm256_set1_epi8('T');
+    const unsigned long long m = 0x0606060606060606ull;
+    for (uint64_t i = 0; i < ng; i++) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 32 * i));
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, vA), _mm256_cmpeq_epi8(v, vC)),
+                                           _mm256_or_si256(_mm256_cmpeq_epi8(v, vG), _mm256_cmpeq_epi8(v, vT)));
+        inval[g0 + i] = ~(uint32_t)_mm256_movemask_epi8(ok);
+        unsigned long long q[4];
+        memcpy(q, src + 32 * i, 32);
+        codes[2 * (g0 + i)] = (uint32_t)(_pext_u64(q[0], m) | (_pext_u64(q[1], m) << 16));
+        codes[2 * (g0 + i) + 1] = (uint32_t)(_pext_u64(q[2], m) | (_pext_u64(q[3], m) << 16));
+    }
+}
+
+inline bool pack_have_avx2() {
+    static const bool have = [] {
+        unsigned a = 0, b = 0, c = 0, d = 0;
+        if (!__get_cpuid_count(7, 0, &a, &b, &c, &d)) return false;
+        const bool avx2 = (b >> 5) & 1u, bmi2 = (b >> 8) & 1u;
+        if (!avx2 || !bmi2) return false;
+        unsigned a1 = 0, b1 = 0, c1 = 0, d1 = 0;  // the OS must save the YMM state: OSXSAVE + XCR0[2:1] = 11
+        if (!__get_cpuid(1, &a1, &b1, &c1, &d1) || !((c1 >> 27) & 1u)) return false;
+        unsigned lo, hi;
+        __asm__ volatile("xgetbv" : "=a"(lo), "=d"(hi) : "c"(0));
+        return ((lo | (hi & 0u)) & 6u) == 6u && getenv("IPCR_FEEDER_NO_AVX2") == nullptr;
+    }();
+    return have;
+}
+#endif
+
+// ng whole groups starting at group g0, their 32 * ng bytes at `src` (a staging buffer: the feeder's pack-only mode
+// never materialises the ASCII buffer)
+inline void pack_groups_staged(const uint8_t *src, uint64_t g0, uint64_t ng, uint32_t *codes, uint32_t *inval) {
+#if defined(__x86_64__)
+    if (pack_have_avx2()) {
+        pack_groups_staged_avx2(src, g0, ng, codes, inval);
+        return;
+    }
+#endif
+    for (uint64_t i = 0; i < ng; i++) {
+        uint32_t w[8];
+        memcpy(w, src + 32 * i, 32);
+        uint32_t c0 = 0, c1 = 0, inv = 0;
+        for (int k = 0; k < 8; k++) {
+            uint32_t c8, i4;
+            pack4_host(w[k], c8, i4);
+            if (k < 4) c0 |= c8 << (8 * k); else c1 |= c8 << (8 * (k - 4));
+            inv |= i4 << (4 * k);
+        }
+        codes[2 * (g0 + i)] = c0;
+        codes[2 * (g0 + i) + 1] = c1;
+        inval[g0 + i] = inv;
+    }
+}
+
+// the ASCII a packed buffer stands for, positions [a, b): A/C/G/T, every hard-mismatch byte as 'N' (for the engine
+// all non-ACGT bytes are the same: a mismatch at their column and an automaton reset, core/engine/ac.go:141-148)
+inline void unpack_host(const uint32_t *codes, const uint32_t *inval, uint64_t a, uint64_t b, uint8_t *out) {
+    static const char kBase[4] = {'A', 'C', 'T', 'G'};
+    for (uint64_t p = a; p < b; p++) {
+        const bool bad = (inval[p >> 5] >> (p & 31u)) & 1u;
+        out[p - a] = bad ? (uint8_t)'N' : (uint8_t)kBase[(codes[p >> 4] >> (2u * (uint32_t)(p & 15u))) & 3u];
+    }
+}
+
 // groups [g0, g1) of a buffer of n bases; returns true if any byte of [32*g0, min(n, 32*g1)) is invalid
 inline bool pack_groups_host(const uint8_t *ascii, uint64_t n, uint64_t g0, uint64_t g1, uint32_t *codes, uint32_t *inval) {
     uint32_t any = 0;
+#if defined(__x86_64__)
+    if (pack_have_avx2() && g0 < std::min<uint64_t>(g1, n / 32)) {  // the whole groups
+        const uint64_t gf = std::min<uint64_t>(g1, n / 32);
+        pack_groups_staged_avx2(ascii + 32 * g0, g0, gf - g0, codes, inval);
+        for (uint64_t g = g0; g < gf; g++) any |= inval[g];
+        g0 = gf;
+    }
+#endif
     for (uint64_t g = g0; g < g1; g++) {
         const uint64_t P0 = g * 32ull;
         uint32_t w[8];

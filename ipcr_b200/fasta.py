@@ -13,11 +13,13 @@ class FastaFile:
     """All records of a FASTA file, normalised like fasta.StreamChunksPathCtx with chunking off
     (core/fasta/path_ctx.go:40-81)."""
 
-    PIN, PACK = 1, 2  # IPCR_FASTA_* flags
+    PIN, PACK, PACK_ONLY = 1, 2, 4  # IPCR_FASTA_* flags
 
-    def __init__(self, path: str, threads: int = 0, pin: bool = False, pack: bool = False):
+    def __init__(self, path: str, threads: int = 0, pin: bool = False, pack: bool = False, pack_only: bool = False):
+        """pack_only: keep ONLY the packed form (the feeder never writes the ASCII records; `records()` then
+        rebuilds them from the codes with every non-ACGT byte as 'N')."""
         err = _capi.errbuf()
-        flags = (self.PIN if pin else 0) | (self.PACK if pack else 0)
+        flags = (self.PIN if pin else 0) | (self.PACK if pack else 0) | (self.PACK_ONLY if pack_only else 0)
         h = _capi.lib().ipcr_gpu_fasta_open(path.encode(), threads, flags, err, len(err))
         if not h:
             raise OSError(err.value.decode("utf-8", "replace"))

@@ -213,8 +213,6 @@ def test_feeder_fast_paths_and_fused_pack(tmp_path):
         ff = FastaFile(str(path), threads=threads)
         assert ff.records() == ref
         ff.close()
-    if L.ipcr_gpu_device_count() == 0:
-        return  # pinned allocations need a driver: the packed half runs on the GPU box
     cat = b"".join(s_ for _id, s_ in ref)
     cw, iw = C.c_uint64(), C.c_uint64()
     L.ipcr_gpu_packed_words(len(cat), C.byref(cw), C.byref(iw))
@@ -222,14 +220,84 @@ def test_feeder_fast_paths_and_fused_pack(tmp_path):
     wi = np.zeros(iw.value, dtype=np.uint32)
     assert L.ipcr_gpu_pack_host(cat, len(cat), wc.ctypes.data, wi.ctypes.data, 2) == 0
     for threads in (1, 5, 8):
-        ff = FastaFile(str(path), threads=threads, pack=True)
-        pc, pi, ng = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.c_uint64()
-        assert L.ipcr_gpu_fasta_packed(ff._h, C.byref(pc), C.byref(pi), C.byref(ng)) == 0
-        assert ng.value == iw.value
-        got_c = np.ctypeslib.as_array(pc, shape=(2 * ng.value,)).copy()
-        got_i = np.ctypeslib.as_array(pi, shape=(ng.value,)).copy()
-        assert np.array_equal(got_c, wc) and np.array_equal(got_i, wi), threads
-        ff.close()
+        for only in (False, True):
+            ff = FastaFile(str(path), threads=threads, pack=not only, pack_only=only)
+            pc, pi, ng = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.c_uint64()
+            assert L.ipcr_gpu_fasta_packed(ff._h, C.byref(pc), C.byref(pi), C.byref(ng)) == 0
+            assert ng.value == iw.value
+            got_c = np.ctypeslib.as_array(pc, shape=(2 * ng.value,)).copy()
+            got_i = np.ctypeslib.as_array(pi, shape=(ng.value,)).copy()
+            assert np.array_equal(got_c, wc) and np.array_equal(got_i, wi), (threads, only)
+            ff.close()
+
+
+def _packed_arrays(ff):
+    import ctypes as C
+
+    import numpy as np
+
+    from ipcr_b200 import _capi
+
+    pc, pi, ng = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.c_uint64()
+    assert _capi.lib().ipcr_gpu_fasta_packed(ff._h, C.byref(pc), C.byref(pi), C.byref(ng)) == 0
+    return (np.ctypeslib.as_array(pc, shape=(2 * ng.value,)).copy(), np.ctypeslib.as_array(pi, shape=(ng.value,)).copy())
+
+
+def test_feeder_pack_only_equals_pack(tmp_path, monkeypatch):
+    """IPCR_FASTA_PACK_ONLY: the feeder never writes the ASCII records -- every thread normalises into a staging
+    buffer and packs from there, the 32-base groups shared by two threads' output ranges (and the ragged last
+    group) are assembled in edge slots.  Codes and bitmap must equal the host packer's on the reference reader's
+    records, for any number of threads, tiny ranges (several thread boundaries inside ONE group, threads that only
+    see headers), ragged totals, lines longer than the staging buffer; the records read back are the reader's with
+    every non-ACGT byte as 'N'."""
+    import ctypes as C
+
+    import numpy as np
+
+    from ipcr_b200 import _capi
+
+    L = _capi.lib()
+    monkeypatch.setenv("IPCR_FEEDER_MT_MIN", "1")
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtNRYn-", dtype=np.uint8)
+
+    def body(n, width):
+        seq = alphabet[rng.integers(0, len(alphabet), n)].tobytes()
+        return b"\n".join(seq[i:i + width] for i in range(0, n, width))
+
+    files = {
+        "tiny": b">a\nACGT\n>b x\nAC\n\n>c\n" + b"G" * 70 + b"\n",
+        "headers_only_middle": b">a\n" + body(300, 60) + b"\n" + b"".join(b">e%d\n" % i for i in range(40)) + b">z\n" + body(97, 13) + b"\n",
+        "dropped_ids": b"ACGT\n> \nACGTACGT\n>k\n" + body(1000, 80) + b"\n>\nTTTT\n>m\n" + body(33, 80) + b"\n",
+        "one_long_line": b">chr\n" + body(200_000, 200_000) + b"\n>t\nacgtn\n",
+        "crlf_padded": (b">r1 d\n" + body(5000, 61) + b"\n>r2\n  " + body(777, 50) + b" \n").replace(b"\n", b"\r\n"),
+        "aligned_total": b">p\n" + body(4096, 64) + b"\n",
+        "empty": b"",
+        "no_records": b"ACGT\nACGT\n",
+    }
+    for name, data in files.items():
+        path = tmp_path / (name + ".fa")
+        path.write_bytes(data)
+        ref = ref_reader(data)
+        cat = b"".join(s_ for _id, s_ in ref)
+        cw, iw = C.c_uint64(), C.c_uint64()
+        L.ipcr_gpu_packed_words(len(cat), C.byref(cw), C.byref(iw))
+        wc = np.zeros(cw.value, dtype=np.uint32)
+        wi = np.zeros(iw.value, dtype=np.uint32)
+        assert L.ipcr_gpu_pack_host(cat, len(cat), wc.ctypes.data, wi.ctypes.data, 1) == 0
+        as_n = [(i, bytes(c if c in b"ACGT" else ord("N") for c in s_)) for i, s_ in ref]
+        for threads in (1, 2, 3, 7, 16, 31):
+            full = FastaFile(str(path), threads=threads, pack=True)
+            only = FastaFile(str(path), threads=threads, pack_only=True)
+            assert only.packed and len(only) == len(ref) and only.total_bases == len(cat), (name, threads)
+            assert only.ids() == [i for i, _ in ref]
+            for ff in (full, only):
+                got_c, got_i = _packed_arrays(ff)
+                assert np.array_equal(got_c, wc) and np.array_equal(got_i, wi), (name, threads, ff is only)
+            assert full.records() == ref
+            assert only.records() == as_n, (name, threads)
+            full.close()
+            only.close()
 
 
 def test_invalid_run_list_round_trips():
