@@ -105,6 +105,109 @@ struct PinBuf {
     PinBuf &operator=(const PinBuf &) = delete;
 };
 
+// Pageable host memory -> device at PCIe speed.  cudaMemcpyAsync from pageable memory is staged by the driver on ONE
+// thread (~11 GB/s measured for the feeder's malloc'ed packed records), and page-locking the source costs ~0.5 s
+// per GB -- more than a one-shot run's whole copy.  Here kThreads host threads copy 2 MB chunks into a small ring of
+// pinned slots (allocated once per scratch) and queue the H2D of each slot on their own stream; `mark`s (slab
+// numbers) let the consumer stream wait for exactly the chunks a slab needs.
+struct HostStager {
+    static constexpr int kThreads = 6, kSlots = 2;
+    static constexpr size_t kChunk = 2u << 20;
+    struct Copy { void *dst; const void *src; size_t bytes; int mark; };
+    PinBuf ring;
+    cudaStream_t stream[kThreads] = {};
+    cudaEvent_t slot_ev[kThreads][kSlots] = {};
+    std::vector<cudaEvent_t> mark_ev;  // [mark * kThreads + t]
+    std::vector<Copy> jobs;
+    std::vector<std::thread> th;
+    std::atomic<int> progress[kThreads];  // marks thread t has recorded so far
+    std::atomic<bool> failed{false};
+    std::string error;
+    std::mutex mu;
+    int device = 0, n_marks = 0;
+
+    void add(void *dst, const void *src, size_t bytes, int mark) {  // marks must not decrease
+        const uint8_t *s8 = static_cast<const uint8_t *>(src);
+        uint8_t *d8 = static_cast<uint8_t *>(dst);
+        for (size_t o = 0; o < bytes; o += kChunk) jobs.push_back(Copy{d8 + o, s8 + o, std::min(kChunk, bytes - o), mark});
+    }
+    void start(int dev, int marks) {
+        device = dev;
+        n_marks = marks;
+        ring.ensure((size_t)kThreads * kSlots * kChunk);
+        for (int t = 0; t < kThreads; t++) {
+            if (!stream[t]) CU(cudaStreamCreateWithFlags(&stream[t], cudaStreamNonBlocking));
+            for (int k = 0; k < kSlots; k++)
+                if (!slot_ev[t][k]) CU(cudaEventCreateWithFlags(&slot_ev[t][k], cudaEventDisableTiming));
+            progress[t].store(0);
+        }
+        while (mark_ev.size() < (size_t)marks * kThreads) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            mark_ev.push_back(e);
+        }
+        failed.store(false);
+        error.clear();
+        for (int t = 0; t < kThreads; t++) th.emplace_back([this, t] { run(t); });
+    }
+    void run(int t) {
+        int done = 0;  // marks recorded
+        try {
+            CU(cudaSetDevice(device));
+            uint8_t *slots = ring.as<uint8_t>() + (size_t)t * kSlots * kChunk;
+            size_t mine = 0;
+            for (size_t c = (size_t)t; c < jobs.size(); c += kThreads, mine++) {
+                const Copy &j = jobs[c];
+                for (; done < j.mark; done++) {  // everything of the earlier marks is queued
+                    CU(cudaEventRecord(mark_ev[(size_t)done * kThreads + t], stream[t]));
+                    progress[t].store(done + 1, std::memory_order_release);
+                }
+                const int k = (int)(mine % kSlots);
+                if (mine >= (size_t)kSlots) CU(cudaEventSynchronize(slot_ev[t][k]));  // the slot's last copy has left
+                memcpy(slots + (size_t)k * kChunk, j.src, j.bytes);
+                CU(cudaMemcpyAsync(j.dst, slots + (size_t)k * kChunk, j.bytes, cudaMemcpyHostToDevice, stream[t]));
+                CU(cudaEventRecord(slot_ev[t][k], stream[t]));
+            }
+            for (; done < n_marks; done++) {
+                CU(cudaEventRecord(mark_ev[(size_t)done * kThreads + t], stream[t]));
+                progress[t].store(done + 1, std::memory_order_release);
+            }
+        } catch (const std::exception &e) {
+            std::lock_guard<std::mutex> lock(mu);
+            error = e.what();
+            failed.store(true);
+            progress[t].store(1 << 30, std::memory_order_release);
+        }
+    }
+    // makes `consumer` wait for every chunk of marks <= mark (blocks the host until those chunks are QUEUED)
+    void wait_mark(int mark, cudaStream_t consumer) {
+        for (int t = 0; t < kThreads; t++) {
+            while (progress[t].load(std::memory_order_acquire) <= mark) std::this_thread::yield();
+            if (failed.load()) break;
+            CU(cudaStreamWaitEvent(consumer, mark_ev[(size_t)mark * kThreads + t], 0));
+        }
+        if (failed.load()) {
+            finish();
+            throw Error("staged host-to-device copy failed: " + error);
+        }
+    }
+    void finish() {  // joins the threads (their copies may still be in flight on their streams)
+        for (auto &x : th) x.join();
+        th.clear();
+        jobs.clear();
+    }
+    ~HostStager() {
+        for (auto &x : th) x.join();
+        for (int t = 0; t < kThreads; t++) {
+            if (stream[t]) cudaStreamSynchronize(stream[t]);
+            for (int k = 0; k < kSlots; k++)
+                if (slot_ev[t][k]) cudaEventDestroy(slot_ev[t][k]);
+            if (stream[t]) cudaStreamDestroy(stream[t]);
+        }
+        for (auto &e : mark_ev) cudaEventDestroy(e);
+    }
+};
+
 // ---- panel tables on one device ---------------------------------------------
 struct PlanTables {
     DevBuf progs, cols, blk_len, slot_cls;
@@ -330,6 +433,7 @@ struct ipcr_scratch {
     ipcr::DevBuf sp_in, sp_out, sp_k[4], sp_ka, sp_kb, sp_ia, sp_ib, sp_tie, sp_rr, sp_ro, sp_pr;  // ipcr_gpu_sort_products
     std::vector<std::unique_ptr<ipcr::GenomeData>> slab_g;  // streamed slabs: packed codes per slab (all in flight at once)
     std::vector<cudaEvent_t> slab_t;
+    std::unique_ptr<ipcr::HostStager> stager;  // pageable packed records -> device (scan_packed_chain)
     // records of the last scan that are still resident (for the device-side visitors)
     std::vector<uint64_t> last_rec_base, last_rec_len;
     const uint8_t *last_ascii = nullptr;
@@ -2167,7 +2271,7 @@ int ipcr_gpu_scan_fasta(ipcr_panel *p, ipcr_scratch *s, ipcr_fasta *f, const ipc
         if (!s->inflight) s->args_used = 0;
         if (chain_ok(s, rinfo.data(), rinfo.size())) {
             PackedHost ph{f->codes, f->inval, f->total, f->runs_ok && !getenv("IPCR_NO_RUNS") ? f->inval_runs.data() : nullptr,
-                          f->inval_runs.size() / 2};
+                          f->inval_runs.size() / 2, f->packed_pinned};
             uint64_t n = 0;
             // ipcr_gpu_init(n > 1): every device takes a slice of the packed arrays over its own PCIe link
             const bool multi = g_n_devices.load() > 1 && f->total >= multi_min_bases();

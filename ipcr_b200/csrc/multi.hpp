@@ -167,6 +167,7 @@ struct PackedHost {
     uint64_t total = 0;               // bases in the concatenated buffer
     const uint64_t *runs = nullptr;   // optional: the bitmap as [start, end) runs (then only the codes cross PCIe)
     uint64_t n_runs = 0;
+    bool pinned = true;               // false: codes / inval are pageable (the feeder page-locks on request only)
 };
 
 static bool scan_packed_chain(ipcr_scratch *s, const PackedHost &ph, const std::vector<ipcr_record_info> &rinfo,
@@ -213,21 +214,42 @@ static bool scan_packed_chain(ipcr_scratch *s, const PackedHost &ph, const std::
             s->launches++;
         }
     }
+    // pageable source (a one-shot FASTA run): several host threads stage the chunks through a pinned ring instead
+    // of the driver's single-threaded staging
+    uint64_t staged_min = 64ull << 20;
+    if (const char *e = getenv("IPCR_STAGED_H2D_MIN")) staged_min = (uint64_t)atoll(e);  // tests: tiny inputs too; -1: never
+    const bool staged = !ph.pinned && total >= staged_min;
+    if (staged && !s->stager) s->stager.reset(new HostStager());
+    struct StagerJoin {  // on every way out: threads joined, their copies landed (the caller may free the source)
+        HostStager *h;
+        ~StagerJoin() {
+            if (!h) return;
+            h->finish();
+            for (int t = 0; t < HostStager::kThreads; t++)
+                if (h->stream[t]) cudaStreamSynchronize(h->stream[t]);
+        }
+    } stager_join{staged ? s->stager.get() : nullptr};
     uint64_t g_done = 0;
     for (int k = 0; k < n_slabs; k++) {
         const uint64_t end = std::min(total, c.cut[k + 1] + kPieceHalo);
         const uint64_t g_want = std::min(groups, (end + kPackChunk - 1) / kPackChunk * (kPackChunk / 32u) + 1);
         if (g_want > g_done) {
-            CU(cudaMemcpyAsync(own.codes.as<uint32_t>() + 2 * g_done, ph.codes + 2 * g_done, (g_want - g_done) * 8,
-                               cudaMemcpyHostToDevice, cs));
-            if (!by_runs)
-                CU(cudaMemcpyAsync(own.inval.as<uint32_t>() + g_done, ph.inval + g_done, (g_want - g_done) * 4,
+            if (staged) {
+                s->stager->add(own.codes.as<uint32_t>() + 2 * g_done, ph.codes + 2 * g_done, (g_want - g_done) * 8, k);
+                if (!by_runs) s->stager->add(own.inval.as<uint32_t>() + g_done, ph.inval + g_done, (g_want - g_done) * 4, k);
+            } else {
+                CU(cudaMemcpyAsync(own.codes.as<uint32_t>() + 2 * g_done, ph.codes + 2 * g_done, (g_want - g_done) * 8,
                                    cudaMemcpyHostToDevice, cs));
+                if (!by_runs)
+                    CU(cudaMemcpyAsync(own.inval.as<uint32_t>() + g_done, ph.inval + g_done, (g_want - g_done) * 4,
+                                       cudaMemcpyHostToDevice, cs));
+            }
             g_done = g_want;
         }
-        CU(cudaEventRecord(s->slab_ev[k], cs));
+        if (!staged) CU(cudaEventRecord(s->slab_ev[k], cs));
     }
-    CU(cudaEventRecord(s->copy_ev[1], cs));
+    if (staged) s->stager->start(s->device, n_slabs);
+    else CU(cudaEventRecord(s->copy_ev[1], cs));
     bool done = false;
     for (int attempt = 0; attempt < 6 && !done; attempt++) {
         const uint64_t site_cap = std::max<uint64_t>(1024, s->site_cap_hint);
@@ -248,11 +270,18 @@ static bool scan_packed_chain(ipcr_scratch *s, const PackedHost &ph, const std::
             g.codes_ext = own.codes.as<uint32_t>() + lo / 16;
             g.inval_ext = own.inval.as<uint32_t>() + lo / 32;
             g.own_bases = hi - lo;
-            if (attempt == 0) CU(cudaStreamWaitEvent(st, s->slab_ev[k], 0));
+            if (attempt == 0) {
+                if (staged) s->stager->wait_mark(k, st);
+                else CU(cudaStreamWaitEvent(st, s->slab_ev[k], 0));
+            }
             CU(cudaEventRecord(s->slab_t[2 * k], st));
             stage1_async(s, g, variant, s->gather.as<uint8_t>() + (size_t)n_blocks * bb, site_cap);
             CU(cudaEventRecord(s->slab_t[2 * k + 1], st));
             n_blocks++;
+        }
+        if (staged && attempt == 0) {  // the copy stream's end-of-copies event, for the timing
+            s->stager->wait_mark(n_slabs - 1, cs);
+            CU(cudaEventRecord(s->copy_ev[1], cs));
         }
         if (n_blocks == 0) {
             *n_prod = 0;

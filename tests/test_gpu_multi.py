@@ -216,7 +216,16 @@ def test_packed_feeder_scan_equals_ascii_and_oracle(oracle, monkeypatch):
         # the bitmap travels as a run list by default (rebuilt on the device); the same with the bitmap itself
         monkeypatch.setenv("IPCR_NO_RUNS", "1")
         assert [(p.sequence_id,) + _tuple(p) for p in packed.scan(cp, sc)] == want, cfgd
+        # pageable packed records go through the multi-threaded pinned staging ring (inputs >= 64 Mbp by default)
+        pageable = FastaFile.from_memory(seqs, ids=ids, pin=False, pack=True)
+        monkeypatch.setenv("IPCR_STAGED_H2D_MIN", "1")
+        for slabs in ("1", "4"):
+            monkeypatch.setenv("IPCR_STREAM_SLABS", slabs)
+            assert [(p.sequence_id,) + _tuple(p) for p in pageable.scan(cp, sc)] == want, (cfgd, "staged+bitmap", slabs)
         monkeypatch.delenv("IPCR_NO_RUNS")
+        assert [(p.sequence_id,) + _tuple(p) for p in pageable.scan(cp, sc)] == want, (cfgd, "staged")
+        monkeypatch.delenv("IPCR_STAGED_H2D_MIN")
+        pageable.close()
         monkeypatch.delenv("IPCR_STREAM_SLABS")
         assert [(p.sequence_id,) + _tuple(p) for p in plain.scan(cp, sc)] == want
         packed.close()
