@@ -2049,6 +2049,8 @@ static uint64_t scan_records(ipcr_scratch *s, const ipcr_seq *recs, size_t n_rec
     if (chain && g_n_devices.load() > 1 && total >= multi_min_bases() && scan_multi_device(s, recs, n_recs, &n)) return n;
     // large inputs: overlap the PCIe copy with the scan, slab by slab
     int n_slabs = (int)std::min<uint64_t>(5, total / (640ull << 20));
+    // pageable records are worth streaming much earlier: the staged copy (HostStager) is what makes them fast
+    if (n_slabs < 2 && chain && total >= staged_min_bases() && n_recs && host_is_pageable(recs[0].seq)) n_slabs = 2;
     if (const char *e = getenv("IPCR_STREAM_SLABS")) n_slabs = atoi(e);
     if (n_slabs >= 2 && total < (1ull << kCandPosBits) && n_recs <= 65535) {
         if (chain && n_slabs <= (int)kPairMaxBlocks && scan_streamed_chain(s, recs, n_recs, n_slabs, &n)) return n;

@@ -53,6 +53,32 @@ static void piece_segments(const PieceCut &c, size_t n_recs, uint64_t lo, uint64
 // Streamed slabs on ONE device: the H2D copy of slab k+1.. runs under stage 1 of slab k
 // (SURVEY.md 8f row 1); every slab leaves a block, stage 2 runs once, the host waits once.
 // ---------------------------------------------------------------------------------------
+// is this host pointer pageable memory (neither cudaMallocHost'ed nor registered)?  The Go host's []byte always is.
+static bool host_is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// smallest pageable input that goes through the pinned staging ring (HostStager) instead of the driver's own staging
+static uint64_t staged_min_bases() {
+    const char *e = getenv("IPCR_STAGED_H2D_MIN");  // tests: tiny inputs too; a huge value: never
+    return e ? (uint64_t)atoll(e) : (64ull << 20);
+}
+
+struct StagerJoin {  // on every way out: threads joined, their copies landed (the caller may free the source)
+    HostStager *h;
+    ~StagerJoin() {
+        if (!h) return;
+        h->finish();
+        for (int t = 0; t < HostStager::kThreads; t++)
+            if (h->stream[t]) cudaStreamSynchronize(h->stream[t]);
+    }
+};
+
 static bool scan_streamed_chain(ipcr_scratch *s, const ipcr_seq *recs, size_t n_recs, int n_slabs, uint64_t *n_prod) {
     cudaStream_t st = s->stream, cs = s->copy_stream;
     const PieceCut c = cut_pieces(recs, n_recs, n_slabs);
@@ -75,17 +101,30 @@ static bool scan_streamed_chain(ipcr_scratch *s, const ipcr_seq *recs, size_t n_
     // 1. every copy is queued now; slab k's event fires once [cut[k], cut[k+1] + halo) is resident
     CU(cudaEventRecord(s->ev[0], st));
     CU(cudaEventRecord(s->copy_ev[0], cs));
+    // pageable records (what a Go / Python caller passes): several host threads stage them through a pinned ring --
+    // the driver's single-threaded staging runs at ~11 GB/s, a fifth of the link
+    bool staged = c.total >= staged_min_bases();
+    for (size_t r = 0; r < n_recs && staged; r++)
+        if (recs[r].len) {
+            staged = host_is_pageable(recs[r].seq);
+            break;
+        }
+    if (staged && !s->stager) s->stager.reset(new HostStager());
+    StagerJoin stager_join{staged ? s->stager.get() : nullptr};
     uint64_t copied_to = 0;
     for (int k = 0; k < n_slabs; k++) {
         const uint64_t want = std::min(c.total, c.cut[k + 1] + kPieceHalo);
         for (size_t r = 0; r < n_recs && copied_to < want; r++) {
             const uint64_t a = std::max(copied_to, c.roff[r]), b = std::min(want, c.roff[r + 1]);
-            if (a < b) CU(cudaMemcpyAsync(base + a, recs[r].seq + (a - c.roff[r]), b - a, cudaMemcpyHostToDevice, cs));
+            if (a >= b) continue;
+            if (staged) s->stager->add(base + a, recs[r].seq + (a - c.roff[r]), b - a, k);
+            else CU(cudaMemcpyAsync(base + a, recs[r].seq + (a - c.roff[r]), b - a, cudaMemcpyHostToDevice, cs));
         }
         copied_to = std::max(copied_to, want);
-        CU(cudaEventRecord(s->slab_ev[k], cs));
+        if (!staged) CU(cudaEventRecord(s->slab_ev[k], cs));
     }
-    CU(cudaEventRecord(s->copy_ev[1], cs));
+    if (staged) s->stager->start(s->device, n_slabs);
+    else CU(cudaEventRecord(s->copy_ev[1], cs));
     // 2. stage 1 per slab into its block, stage 2 once; capacities / plan variant may ask for a second round
     bool done = false;
     for (int attempt = 0; attempt < 6 && !done; attempt++) {
@@ -107,11 +146,18 @@ static bool scan_streamed_chain(ipcr_scratch *s, const ipcr_seq *recs, size_t n_
             g.codes_ext = g.inval_ext = nullptr;
             g.own_bases = hi - lo;
             g.planes_ready = g.codes_ready = false;
-            if (attempt == 0) CU(cudaStreamWaitEvent(st, s->slab_ev[k], 0));
+            if (attempt == 0) {
+                if (staged) s->stager->wait_mark(k, st);
+                else CU(cudaStreamWaitEvent(st, s->slab_ev[k], 0));
+            }
             CU(cudaEventRecord(s->slab_t[2 * k], st));
             stage1_async(s, g, variant, s->gather.as<uint8_t>() + (size_t)n_blocks * bb, site_cap);
             CU(cudaEventRecord(s->slab_t[2 * k + 1], st));
             n_blocks++;
+        }
+        if (staged && attempt == 0) {  // the copy stream's end-of-copies event, for the timing
+            s->stager->wait_mark(n_slabs - 1, cs);
+            CU(cudaEventRecord(s->copy_ev[1], cs));
         }
         if (n_blocks == 0) {
             *n_prod = 0;
@@ -216,19 +262,9 @@ static bool scan_packed_chain(ipcr_scratch *s, const PackedHost &ph, const std::
     }
     // pageable source (a one-shot FASTA run): several host threads stage the chunks through a pinned ring instead
     // of the driver's single-threaded staging
-    uint64_t staged_min = 64ull << 20;
-    if (const char *e = getenv("IPCR_STAGED_H2D_MIN")) staged_min = (uint64_t)atoll(e);  // tests: tiny inputs too; -1: never
-    const bool staged = !ph.pinned && total >= staged_min;
+    const bool staged = !ph.pinned && total >= staged_min_bases();
     if (staged && !s->stager) s->stager.reset(new HostStager());
-    struct StagerJoin {  // on every way out: threads joined, their copies landed (the caller may free the source)
-        HostStager *h;
-        ~StagerJoin() {
-            if (!h) return;
-            h->finish();
-            for (int t = 0; t < HostStager::kThreads; t++)
-                if (h->stream[t]) cudaStreamSynchronize(h->stream[t]);
-        }
-    } stager_join{staged ? s->stager.get() : nullptr};
+    StagerJoin stager_join{staged ? s->stager.get() : nullptr};
     uint64_t g_done = 0;
     for (int k = 0; k < n_slabs; k++) {
         const uint64_t end = std::min(total, c.cut[k + 1] + kPieceHalo);

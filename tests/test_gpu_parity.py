@@ -514,6 +514,17 @@ def test_streamed_batch_equals_plain(oracle, monkeypatch):
             monkeypatch.setenv("IPCR_STREAM_SLABS", slabs)
             got = [(p.sequence_id,) + _tuple(p) for p in D.scan_batch(cp, sc, seqs, seq_ids=[f"r{i}" for i in range(4)])]
             assert got == want, (cfgd, slabs)
+        # the records are Python bytes = pageable host memory: the same through the multi-threaded pinned staging ring
+        # (by default only inputs >= 64 Mbp take it), with the slab count left to the library and forced
+        monkeypatch.setenv("IPCR_STAGED_H2D_MIN", "1")
+        for slabs in (None, "2", "5"):
+            if slabs is None:
+                monkeypatch.delenv("IPCR_STREAM_SLABS")
+            else:
+                monkeypatch.setenv("IPCR_STREAM_SLABS", slabs)
+            got = [(p.sequence_id,) + _tuple(p) for p in D.scan_batch(cp, sc, seqs, seq_ids=[f"r{i}" for i in range(4)])]
+            assert got == want, (cfgd, "staged", slabs)
+        monkeypatch.delenv("IPCR_STAGED_H2D_MIN")
         monkeypatch.delenv("IPCR_STREAM_SLABS")
 
 
