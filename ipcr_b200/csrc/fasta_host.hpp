@@ -26,6 +26,7 @@
 #include <emmintrin.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -78,6 +79,84 @@ inline void fasta_for_lines(const uint8_t *d, size_t n, size_t lo, size_t hi, F 
 inline void fasta_trim(const uint8_t *d, size_t &a, size_t &b) {
     while (a < b && fasta_is_space(d[a])) a++;
     while (b > a && fasta_is_space(d[b - 1])) b--;
+}
+
+// pass 1 over the lines that START in [lo, hi): kept bytes per (open record | header) -> pc
+inline void fasta_count_range(const uint8_t *d, size_t n, size_t lo, const size_t hi, FastaPiece &pc) {
+    uint64_t *cur = &pc.head_kept;
+    // slow path: line by line (headers, lines with white space at their ends)
+    auto lines = [&](size_t lo, size_t hi) {
+        fasta_for_lines(d, n, lo, hi, [&](size_t a, size_t b) {
+            if (b > a && d[a] == '>') {
+                pc.hdrs.push_back({fasta_header_id(d + a + 1, b - a - 1), 0});
+                cur = &pc.hdrs.back().kept;
+                return;
+            }
+            fasta_trim(d, a, b);
+            *cur += b - a;
+        });
+    };
+    // fast path: whole lines that hold no '>' and no white space except their '\n' keep every other byte.
+    // p always sits at a line start; blocks of 64 bytes are classified with SSE2 compares.
+    size_t p = lo;
+    const __m128i v_nl = _mm_set1_epi8('\n'), v_gt = _mm_set1_epi8('>'), v_sp = _mm_set1_epi8(' ');
+    const __m128i v_lo = _mm_set1_epi8((char)(-0x09 - 128)), v_span = _mm_set1_epi8((char)(0x0D - 0x09 + 1 - 128));
+    while (p < hi) {
+        size_t q = p;
+        uint64_t kept = 0;
+        size_t last_nl = p;  // one past the last newline seen in clean blocks
+        bool dirty = false;
+        while (q + 64 <= hi) {
+            uint32_t nl_bits[4];
+            uint32_t bad = 0;
+            for (int k = 0; k < 4; k++) {
+                const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(d + q + 16 * k));
+                const uint32_t nl = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, v_nl));
+                // bytes 0x09..0x0D: (v - 0x09) < 5 unsigned, done as a signed compare after biasing by 128
+                const __m128i ws = _mm_cmplt_epi8(_mm_add_epi8(v, v_lo), v_span);
+                const uint32_t other = (uint32_t)_mm_movemask_epi8(
+                    _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(v, v_gt), _mm_cmpeq_epi8(v, v_sp)), ws));
+                nl_bits[k] = nl;
+                bad |= other & ~nl;
+            }
+            if (bad) {
+                dirty = true;
+                break;
+            }
+            uint32_t cnt = 0;
+            for (int k = 0; k < 4; k++) {
+                cnt += (uint32_t)__builtin_popcount(nl_bits[k]);
+                if (nl_bits[k]) last_nl = q + 16 * k + (32 - __builtin_clz(nl_bits[k]));
+            }
+            kept += 64 - cnt;
+            q += 64;
+        }
+        // the clean blocks cover [p, q): whole lines up to last_nl count as they are, the unfinished line
+        // (from last_nl) goes to the slow path together with whatever follows in the dirty block
+        if (last_nl > p) {
+            *cur += kept - (q - last_nl);
+            p = last_nl;
+        }
+        if (!dirty && q + 64 > hi) {  // tail of the range
+            lines(p, hi);
+            break;
+        }
+        // slow path over the lines that start before the end of the dirty block
+        size_t stop = std::min(hi, q + 64);
+        const uint8_t *nl = static_cast<const uint8_t *>(memchr(d + stop - 1, '\n', n - (stop - 1)));
+        stop = nl ? (size_t)(nl - d) + 1 : n;
+        stop = std::min(stop, hi);  // lines START inside [p, hi); fasta_for_lines reads each to its own end
+        lines(p, stop);
+        p = stop;
+        if (stop >= hi) break;
+    }
+}
+
+// the line start at or after p (range boundaries are snapped to line starts)
+inline size_t fasta_snap(const uint8_t *d, size_t n, size_t p) {
+    if (p == 0 || p >= n || d[p - 1] == '\n') return std::min(p, n);
+    const uint8_t *nl = static_cast<const uint8_t *>(memchr(d + p, '\n', n - p));
+    return nl ? (size_t)(nl - d) + 1 : n;
 }
 
 // Parses `n` bytes of FASTA text.  `alloc(total)` must return a buffer for the sequence bytes.
@@ -135,9 +214,143 @@ struct FastaPackStage {
     }
 };
 
+// Pack-only parse in ONE trip through memory.  The file is cut into 512 KB blocks (at line starts) that the threads
+// claim in order.  A thread walks its block ONCE, line by line (header / TrimSpace / upper-case rules), writing the
+// kept bytes into a block-sized staging buffer (which stays in its L2) and counting them per record.  It then waits
+// for the predecessor block's published (output offset, open-record state) -- the chain advances at the pace every
+// thread works at, so nobody waits long --, publishes its own, and packs its staged bytes into the final arrays at
+// that offset.  Whether the bytes before the block's first header are kept depends on the predecessor: they are
+// staged anyway and skipped at pack time if the open record was a dropped one.  The two-pass form reads the file
+// twice from DRAM and classifies every byte twice; this one once.  The packed arrays are allocated for the upper
+// bound n bases (untouched pages cost nothing); a block's bytes in the groups it shares with its neighbours are
+// kept in per-block fragments and assembled at the end.
+template <class Alloc>
+inline void fasta_parse_chained(const uint8_t *d, size_t n, int threads, std::vector<FastaRecord> &recs, uint64_t &total,
+                                Alloc &&alloc, FastaPackTarget *pack) {
+    recs.clear();
+    total = 0;
+    if (threads < 1) threads = 1;
+    alloc((uint64_t)n);  // the callback allocates the pack target; n bases is an upper bound of the total
+    size_t block = (size_t)512 << 10;
+    if (const char *e = getenv("IPCR_FEEDER_BLOCK")) block = (size_t)std::max<long long>(1, atoll(e));  // tests
+    const size_t nb = std::max<size_t>(1, (n + block - 1) / block);
+    std::vector<size_t> cut(nb + 1, n);
+    cut[0] = 0;
+    for (size_t i = 1; i < nb; i++) cut[i] = std::max(cut[i - 1], fasta_snap(d, n, i * block));
+    struct Blk {
+        FastaPiece pc;
+        uint64_t start = 0, end = 0;
+        bool open_in = false, open_out = false;
+        uint8_t head[32], tail[32];
+        uint32_t head_len = 0, tail_len = 0;
+        uint64_t tail_at = 0;
+        std::atomic<int> ready{0};
+    };
+    std::vector<Blk> blk(nb);
+    std::atomic<size_t> next{0};
+    const bool timing = getenv("IPCR_FEEDER_TIMING") != nullptr;
+    const auto t_p0 = std::chrono::steady_clock::now();
+    auto worker = [&] {
+        std::vector<uint8_t> stage;
+        for (size_t i = next++; i < nb; i = next++) {
+            Blk &b = blk[i];
+            const size_t lo = cut[i], hi = cut[i + 1];
+            if (stage.size() < hi - lo + 64) stage.resize(hi - lo + 64);
+            // the one walk: kept bytes -> stage, counts -> b.pc
+            uint8_t *out = stage.data();
+            size_t w = 0;
+            bool keep = true;  // before the first header: decided later (open_in)
+            uint64_t *cur = &b.pc.head_kept;
+            fasta_for_lines(d, n, lo, hi, [&](size_t a0, size_t b0) {
+                if (b0 > a0 && d[a0] == '>') {
+                    b.pc.hdrs.push_back({fasta_header_id(d + a0 + 1, b0 - a0 - 1), 0});
+                    cur = &b.pc.hdrs.back().kept;
+                    keep = !b.pc.hdrs.back().id.empty();
+                    return;
+                }
+                fasta_trim(d, a0, b0);
+                const size_t k = b0 - a0;
+                *cur += k;  // counted for dropped records too, like the two-pass form (never added up)
+                if (!keep) return;
+                FastaPackStage::norm(out + w, d + a0, k);
+                w += k;
+            });
+            if (i > 0) {
+                while (!blk[i - 1].ready.load(std::memory_order_acquire)) std::this_thread::yield();
+                b.start = blk[i - 1].end;
+                b.open_in = blk[i - 1].open_out;
+            }
+            const uint8_t *src = stage.data() + (b.open_in ? 0 : b.pc.head_kept);
+            const uint64_t kept = w - (b.open_in ? 0 : b.pc.head_kept);
+            b.end = b.start + kept;
+            b.open_out = b.pc.hdrs.empty() ? b.open_in : !b.pc.hdrs.back().id.empty();
+            b.ready.store(1, std::memory_order_release);
+            // pack at the final offset: fragment up to the next group boundary, whole groups, fragment behind them
+            b.head_len = (uint32_t)std::min<uint64_t>(kept, (32 - b.start % 32) % 32);
+            memcpy(b.head, src, b.head_len);
+            const uint64_t ng = (kept - b.head_len) / 32;
+            if (ng) pack_groups_staged(src + b.head_len, (b.start + b.head_len) / 32, ng, pack->codes, pack->inval);
+            b.tail_at = b.start + b.head_len + 32 * ng;
+            b.tail_len = (uint32_t)(b.end - b.tail_at);
+            memcpy(b.tail, src + b.head_len + 32 * ng, b.tail_len);
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        const int nt = (int)std::min<size_t>((size_t)threads, nb);
+        for (int t = 1; t < nt; t++) th.emplace_back(worker);
+        worker();
+        for (auto &x : th) x.join();
+    }
+    const auto t_p1 = std::chrono::steady_clock::now();
+    // record table
+    bool open = false;
+    for (size_t i = 0; i < nb; i++) {
+        if (open) recs.back().len += blk[i].pc.head_kept;
+        uint64_t off = blk[i].start + (open ? blk[i].pc.head_kept : 0);
+        for (auto &h : blk[i].pc.hdrs) {
+            open = !h.id.empty();
+            if (open) {
+                FastaRecord r;
+                r.id = h.id;
+                r.off = off;
+                r.len = h.kept;
+                recs.push_back(std::move(r));
+                off += h.kept;
+            }
+        }
+    }
+    total = blk[nb - 1].end;
+    // groups shared by neighbouring blocks (and the ragged last group): assemble the fragments, pack
+    struct Frag { uint64_t at; const uint8_t *src; uint32_t len; };
+    std::vector<Frag> frags;
+    for (size_t i = 0; i < nb; i++) {
+        if (blk[i].head_len) frags.push_back(Frag{blk[i].start, blk[i].head, blk[i].head_len});
+        if (blk[i].tail_len) frags.push_back(Frag{blk[i].tail_at, blk[i].tail, blk[i].tail_len});
+    }
+    std::vector<uint64_t> edge_g;
+    for (const Frag &f : frags) edge_g.push_back(f.at / 32);
+    edge_g.erase(std::unique(edge_g.begin(), edge_g.end()), edge_g.end());  // frags are in offset order
+    std::vector<uint8_t> edge(edge_g.size() * 32 + 32, 0);
+    for (const Frag &f : frags) {
+        const size_t k = (size_t)(std::lower_bound(edge_g.begin(), edge_g.end(), f.at / 32) - edge_g.begin());
+        memcpy(edge.data() + k * 32 + f.at % 32, f.src, f.len);
+    }
+    for (size_t k = 0; k < edge_g.size(); k++) pack_groups_staged(edge.data() + k * 32, edge_g[k], 1, pack->codes, pack->inval);
+    pack_groups_host(nullptr, 0, (total + 31) / 32, packed_groups(total), pack->codes, pack->inval);  // padding groups
+    if (timing)
+        fprintf(stderr, "[feeder] one trip: %zu blocks, walk + pack %.3f s, tables + edge groups %.3f s\n", nb,
+                std::chrono::duration<double>(t_p1 - t_p0).count(),
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_p1).count());
+}
+
 template <class Alloc>
 inline void fasta_parse(const uint8_t *d, size_t n, int threads, std::vector<FastaRecord> &recs, uint64_t &total,
                         Alloc &&alloc, FastaPackTarget *pack = nullptr) {
+    if (pack && pack->only && !getenv("IPCR_FEEDER_TWO_PASS")) {
+        fasta_parse_chained(d, n, threads, recs, total, alloc, pack);
+        return;
+    }
     recs.clear();
     total = 0;
     if (threads < 1) threads = 1;
@@ -159,77 +372,7 @@ inline void fasta_parse(const uint8_t *d, size_t n, int threads, std::vector<Fas
         cut[t] = std::min(p, n);
     }
     std::vector<FastaPiece> pieces((size_t)threads);
-    auto pass1 = [&](int t) {
-        FastaPiece &pc = pieces[t];
-        uint64_t *cur = &pc.head_kept;
-        // slow path: line by line (headers, lines with white space at their ends)
-        auto lines = [&](size_t lo, size_t hi) {
-            fasta_for_lines(d, n, lo, hi, [&](size_t a, size_t b) {
-                if (b > a && d[a] == '>') {
-                    pc.hdrs.push_back({fasta_header_id(d + a + 1, b - a - 1), 0});
-                    cur = &pc.hdrs.back().kept;
-                    return;
-                }
-                fasta_trim(d, a, b);
-                *cur += b - a;
-            });
-        };
-        // fast path: whole lines that hold no '>' and no white space except their '\n' keep every other byte.
-        // p always sits at a line start; blocks of 64 bytes are classified with SSE2 compares.
-        size_t p = cut[t];
-        const size_t hi = cut[t + 1];
-        const __m128i v_nl = _mm_set1_epi8('\n'), v_gt = _mm_set1_epi8('>'), v_sp = _mm_set1_epi8(' ');
-        const __m128i v_lo = _mm_set1_epi8((char)(-0x09 - 128)), v_span = _mm_set1_epi8((char)(0x0D - 0x09 + 1 - 128));
-        while (p < hi) {
-            size_t q = p;
-            uint64_t kept = 0;
-            size_t last_nl = p;  // one past the last newline seen in clean blocks
-            bool dirty = false;
-            while (q + 64 <= hi) {
-                uint32_t nl_bits[4];
-                uint32_t bad = 0;
-                for (int k = 0; k < 4; k++) {
-                    const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(d + q + 16 * k));
-                    const uint32_t nl = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, v_nl));
-                    // bytes 0x09..0x0D: (v - 0x09) < 5 unsigned, done as a signed compare after biasing by 128
-                    const __m128i ws = _mm_cmplt_epi8(_mm_add_epi8(v, v_lo), v_span);
-                    const uint32_t other = (uint32_t)_mm_movemask_epi8(
-                        _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(v, v_gt), _mm_cmpeq_epi8(v, v_sp)), ws));
-                    nl_bits[k] = nl;
-                    bad |= other & ~nl;
-                }
-                if (bad) {
-                    dirty = true;
-                    break;
-                }
-                uint32_t cnt = 0;
-                for (int k = 0; k < 4; k++) {
-                    cnt += (uint32_t)__builtin_popcount(nl_bits[k]);
-                    if (nl_bits[k]) last_nl = q + 16 * k + (32 - __builtin_clz(nl_bits[k]));
-                }
-                kept += 64 - cnt;
-                q += 64;
-            }
-            // the clean blocks cover [p, q): whole lines up to last_nl count as they are, the unfinished line
-            // (from last_nl) goes to the slow path together with whatever follows in the dirty block
-            if (last_nl > p) {
-                *cur += kept - (q - last_nl);
-                p = last_nl;
-            }
-            if (!dirty && q + 64 > hi) {  // tail of the range
-                lines(p, hi);
-                break;
-            }
-            // slow path over the lines that start before the end of the dirty block
-            size_t stop = std::min(hi, q + 64);
-            const uint8_t *nl = static_cast<const uint8_t *>(memchr(d + stop - 1, '\n', n - (stop - 1)));
-            stop = nl ? (size_t)(nl - d) + 1 : n;
-            stop = std::min(stop, hi);  // lines START inside [p, hi); fasta_for_lines reads each to its own end
-            lines(p, stop);
-            p = stop;
-            if (stop >= hi) break;
-        }
-    };
+    auto pass1 = [&](int t) { fasta_count_range(d, n, cut[t], cut[t + 1], pieces[t]); };
     const bool timing = getenv("IPCR_FEEDER_TIMING") != nullptr;
     const auto t_p0 = std::chrono::steady_clock::now();
     {

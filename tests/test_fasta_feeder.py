@@ -286,18 +286,81 @@ def test_feeder_pack_only_equals_pack(tmp_path, monkeypatch):
         wi = np.zeros(iw.value, dtype=np.uint32)
         assert L.ipcr_gpu_pack_host(cat, len(cat), wc.ctypes.data, wi.ctypes.data, 1) == 0
         as_n = [(i, bytes(c if c in b"ACGT" else ord("N") for c in s_)) for i, s_ in ref]
-        for threads in (1, 2, 3, 7, 16, 31):
+        # pack-only runs in ONE trip by default (blocks claimed in order, offsets through a chain of published
+        # prefixes); tiny blocks put many block boundaries inside one group.  IPCR_FEEDER_TWO_PASS: the older form
+        for mode in ("two_pass", "1048576", "37", "1000", "1"):
+            if mode == "two_pass":
+                monkeypatch.setenv("IPCR_FEEDER_TWO_PASS", "1")
+            else:
+                monkeypatch.delenv("IPCR_FEEDER_TWO_PASS", raising=False)
+                monkeypatch.setenv("IPCR_FEEDER_BLOCK", mode)
+            for threads in (1, 2, 3, 7, 16, 31):
+                only = FastaFile(str(path), threads=threads, pack_only=True)
+                assert only.packed and len(only) == len(ref) and only.total_bases == len(cat), (name, mode, threads)
+                assert only.ids() == [i for i, _ in ref]
+                got_c, got_i = _packed_arrays(only)
+                assert np.array_equal(got_c, wc) and np.array_equal(got_i, wi), (name, mode, threads)
+                assert only.records() == as_n, (name, mode, threads)
+                only.close()
+        monkeypatch.delenv("IPCR_FEEDER_BLOCK", raising=False)
+        for threads in (1, 3, 16):
             full = FastaFile(str(path), threads=threads, pack=True)
-            only = FastaFile(str(path), threads=threads, pack_only=True)
-            assert only.packed and len(only) == len(ref) and only.total_bases == len(cat), (name, threads)
-            assert only.ids() == [i for i, _ in ref]
-            for ff in (full, only):
-                got_c, got_i = _packed_arrays(ff)
-                assert np.array_equal(got_c, wc) and np.array_equal(got_i, wi), (name, threads, ff is only)
+            got_c, got_i = _packed_arrays(full)
+            assert np.array_equal(got_c, wc) and np.array_equal(got_i, wi), (name, threads)
             assert full.records() == ref
-            assert only.records() == as_n, (name, threads)
             full.close()
+
+
+def test_feeder_pack_only_fuzz(tmp_path, monkeypatch):
+    """Byte soup against the restatement of the reference reader: random mixes of sequence runs, newlines, CRLF,
+    blanks and tabs at line ends and inside lines, '>' at line starts and inside lines, empty ids, no final newline --
+    through the one-trip pack-only parse (32-byte clean-chunk fast path, line rules for everything else) with
+    block sizes from 1 byte up, and through the two-pass form."""
+    import ctypes as C
+
+    import numpy as np
+
+    from ipcr_b200 import _capi
+
+    L = _capi.lib()
+    monkeypatch.setenv("IPCR_FEEDER_MT_MIN", "1")
+    rng = random.Random(2024)
+    tokens = [b"\n", b"\n", b"\r\n", b" ", b"\t", b">", b">id ", b"> \n", b">x\ty\n", b"\n\n", b"\x0b", b"N", b"acgt", b"-"]
+    for it in range(120):
+        parts = []
+        for _ in range(rng.randint(1, 60)):
+            if rng.random() < 0.6:
+                parts.append(bytes(rng.choice(b"ACGTacgtNn") for _ in range(rng.choice([1, 5, 31, 32, 33, 64, 80, 200]))))
+                parts.append(b"\n" if rng.random() < 0.8 else b"")
+            else:
+                parts.append(rng.choice(tokens))
+        data = b"".join(parts)
+        if rng.random() < 0.5:
+            data = b">first\n" + data
+        path = tmp_path / f"fuzz{it}.fa"
+        path.write_bytes(data)
+        ref = ref_reader(data)
+        cat = b"".join(s_ for _id, s_ in ref)
+        cw, iw = C.c_uint64(), C.c_uint64()
+        L.ipcr_gpu_packed_words(len(cat), C.byref(cw), C.byref(iw))
+        wc = np.zeros(cw.value, dtype=np.uint32)
+        wi = np.zeros(iw.value, dtype=np.uint32)
+        assert L.ipcr_gpu_pack_host(cat, len(cat), wc.ctypes.data, wi.ctypes.data, 1) == 0
+        for mode in ("two_pass", "1048576", str(rng.randint(1, 200)), "64"):
+            if mode == "two_pass":
+                monkeypatch.setenv("IPCR_FEEDER_TWO_PASS", "1")
+            else:
+                monkeypatch.delenv("IPCR_FEEDER_TWO_PASS", raising=False)
+                monkeypatch.setenv("IPCR_FEEDER_BLOCK", mode)
+            only = FastaFile(str(path), threads=rng.choice([1, 2, 5]), pack_only=True)
+            assert [(i, n) for i, n in zip(only.ids(), [len(s_) for _i, s_ in ref])] == [(i, len(s_)) for i, s_ in ref], (it, mode)
+            assert only.total_bases == len(cat), (it, mode, data)
+            got_c, got_i = _packed_arrays(only)
+            assert np.array_equal(got_c, wc) and np.array_equal(got_i, wi), (it, mode, data)
             only.close()
+        plain = FastaFile(str(path), threads=2)
+        assert plain.records() == ref, (it, data)
+        plain.close()
 
 
 def test_invalid_run_list_round_trips():
