@@ -303,6 +303,9 @@ int ipcr_gpu_fasta_is_packed(const ipcr_fasta *f);
 /* the packed form of the handle's whole sequence buffer (records back to back): 2 * n_groups code words,
  * n_groups bitmap words; owned by the handle */
 int ipcr_gpu_fasta_packed(const ipcr_fasta *f, const uint32_t **codes, const uint32_t **inval, uint64_t *n_groups);
+/* the handle's bitmap as the run list ipcr_gpu_scan_fasta ships (see ipcr_gpu_packed_runs); returns 1 when the handle
+ * is not packed or holds too many runs for a list (*n_runs = 0 then) */
+int ipcr_gpu_fasta_runs(const ipcr_fasta *f, const uint64_t **runs, uint64_t *n_runs);
 /* the host packer the feeder applies (bit-for-bit what the device pack kernel writes):
  * codes[*code_words], inval[*inval_words] for n_bases bases, padding included */
 void ipcr_gpu_packed_words(uint64_t n_bases, uint64_t *code_words, uint64_t *inval_words);

@@ -129,7 +129,7 @@ SYMBOLS = [
     "ipcr_gpu_genome_upload", "ipcr_gpu_genome_adopt", "ipcr_gpu_genome_destroy",
     "ipcr_gpu_genome_bases", "ipcr_gpu_genome_records", "ipcr_gpu_scan_genome",
     "ipcr_gpu_find_sites", "ipcr_gpu_find_sites_device", "ipcr_gpu_pair_sites",
-    "ipcr_gpu_fasta_open", "ipcr_gpu_fasta_close", "ipcr_gpu_fasta_num_records",
+    "ipcr_gpu_fasta_open", "ipcr_gpu_fasta_close", "ipcr_gpu_fasta_num_records", "ipcr_gpu_fasta_runs",
     "ipcr_gpu_fasta_total_bases", "ipcr_gpu_fasta_record", "ipcr_gpu_scan_fasta",
     "ipcr_gpu_probe_annotate", "ipcr_gpu_amplicons", "ipcr_gpu_nested",
     "ipcr_gpu_product_mismatch_idx", "ipcr_gpu_last_timing", "ipcr_gpu_synth_fill",
@@ -192,6 +192,7 @@ def lib():
         P(RecordInfoC), *ERR)
     sig("ipcr_gpu_pair_sites", C.c_int, V, V, P(SiteC), U64, P(RecordInfoC), SZ, P(P(ProductC)), P(U64), *ERR)
     sig("ipcr_gpu_fasta_open", V, C.c_char_p, C.c_int, C.c_int, *ERR)
+    sig("ipcr_gpu_fasta_runs", C.c_int, V, P(P(U64)), P(U64))
     sig("ipcr_gpu_fasta_from_memory", V, P(SeqC), P(C.c_char_p), SZ, C.c_int, C.c_int, *ERR)
     sig("ipcr_gpu_fasta_is_packed", C.c_int, V)
     sig("ipcr_gpu_fasta_packed", C.c_int, V, P(P(C.c_uint32)), P(P(C.c_uint32)), P(U64))

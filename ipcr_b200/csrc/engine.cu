@@ -1960,9 +1960,16 @@ struct ipcr_fasta {
                 if (recs[r].len) rec_reset[r] = 1;
         }
     }
-    void find_runs(int threads) {
+    void find_runs(int threads, const std::vector<std::pair<uint64_t, uint64_t>> *dirty = nullptr) {
         const uint64_t groups = ipcr::packed_groups(total);
-        runs_ok = ipcr::packed_invalid_runs_mt(inval, groups, std::max<uint64_t>(4096, groups / 64), inval_runs, threads);
+        const uint64_t max_runs = std::max<uint64_t>(4096, groups / 64);
+        uint64_t covered = 0;
+        if (dirty)
+            for (const auto &r : *dirty) covered += r.second - r.first;
+        if (dirty && covered <= groups / 8)  // the feeder knows where the set bits are: look only there
+            runs_ok = ipcr::packed_invalid_runs_ranges(inval, *dirty, max_runs, inval_runs);
+        else
+            runs_ok = ipcr::packed_invalid_runs_mt(inval, groups, max_runs, inval_runs, threads);
         if (!runs_ok) inval_runs.clear();
     }
     std::vector<uint8_t> rec_reset;  // per record: holds a non-ACGT byte (the feeder upper-cased a-z already)
@@ -2121,10 +2128,21 @@ ipcr_fasta *ipcr_gpu_fasta_open(const char *path, int threads, int pin, char *er
         fprintf(stderr, "[feeder] %zu bytes, %d threads: allocations %.3f s (packed: %s, page-locked: %s), parse + copy + pack %.3f s\n",
                 fb.size, threads, alloc_s, want_pack ? "yes" : "no", pin ? "yes" : "no",
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() - alloc_s);
+    const auto t_parsed = std::chrono::steady_clock::now();
     if (want_pack) {
-        f->find_runs(threads);
+        f->find_runs(threads, pk.dirty_known ? &pk.dirty : nullptr);
         f->find_rec_reset();
     }
+    const auto t_runs = std::chrono::steady_clock::now();
+    if (fb.map) {  // unmapping 3 GB of touched pages takes ~20 ms: not on the caller's clock
+        void *m = fb.map;
+        const size_t len = fb.map_len;
+        fb.map = nullptr;
+        std::thread([m, len] { munmap(m, len); }).detach();
+    }
+    if (getenv("IPCR_FEEDER_TIMING"))
+        fprintf(stderr, "[feeder] run list + record flags %.3f s (%zu runs)\n",
+                std::chrono::duration<double>(t_runs - t_parsed).count(), f->inval_runs.size() / 2);
     return f.release();
     ABI_CATCH(nullptr)
 }
@@ -2180,6 +2198,15 @@ ipcr_fasta *ipcr_gpu_fasta_from_memory(const ipcr_seq *recs, const char *const *
 }
 
 int ipcr_gpu_fasta_is_packed(const ipcr_fasta *f) { return f && f->codes ? 1 : 0; }
+
+int ipcr_gpu_fasta_runs(const ipcr_fasta *f, const uint64_t **runs, uint64_t *n_runs) {
+    if (runs) *runs = nullptr;
+    if (n_runs) *n_runs = 0;
+    if (!f || !f->codes || !f->runs_ok) return 1;
+    if (runs) *runs = f->inval_runs.data();
+    if (n_runs) *n_runs = f->inval_runs.size() / 2;
+    return 0;
+}
 
 int ipcr_gpu_fasta_packed(const ipcr_fasta *f, const uint32_t **codes, const uint32_t **inval, uint64_t *n_groups) {
     if (!f || !f->codes) return 1;

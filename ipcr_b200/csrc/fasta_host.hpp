@@ -167,6 +167,9 @@ struct FastaPackTarget {  // optional: the packed form (pack_host.hpp) of the se
     // ragged last group, are assembled in 32-byte edge slots and packed after the join.  Saves writing -- and
     // page-faulting in -- 1 B/bp of memory nobody reads when the scan takes the packed form.
     bool only = false;
+    // filled by the one-trip parse: sorted, disjoint group ranges outside which the bitmap is all zero
+    std::vector<std::pair<uint64_t, uint64_t>> dirty;
+    bool dirty_known = false;
 };
 
 // pass 2 of the pack-only mode: the normalised bytes of one thread's output range [start, end) -> codes / bitmap
@@ -244,6 +247,8 @@ inline void fasta_parse_chained(const uint8_t *d, size_t n, int threads, std::ve
         uint8_t head[32], tail[32];
         uint32_t head_len = 0, tail_len = 0;
         uint64_t tail_at = 0;
+        uint64_t g0 = 0, ng = 0;  // the whole groups this block packed
+        bool any_inval = false;   // ... and whether one of their bitmap words is non-zero
         std::atomic<int> ready{0};
     };
     std::vector<Blk> blk(nb);
@@ -289,7 +294,9 @@ inline void fasta_parse_chained(const uint8_t *d, size_t n, int threads, std::ve
             b.head_len = (uint32_t)std::min<uint64_t>(kept, (32 - b.start % 32) % 32);
             memcpy(b.head, src, b.head_len);
             const uint64_t ng = (kept - b.head_len) / 32;
-            if (ng) pack_groups_staged(src + b.head_len, (b.start + b.head_len) / 32, ng, pack->codes, pack->inval);
+            b.g0 = (b.start + b.head_len) / 32;
+            b.ng = ng;
+            if (ng) b.any_inval = pack_groups_staged(src + b.head_len, b.g0, ng, pack->codes, pack->inval) != 0;
             b.tail_at = b.start + b.head_len + 32 * ng;
             b.tail_len = (uint32_t)(b.end - b.tail_at);
             memcpy(b.tail, src + b.head_len + 32 * ng, b.tail_len);
@@ -336,8 +343,16 @@ inline void fasta_parse_chained(const uint8_t *d, size_t n, int threads, std::ve
         const size_t k = (size_t)(std::lower_bound(edge_g.begin(), edge_g.end(), f.at / 32) - edge_g.begin());
         memcpy(edge.data() + k * 32 + f.at % 32, f.src, f.len);
     }
-    for (size_t k = 0; k < edge_g.size(); k++) pack_groups_staged(edge.data() + k * 32, edge_g[k], 1, pack->codes, pack->inval);
+    std::vector<std::pair<uint64_t, uint64_t>> dirty;
+    for (size_t k = 0; k < edge_g.size(); k++)
+        if (pack_groups_staged(edge.data() + k * 32, edge_g[k], 1, pack->codes, pack->inval)) dirty.push_back({edge_g[k], edge_g[k] + 1});
     pack_groups_host(nullptr, 0, (total + 31) / 32, packed_groups(total), pack->codes, pack->inval);  // padding groups
+    for (size_t i = 0; i < nb; i++)
+        if (blk[i].any_inval) dirty.push_back({blk[i].g0, blk[i].g0 + blk[i].ng});
+    dirty.push_back({(total + 31) / 32, packed_groups(total)});
+    std::sort(dirty.begin(), dirty.end());
+    pack->dirty.swap(dirty);
+    pack->dirty_known = true;
     if (timing)
         fprintf(stderr, "[feeder] one trip: %zu blocks, walk + pack %.3f s, tables + edge groups %.3f s\n", nb,
                 std::chrono::duration<double>(t_p1 - t_p0).count(),

@@ -14,6 +14,7 @@
 #include <immintrin.h>
 #endif
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace ipcr {
@@ -42,19 +43,23 @@ inline void pack4_host(uint32_t w, uint32_t &code8, uint32_t &inv4) {
 // compares, one movemask = the 32 bitmap bits); its code is bits 1..2 of the byte, gathered 8 bytes at a time by PEXT.
 // ~20 instructions per 32 bases instead of ~110.
 __attribute__((target("avx2,bmi2")))
-inline void pack_groups_staged_avx2(const uint8_t *src, uint64_t g0, uint64_t ng, uint32_t *codes, uint32_t *inval) {
+inline uint32_t pack_groups_staged_avx2(const uint8_t *src, uint64_t g0, uint64_t ng, uint32_t *codes, uint32_t *inval) {
+    uint32_t any = 0;
     const __m256i vA = _mm256_set1_epi8('A'), vC = _mm256_set1_epi8('C'), vG = _mm256_set1_epi8('G'), vT = _mm256_set1_epi8('T');
     const unsigned long long m = 0x0606060606060606ull;
     for (uint64_t i = 0; i < ng; i++) {
         const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 32 * i));
         const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, vA), _mm256_cmpeq_epi8(v, vC)),
                                            _mm256_or_si256(_mm256_cmpeq_epi8(v, vG), _mm256_cmpeq_epi8(v, vT)));
-        inval[g0 + i] = ~(uint32_t)_mm256_movemask_epi8(ok);
+        const uint32_t bad = ~(uint32_t)_mm256_movemask_epi8(ok);
+        inval[g0 + i] = bad;
+        any |= bad;
         unsigned long long q[4];
         memcpy(q, src + 32 * i, 32);
         codes[2 * (g0 + i)] = (uint32_t)(_pext_u64(q[0], m) | (_pext_u64(q[1], m) << 16));
         codes[2 * (g0 + i) + 1] = (uint32_t)(_pext_u64(q[2], m) | (_pext_u64(q[3], m) << 16));
     }
+    return any;
 }
 
 inline bool pack_have_avx2() {
@@ -75,13 +80,12 @@ inline bool pack_have_avx2() {
 
 // ng whole groups starting at group g0, their 32 * ng bytes at `src` (a staging buffer: the feeder's pack-only mode
 // never materialises the ASCII buffer)
-inline void pack_groups_staged(const uint8_t *src, uint64_t g0, uint64_t ng, uint32_t *codes, uint32_t *inval) {
+// returns the OR of the bitmap words it wrote (0: no hard-mismatch byte in there)
+inline uint32_t pack_groups_staged(const uint8_t *src, uint64_t g0, uint64_t ng, uint32_t *codes, uint32_t *inval) {
 #if defined(__x86_64__)
-    if (pack_have_avx2()) {
-        pack_groups_staged_avx2(src, g0, ng, codes, inval);
-        return;
-    }
+    if (pack_have_avx2()) return pack_groups_staged_avx2(src, g0, ng, codes, inval);
 #endif
+    uint32_t any = 0;
     for (uint64_t i = 0; i < ng; i++) {
         uint32_t w[8];
         memcpy(w, src + 32 * i, 32);
@@ -95,7 +99,9 @@ inline void pack_groups_staged(const uint8_t *src, uint64_t g0, uint64_t ng, uin
         codes[2 * (g0 + i)] = c0;
         codes[2 * (g0 + i) + 1] = c1;
         inval[g0 + i] = inv;
+        any |= inv;
     }
+    return any;
 }
 
 // the ASCII a packed buffer stands for, positions [a, b): A/C/G/T, every hard-mismatch byte as 'N' (for the engine
@@ -227,6 +233,28 @@ inline bool packed_invalid_runs_mt(const uint32_t *inval, uint64_t groups, uint6
             else {
                 runs.push_back(part[(size_t)t][i]);
                 runs.push_back(part[(size_t)t][i + 1]);
+            }
+        }
+        if (runs.size() / 2 > max_runs) return false;
+    }
+    return true;
+}
+
+// the same from a sorted list of disjoint group ranges [g0, g1) that hold every set bit (the one-trip feeder knows
+// which of its blocks wrote a non-zero bitmap word): a clean genome costs nothing, one with a few N runs a few blocks
+inline bool packed_invalid_runs_ranges(const uint32_t *inval, const std::vector<std::pair<uint64_t, uint64_t>> &ranges,
+                                       uint64_t max_runs, std::vector<uint64_t> &runs) {
+    runs.clear();
+    std::vector<uint64_t> part;
+    for (const auto &r : ranges) {
+        if (r.second <= r.first) continue;
+        if (!packed_invalid_runs(inval + r.first, r.second - r.first, max_runs, part)) return false;
+        for (size_t i = 0; i + 1 < part.size(); i += 2) {
+            const uint64_t a = part[i] + r.first * 32ull, b = part[i + 1] + r.first * 32ull;
+            if (!runs.empty() && runs.back() == a) runs.back() = b;
+            else {
+                runs.push_back(a);
+                runs.push_back(b);
             }
         }
         if (runs.size() / 2 > max_runs) return false;

@@ -232,15 +232,28 @@ def test_feeder_fast_paths_and_fused_pack(tmp_path):
 
 
 def _packed_arrays(ff):
+    """(codes, bitmap) of a packed handle; also checks the handle's run list (what ipcr_gpu_scan_fasta ships instead of
+    the bitmap -- the one-trip feeder derives it from the blocks that wrote a non-zero bitmap word) against the runs
+    of the bitmap itself."""
     import ctypes as C
 
     import numpy as np
 
     from ipcr_b200 import _capi
 
+    L = _capi.lib()
     pc, pi, ng = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.c_uint64()
-    assert _capi.lib().ipcr_gpu_fasta_packed(ff._h, C.byref(pc), C.byref(pi), C.byref(ng)) == 0
-    return (np.ctypeslib.as_array(pc, shape=(2 * ng.value,)).copy(), np.ctypeslib.as_array(pi, shape=(ng.value,)).copy())
+    assert L.ipcr_gpu_fasta_packed(ff._h, C.byref(pc), C.byref(pi), C.byref(ng)) == 0
+    codes = np.ctypeslib.as_array(pc, shape=(2 * ng.value,)).copy()
+    inval = np.ctypeslib.as_array(pi, shape=(ng.value,)).copy()
+    pr, nr = C.POINTER(C.c_uint64)(), C.c_uint64()
+    if L.ipcr_gpu_fasta_runs(ff._h, C.byref(pr), C.byref(nr)) == 0:
+        got = [int(pr[i]) for i in range(2 * nr.value)]
+        cap = max(16, 2 * nr.value + 16)
+        buf = (C.c_uint64 * (2 * cap))()
+        n = L.ipcr_gpu_packed_runs(inval.ctypes.data_as(C.POINTER(C.c_uint32)), ff.total_bases, buf, cap, 1)
+        assert n == nr.value and got == [int(buf[i]) for i in range(2 * n)], (got[:8], n)
+    return codes, inval
 
 
 def test_feeder_pack_only_equals_pack(tmp_path, monkeypatch):
