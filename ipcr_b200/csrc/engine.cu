@@ -1079,7 +1079,8 @@ static const SeedIndex &seed_get(ipcr_scratch *s, int variant) {
         std::lock_guard<std::mutex> l2(attr_mu);
         for (auto fn : {k_seed_scan<1>, k_seed_scan<2>, k_seed_scan<2, 1>, k_seed_scan<2, 4>, k_seed_scan<2, 5>,
                         k_seed_scan<2, 2>, k_seed_scan<2, 8>,
-                        k_seed_scan<1, 0, 2>, k_seed_scan<2, 0, 2>, k_seed_scan<1, 0, 4>, k_seed_scan<2, 0, 4>})
+                        k_seed_scan<1, 0, 2>, k_seed_scan<2, 0, 2>, k_seed_scan<1, 0, 4>, k_seed_scan<2, 0, 4>,
+                        k_seed_scan<1, 1, 2>, k_seed_scan<2, 1, 2>, k_seed_scan<1, 1, 4>, k_seed_scan<2, 1, 4>})
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSeedBloomWords * 4)));
         t->seed_ready[variant] = true;
     }
@@ -1101,6 +1102,10 @@ static void launch_seed_scan(ipcr_scratch *s, const SeedIndex &ix, const SeedSca
     if (const char *e = getenv("IPCR_SEED_PREFETCH")) a.prefetch = atoi(e) != 0 ? 1u : 0u;
     if (ix.pigeon) k_seed_scan<3><<<grid, 1024, kSeedHalfWords * 2 * 4, s->stream>>>(a);
     else if (!ix.use_bloom) k_seed_scan<0><<<grid, 1024, 0, s->stream>>>(a);
+    else if (ix.stride == 4 && var == 1 && ix.bloom_k == 1) k_seed_scan<1, 1, 4><<<grid, 1024, smem, s->stream>>>(a);
+    else if (ix.stride == 4 && var == 1) k_seed_scan<2, 1, 4><<<grid, 1024, smem, s->stream>>>(a);
+    else if (ix.stride == 2 && var == 1 && ix.bloom_k == 1) k_seed_scan<1, 1, 2><<<grid, 1024, smem, s->stream>>>(a);
+    else if (ix.stride == 2 && var == 1) k_seed_scan<2, 1, 2><<<grid, 1024, smem, s->stream>>>(a);
     else if (ix.stride == 4 && ix.bloom_k == 1) k_seed_scan<1, 0, 4><<<grid, 1024, smem, s->stream>>>(a);
     else if (ix.stride == 4) k_seed_scan<2, 0, 4><<<grid, 1024, smem, s->stream>>>(a);
     else if (ix.stride == 2 && ix.bloom_k == 1) k_seed_scan<1, 0, 2><<<grid, 1024, smem, s->stream>>>(a);
