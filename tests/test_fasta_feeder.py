@@ -278,6 +278,15 @@ def test_feeder_pack_only_equals_pack(tmp_path, monkeypatch):
         seq = alphabet[rng.integers(0, len(alphabet), n)].tobytes()
         return b"\n".join(seq[i:i + width] for i in range(0, n, width))
 
+    def n_run_genome(n, runs, width):
+        seq = bytearray(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].tobytes())
+        for _ in range(runs):
+            a, k = int(rng.integers(0, n - 1)), int(rng.integers(1, 300))
+            k = min(k, n - a)
+            seq[a:a + k] = b"N" * k
+        seq = bytes(seq)
+        return b"\n".join(seq[i:i + width] for i in range(0, n, width))
+
     files = {
         "tiny": b">a\nACGT\n>b x\nAC\n\n>c\n" + b"G" * 70 + b"\n",
         "headers_only_middle": b">a\n" + body(300, 60) + b"\n" + b"".join(b">e%d\n" % i for i in range(40)) + b">z\n" + body(97, 13) + b"\n",
@@ -285,6 +294,9 @@ def test_feeder_pack_only_equals_pack(tmp_path, monkeypatch):
         "one_long_line": b">chr\n" + body(200_000, 200_000) + b"\n>t\nacgtn\n",
         "crlf_padded": (b">r1 d\n" + body(5000, 61) + b"\n>r2\n  " + body(777, 50) + b" \n").replace(b"\n", b"\r\n"),
         "aligned_total": b">p\n" + body(4096, 64) + b"\n",
+        # a clean genome with a few N runs (1 .. 300 bases, many across block boundaries): the run list then comes from
+        # the few blocks that wrote a non-zero bitmap word, and runs that continue into the next block must be merged
+        "n_runs": b">g\n" + n_run_genome(200_000, 25, 80) + b"\n>h\n" + n_run_genome(30_000, 6, 61) + b"\n",
         "empty": b"",
         "no_records": b"ACGT\nACGT\n",
     }
